@@ -1,0 +1,167 @@
+/*
+ * vppb.h — C-ABI of the B200-native dense-pixel path behind the Video++ (matt-42/vpp) API.
+ *
+ * Video++ is a header-only C++14 template library, so the reference has no FFI of its own for
+ * this path: the boundary it exposes is the template API of vpp/core and vpp/algorithms.  This
+ * header is the thin extern-"C" shim the new C++14 headers (vpp_b200/include/vpp) and the
+ * Python/ctypes host (vpp_b200/capi.py) bind to; every entry point cites the reference
+ * template (file:line, relative to the reference tree) whose work it performs on the GPU.
+ *
+ * Conventions
+ *   - every function returns an int status: 0 = OK, <0 = VPPB_E_* ; vppb_last_error() gives text.
+ *   - plain pointers and sizes only; `stream` is a cudaStream_t passed as void* (NULL = default).
+ *   - coordinates are (row, col) as in the reference (vint2{r,c}).
+ *   - images are described by vppb_img: `base` is the DEVICE address of pixel (0,0); rows are
+ *     `pitch` bytes apart; `border` rows/cols of real, addressable memory surround the domain
+ *     (imageNd.hpp:151-196).  No function allocates device memory unless it says so.
+ *   - there is no CPU fallback: without a CUDA device every compute entry returns VPPB_E_CUDA.
+ */
+#ifndef VPPB_H_
+#define VPPB_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VPPB_VERSION 100
+
+enum {
+  VPPB_OK = 0,
+  VPPB_E_CUDA = -1,     /* CUDA runtime / driver error (text in vppb_last_error) */
+  VPPB_E_ARG = -2,      /* invalid argument (NULL image, mismatched domains, bad element size) */
+  VPPB_E_BORDER = -3,   /* image border too small for the stencil (fast.hpp:937-938 throws here) */
+  VPPB_E_CAPACITY = -4, /* output capacity too small; count_out holds the required size */
+  VPPB_E_NCCL = -5
+};
+
+/* imageNd<V,2> descriptor (imageNd.hh:16-40 imageNd_data). */
+typedef struct vppb_img {
+  void* base;         /* device pointer to pixel (0,0) == imageNd_data::begin_ */
+  void* alloc;        /* start of the owned allocation (NULL for borrowed/_data views and subimages) */
+  int32_t nrows;      /* domain rows */
+  int32_t ncols;      /* domain cols */
+  int32_t pitch;      /* bytes between successive rows */
+  int32_t border;     /* addressable border pixels on each side */
+  int32_t elem_bytes; /* sizeof(V): 1 (u8), 3 (vuchar3), 4 (int/float), 8 (vint2/vfloat2) ... */
+  int32_t align;      /* row alignment in bytes the allocation was made with (0 = unknown) */
+} vppb_img;
+
+/* keypoint / flow records exchanged with the host (vint2 / vfloat2 are (row, col)). */
+typedef struct vppb_int2 { int32_t r, c; } vppb_int2;
+typedef struct vppb_float2 { float r, c; } vppb_float2;
+
+/* ---- library ---------------------------------------------------------------------------- */
+int vppb_version(void);
+const char* vppb_last_error(void);
+/* Select the CUDA device used by the calling thread and warm the context. */
+int vppb_init(int device);
+int vppb_device_count(int* n);
+int vppb_sync(void* stream);
+
+/* ---- image2d<V> storage (imageNd.hpp:151-196 allocate; :224-234 coords_to_offset) --------- */
+/* Host-only layout arithmetic (no GPU needed): pitch, total buffer bytes and the byte offset of
+ * pixel (0,0) from the aligned buffer start for an image of nrows x ncols elements of elem_bytes
+ * with `border` and row alignment `align` (reference default 16/32, ours 128). */
+int vppb_layout(int32_t nrows, int32_t ncols, int32_t elem_bytes, int32_t border, int32_t align,
+                int32_t* pitch, int64_t* total_bytes, int64_t* origin_offset);
+/* cudaMalloc an image with the reference layout; border content is uninitialised (as malloc). */
+int vppb_alloc(vppb_img* out, int32_t nrows, int32_t ncols, int32_t elem_bytes, int32_t border, int32_t align);
+/* Describe an image inside a caller-owned device buffer of at least total_bytes (vppb_layout)
+ * — the `_data=`/`_pitch=` constructor (imageNd.hpp:99-141) for buffers laid out by vppb_layout. */
+int vppb_wrap(vppb_img* out, void* device_buffer, int32_t nrows, int32_t ncols, int32_t elem_bytes,
+              int32_t border, int32_t align);
+int vppb_free(vppb_img* img);
+/* img | box  (imageNd.hpp:324-341): view of rows [r0,r1] x cols [c0,c1], re-based to (0,0). */
+int vppb_subimage(const vppb_img* img, int32_t r0, int32_t c0, int32_t r1, int32_t c1, vppb_img* out);
+/* Host <-> device.  `host` addresses host pixel (0,0), rows host_pitch bytes apart; with_border
+ * != 0 also transfers the border frame (host buffer must hold it at negative offsets). */
+int vppb_upload(const vppb_img* dst, const void* host, int64_t host_pitch, int with_border, void* stream);
+int vppb_download(const vppb_img* src, void* host, int64_t host_pitch, int with_border, void* stream);
+
+/* ---- pixel_wise named kernels (pixel_wise.hpp:69-165) ------------------------------------- */
+/* pixel_wise(A,B,C) | [](int& a,int& b,int& c){ a = b + c; }   benchmarks/image_add.cc:51-57 */
+int vppb_pw_add_i32(const vppb_img* a, const vppb_img* b, const vppb_img* c, void* stream);
+/* fill(img, v) fill.hh:12-15; `value` points to elem_bytes host bytes. with_border -> fill.hh:24-28 */
+int vppb_fill(const vppb_img* img, const void* value, int with_border, void* stream);
+/* copy(src,dst) copy.hh:10-19 (with_border=0) / copy_with_border copy.hh:22-27 (with_border=1) */
+int vppb_copy2d(const vppb_img* src, const vppb_img* dst, int with_border, void* stream);
+/* fill_border_with_value fill.hh:32-45 / fill_border_mirror :48-83 / fill_border_closest :86-121 */
+int vppb_fill_border_value(const vppb_img* img, const void* value, void* stream);
+int vppb_fill_border_mirror(const vppb_img* img, void* stream);
+int vppb_fill_border_closest(const vppb_img* img, void* stream);
+/* sum(img) sum.hh:12-19 for u8 / i8 / i32 images: promoted (int) accumulator, wraps like int. */
+int vppb_sum_i32(const vppb_img* img, int is_signed, int64_t* out_host, void* stream);
+
+/* ---- 5x5 box stencil (relative_access / box_nbh2d user kernel) ---------------------------- */
+/* out = (sum of the 25 neighbours) / 25 per channel, integer division.
+ * u8c3: image2d<vuchar3> (BASELINE config 2; vint3 accumulate, examples/box_filter.cc:23-32 form)
+ * i32 : image2d<int>     (benchmarks/box_5x5_filter2.cc:71-81).  `in` needs border >= 2, filled. */
+int vppb_box5x5_u8c3(const vppb_img* in, const vppb_img* out, void* stream);
+int vppb_box5x5_i32(const vppb_img* in, const vppb_img* out, void* stream);
+/* same on single-channel u8 (image2d<unsigned char>) */
+int vppb_box5x5_u8(const vppb_img* in, const vppb_img* out, void* stream);
+
+/* ---- Scharr + pyramid (scharr.hh:46-87, pyramid.hh:12-81,133-198) ------------------------- */
+/* scharr(in u8, out vector<Vt,2>): out elem 8 bytes; as_float=0 -> vint2 (truncated), 1 -> vfloat2 */
+int vppb_scharr_u8(const vppb_img* in, const vppb_img* out, int as_float, void* stream);
+/* One pyramid step: out(r,c) = lowpass5x5sep(in)(2r,2c)  (antialiasing_lowpass_filter + subsample2,
+ * fused; the mirror-filled H temp of pyramid.hh:36 is reproduced by index mirroring).
+ * kind: 0 = u8, 1 = vint2 (integer /16 per component), 2 = vfloat2.  `in` needs border >= 2, filled. */
+int vppb_lowpass_sub2(const vppb_img* in, const vppb_img* out, int kind, void* stream);
+
+/* ---- FAST9 (fast.hpp:253-508, 643-799, 889-955) ------------------------------------------- */
+enum { VPPB_FAST_REFERENCE_RING = 0, VPPB_FAST_TRUE_RING = 1 };
+enum { VPPB_FAST_ALL = 0, VPPB_FAST_LOCAL_MAXIMA = 1, VPPB_FAST_BLOCKWISE = 2 };
+/* Workspace bytes needed by vppb_fast9_u8 for an nrows x ncols image. */
+int64_t vppb_fast9_workspace_bytes(int32_t nrows, int32_t ncols, int32_t block_size);
+/* fast9(A, th, [_local_maxima|_blockwise, _block_size=, _mask=, _scores=]).
+ * mask may be NULL (== 0xFF everywhere).  kps_out (device, capacity records) receives the
+ * keypoints in raster order; scores_out (device int32, may be NULL) the matching scores
+ * (raw score for mode ALL, score/16 for the maxima modes, fast.hpp:670-671,698-704);
+ * count_out (host) the number of keypoints found.  ring selects the reference's ring
+ * (a4/a12 sampled on row r-3, fast.hpp:367-368) or the true Bresenham ring. */
+int vppb_fast9_u8(const vppb_img* img, int32_t th, const vppb_img* mask, int32_t mode, int32_t block_size,
+                  int32_t ring, void* workspace, int64_t workspace_bytes,
+                  vppb_int2* kps_out, int32_t* scores_out, int32_t capacity, int32_t* count_out,
+                  void* stream);
+/* fast9_scores (fast.hpp:643-652): score of n given points (device arrays). */
+int vppb_fast9_scores(const vppb_img* img, int32_t th, const vppb_int2* kps, int32_t n, int32_t* scores_out,
+                      void* stream);
+
+/* ---- Lucas-Kanade (lucas_kanade.hpp:12-184, lk.hh:42-175, pyrlk_match.hh:15-55) ----------- */
+enum { VPPB_LK_ERR_SAD = 0 /* lucas_kanade.hpp:116-128 */, VPPB_LK_ERR_SAD_OVER_MAD = 1 /* lk.hh:151-173 */ };
+typedef struct vppb_lk_params {
+  int32_t nlevels;      /* pyramid levels passed in prev/next/grad (level 0 = full resolution) */
+  int32_t min_scale;    /* finest level processed (pyrlk_match.hh:32) */
+  int32_t winsize;      /* square window side (odd, <= 15) */
+  int32_t max_iter;     /* loop runs k = 0..max_iter inclusive (lucas_kanade.hpp:87) */
+  int32_t grad_is_float;/* gradient pyramid element: 0 = vint2, 1 = vfloat2 */
+  int32_t err_mode;     /* VPPB_LK_ERR_* */
+  int32_t gate_on_max_err; /* 1: pyrlk_match.hh:37-41 (tr updated only if err < max_err); 0: lucas_kanade.hpp:177 */
+  float min_ev;         /* reject if min |eig(G/cpt)| < min_ev */
+  float delta;          /* convergence threshold on ||nk|| */
+  float max_err;
+  float factor;         /* pyramid factor (2) */
+  float pred_div;       /* prediction divisor 2^nscales of lucas_kanade.hpp:163 */
+} vppb_lk_params;
+/* For each of n keypoints (device vppb_float2, (row,col) at level 0; `prediction` may be NULL):
+ * coarse-to-fine LK; flow_out[i] = final tr, err_out[i] = final distance. u8 images. */
+int vppb_lk_match_u8(const vppb_img* prev, const vppb_img* next, const vppb_img* grad,
+                     const vppb_lk_params* params, const vppb_float2* kps, const vppb_float2* prediction,
+                     int32_t n, vppb_float2* flow_out, float* err_out, void* stream);
+
+/* ---- multi-GPU row tiles ------------------------------------------------------------------ */
+/* Pack / unpack the `halo` edge rows of a row tile into/from a contiguous device staging buffer
+ * (the payload of the one grouped NCCL neighbour exchange per frame).  which: 0 = top rows
+ * [0,halo), 1 = bottom rows [nrows-halo, nrows) for pack; for unpack 0 = border rows
+ * [-halo,0), 1 = border rows [nrows, nrows+halo).  Full buffer width (incl. column border). */
+int64_t vppb_halo_bytes(const vppb_img* img, int32_t halo);
+int vppb_halo_pack(const vppb_img* img, int32_t halo, int which, void* staging, void* stream);
+int vppb_halo_unpack(const vppb_img* img, int32_t halo, int which, const void* staging, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VPPB_H_ */

@@ -1,0 +1,73 @@
+// Shared helpers for the sm_100a kernels behind include/vppb.h.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/vppb.h"
+
+namespace vppb {
+
+// thread-local error text returned by vppb_last_error()
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+
+#define VPPB_CUDA(call)                                   \
+  do {                                                    \
+    cudaError_t e__ = (call);                             \
+    if (e__ != cudaSuccess) return ::vppb::cuda_fail(e__, #call); \
+  } while (0)
+
+#define VPPB_LAUNCH_CHECK(name)                           \
+  do {                                                    \
+    cudaError_t e__ = cudaGetLastError();                 \
+    if (e__ != cudaSuccess) return ::vppb::cuda_fail(e__, name); \
+  } while (0)
+
+#define VPPB_REQUIRE(cond, code, ...)                     \
+  do {                                                    \
+    if (!(cond)) { ::vppb::set_error(__VA_ARGS__); return (code); } \
+  } while (0)
+
+inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// Number of SMs of the current device (148 on B200); cached per process.
+int sm_count();
+
+// Device-side image view (a trimmed vppb_img passed by value to kernels).
+struct Img {
+  unsigned char* base;  // pixel (0,0)
+  int nrows, ncols, pitch, border;
+};
+
+inline Img view(const vppb_img* i) {
+  Img v;
+  v.base = static_cast<unsigned char*>(i->base);
+  v.nrows = i->nrows; v.ncols = i->ncols; v.pitch = i->pitch; v.border = i->border;
+  return v;
+}
+
+inline bool same_domain(const vppb_img* a, const vppb_img* b) {
+  return a->nrows == b->nrows && a->ncols == b->ncols;
+}
+
+template <typename T>
+__device__ __forceinline__ T* row_ptr(const Img& im, int r) {
+  return reinterpret_cast<T*>(im.base + (long long)r * im.pitch);
+}
+
+// streaming 128-bit accesses: every byte of a map is touched exactly once, keep it out of L1
+__device__ __forceinline__ int4 ld_stream(const int4* p) {
+  int4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_stream(int4* p, const int4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.s32 [%0], {%1,%2,%3,%4};"
+               :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+}  // namespace vppb

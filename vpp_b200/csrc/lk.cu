@@ -1,0 +1,305 @@
+// Pyramidal Lucas-Kanade point matcher.
+// Reference: vpp/algorithms/lucas_kanade/lucas_kanade.hpp:12-131 (lk_internals::match) and
+// :135-184 (driver), vpp/algorithms/pyrlk/lk.hh:42-175 (lk_match_point_square_win<WS>),
+// vpp/algorithms/pyrlk/pyrlk_match.hh:15-55 (driver), vpp/core/imageNd.hpp:280-300
+// (linear_interpolate: float32 4-tap, summed left to right, result truncated to the pixel type).
+//
+// One warp per keypoint, all pyramid levels in one launch (the pyramids stay resident in L2:
+// 1080p x 3 levels x (u8 + u8 + 8-byte gradient) ~ 27 MB).  Lanes own the window pixels
+// (WS*WS <= 225 -> up to 8 per lane), sample A / grad once per level and B once per iteration.
+// The reference accumulates G, b_k and the error strictly in row-major window order in float32;
+// because the truncating interpolation makes the iteration discontinuous, a different summation
+// order can move the result by far more than 1e-4.  The reductions therefore replay the
+// reference order exactly: every lane broadcasts its terms with warp shuffles and every lane
+// performs the same sequential float additions (so all lanes hold the same v, G, b_k and control
+// flow stays warp-uniform).  Not HBM-bound: ~2 KB of compulsory traffic per keypoint;
+// throughput is set by the 2 x WS^2 dependent FADDs per iteration.
+// The library is compiled with -fmad=false; products and sums below must not be contracted.
+#include "common.cuh"
+
+#include <float.h>
+
+namespace vppb {
+
+constexpr int LK_MAX_LEVELS = 8;
+constexpr unsigned FULL = 0xffffffffu;
+
+struct LkLevels {
+  Img prev[LK_MAX_LEVELS], next[LK_MAX_LEVELS], grad[LK_MAX_LEVELS];
+};
+
+// clamp so that the 2x2 footprint stays inside the allocated frame (the reference reads whatever
+// lies there; documented deviation, never hit by in-range keypoints)
+__device__ __forceinline__ int clamp_tap(int x, int n, int border) { return min(max(x, -border), n + border - 2); }
+
+// imageNd.hpp:280-300 on image2d<unsigned char>; returns the truncated uchar as int
+__device__ __forceinline__ int interp_u8(const Img& im, float p0, float p1) {
+  const int x0 = (int)p0, x1 = (int)p1;
+  const float a0 = __fsub_rn(p0, (float)x0), a1 = __fsub_rn(p1, (float)x1);
+  const unsigned char* l1 = im.base + (long long)clamp_tap(x0, im.nrows, im.border) * im.pitch + clamp_tap(x1, im.ncols, im.border);
+  const unsigned char* l2 = l1 + im.pitch;
+  const float b0 = __fsub_rn(1.f, a0), b1 = __fsub_rn(1.f, a1);
+  float res = __fmul_rn(__fmul_rn(b0, b1), (float)l1[0]);
+  res = __fadd_rn(res, __fmul_rn(__fmul_rn(a0, b1), (float)l2[0]));
+  res = __fadd_rn(res, __fmul_rn(__fmul_rn(b0, a1), (float)l1[1]));
+  res = __fadd_rn(res, __fmul_rn(__fmul_rn(a0, a1), (float)l2[1]));
+  return (int)(unsigned char)res;
+}
+
+// same on image2d<vint2> (result truncated per component) or image2d<vfloat2>
+template <bool GRAD_FLOAT>
+__device__ __forceinline__ float2 interp_grad(const Img& im, float p0, float p1) {
+  const int x0 = (int)p0, x1 = (int)p1;
+  const float a0 = __fsub_rn(p0, (float)x0), a1 = __fsub_rn(p1, (float)x1);
+  const unsigned char* l1 = im.base + (long long)clamp_tap(x0, im.nrows, im.border) * im.pitch + (long long)clamp_tap(x1, im.ncols, im.border) * 8;
+  const unsigned char* l2 = l1 + im.pitch;
+  float v00x, v00y, v10x, v10y, v01x, v01y, v11x, v11y;
+  if (GRAD_FLOAT) {
+    const float2 t00 = *reinterpret_cast<const float2*>(l1), t01 = *reinterpret_cast<const float2*>(l1 + 8);
+    const float2 t10 = *reinterpret_cast<const float2*>(l2), t11 = *reinterpret_cast<const float2*>(l2 + 8);
+    v00x = t00.x; v00y = t00.y; v01x = t01.x; v01y = t01.y; v10x = t10.x; v10y = t10.y; v11x = t11.x; v11y = t11.y;
+  } else {
+    const int2 t00 = *reinterpret_cast<const int2*>(l1), t01 = *reinterpret_cast<const int2*>(l1 + 8);
+    const int2 t10 = *reinterpret_cast<const int2*>(l2), t11 = *reinterpret_cast<const int2*>(l2 + 8);
+    v00x = (float)t00.x; v00y = (float)t00.y; v01x = (float)t01.x; v01y = (float)t01.y;
+    v10x = (float)t10.x; v10y = (float)t10.y; v11x = (float)t11.x; v11y = (float)t11.y;
+  }
+  const float b0 = __fsub_rn(1.f, a0), b1 = __fsub_rn(1.f, a1);
+  const float w00 = __fmul_rn(b0, b1), w10 = __fmul_rn(a0, b1), w01 = __fmul_rn(b0, a1), w11 = __fmul_rn(a0, a1);
+  float rx = __fmul_rn(w00, v00x), ry = __fmul_rn(w00, v00y);
+  rx = __fadd_rn(rx, __fmul_rn(w10, v10x)); ry = __fadd_rn(ry, __fmul_rn(w10, v10y));
+  rx = __fadd_rn(rx, __fmul_rn(w01, v01x)); ry = __fadd_rn(ry, __fmul_rn(w01, v01y));
+  rx = __fadd_rn(rx, __fmul_rn(w11, v11x)); ry = __fadd_rn(ry, __fmul_rn(w11, v11y));
+  if (!GRAD_FLOAT) { rx = (float)(int)rx; ry = (float)(int)ry; }  // cast<vint2> then gx = g[0] (int -> float)
+  return make_float2(rx, ry);
+}
+
+// Sum t[0..npix) in window order with the reference's sequential float additions.
+template <int PPL>
+__device__ __forceinline__ float seq_sum(const float (&t)[PPL], int npix) {
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < PPL; j++) {
+    const int cnt = min(32, npix - 32 * j);
+#pragma unroll 8
+    for (int l = 0; l < cnt; l++) s = __fadd_rn(s, __shfl_sync(FULL, t[j], l));
+  }
+  return s;
+}
+template <int PPL>
+__device__ __forceinline__ void seq_sum2(const float (&t0)[PPL], const float (&t1)[PPL], int npix, float& s0, float& s1) {
+  s0 = 0.f; s1 = 0.f;
+#pragma unroll
+  for (int j = 0; j < PPL; j++) {
+    const int cnt = min(32, npix - 32 * j);
+#pragma unroll 8
+    for (int l = 0; l < cnt; l++) {
+      s0 = __fadd_rn(s0, __shfl_sync(FULL, t0[j], l));
+      s1 = __fadd_rn(s1, __shfl_sync(FULL, t1[j], l));
+    }
+  }
+}
+
+__device__ __forceinline__ bool finite2(float a, float b) { return isfinite(a) && isfinite(b); }
+
+template <int PPL, bool GRAD_FLOAT>
+__global__ void __launch_bounds__(128) k_lk_match(LkLevels L, vppb_lk_params P, const vppb_float2* __restrict__ kps,
+                                                  const vppb_float2* __restrict__ prediction, int n, vppb_float2* __restrict__ flow_out,
+                                                  float* __restrict__ err_out) {
+  const int lane = threadIdx.x & 31;
+  const int kp_idx = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  if (kp_idx >= n) return;  // warp-uniform
+  const int ws = P.winsize, hws = ws / 2, npix = ws * ws;
+  const float kp0 = kps[kp_idx].r, kp1 = kps[kp_idx].c;
+
+  // window offsets of this lane's pixels
+  float off_r[PPL], off_c[PPL];
+  bool have[PPL];
+#pragma unroll
+  for (int j = 0; j < PPL; j++) {
+    const int i = lane + 32 * j;
+    have[j] = i < npix;
+    off_r[j] = (float)(i / ws - hws);
+    off_c[j] = (float)(i % ws - hws);
+  }
+
+  float tr0 = 0.f, tr1 = 0.f, dist = 0.f;
+  if (prediction) {  // lucas_kanade.hpp:163
+    tr0 = __fdiv_rn(prediction[kp_idx].r, P.pred_div);
+    tr1 = __fdiv_rn(prediction[kp_idx].c, P.pred_div);
+  }
+
+  for (int S = P.nlevels - 1; S >= P.min_scale; S--) {
+    tr0 = __fmul_rn(tr0, P.factor);
+    tr1 = __fmul_rn(tr1, P.factor);
+    const Img& A = L.prev[S];
+    const Img& B = L.next[S];
+    const Img& Ag = L.grad[S];
+    const float scale = (float)(1 << S);
+    const float p0 = __fdiv_rn(kp0, scale), p1 = __fdiv_rn(kp1, scale);
+
+    // ---- G and the cached samples (lucas_kanade.hpp:24-43, 69-83)
+    float gs0[PPL], gs1[PPL], asv[PPL], t00[PPL], t01[PPL], t11[PPL];
+    bool valid[PPL];
+    int cpt = 0;
+#pragma unroll
+    for (int j = 0; j < PPL; j++) {
+      const float n0 = __fadd_rn(p0, off_r[j]), n1 = __fadd_rn(p1, off_c[j]);
+      const int i0 = (int)n0, i1 = (int)n1;
+      valid[j] = have[j] && i0 >= 0 && i0 < A.nrows && i1 >= 0 && i1 < A.ncols;
+      gs0[j] = 0.f; gs1[j] = 0.f; asv[j] = 0.f;
+      if (valid[j]) {
+        const float2 g = interp_grad<GRAD_FLOAT>(Ag, n0, n1);
+        gs0[j] = g.x; gs1[j] = g.y;
+        asv[j] = (float)interp_u8(A, n0, n1);
+      }
+      t00[j] = __fmul_rn(gs0[j], gs0[j]);
+      t01[j] = __fmul_rn(gs0[j], gs1[j]);
+      t11[j] = __fmul_rn(gs1[j], gs1[j]);
+      cpt += __popc(__ballot_sync(FULL, valid[j]));
+    }
+    float G00, G01, G11;
+    seq_sum2<PPL>(t00, t01, npix, G00, G01);
+    G11 = seq_sum<PPL>(t11, npix);
+
+    float m0 = -1.f, m1 = -1.f, merr = FLT_MAX;  // result of this level's match
+    bool done = false;
+
+    // ---- minimum eigenvalue of G / cpt (lucas_kanade.hpp:45-52); closed form for a symmetric 2x2
+    {
+      const float cf = (float)cpt;
+      const float a = __fdiv_rn(G00, cf), b = __fdiv_rn(G01, cf), d = __fdiv_rn(G11, cf);
+      const float half = __fmul_rn(__fadd_rn(a, d), 0.5f), diff = __fmul_rn(__fsub_rn(a, d), 0.5f);
+      const float root = __fsqrt_rn(__fadd_rn(__fmul_rn(diff, diff), __fmul_rn(b, b)));
+      const float e1 = fabsf(__fadd_rn(half, root)), e2 = fabsf(__fsub_rn(half, root));
+      float min_ev = 99999.f;
+      if (e1 < min_ev) min_ev = e1;
+      if (e2 < min_ev) min_ev = e2;
+      if (min_ev < P.min_ev) { m0 = -1.f; m1 = -1.f; merr = FLT_MAX; done = true; }
+    }
+
+    if (!done) {
+      // G^-1 (Eigen 2x2: invdet = 1/det; [d,-b;-c,a] * invdet)
+      const float det = __fsub_rn(__fmul_rn(G00, G11), __fmul_rn(G01, G01));
+      const float invdet = __fdiv_rn(1.f, det);
+      const float I00 = __fmul_rn(G11, invdet), I01 = __fmul_rn(-G01, invdet), I11 = __fmul_rn(G00, invdet);
+
+      float v0 = __fadd_rn(p0, tr0), v1 = __fadd_rn(p1, tr1);
+      float nk0 = 1.f, nk1 = 1.f;
+      bool failed = false;
+      for (int k = 0; k <= P.max_iter; k++) {
+        const float nrm = __fsqrt_rn(__fadd_rn(__fmul_rn(nk0, nk0), __fmul_rn(nk1, nk1)));
+        if (!(nrm >= P.delta)) break;
+        float c0[PPL], c1[PPL];
+#pragma unroll
+        for (int j = 0; j < PPL; j++) {
+          c0[j] = 0.f; c1[j] = 0.f;
+          if (valid[j]) {
+            const float dt = __fsub_rn(asv[j], (float)interp_u8(B, __fadd_rn(v0, off_r[j]), __fadd_rn(v1, off_c[j])));
+            c0[j] = __fmul_rn(gs0[j], dt);
+            c1[j] = __fmul_rn(gs1[j], dt);
+          }
+        }
+        float bk0, bk1;
+        seq_sum2<PPL>(c0, c1, npix, bk0, bk1);
+        nk0 = __fadd_rn(__fmul_rn(I00, bk0), __fmul_rn(I01, bk1));
+        nk1 = __fadd_rn(__fmul_rn(I01, bk0), __fmul_rn(I11, bk1));
+        v0 = __fadd_rn(v0, nk0);
+        v1 = __fadd_rn(v1, nk1);
+        const int iv0 = (int)v0, iv1 = (int)v1;
+        if (!finite2(v0, v1) || iv0 < 0 || iv0 >= B.nrows || iv1 < 0 || iv1 >= B.ncols) { failed = true; break; }
+      }
+      if (failed) {
+        m0 = 0.f; m1 = 0.f; merr = FLT_MAX;
+      } else {
+        // ---- matching error (lucas_kanade.hpp:116-128 / lk.hh:151-173)
+        float e[PPL];
+#pragma unroll
+        for (int j = 0; j < PPL; j++) {
+          e[j] = 0.f;
+          if (have[j]) {
+            const int bi = interp_u8(B, __fadd_rn(v0, off_r[j]), __fadd_rn(v1, off_c[j]));
+            e[j] = fabsf((float)((int)asv[j] - bi));
+          }
+        }
+        float err = seq_sum<PPL>(e, npix);
+        const int cpt2 = cpt + npix;
+        if (P.err_mode == VPPB_LK_ERR_SAD) {
+          merr = __fdiv_rn(err, (float)cpt2);
+        } else {
+          const float wsq = (float)npix;
+          float avg = __fdiv_rn(seq_sum<PPL>(asv, npix), wsq);
+          float dv[PPL];
+#pragma unroll
+          for (int j = 0; j < PPL; j++) dv[j] = have[j] ? fabsf(__fsub_rn(avg, asv[j])) : 0.f;
+          const float stddev = __fdiv_rn(seq_sum<PPL>(dv, npix), wsq);
+          merr = __fdiv_rn(err, __fmul_rn((float)cpt2, stddev));
+        }
+        m0 = __fsub_rn(v0, p0);
+        m1 = __fsub_rn(v1, p1);
+      }
+    }
+
+    // ---- drivers: lucas_kanade.hpp:177-178 (unconditional) / pyrlk_match.hh:37-41 (gated)
+    if (!P.gate_on_max_err || merr < P.max_err) { tr0 = m0; tr1 = m1; }
+    dist = merr;
+  }
+
+  if (lane == 0) {
+    flow_out[kp_idx].r = tr0;
+    flow_out[kp_idx].c = tr1;
+    err_out[kp_idx] = dist;
+  }
+}
+
+template <bool GF>
+static void lk_launch(int ppl, int grid, cudaStream_t st, const LkLevels& L, const vppb_lk_params& P, const vppb_float2* kps,
+                      const vppb_float2* pred, int n, vppb_float2* flow, float* err) {
+  switch (ppl) {
+    case 1: k_lk_match<1, GF><<<grid, 128, 0, st>>>(L, P, kps, pred, n, flow, err); break;
+    case 2: k_lk_match<2, GF><<<grid, 128, 0, st>>>(L, P, kps, pred, n, flow, err); break;
+    case 3: k_lk_match<3, GF><<<grid, 128, 0, st>>>(L, P, kps, pred, n, flow, err); break;
+    case 4: k_lk_match<4, GF><<<grid, 128, 0, st>>>(L, P, kps, pred, n, flow, err); break;
+    case 6: k_lk_match<6, GF><<<grid, 128, 0, st>>>(L, P, kps, pred, n, flow, err); break;
+    default: k_lk_match<8, GF><<<grid, 128, 0, st>>>(L, P, kps, pred, n, flow, err); break;
+  }
+}
+
+}  // namespace vppb
+
+using namespace vppb;
+
+extern "C" {
+
+int vppb_lk_match_u8(const vppb_img* prev, const vppb_img* next, const vppb_img* grad, const vppb_lk_params* params,
+                     const vppb_float2* kps, const vppb_float2* prediction, int32_t n, vppb_float2* flow_out, float* err_out,
+                     void* stream) {
+  VPPB_REQUIRE(prev && next && grad && params, VPPB_E_ARG, "vppb_lk_match_u8: NULL argument");
+  VPPB_REQUIRE(n == 0 || (kps && flow_out && err_out), VPPB_E_ARG, "vppb_lk_match_u8: NULL keypoint/output array");
+  const vppb_lk_params& P = *params;
+  VPPB_REQUIRE(P.nlevels >= 1 && P.nlevels <= LK_MAX_LEVELS && P.min_scale >= 0 && P.min_scale < P.nlevels, VPPB_E_ARG,
+               "vppb_lk_match_u8: nlevels %d / min_scale %d out of range", P.nlevels, P.min_scale);
+  VPPB_REQUIRE(P.winsize >= 1 && P.winsize <= 15 && (P.winsize & 1), VPPB_E_ARG, "vppb_lk_match_u8: winsize %d must be odd and <= 15", P.winsize);
+  LkLevels L;
+  for (int s = 0; s < P.nlevels; s++) {
+    VPPB_REQUIRE(prev[s].base && next[s].base && grad[s].base, VPPB_E_ARG, "vppb_lk_match_u8: level %d has a NULL image", s);
+    VPPB_REQUIRE(prev[s].elem_bytes == 1 && next[s].elem_bytes == 1 && grad[s].elem_bytes == 8, VPPB_E_ARG,
+                 "vppb_lk_match_u8: level %d element sizes must be 1/1/8", s);
+    VPPB_REQUIRE(same_domain(&prev[s], &next[s]) && same_domain(&prev[s], &grad[s]), VPPB_E_ARG, "vppb_lk_match_u8: level %d domains differ", s);
+    VPPB_REQUIRE(prev[s].border >= 1 && next[s].border >= 1 && grad[s].border >= 1, VPPB_E_BORDER, "vppb_lk_match_u8: level %d needs border >= 1", s);
+    VPPB_REQUIRE(((uintptr_t)grad[s].base % 8) == 0 && (grad[s].pitch % 8) == 0, VPPB_E_ARG, "vppb_lk_match_u8: gradient level %d not 8-byte aligned", s);
+    L.prev[s] = view(&prev[s]); L.next[s] = view(&next[s]); L.grad[s] = view(&grad[s]);
+  }
+  if (n == 0) return VPPB_OK;
+  const int npix = P.winsize * P.winsize;
+  int ppl = (npix + 31) / 32;
+  if (ppl == 5) ppl = 6;
+  if (ppl == 7) ppl = 8;
+  const int grid = (n + 3) / 4;  // 4 warps (keypoints) per CTA
+  if (P.grad_is_float) lk_launch<true>(ppl, grid, as_stream(stream), L, P, kps, prediction, n, flow_out, err_out);
+  else lk_launch<false>(ppl, grid, as_stream(stream), L, P, kps, prediction, n, flow_out, err_out);
+  VPPB_LAUNCH_CHECK("vppb_lk_match_u8");
+  return VPPB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,245 @@
+"""Host-side mirror of the Video++ operator surface for the dense-pixel path (Python flavour).
+
+Same names, argument meaning and error behaviour as the reference templates they cite; all
+pixel work happens in the CUDA library behind include/vppb.h.  (The C++14 flavour of the same
+surface lives in vpp_b200/include/vpp.)
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+from .capi import check, lib
+from .image import DEFAULT_ALIGNMENT, Image2d
+
+
+def _val(img, value):
+    return np.ascontiguousarray(np.broadcast_to(np.asarray(value, dtype=img.dtype), (img.channels,)))
+
+
+# ---- pixel_wise named kernels ---------------------------------------------------------------
+def pixel_wise_add(a, b, c, stream=None):
+    """pixel_wise(A,B,C) | [](int& a,int& b,int& c){ a = b + c; }  (benchmarks/image_add.cc:51-57)"""
+    check(lib.vppb_pw_add_i32(a.ptr(), b.ptr(), c.ptr(), stream))
+
+
+def fill(img, value, stream=None):  # fill.hh:12-15
+    v = _val(img, value)
+    check(lib.vppb_fill(img.ptr(), v.ctypes.data, 0, stream))
+
+
+def fill_with_border(img, value, stream=None):  # fill.hh:24-28
+    v = _val(img, value)
+    check(lib.vppb_fill(img.ptr(), v.ctypes.data, 1, stream))
+
+
+def fill_border_with_value(img, value, stream=None):  # fill.hh:32-45
+    v = _val(img, value)
+    check(lib.vppb_fill_border_value(img.ptr(), v.ctypes.data, stream))
+
+
+def fill_border_mirror(img, stream=None):  # fill.hh:48-83
+    check(lib.vppb_fill_border_mirror(img.ptr(), stream))
+
+
+def fill_border_closest(img, stream=None):  # fill.hh:86-121
+    check(lib.vppb_fill_border_closest(img.ptr(), stream))
+
+
+def copy(src, dst, stream=None):  # copy.hh:10-19
+    check(lib.vppb_copy2d(src.ptr(), dst.ptr(), 0, stream))
+
+
+def copy_with_border(src, dst, stream=None):  # copy.hh:22-27
+    check(lib.vppb_copy2d(src.ptr(), dst.ptr(), 1, stream))
+
+
+def clone(img, border=None, aligned=None):  # clone.hh:10-20
+    n = Image2d(img.nrows, img.ncols, img.pixel, border=img.border if border is None else border,
+                aligned=(img.alignment or DEFAULT_ALIGNMENT) if aligned is None else aligned)
+    copy_with_border(img, n)
+    return n
+
+
+def sum(img, stream=None):  # sum.hh:12-19 (char / uchar / int images; accumulator int)
+    out = C.c_int64()
+    check(lib.vppb_sum_i32(img.ptr(), 1 if img.pixel in ("i8", "i32") else 0, C.byref(out), stream))
+    return out.value
+
+
+# ---- stencils -------------------------------------------------------------------------------
+def box5x5(src, dst, stream=None):
+    """pixel_wise(dst, relative_access(src)) | sum of the 5x5 neighbourhood / 25
+    (benchmarks/box_5x5_filter2.cc:71-81; vuchar3 form examples/box_filter.cc:23-32)."""
+    fn = {"vuchar3": lib.vppb_box5x5_u8c3, "u8": lib.vppb_box5x5_u8, "i32": lib.vppb_box5x5_i32}[src.pixel]
+    check(fn(src.ptr(), dst.ptr(), stream))
+
+
+def scharr(src, dst, stream=None):  # scharr.hh:46-87
+    check(lib.vppb_scharr_u8(src.ptr(), dst.ptr(), 1 if dst.pixel == "vfloat2" else 0, stream))
+
+
+_LP_KIND = {"u8": 0, "vint2": 1, "vfloat2": 2}
+
+
+class Pyramid2d:
+    """pyramid2d<V> (pyramid.hh:126-215): levels of size 1 + n/factor, factor 2 only."""
+
+    def __init__(self, src_or_shape, nlevels, factor=2, pixel=None, border=0, aligned=DEFAULT_ALIGNMENT):
+        assert factor == 2, "only the factor-2 path (pyramid.hh:174-182) is built"
+        self.factor = float(factor)
+        img = src_or_shape if isinstance(src_or_shape, Image2d) else None
+        nr, nc = (img.nrows, img.ncols) if img is not None else src_or_shape
+        self.pixel = pixel or img.pixel
+        self.levels = []
+        for _ in range(nlevels):
+            self.levels.append(Image2d(nr, nc, self.pixel, border=border, aligned=aligned))
+            nr, nc = int(1 + nr / factor), int(1 + nc / factor)  # pyramid.hh:140,154
+        if img is not None:
+            self.update(img)
+
+    def __getitem__(self, i):
+        return self.levels[i]
+
+    def __len__(self):
+        return len(self.levels)
+
+    size = __len__
+
+    def propagate_level0(self, stream=None):  # pyramid.hh:169-192
+        fill_border_mirror(self.levels[0], stream)
+        for i in range(1, len(self.levels)):
+            check(lib.vppb_lowpass_sub2(self.levels[i - 1].ptr(), self.levels[i].ptr(), _LP_KIND[self.pixel], stream))
+            fill_border_mirror(self.levels[i], stream)
+
+    def update(self, img, stream=None):  # pyramid.hh:194-198
+        copy(img, self.levels[0], stream)
+        self.propagate_level0(stream)
+
+    def desc_array(self):
+        arr = (capi.VppbImg * len(self.levels))()
+        for i, l in enumerate(self.levels):
+            arr[i] = l.desc
+        return arr
+
+
+# ---- FAST9 ----------------------------------------------------------------------------------
+class _DeviceBuffer:
+    def __init__(self, nbytes):
+        self.img = capi.VppbImg()
+        check(lib.vppb_alloc(C.byref(self.img), 1, max(int(nbytes), 1), 1, 0, 256))
+        self.nbytes = int(nbytes)
+
+    @property
+    def ptr(self):
+        return self.img.base
+
+    def to_host(self, dtype, count):
+        out = np.empty(count, dtype=dtype)
+        if count:
+            view = capi.VppbImg()
+            C.memmove(C.byref(view), C.byref(self.img), C.sizeof(capi.VppbImg))
+            view.ncols = out.nbytes
+            check(lib.vppb_download(C.byref(view), out.ctypes.data, out.nbytes, 0, None))
+            check(lib.vppb_sync(None))
+        return out
+
+    def from_host(self, arr):
+        arr = np.ascontiguousarray(arr)
+        if arr.nbytes:
+            view = capi.VppbImg()
+            C.memmove(C.byref(view), C.byref(self.img), C.sizeof(capi.VppbImg))
+            view.ncols = arr.nbytes
+            check(lib.vppb_upload(C.byref(view), arr.ctypes.data, arr.nbytes, 0, None))
+            check(lib.vppb_sync(None))
+        return self
+
+    def __del__(self):
+        try:
+            lib.vppb_free(C.byref(self.img))
+        except Exception:
+            pass
+
+
+def fast9(img, th, local_maxima=False, blockwise=False, block_size=10, mask=None, scores=None, ring="reference",
+          capacity=None, stream=None):
+    """std::vector<vint2> fast9(A, th, [_local_maxima | _blockwise, _block_size=, _mask=, _scores=&vec])
+    (fast.hpp:931-955).  Returns an (n, 2) int32 array of (row, col) in raster order; if `scores` is a
+    list it is replaced by the matching scores.  Raises RuntimeError if A.border() < 3 (fast.hpp:937-938)."""
+    mode = capi.FAST_LOCAL_MAXIMA if local_maxima else (capi.FAST_BLOCKWISE if blockwise else capi.FAST_ALL)
+    ring_id = capi.FAST_REFERENCE_RING if ring == "reference" else capi.FAST_TRUE_RING
+    ws = _DeviceBuffer(lib.vppb_fast9_workspace_bytes(img.nrows, img.ncols, block_size))
+    cap = capacity if capacity is not None else max(1024, (img.nrows * img.ncols) // 8)
+    count = C.c_int32()
+    while True:
+        kps = _DeviceBuffer(cap * 8)
+        sc = _DeviceBuffer(cap * 4) if scores is not None else None
+        rc = lib.vppb_fast9_u8(img.ptr(), th, mask.ptr() if mask is not None else None, mode, block_size, ring_id, ws.ptr,
+                               ws.nbytes, kps.ptr, sc.ptr if sc else None, cap, C.byref(count), stream)
+        if rc == capi.VPPB_E_CAPACITY and capacity is None:
+            cap = count.value
+            continue
+        check(rc)
+        break
+    out = kps.to_host(np.int32, count.value * 2).reshape(-1, 2)
+    if scores is not None:
+        scores[:] = list(sc.to_host(np.int32, count.value))
+    return out
+
+
+def fast9_scores(img, th, keypoints, stream=None):  # fast.hpp:643-652
+    kp = np.ascontiguousarray(keypoints, dtype=np.int32).reshape(-1, 2)
+    d_kp = _DeviceBuffer(kp.nbytes).from_host(kp)
+    d_sc = _DeviceBuffer(len(kp) * 4)
+    check(lib.vppb_fast9_scores(img.ptr(), th, d_kp.ptr, len(kp), d_sc.ptr, stream))
+    return d_sc.to_host(np.int32, len(kp))
+
+
+# ---- Lucas-Kanade -----------------------------------------------------------------------------
+def _lk_run(pyr_prev, pyr_next, pyr_grad, params, keypoints, prediction, stream):
+    kp = np.ascontiguousarray(keypoints, dtype=np.float32).reshape(-1, 2)
+    n = len(kp)
+    d_kp = _DeviceBuffer(kp.nbytes).from_host(kp)
+    d_pred = None
+    if prediction is not None:
+        d_pred = _DeviceBuffer(kp.nbytes).from_host(np.ascontiguousarray(prediction, dtype=np.float32).reshape(-1, 2))
+    d_flow = _DeviceBuffer(n * 8)
+    d_err = _DeviceBuffer(n * 4)
+    check(lib.vppb_lk_match_u8(pyr_prev.desc_array(), pyr_next.desc_array(), pyr_grad.desc_array(), C.byref(params), d_kp.ptr,
+                               d_pred.ptr if d_pred else None, n, d_flow.ptr, d_err.ptr, stream))
+    return d_flow.to_host(np.float32, n * 2).reshape(-1, 2), d_err.to_host(np.float32, n)
+
+
+def lucas_kanade(i1, i2, keypoints, niterations=21, winsize=11, nscales=3, min_ev=0.0001, delta=0.1, prediction=None,
+                 stream=None):
+    """lucas_kanade(i1, i2, _keypoints=, _flow=, ...) (lucas_kanade.hpp:135-184).
+    Returns (flow[n,2], dist[n]) — the values the reference hands to the _flow callback.
+    As in the reference, min_ev and delta are stored in `int` (lucas_kanade.hpp:143-144) and so
+    truncate (0.0001 -> 0, 0.1 -> 0); pyramids and the vint2 Scharr gradient pyramid are built here."""
+    border = winsize // 2
+    prev = Pyramid2d(i1, nscales, 2, border=border)
+    nxt = Pyramid2d(i2, nscales, 2, border=border)
+    grad = Pyramid2d((i1.nrows, i1.ncols), nscales, 2, pixel="vint2", border=border)
+    scharr(prev[0], grad[0], stream)
+    grad.propagate_level0(stream)
+    P = capi.VppbLkParams(nlevels=nscales, min_scale=0, winsize=winsize, max_iter=niterations, grad_is_float=0,
+                          err_mode=capi.LK_ERR_SAD, gate_on_max_err=0, min_ev=float(int(min_ev)), delta=float(int(delta)),
+                          max_err=0.0, factor=2.0, pred_div=float(2 ** nscales))
+    return _lk_run(prev, nxt, grad, P, keypoints, prediction, stream)
+
+
+def pyrlk_match(pyr_prev, pyr_prev_grad, pyr_next, keypoints, winsize, min_ev, max_err, max_iteration, convergence_delta,
+                min_scale=0, stream=None):
+    """pyrlk_match(..., lk_match_point_square_win<WS>(), min_ev, max_err, max_iter, delta[, min_scale])
+    (pyrlk_match.hh:15-55).  Returns (flow, dist, keep): keep[i] is False where the reference calls
+    keypoints.remove(i) (dist > max_err or the moved point leaves the level-0 domain)."""
+    P = capi.VppbLkParams(nlevels=len(pyr_prev), min_scale=min_scale, winsize=winsize, max_iter=int(max_iteration),
+                          grad_is_float=1 if pyr_prev_grad.pixel == "vfloat2" else 0, err_mode=capi.LK_ERR_SAD_OVER_MAD,
+                          gate_on_max_err=1, min_ev=min_ev, delta=convergence_delta, max_err=max_err,
+                          factor=pyr_prev.factor, pred_div=1.0)
+    flow, dist = _lk_run(pyr_prev, pyr_next, pyr_prev_grad, P, keypoints, None, stream)
+    kp = np.asarray(keypoints, dtype=np.float32).reshape(-1, 2)
+    moved = (kp + flow).astype(np.int32)  # cast<vint2>: truncation
+    inside = (moved[:, 0] >= 0) & (moved[:, 0] < pyr_prev[0].nrows) & (moved[:, 1] >= 0) & (moved[:, 1] < pyr_prev[0].ncols)
+    keep = ~(dist > max_err) & inside
+    return flow, dist, keep
