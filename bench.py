@@ -1,0 +1,520 @@
+#!/usr/bin/env python
+"""bench.py — the hot path of BASELINE.json on N B200s of one node, one JSON line on stdout.
+
+Headline metric: Mpix/s of the 5x5 box filter on image2d<vuchar3> (BASELINE configs[1]).
+  --gpus 1 : a batch of 1920x1080 vuchar3 frames (batch sized > L2), one box5x5 launch per frame.
+  --gpus N : 7680x4320 vuchar3 frames row-tiled over N ranks; each step = ONE grouped NCCL halo
+             exchange (2 edge rows per neighbour per frame, all frames of the batch packed) + the
+             box kernel on every tile.  Same frames for every N  ->  "scaling": "strong".
+  value  : whole-job Mpix/s with inputs resident in HBM (CUDA events on the launch stream, max over ranks).
+  e2e    : same metric through the C-ABI with HOST buffers (pinned): upload + mirror border fill +
+           box5x5 + download inside the timed region, for every frame of the batch.
+  extras : pixel_wise add (4K int32), FAST9 (4K) and pyrLK (1080p, 3 levels, 10k kps, 7x7) numbers.
+--impl reference times the reference's CPU implementation (oracle/_ref if built, else the oracle
+port compiled with the reference's benchmark flags -O3 -march=native -fopenmp) on the host cores.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {"1080p": (1080, 1920), "4k": (2160, 3840), "8k": (4320, 7680)}
+BOX_BYTES_PER_PX = 6.0  # algorithmic: 3 B read + 3 B written per vuchar3 pixel
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def host_threads():
+    """Threads the CPU arm may use: logical CPUs, clipped by affinity and by the cgroup CPU quota."""
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
+    for path in ("/sys/fs/cgroup/cpu.max",):
+        try:
+            q, per = open(path).read().split()[:2]
+            if q != "max":
+                n = max(1, min(n, int(float(q) / float(per))))
+        except Exception:
+            pass
+    return n
+
+
+def pick_threads(lib, fn):
+    """All the host threads the reference can use: try the full count and half of it (SMT), keep the faster."""
+    best, best_t = None, None
+    full = host_threads()
+    for n in sorted({full, max(1, full // 2)}, reverse=True):
+        lib.vo_set_num_threads(n)
+        fn()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            fn()
+        dt = time.perf_counter() - t0
+        if best_t is None or dt < best_t:
+            best, best_t = n, dt
+    lib.vo_set_num_threads(best)
+    return best
+
+
+def make_frames(h, w, nframes, seed=42):
+    rng = np.random.default_rng(seed)
+    return [rng.integers(0, 256, (h, w, 3), dtype=np.uint8) for _ in range(nframes)]
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def cpu_box_bench(h, w, steps, warmup, budget_s, want_ref=True):
+    """Reference CPU path for the headline workload: image2d<vuchar3> 5x5 box, OpenMP over rows."""
+    from tests import oracle as orc
+
+    kind, lib, fn = "port", orc.load(omp=True), None
+    ref_path = os.path.join(ROOT, "oracle", "_ref", "libvppref.so")
+    if want_ref and os.path.exists(ref_path):
+        try:
+            r = C.CDLL(ref_path)
+            r.vppref_box5x5_u8c3.argtypes = [C.POINTER(orc.VoImg), C.POINTER(orc.VoImg)]
+            fn, kind = r.vppref_box5x5_u8c3, "reference"
+            cores = r.vppref_num_threads()
+        except Exception:
+            fn = None
+    if fn is None:
+        fn = lambda a, b: lib.vo_box5x5_u8(a, b, 3)
+        cores = lib.vo_num_threads()
+    src = make_frames(h, w, 1)[0]
+    hs = orc.HostImage(h, w, "vuchar3", border=2, aligned=32, data=src, fill_border="mirror")
+    hd = orc.HostImage(h, w, "vuchar3", aligned=32)
+    if kind == "port":
+        cores = pick_threads(lib, lambda: fn(hs.ptr(), hd.ptr()))
+    t0 = time.perf_counter()
+    fn(hs.ptr(), hd.ptr())
+    one = time.perf_counter() - t0
+    per_step = max(1, min(64, int(budget_s / max(one, 1e-4) / max(steps + warmup, 1))))
+    for _ in range(warmup):
+        for _ in range(per_step):
+            fn(hs.ptr(), hd.ptr())
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        for _ in range(per_step):
+            fn(hs.ptr(), hd.ptr())
+    dt = time.perf_counter() - t0
+    mpix = steps * per_step * h * w / 1e6 / dt
+    return {"value": mpix, "unit": "Mpix/s", "cores": int(cores), "kind": kind,
+            "sample": "%d frames of %dx%d vuchar3 per step x %d steps (%.1f s)" % (per_step, w, h, steps, dt)}, dt / steps * 1e3
+
+
+def cpu_extras(budget_s=6.0):
+    """pyrLK (pyrlk-style OpenMP over keypoints) and 4K add on the host cores, bounded samples."""
+    from tests import oracle as orc, scenes
+    from tests.oracle_ops import oracle_grad_pyramid, oracle_lk, oracle_pyramid
+
+    o = orc.load(omp=True)
+    o.vo_set_num_threads(host_threads())
+    out = {}
+    f1, f2, pts = scenes.lk_pair(1080, 1920, 10000, seed=5)
+    prev, nxt = oracle_pyramid(f1, 3, "u8", 3, o), oracle_pyramid(f2, 3, "u8", 3, o)
+    grad = oracle_grad_pyramid(prev, "vint2", 3, o)
+    P = orc.VoLkParams(nlevels=3, min_scale=0, winsize=7, max_iter=21, grad_is_float=0, err_mode=0, gate_on_max_err=0, min_ev=0.0,
+                       delta=0.0, max_err=0.0, factor=2.0, pred_div=8.0)
+    oracle_lk(prev, nxt, grad, P, pts, lib=o)
+    t0, reps = time.perf_counter(), 0
+    while time.perf_counter() - t0 < budget_s / 2 and reps < 50:
+        oracle_lk(prev, nxt, grad, P, pts, lib=o)
+        reps += 1
+    out["pyrlk_kpts_per_s"] = reps * len(pts) / (time.perf_counter() - t0)
+    b = np.random.default_rng(1).integers(0, 2 ** 30, (2, 2160, 3840), dtype=np.int32)
+    ha, hb, hc = orc.HostImage(2160, 3840, "i32", aligned=32), orc.HostImage(2160, 3840, "i32", aligned=32, data=b[0]), \
+        orc.HostImage(2160, 3840, "i32", aligned=32, data=b[1])
+    o.vo_pw_add_i32(ha.ptr(), hb.ptr(), hc.ptr())
+    t0, reps = time.perf_counter(), 0
+    while time.perf_counter() - t0 < budget_s / 4 and reps < 200:
+        o.vo_pw_add_i32(ha.ptr(), hb.ptr(), hc.ptr())
+        reps += 1
+    out["add_i32_4k_mpix_per_s"] = reps * 2160 * 3840 / 1e6 / (time.perf_counter() - t0)
+    out["cores"] = o.vo_num_threads()
+    return out
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=None, choices=[None] + list(WORKLOADS))
+    ap.add_argument("--frames", type=int, default=None, help="frames per step (batch)")
+    ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--streams", type=int, default=4, help="CUDA streams the frames of a step are spread over")
+    ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work for the cpu_baseline sample")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    n_gpus = max(args.gpus, 1)
+    workload = args.workload or ("1080p" if n_gpus == 1 else "8k")
+    H, W = WORKLOADS[workload]
+    nframes = args.frames or {"1080p": 32, "4k": 8, "8k": 4}[workload]
+    steps, warmup = args.steps, max(args.warmup, 3)
+
+    base = {"metric": "box5x5_vuchar3_throughput", "unit": "Mpix/s", "n_gpus": n_gpus, "steps": steps, "warmup": warmup,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "5x5 box_filter on %dx%d image2d<vuchar3>, batch of %d frames/step%s" % (
+                W, H, nframes, "" if n_gpus == 1 else ", row-tiled over %d GPUs, one grouped NCCL halo exchange per step" % n_gpus),
+                "frame": [H, W], "frames_per_step": nframes, "border": 2, "row_align": 128,
+                "l2": "batch in+out %.0f MB > 126 MB L2, frames cycled" % (2 * nframes * H * W * 3 / 1e6)}}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        cb, ms = cpu_box_bench(H, W, steps, warmup, args.cpu_budget)
+        line = dict(base)
+        line.update({"impl": "reference", "value": cb["value"], "ms_per_step": ms, "cpu_baseline": cb, "gpu_launches": 0,
+                     "e2e": {"value": cb["value"], "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import __graft_entry__ as g
+
+    g.build(only_if_missing=True)
+    import vpp_b200 as vpp
+    from vpp_b200 import capi
+
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    else:
+        torch.cuda.set_device(0)
+    capi.check(capi.lib.vppb_init(local_rank if world > 1 else 0))
+    dev = torch.device("cuda", local_rank if world > 1 else 0)
+    stream = torch.cuda.current_stream()
+    sp = C.c_void_p(stream.cuda_stream)
+
+    # ---- row tile of this rank (whole frame at N=1)
+    r0, r1 = (H * rank) // world, (H * (rank + 1)) // world
+    th = r1 - r0
+    frames = make_frames(H, W, nframes)
+    padded = [np.pad(f, ((2, 2), (2, 2), (0, 0)), mode="symmetric") for f in frames]
+    src, dst = [], []
+    for f in padded:
+        s = vpp.Image2d(th, W, "vuchar3", border=2)
+        s.upload(f[r0:r1 + 4], with_border=True)  # rows r0-2 .. r1+1: true halos, used only as the parity reference at N>1
+        src.append(s)
+        dst.append(vpp.Image2d(th, W, "vuchar3"))
+    halo = 2
+    up, down = rank - 1, rank + 1
+    hb = int(capi.lib.vppb_halo_bytes(src[0].ptr(), halo))
+    if world > 1:
+        send_up = torch.empty(nframes * hb, dtype=torch.uint8, device=dev)
+        send_dn = torch.empty_like(send_up)
+        recv_up = torch.empty_like(send_up)
+        recv_dn = torch.empty_like(send_up)
+        # scramble the interior tiles' halo rows so that a broken exchange cannot go unnoticed
+        for s in src:
+            if up >= 0:
+                capi.check(capi.lib.vppb_fill((s | vpp.Box2d((-2, -2), (-1, W + 1))).ptr(), (C.c_ubyte * 3)(7, 7, 7), 0, sp))
+            if down < world:
+                capi.check(capi.lib.vppb_fill((s | vpp.Box2d((th, -2), (th + 1, W + 1))).ptr(), (C.c_ubyte * 3)(9, 9, 9), 0, sp))
+
+    launches_per_step = 0
+    side = [torch.cuda.Stream(device=dev) for _ in range(max(args.streams, 1))] if args.streams > 1 else []
+    side_p = [C.c_void_p(s_.cuda_stream) for s_ in side]
+    fork = torch.cuda.Event()
+    base["config"]["streams"] = max(args.streams, 1)
+
+    def step():
+        nonlocal launches_per_step
+        n = 0
+        if world > 1:
+            ops = []
+            for i, s in enumerate(src):
+                if up >= 0:
+                    capi.check(capi.lib.vppb_halo_pack(s.ptr(), halo, 0, C.c_void_p(send_up.data_ptr() + i * hb), sp)); n += 1
+                if down < world:
+                    capi.check(capi.lib.vppb_halo_pack(s.ptr(), halo, 1, C.c_void_p(send_dn.data_ptr() + i * hb), sp)); n += 1
+            if up >= 0:
+                ops += [dist.P2POp(dist.isend, send_up, up), dist.P2POp(dist.irecv, recv_up, up)]
+            if down < world:
+                ops += [dist.P2POp(dist.isend, send_dn, down), dist.P2POp(dist.irecv, recv_dn, down)]
+            for w_ in dist.batch_isend_irecv(ops):
+                w_.wait()
+            for i, s in enumerate(src):
+                if up >= 0:
+                    capi.check(capi.lib.vppb_halo_unpack(s.ptr(), halo, 0, C.c_void_p(recv_up.data_ptr() + i * hb), sp)); n += 1
+                if down < world:
+                    capi.check(capi.lib.vppb_halo_unpack(s.ptr(), halo, 1, C.c_void_p(recv_dn.data_ptr() + i * hb), sp)); n += 1
+        if len(side) > 1:
+            fork.record(stream)
+            for k, s_ in enumerate(side):
+                s_.wait_event(fork)
+            for i, (s, d) in enumerate(zip(src, dst)):
+                capi.check(capi.lib.vppb_box5x5_u8c3(s.ptr(), d.ptr(), side_p[i % len(side)])); n += 1
+            for s_ in side:
+                stream.wait_stream(s_)
+        else:
+            for s, d in zip(src, dst):
+                capi.check(capi.lib.vppb_box5x5_u8c3(s.ptr(), d.ptr(), sp)); n += 1
+        launches_per_step = n
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank if world > 1 else 0)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for _ in range(steps):
+        step()
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    value = steps * nframes * H * W / 1e6 / (ms_total / 1e3)
+
+    # ---- parity spot check of what was just timed (frame 0, this rank's tile) against the oracle
+    from tests import oracle as orc
+    hs = orc.HostImage(th, W, "vuchar3", border=2, aligned=32)
+    hs.set(padded[0][r0:r1 + 4], with_border=True)
+    hd = orc.HostImage(th, W, "vuchar3", aligned=32)
+    orc.load(omp=True).vo_box5x5_u8(hs.ptr(), hd.ptr(), 3)
+    parity_ok = bool(np.array_equal(dst[0].download(), hd.get()))
+
+    # ---- kernel-only timing for the roofline: the box kernel alone, per launch, same stream
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    reps = 5
+    k0.record(stream)
+    for _ in range(reps):
+        for s, d in zip(src, dst):
+            capi.check(capi.lib.vppb_box5x5_u8c3(s.ptr(), d.ptr(), sp))
+    k1.record(stream)
+    torch.cuda.synchronize()
+    us_per_launch = k0.elapsed_time(k1) * 1e3 / (reps * nframes)
+    peak, peak_src = peaks()
+    alg_bytes = BOX_BYTES_PER_PX * th * W
+    achieved = alg_bytes / (us_per_launch * 1e-6) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "box_traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get(workload if n_gpus == 1 else "%s_tile%d" % (workload, n_gpus))
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": "k_box5_bytes_tma<3>", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": peak_src, "us_per_launch": us_per_launch, "algorithmic_bytes_per_launch": alg_bytes}
+
+    # ---- e2e: HOST buffers through the C-ABI (pinned), copies inside the timed region
+    host_in = [torch.from_numpy(np.ascontiguousarray(f[r0:r1])).pin_memory() for f in frames]
+    host_out = [torch.empty((th, W, 3), dtype=torch.uint8).pin_memory() for _ in frames]
+    e_src = [vpp.Image2d(th, W, "vuchar3", border=2) for _ in range(2)]
+    e_dst = [vpp.Image2d(th, W, "vuchar3") for _ in range(2)]
+    streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
+    rowb = W * 3
+
+    def e2e_step():
+        for i in range(nframes):
+            k = i & 1
+            st = C.c_void_p(streams[k].cuda_stream)
+            capi.check(capi.lib.vppb_upload(e_src[k].ptr(), C.c_void_p(host_in[i].data_ptr()), rowb, 0, st))
+            capi.check(capi.lib.vppb_fill_border_mirror(e_src[k].ptr(), st))
+            capi.check(capi.lib.vppb_box5x5_u8c3(e_src[k].ptr(), e_dst[k].ptr(), st))
+            capi.check(capi.lib.vppb_download(e_dst[k].ptr(), C.c_void_p(host_out[i].data_ptr()), rowb, 0, st))
+        for s_ in streams:
+            s_.synchronize()
+
+    e2e = None
+    if n_gpus == 1:
+        for _ in range(2):
+            e2e_step()
+        torch.cuda.synchronize()
+        esteps = max(3, steps // 4)
+        t0 = time.perf_counter()
+        for _ in range(esteps):
+            e2e_step()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        e2e = {"value": esteps * nframes * H * W / 1e6 / dt, "unit": "Mpix/s", "h2d_bytes_per_step": nframes * th * rowb,
+               "d2h_bytes_per_step": nframes * th * rowb, "ms_per_step": dt / esteps * 1e3,
+               "note": "pinned host frames -> vppb_upload -> fill_border_mirror -> box5x5 -> vppb_download, 2 streams"}
+        # the end-to-end result must equal the oracle's too (interior tile rows; top/bottom come from the mirror fill)
+        if world == 1:
+            parity_ok = parity_ok and bool(np.array_equal(host_out[0].numpy(), hd.get()))
+
+    line = dict(base)
+    line.update({"value": value, "ms_per_step": ms_total / steps, "clocks": clocks, "roofline": roofline, "e2e": e2e,
+                 "gpu_launches": launches_per_step * steps, "parity_checked": parity_ok})
+
+    if rank == 0 and n_gpus == 1:
+        cb, _ = cpu_box_bench(H, W, 3, 1, args.cpu_budget, want_ref=True)
+        line["cpu_baseline"] = cb
+        if not args.no_extras:
+            line["extras"] = gpu_extras(vpp, capi, torch, stream, sp)
+            try:
+                line["extras"]["cpu"] = cpu_extras()
+            except Exception as ex:  # pragma: no cover
+                line["extras"]["cpu"] = {"error": repr(ex)}
+    if rank == 0:
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0 if parity_ok else 3
+
+
+def gpu_extras(vpp, capi, torch, stream, sp):
+    """Other rows of the hot path, device-resident inputs, CUDA-event timing."""
+    from tests import scenes
+
+    peak, _ = peaks()
+    out = {}
+
+    def timed(fn, reps):
+        fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for _ in range(reps):
+            fn()
+        b.record(stream)
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    # pixel_wise add, 4K int32, 4 triples cycled (398 MB > L2)
+    rng = np.random.default_rng(1)
+    trip = []
+    for _ in range(4):
+        b, c = rng.integers(0, 2 ** 30, (2, 2160, 3840), dtype=np.int32)
+        trip.append((vpp.Image2d(2160, 3840, "i32"), vpp.Image2d.from_host(b, "i32"), vpp.Image2d.from_host(c, "i32")))
+
+    def add_all():
+        for a_, b_, c_ in trip:
+            capi.check(capi.lib.vppb_pw_add_i32(a_.ptr(), b_.ptr(), c_.ptr(), sp))
+
+    ms = timed(add_all, 20) / len(trip)
+    out["add_i32_4k"] = {"mpix_per_s": 2160 * 3840 / 1e6 / (ms / 1e3), "us_per_launch": ms * 1e3,
+                         "hbm_frac": 12.0 * 2160 * 3840 / (ms / 1e3) / 1e9 / peak}
+    del trip
+    # 4K box on vuchar3
+    f = rng.integers(0, 256, (2160, 3840, 3), dtype=np.uint8)
+    pairs = []
+    for _ in range(6):
+        s = vpp.Image2d.from_host(f, "vuchar3", border=2)
+        vpp.fill_border_mirror(s)
+        pairs.append((s, vpp.Image2d(2160, 3840, "vuchar3")))
+
+    def box_all():
+        for s_, d_ in pairs:
+            capi.check(capi.lib.vppb_box5x5_u8c3(s_.ptr(), d_.ptr(), sp))
+
+    ms = timed(box_all, 10) / len(pairs)
+    out["box5x5_vuchar3_4k"] = {"mpix_per_s": 2160 * 3840 / 1e6 / (ms / 1e3), "us_per_launch": ms * 1e3,
+                                "hbm_frac": 6.0 * 2160 * 3840 / (ms / 1e3) / 1e9 / peak}
+    del pairs
+    # FAST9 4K (includes the count read-back the API performs)
+    img = scenes.rectangles_scene(2160, 3840, seed=42)
+    G = vpp.Image2d.from_host(img, "u8", border=3)
+    vpp.fill_border_mirror(G)
+    nk = len(vpp.fast9(G, 20))
+    ms = timed(lambda: vpp.fast9(G, 20, capacity=max(nk, 1)), 5)
+    out["fast9_4k"] = {"mpix_per_s": 2160 * 3840 / 1e6 / (ms / 1e3), "ms": ms, "keypoints": nk,
+                       "note": "python wrapper incl. workspace alloc + keypoint download"}
+    # pyrLK 1080p: pyramid build + LK of 10k keypoints
+    f1, f2, pts = scenes.lk_pair(1080, 1920, 10000, seed=5)
+    I1, I2 = vpp.Image2d.from_host(f1, "u8"), vpp.Image2d.from_host(f2, "u8")
+    prev, nxt = vpp.Pyramid2d(I1, 3, 2, border=3), vpp.Pyramid2d(I2, 3, 2, border=3)
+    grad = vpp.Pyramid2d((1080, 1920), 3, 2, pixel="vint2", border=3)
+    from vpp_b200.ops import _DeviceBuffer
+
+    d_kp = _DeviceBuffer(pts.nbytes).from_host(pts)
+    d_flow, d_err = _DeviceBuffer(len(pts) * 8), _DeviceBuffer(len(pts) * 4)
+    P = capi.VppbLkParams(nlevels=3, min_scale=0, winsize=7, max_iter=21, grad_is_float=0, err_mode=0, gate_on_max_err=0, min_ev=0.0,
+                          delta=0.0, max_err=0.0, factor=2.0, pred_div=8.0)
+    pa, na, ga = prev.desc_array(), nxt.desc_array(), grad.desc_array()
+
+    def build():
+        prev.update(I1, sp); nxt.update(I2, sp)
+        vpp.scharr(prev[0], grad[0], sp)
+        grad.propagate_level0(sp)
+
+    def lk():
+        capi.check(capi.lib.vppb_lk_match_u8(pa, na, ga, C.byref(P), d_kp.ptr, None, len(pts), d_flow.ptr, d_err.ptr, sp))
+
+    build()
+    ms_build = timed(build, 10)
+    ms_lk = timed(lk, 10)
+    out["pyrlk_1080p_10k"] = {"kpts_per_s_match_only": len(pts) / (ms_lk / 1e3), "kpts_per_s_with_pyramids": len(pts) / ((ms_lk + ms_build) / 1e3),
+                              "ms_match": ms_lk, "ms_pyramids_scharr": ms_build}
+    return out
+
+
+if __name__ == "__main__":
+    sys.exit(main())

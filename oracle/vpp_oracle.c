@@ -22,6 +22,14 @@ int vo_num_threads(void) {
 #endif
 }
 
+void vo_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 #define ROW(img, r) ((img)->base + (int64_t)(r) * (img)->pitch)
 
 /* imageNd.hpp:151-196: border bytes and pitch rounded up to the alignment; begin_ =

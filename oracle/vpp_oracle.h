@@ -80,6 +80,7 @@ void vo_lk_match_u8(const vo_img* prev, const vo_img* next, const vo_img* grad, 
                     const vo_float2* kps, const vo_float2* prediction, int n, vo_float2* flow_out, float* err_out);
 
 int vo_num_threads(void);
+void vo_set_num_threads(int n);
 
 #ifdef __cplusplus
 }

@@ -146,7 +146,7 @@ int vo_interp_u8(const vo_img* im, float p0, float p1) {
   const unsigned char* l1 = ROW(im, clamp_tap(x0, im->nrows, im->border)) + clamp_tap(x1, im->ncols, im->border);
   const unsigned char* l2 = l1 + im->pitch;
   float res = (1 - a0) * (1 - a1) * (float)l1[0] + a0 * (1 - a1) * (float)l2[0] + (1 - a0) * a1 * (float)l1[1] + a0 * a1 * (float)l2[1];
-  return (int)(unsigned char)res;
+  return (int)(unsigned char)(int)res; /* cvttss2si, then the low byte */
 }
 
 static void interp_grad(const vo_img* im, int is_float, float p0, float p1, float* gx, float* gy) {

@@ -23,14 +23,18 @@ def _blur1461(a):
     return a
 
 
-def smooth_noise(nrows, ncols, seed=42, passes=3):
-    """Band-limited noise: white noise blurred `passes` times with 1-4-6-4-1, contrast-stretched to u8."""
+def smooth_noise(nrows, ncols, seed=42, sigmas=(1.5, 5.0, 14.0)):
+    """Multi-octave band-limited noise in [0,1]: white noise Gaussian-blurred at several scales so
+    that every pyramid level (factor 2, up to 4 levels) still carries texture."""
+    from scipy.ndimage import gaussian_filter
+
     rng = np.random.default_rng(seed)
-    a = rng.standard_normal((nrows, ncols))
-    for _ in range(passes):
-        a = _blur1461(a)
-    a = (a - a.min()) / (a.max() - a.min())
-    return a
+    a = np.zeros((nrows, ncols))
+    for s in sigmas:
+        o = gaussian_filter(rng.standard_normal((nrows, ncols)), sigma=s, mode="reflect")
+        a += o / o.std()
+    lo, hi = np.percentile(a, 0.5), np.percentile(a, 99.5)
+    return np.clip((a - lo) / (hi - lo), 0, 1)
 
 
 def warp(a, dr, dc):

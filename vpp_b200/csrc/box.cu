@@ -3,12 +3,8 @@
 // (image2d<int>) and examples/box_filter.cc:23-32 (image2d<vuchar3>, vint3 accumulator).
 //
 // Byte images (u8, vuchar3) run as byte streams: a vuchar3 row is 3*ncols bytes and the
-// horizontal taps sit CS = 3 bytes apart.  One CTA streams a 1024-byte-wide column strip
-// top-to-bottom: a producer thread issues TMA tile loads (cp.async.bulk.tensor.2d, 10 rows x
-// 1056 bytes per stage, 4-stage mbarrier ring), 64 consumer threads each own 16 output bytes,
-// do the horizontal 5-tap sum in packed 16-bit lanes, and keep the vertical 5-row window as a
-// register ring, so every input byte is fetched from L2/HBM once per strip and the vertical halo
-// costs 4 rows per segment.  HBM-bound: 2 bytes of traffic per output byte.
+// horizontal taps sit CS = 3 bytes apart.  Tiles are staged in shared memory by TMA
+// (cp.async.bulk.tensor.2d + mbarrier); see k_box5_bytes_tma below for the two-phase scheme.
 #include "common.cuh"
 #include "tma.cuh"
 
@@ -67,50 +63,28 @@ __global__ void k_box5_direct(Img in, Img out, int row_elems) {
   }
 }
 
-// ------------------------------------------------------------------ TMA strip kernel (bytes)
-constexpr int BX_TW = 1024;           // output bytes per strip row
-constexpr int BX_BOXW = 1056;         // TW + 16 left + 16 right (halo rounded to the 16-byte TMA granule)
-constexpr int BX_CH = 10;             // rows per stage: two turns of the 5-row ring
-constexpr int BX_STAGES = 4;
-constexpr int BX_STAGE_BYTES = 10624; // BX_CH * BX_BOXW rounded up to 128
-constexpr int BX_CONSUMERS = 64;
-constexpr int BX_THREADS = BX_CONSUMERS + 32;
+// ------------------------------------------------------------------ TMA tile kernel (bytes)
+// One CTA per tile of 992 x 16 output bytes.  Thread 0 issues ONE TMA load of the 1024-byte x
+// 20-row input box (16 bytes of halo-and-alignment left and right, 2 rows above/below) and the
+// whole CTA waits on its mbarrier.
+//   phase 1 (vertical): thread = (16-byte column group, 8 output rows).  Bytes are split into
+//     packed 16-bit lanes E = (b0,b2), O = (b1,b3) of each word and the 5-row column sums are kept
+//     as a running window in registers (ring of 5 rows), written to shared memory as u16 pairs.
+//   phase 2 (horizontal + divide): thread = (row, 16-byte output group).  The 5 taps CS bytes
+//     apart are whole or word-straddling lane pairs of the column sums (one PRMT each), summed
+//     with IADD3, divided by 25 with an exact multiply-shift and packed back to bytes.
+// 4 CTAs (16 warps) are resident per SM; every input byte is fetched once per tile (+25 % halo
+// rows, served by L2).  HBM-bound: 2 bytes of traffic per output byte.
+constexpr int BX_BOXW = 1024;           // bytes per box row (64 column groups of 16 bytes)
+constexpr int BX_OUTW = 992;            // output bytes per tile row (62 groups)
+constexpr int BX_TH = 16;               // output rows per tile
+constexpr int BX_INH = BX_TH + 4;       // input rows per tile
+constexpr int BX_THREADS = 128;
+constexpr int BX_RAW_BYTES = BX_INH * BX_BOXW;            // 20480
+constexpr int BX_CS_ROW_WORDS = BX_BOXW / 4;              // 256 words per plane per row
+constexpr int BX_CS_BYTES = BX_TH * 2 * BX_CS_ROW_WORDS * 4;  // E and O planes: 32768
+constexpr int BX_SMEM = BX_RAW_BYTES + BX_CS_BYTES + 16;
 constexpr unsigned BX_DIV25 = 671089u;  // floor(s/25) == (s * 671089) >> 24 for 0 <= s <= 6375 (checked exhaustively)
-
-// Horizontal 5-tap sums of the 16 bytes a thread owns, as 8 packed 16-bit pairs.
-// Lane layout: E pair of word i = (byte0, byte2), O pair = (byte1, byte3).
-template <int CS>
-__device__ __forceinline__ void box_hsum_row(const unsigned char* srow, uint32_t HE[4], uint32_t HO[4]) {
-  const uint2 a = *reinterpret_cast<const uint2*>(srow + 8);
-  const uint4 b = *reinterpret_cast<const uint4*>(srow + 16);
-  const uint2 c = *reinterpret_cast<const uint2*>(srow + 32);
-  const uint32_t w[8] = {a.x, a.y, b.x, b.y, b.z, b.w, c.x, c.y};  // words k-2 .. k+5, own = w[2..5]
-  uint32_t E[8], O[8], SE[7], SO[7];
-#pragma unroll
-  for (int i = 0; i < 8; i++) {
-    E[i] = w[i] & 0x00FF00FFu;
-    O[i] = __byte_perm(w[i], 0u, 0x4341);
-  }
-#pragma unroll
-  for (int i = 0; i < 7; i++) {
-    SE[i] = __byte_perm(E[i], E[i + 1], 0x5432);  // (byte2 of word i, byte0 of word i+1)
-    SO[i] = __byte_perm(O[i], O[i + 1], 0x5432);  // (byte3 of word i, byte1 of word i+1)
-  }
-#pragma unroll
-  for (int j = 0; j < 4; j++) {
-    const int i = j + 2;
-    if (CS == 3) {
-      // lanes (x, x+2): taps x-6, x-3, x, x+3, x+6
-      HE[j] = SE[i - 2] + O[i - 1] + E[i] + SO[i] + SE[i + 1];
-      // lanes (x+1, x+3)
-      HO[j] = SO[i - 2] + SE[i - 1] + O[i] + E[i + 1] + SO[i + 1];
-    } else {
-      // CS == 1: taps x-2 .. x+2
-      HE[j] = SE[i - 1] + SO[i - 1] + E[i] + O[i] + SE[i];
-      HO[j] = SO[i - 1] + E[i] + O[i] + SE[i] + SO[i];
-    }
-  }
-}
 
 __device__ __forceinline__ uint32_t box_div_pack(uint32_t se, uint32_t so) {
   const uint32_t pel = (se & 0xFFFFu) * BX_DIV25, peh = (se >> 16) * BX_DIV25;
@@ -121,97 +95,99 @@ __device__ __forceinline__ uint32_t box_div_pack(uint32_t se, uint32_t so) {
 }
 
 template <int CS>
-__global__ void __launch_bounds__(BX_THREADS) k_box5_bytes_tma(const __grid_constant__ CUtensorMap tmap, Img out, int rowbytes,
-                                                              int strips, int segs, int seg_chunks, int vec_store) {
+__global__ void __launch_bounds__(BX_THREADS, 4) k_box5_bytes_tma(const __grid_constant__ CUtensorMap tmap, Img out, int rowbytes, int strips,
+                                                                 int vec_store) {
   extern __shared__ __align__(128) unsigned char smem[];
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + BX_STAGES * BX_STAGE_BYTES);
-  uint64_t* empty = full + BX_STAGES;
+  unsigned char* raw = smem;
+  uint32_t* csE = reinterpret_cast<uint32_t*>(smem + BX_RAW_BYTES);
+  uint32_t* csO = csE + BX_TH * BX_CS_ROW_WORDS;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + BX_RAW_BYTES + BX_CS_BYTES);
   const int tid = threadIdx.x;
-  const int items = strips * segs;
-  const int seg_rows = seg_chunks * BX_CH - 4;
+  const int strip = blockIdx.x % strips, rt = blockIdx.x / strips;
+  const int x0 = strip * BX_OUTW, y0 = rt * BX_TH;
 
   if (tid == 0) {
-    for (int s = 0; s < BX_STAGES; s++) {
-      mbar_init(&full[s], 1);
-      mbar_init(&empty[s], BX_CONSUMERS / 32);
-    }
+    mbar_init(bar, 1);
     fence_barrier_init();
+    mbar_arrive_expect_tx(bar, BX_RAW_BYTES);
+    // tensor origin = 16 bytes left of x = 0, 2 rows above y = 0; elements are 8 bytes; the box starts at
+    // x0 - 16.  (Measured on B200: the innermost box coordinate times the element size must be a multiple
+    // of 16 bytes, otherwise UTMALDG raises "illegal instruction" - dbg/tma_test.cu.)
+    tma_load_2d(raw, &tmap, x0 / 8, y0, bar);
+  }
+  __syncthreads();  // barrier init visible to the waiters
+  mbar_wait(bar, 0);
+
+  // ---------------- phase 1: 5-row column sums
+  {
+    const int cg = tid & 63, rg = tid >> 6;
+    const unsigned char* col = raw + (rg * 8) * BX_BOXW + cg * 16;
+    uint32_t ringE[5][4], ringO[5][4], VE[4], VO[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) { VE[q] = 0; VO[q] = 0; }
+#pragma unroll
+    for (int j = 0; j < 12; j++) {
+      const uint4 v = *reinterpret_cast<const uint4*>(col + j * BX_BOXW);
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+      const int slot = j % 5;
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const uint32_t e = w[q] & 0x00FF00FFu, o = __byte_perm(w[q], 0u, 0x4341);
+        if (j >= 5) { VE[q] += e - ringE[slot][q]; VO[q] += o - ringO[slot][q]; }
+        else { VE[q] += e; VO[q] += o; }
+        ringE[slot][q] = e;
+        ringO[slot][q] = o;
+      }
+      if (j >= 4) {
+        const int orow = rg * 8 + j - 4;
+        *reinterpret_cast<uint4*>(csE + orow * BX_CS_ROW_WORDS + cg * 4) = make_uint4(VE[0], VE[1], VE[2], VE[3]);
+        *reinterpret_cast<uint4*>(csO + orow * BX_CS_ROW_WORDS + cg * 4) = make_uint4(VO[0], VO[1], VO[2], VO[3]);
+      }
+    }
   }
   __syncthreads();
 
-  if (tid >= BX_CONSUMERS) {
-    // ---------------- producer: one elected thread feeds the ring
-    if (tid == BX_CONSUMERS) {
-      tma_prefetch_desc(&tmap);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int item = blockIdx.x; item < items; item += gridDim.x) {
-        const int strip = item % strips, seg = item / strips;
-        const int xe = strip * (BX_TW / 8);  // tensor elements are 8 bytes; origin sits 16 bytes left of x = 0
-        const int y0 = seg * seg_rows;       // tensor row 0 is image row -2
-        for (int ch = 0; ch < seg_chunks; ch++) {
-          mbar_wait(&empty[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full[stage], BX_CH * BX_BOXW);
-          tma_load_2d(smem + stage * BX_STAGE_BYTES, &tmap, xe, y0 + ch * BX_CH, &full[stage]);
-          if (++stage == BX_STAGES) { stage = 0; phase ^= 1; }
-        }
-      }
+  // ---------------- phase 2: horizontal taps, divide, store
+  const int rows_here = min(BX_TH, out.nrows - y0);
+  for (int u = tid; u < BX_TH * 62; u += BX_THREADS) {
+    const int row = u / 62, og = u - row * 62;
+    const int x = x0 + og * 16;
+    if (row >= rows_here || x >= rowbytes) continue;
+    // own words are box words 4og+4 .. 4og+7 (the box starts 16 bytes left of x0); window = words k-2 .. k+5
+    const uint32_t* pe = csE + row * BX_CS_ROW_WORDS + og * 4 + 2;
+    const uint32_t* po = csO + row * BX_CS_ROW_WORDS + og * 4 + 2;
+    const uint2 e0 = *reinterpret_cast<const uint2*>(pe), e2 = *reinterpret_cast<const uint2*>(pe + 6);
+    const uint4 e1 = *reinterpret_cast<const uint4*>(pe + 2);
+    const uint2 o0 = *reinterpret_cast<const uint2*>(po), o2 = *reinterpret_cast<const uint2*>(po + 6);
+    const uint4 o1 = *reinterpret_cast<const uint4*>(po + 2);
+    const uint32_t E[8] = {e0.x, e0.y, e1.x, e1.y, e1.z, e1.w, e2.x, e2.y};
+    const uint32_t O[8] = {o0.x, o0.y, o1.x, o1.y, o1.z, o1.w, o2.x, o2.y};
+    uint32_t SE[7], SO[7];
+#pragma unroll
+    for (int i = 0; i < 7; i++) {
+      SE[i] = __byte_perm(E[i], E[i + 1], 0x5432);  // lanes (byte2 of word i, byte0 of word i+1)
+      SO[i] = __byte_perm(O[i], O[i + 1], 0x5432);  // lanes (byte3 of word i, byte1 of word i+1)
     }
-    return;
-  }
-
-  // ---------------- consumers
-  int stage = 0;
-  uint32_t phase = 0;
-  for (int item = blockIdx.x; item < items; item += gridDim.x) {
-    const int strip = item % strips, seg = item / strips;
-    const int x = strip * BX_TW + tid * 16;  // first output byte of this thread
-    const int y0 = seg * seg_rows;
-    const int y_end = min(y0 + seg_rows, out.nrows);
-    uint32_t ringE[5][4], ringO[5][4], VE[4], VO[4];
+    uint32_t ow[4];
 #pragma unroll
-    for (int q = 0; q < 4; q++) {
-      VE[q] = 0; VO[q] = 0;
-#pragma unroll
-      for (int s = 0; s < 5; s++) { ringE[s][q] = 0; ringO[s][q] = 0; }
-    }
-    for (int ch = 0; ch < seg_chunks; ch++) {
-      mbar_wait(&full[stage], phase);
-      const unsigned char* sbase = smem + stage * BX_STAGE_BYTES + tid * 16;
-#pragma unroll
-      for (int j = 0; j < BX_CH; j++) {
-        const int slot = j % 5;
-        uint32_t HE[4], HO[4];
-        box_hsum_row<CS>(sbase + j * BX_BOXW, HE, HO);
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-          VE[q] += HE[q] - ringE[slot][q];
-          VO[q] += HO[q] - ringO[slot][q];
-          ringE[slot][q] = HE[q];
-          ringO[slot][q] = HO[q];
-        }
-        const int in_idx = ch * BX_CH + j;  // input row y0 - 2 + in_idx just entered the window
-        const int oy = y0 + in_idx - 4;
-        if (in_idx >= 4 && oy < y_end && x < rowbytes) {
-          uint4 o;
-          o.x = box_div_pack(VE[0], VO[0]);
-          o.y = box_div_pack(VE[1], VO[1]);
-          o.z = box_div_pack(VE[2], VO[2]);
-          o.w = box_div_pack(VE[3], VO[3]);
-          unsigned char* dst = out.base + (long long)oy * out.pitch + x;
-          if (vec_store && x + 16 <= rowbytes) {
-            *reinterpret_cast<uint4*>(dst) = o;
-          } else {
-            const uint32_t ow[4] = {o.x, o.y, o.z, o.w};
-#pragma unroll
-            for (int k = 0; k < 16; k++)
-              if (x + k < rowbytes) dst[k] = (unsigned char)(ow[k >> 2] >> ((k & 3) * 8));
-          }
-        }
+    for (int j = 0; j < 4; j++) {
+      const int i = j + 2;
+      uint32_t he, ho;
+      if (CS == 3) {
+        he = SE[i - 2] + O[i - 1] + E[i] + SO[i] + SE[i + 1];      // lanes (x, x+2): taps x-6, x-3, x, x+3, x+6
+        ho = SO[i - 2] + SE[i - 1] + O[i] + E[i + 1] + SO[i + 1];  // lanes (x+1, x+3)
+      } else {
+        he = SE[i - 1] + SO[i - 1] + E[i] + O[i] + SE[i];          // CS == 1: taps x-2 .. x+2
+        ho = SO[i - 1] + E[i] + O[i] + SE[i] + SO[i];
       }
-      __syncwarp();
-      if ((tid & 31) == 0) mbar_arrive(&empty[stage]);
-      if (++stage == BX_STAGES) { stage = 0; phase ^= 1; }
+      ow[j] = box_div_pack(he, ho);
+    }
+    unsigned char* dst = out.base + (long long)(y0 + row) * out.pitch + x;
+    if (vec_store && x + 16 <= rowbytes) {
+      *reinterpret_cast<uint4*>(dst) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+    } else {
+      for (int k = 0; k < 16; k++)
+        if (x + k < rowbytes) dst[k] = (unsigned char)(ow[k >> 2] >> ((k & 3) * 8));
     }
   }
 }
@@ -247,24 +223,17 @@ static int box5_bytes(const vppb_img* in, const vppb_img* out, void* stream, con
     unsigned char* origin = static_cast<unsigned char*>(in->base) - 2LL * in->pitch - 16;
     const uint64_t width_el = ((uint64_t)rowbytes + 32 + 7) / 8;
     int rc = encode_tensor_map_2d(&tmap, origin, CU_TENSOR_MAP_DATA_TYPE_UINT64, 8, width_el, (uint64_t)in->nrows + 4,
-                                  (uint64_t)in->pitch, BX_BOXW / 8, BX_CH);
+                                  (uint64_t)in->pitch, BX_BOXW / 8, BX_INH);
     if (rc) return rc;
-    const int strips = (rowbytes + BX_TW - 1) / BX_TW;
-    const int sms = sm_count();
-    int seg_chunks = 2;
-    const int cand[5] = {8, 6, 4, 3, 2};
-    for (int k = 0; k < 5; k++) {
-      int sr = cand[k] * BX_CH - 4;
-      long long it = (long long)strips * ((in->nrows + sr - 1) / sr);
-      if (it >= (3LL * sms) / 2) { seg_chunks = cand[k]; break; }
-    }
-    const int seg_rows = seg_chunks * BX_CH - 4;
-    const int segs = (in->nrows + seg_rows - 1) / seg_rows;
-    const int items = strips * segs;
-    const int grid = items < sms * 5 ? items : sms * 5;
+    const int strips = (rowbytes + BX_OUTW - 1) / BX_OUTW;
+    const int row_tiles = (in->nrows + BX_TH - 1) / BX_TH;
     const int vec_store = (((uintptr_t)out->base % 16) == 0 && (out->pitch % 16) == 0) ? 1 : 0;
-    const size_t smem = BX_STAGES * BX_STAGE_BYTES + 2 * BX_STAGES * sizeof(uint64_t);
-    k_box5_bytes_tma<CS><<<grid, BX_THREADS, smem, st>>>(tmap, view(out), rowbytes, strips, segs, seg_chunks, vec_store);
+    static bool attr_set[2] = {false, false};
+    if (!attr_set[CS == 3]) {
+      VPPB_CUDA(cudaFuncSetAttribute(k_box5_bytes_tma<CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, BX_SMEM));
+      attr_set[CS == 3] = true;
+    }
+    k_box5_bytes_tma<CS><<<strips * row_tiles, BX_THREADS, BX_SMEM, st>>>(tmap, view(out), rowbytes, strips, vec_store);
   } else {
     long long total = (long long)in->nrows * rowbytes;
     long long blocks = (total + 255) / 256;

@@ -43,7 +43,9 @@ __device__ __forceinline__ int interp_u8(const Img& im, float p0, float p1) {
   res = __fadd_rn(res, __fmul_rn(__fmul_rn(a0, b1), (float)l2[0]));
   res = __fadd_rn(res, __fmul_rn(__fmul_rn(b0, a1), (float)l1[1]));
   res = __fadd_rn(res, __fmul_rn(__fmul_rn(a0, a1), (float)l2[1]));
-  return (int)(unsigned char)res;
+  // static_cast<unsigned char>(float): truncate to int, keep the low byte (what the x86 reference build does
+  // for the out-of-range values that extrapolated samples can produce)
+  return ((int)res) & 255;
 }
 
 // same on image2d<vint2> (result truncated per component) or image2d<vfloat2>
