@@ -77,13 +77,15 @@ __global__ void k_box5_direct(Img in, Img out, int row_elems) {
 // rows, served by L2).  HBM-bound: 2 bytes of traffic per output byte.
 constexpr int BX_BOXW = 1024;           // bytes per box row (64 column groups of 16 bytes)
 constexpr int BX_OUTW = 992;            // output bytes per tile row (62 groups)
-constexpr int BX_TH = 16;               // output rows per tile
-constexpr int BX_INH = BX_TH + 4;       // input rows per tile
 constexpr int BX_THREADS = 128;
-constexpr int BX_RAW_BYTES = BX_INH * BX_BOXW;            // 20480
 constexpr int BX_CS_ROW_WORDS = BX_BOXW / 4;              // 256 words per plane per row
-constexpr int BX_CS_BYTES = BX_TH * 2 * BX_CS_ROW_WORDS * 4;  // E and O planes: 32768
-constexpr int BX_SMEM = BX_RAW_BYTES + BX_CS_BYTES + 16;
+// TH = output rows per tile (16: 4 CTAs/SM, +25 % halo rows; 8: 8 CTAs/SM, +50 % halo rows)
+template <int TH> struct BoxCfg {
+  static constexpr int INH = TH + 4;                          // input rows per tile
+  static constexpr int RAW_BYTES = INH * BX_BOXW;
+  static constexpr int CS_BYTES = TH * 2 * BX_CS_ROW_WORDS * 4;  // E and O planes
+  static constexpr int SMEM = RAW_BYTES + CS_BYTES + 16;
+};
 constexpr unsigned BX_DIV25 = 671089u;  // floor(s/25) == (s * 671089) >> 24 for 0 <= s <= 6375 (checked exhaustively)
 
 __device__ __forceinline__ uint32_t box_div_pack(uint32_t se, uint32_t so) {
@@ -94,9 +96,11 @@ __device__ __forceinline__ uint32_t box_div_pack(uint32_t se, uint32_t so) {
   return __byte_perm(lo, hi, 0x5410);
 }
 
-template <int CS>
-__global__ void __launch_bounds__(BX_THREADS, 4) k_box5_bytes_tma(const __grid_constant__ CUtensorMap tmap, Img out, int rowbytes, int strips,
+template <int CS, int BX_TH>
+__global__ void __launch_bounds__(BX_THREADS, BX_TH == 16 ? 4 : 6) k_box5_bytes_tma(const __grid_constant__ CUtensorMap tmap, Img out, int rowbytes, int strips,
                                                                  int vec_store) {
+  constexpr int BX_RAW_BYTES = BoxCfg<BX_TH>::RAW_BYTES, BX_CS_BYTES = BoxCfg<BX_TH>::CS_BYTES;
+  constexpr int RG_ROWS = BX_TH / 2;  // output rows per phase-1 row group
   extern __shared__ __align__(128) unsigned char smem[];
   unsigned char* raw = smem;
   uint32_t* csE = reinterpret_cast<uint32_t*>(smem + BX_RAW_BYTES);
@@ -121,12 +125,12 @@ __global__ void __launch_bounds__(BX_THREADS, 4) k_box5_bytes_tma(const __grid_c
   // ---------------- phase 1: 5-row column sums
   {
     const int cg = tid & 63, rg = tid >> 6;
-    const unsigned char* col = raw + (rg * 8) * BX_BOXW + cg * 16;
+    const unsigned char* col = raw + (rg * RG_ROWS) * BX_BOXW + cg * 16;
     uint32_t ringE[5][4], ringO[5][4], VE[4], VO[4];
 #pragma unroll
     for (int q = 0; q < 4; q++) { VE[q] = 0; VO[q] = 0; }
 #pragma unroll
-    for (int j = 0; j < 12; j++) {
+    for (int j = 0; j < RG_ROWS + 4; j++) {
       const uint4 v = *reinterpret_cast<const uint4*>(col + j * BX_BOXW);
       const uint32_t w[4] = {v.x, v.y, v.z, v.w};
       const int slot = j % 5;
@@ -139,7 +143,7 @@ __global__ void __launch_bounds__(BX_THREADS, 4) k_box5_bytes_tma(const __grid_c
         ringO[slot][q] = o;
       }
       if (j >= 4) {
-        const int orow = rg * 8 + j - 4;
+        const int orow = rg * RG_ROWS + j - 4;
         *reinterpret_cast<uint4*>(csE + orow * BX_CS_ROW_WORDS + cg * 4) = make_uint4(VE[0], VE[1], VE[2], VE[3]);
         *reinterpret_cast<uint4*>(csO + orow * BX_CS_ROW_WORDS + cg * 4) = make_uint4(VO[0], VO[1], VO[2], VO[3]);
       }
@@ -210,6 +214,19 @@ static bool tma_eligible(const vppb_img* in) {
   return true;
 }
 
+// rows per tile: 16 amortises the 4 halo rows better, 8 gives twice the CTAs (small frames cannot
+// fill 148 SMs x 4 CTAs with 16-row tiles).  VPPB_BOX_TH=8|16 overrides for experiments.
+static int box_tile_rows(int nrows, int rowbytes) {
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("VPPB_BOX_TH");
+    forced = e ? atoi(e) : 0;
+  }
+  if (forced == 8 || forced == 16) return forced;
+  const long long tiles16 = (long long)((rowbytes + BX_OUTW - 1) / BX_OUTW) * ((nrows + 15) / 16);
+  return tiles16 >= 4LL * sm_count() ? 16 : 8;
+}
+
 template <int CS>
 static int box5_bytes(const vppb_img* in, const vppb_img* out, void* stream, const char* name) {
   VPPB_REQUIRE(in && out && in->base && out->base, VPPB_E_ARG, "%s: NULL image", name);
@@ -222,18 +239,23 @@ static int box5_bytes(const vppb_img* in, const vppb_img* out, void* stream, con
     CUtensorMap tmap;
     unsigned char* origin = static_cast<unsigned char*>(in->base) - 2LL * in->pitch - 16;
     const uint64_t width_el = ((uint64_t)rowbytes + 32 + 7) / 8;
+    const int th = box_tile_rows(in->nrows, rowbytes);
     int rc = encode_tensor_map_2d(&tmap, origin, CU_TENSOR_MAP_DATA_TYPE_UINT64, 8, width_el, (uint64_t)in->nrows + 4,
-                                  (uint64_t)in->pitch, BX_BOXW / 8, BX_INH);
+                                  (uint64_t)in->pitch, BX_BOXW / 8, th + 4);
     if (rc) return rc;
     const int strips = (rowbytes + BX_OUTW - 1) / BX_OUTW;
-    const int row_tiles = (in->nrows + BX_TH - 1) / BX_TH;
+    const int row_tiles = (in->nrows + th - 1) / th;
     const int vec_store = (((uintptr_t)out->base % 16) == 0 && (out->pitch % 16) == 0) ? 1 : 0;
     static bool attr_set[2] = {false, false};
     if (!attr_set[CS == 3]) {
-      VPPB_CUDA(cudaFuncSetAttribute(k_box5_bytes_tma<CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, BX_SMEM));
+      VPPB_CUDA(cudaFuncSetAttribute(k_box5_bytes_tma<CS, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, BoxCfg<16>::SMEM));
+      VPPB_CUDA(cudaFuncSetAttribute(k_box5_bytes_tma<CS, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, BoxCfg<8>::SMEM));
       attr_set[CS == 3] = true;
     }
-    k_box5_bytes_tma<CS><<<strips * row_tiles, BX_THREADS, BX_SMEM, st>>>(tmap, view(out), rowbytes, strips, vec_store);
+    if (th == 16)
+      k_box5_bytes_tma<CS, 16><<<strips * row_tiles, BX_THREADS, BoxCfg<16>::SMEM, st>>>(tmap, view(out), rowbytes, strips, vec_store);
+    else
+      k_box5_bytes_tma<CS, 8><<<strips * row_tiles, BX_THREADS, BoxCfg<8>::SMEM, st>>>(tmap, view(out), rowbytes, strips, vec_store);
   } else {
     long long total = (long long)in->nrows * rowbytes;
     long long blocks = (total + 255) / 256;
