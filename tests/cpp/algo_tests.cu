@@ -1,0 +1,95 @@
+// C++ host API tests for the algorithms: the reference's LK integration test (tests/pyrlk.cc:14-50)
+// on the committed fixture, plus FAST9 / Scharr / pyramid sanity checks through the reference's names.
+#undef NDEBUG
+#include <cassert>
+#include <cstdio>
+#include <fstream>
+#include <vpp/vpp.hh>
+#include <vpp/algorithms/fast_detector/fast.hh>
+#include <vpp/algorithms/filters/scharr.hh>
+#include <vpp/algorithms/lucas_kanade.hh>
+#include <vpp/algorithms/pyrlk/pyrlk_match.hh>
+
+using namespace vpp;
+
+static image2d<uint8_t> load_u8(const std::string& path, int nr, int nc) {
+  image2d<uint8_t> img(nr, nc);
+  std::ifstream f(path, std::ios::binary);
+  assert(f.good());
+  for (int r = 0; r < nr; r++) f.read((char*)&img(r, 0), nc);
+  return img;
+}
+
+struct kp_t { vfloat2 position; int age = 1; bool alive() const { return age > 0; } };
+struct kp_container {
+  std::vector<kp_t> k;
+  int size() const { return (int)k.size(); }
+  kp_t& operator[](int i) { return k[i]; }
+  void remove(int i) { k[i].age = 0; }
+  void move(int i, vfloat2 p) { k[i].position = p; k[i].age++; }
+};
+
+int main(int argc, char** argv) {
+  vppb_check(vppb_init(0));
+  std::string gold = argc > 1 ? argv[1] : "tests/golden";
+
+  {  // tests/pyrlk.cc:14-50
+    image2d<uint8_t> i1 = load_u8(gold + "/pyrlk_i1_100x100.u8", 100, 100), i2 = load_u8(gold + "/pyrlk_i2_100x100.u8", 100, 100);
+    std::vector<vfloat2> keypoints;
+    keypoints.push_back(vfloat2(50, 50));
+    int calls = 0;
+    lucas_kanade(i1, i2, _keypoints = keypoints, _niterations = 50, _winsize = 5, _min_ev = 0.001, _delta = 0.01, _nscales = 2,
+                 _flow = [&](vfloat2 p, vfloat2 f, float d) {
+                   assert(p == vfloat2(50.f, 50.f));
+                   assert((f - vfloat2(2.f, 2.f)).norm() < 0.05);
+                   std::printf("lucas_kanade flow (%f, %f) dist %f\n", f[0], f[1], d);
+                   calls++;
+                 });
+    assert(calls == 1);
+
+    // pyrlk_match on the same scene (float gradient, as benchmarks/pyrlk_opencv_comparison.cc:49-60 builds them)
+    pyramid2d<uint8_t> prev(i1, 2, 2, _border = 4), next(i2, 2, 2, _border = 4);
+    pyramid2d<vfloat2> grad(i1.domain(), 2, 2, _border = 4);
+    scharr(prev[0], grad[0]);
+    grad.propagate_level0();
+    kp_container kc;
+    kc.k.resize(2);
+    kc.k[0].position = vfloat2(50, 50);
+    kc.k[1].position = vfloat2(10, 10);  // flat area: rejected by the min eigenvalue test -> removed
+    pyrlk_match(prev, grad, next, kc, lk_match_point_square_win<5>(), 0.001f, 1e9f, 50, 0.01f);
+    assert(kc.k[0].alive() && (kc.k[0].position - vfloat2(52.f, 52.f)).norm() < 0.1);
+    assert(!kc.k[1].alive());
+  }
+  {  // FAST9: a bright square on black has exactly its 4 corners as local maxima candidates; border rule
+    image2d<uint8_t> img(64, 64, _border = 3);
+    fill(img, 0);
+    fill(img, (uint8_t)255, box2d(vint2(20, 20), vint2(40, 40)));
+    fill_border_mirror(img);
+    std::vector<int> scores;
+    auto kps = fast9(img, 20, _scores = &scores, _ring = 1);
+    assert(!kps.empty() && kps.size() == scores.size());
+    for (size_t i = 1; i < kps.size(); i++) assert(kps[i - 1][0] < kps[i][0] || (kps[i - 1][0] == kps[i][0] && kps[i - 1][1] < kps[i][1]));
+    bool has_corner = false;
+    for (auto p : kps) has_corner |= (p == vint2(20, 20));
+    assert(has_corner);
+    auto lm = fast9(img, 20, _local_maxima, _ring = 1);
+    assert(!lm.empty() && lm.size() <= kps.size());
+    auto bw = fast9(img, 20, _blockwise, _block_size = 8, _ring = 1);
+    assert(!bw.empty() && bw.size() <= kps.size());
+    assert(fast9_score(img, 20, vint2(20, 20)) > 0);
+    bool threw = false;
+    try { fast9(image2d<uint8_t>(10, 10, _border = 2), 10); } catch (std::runtime_error&) { threw = true; }  // fast.hpp:937-938
+    assert(threw);
+  }
+  {  // pyramid level sizes (pyramid.hh:140) and Scharr of a ramp
+    pyramid2d<uint8_t> p(make_box2d(1080, 1920), 3, 2, _border = 2);
+    assert(p[1].nrows() == 541 && p[1].ncols() == 961 && p[2].nrows() == 271 && p[2].ncols() == 481);
+    image2d<uint8_t> ramp(32, 32, _border = 1);
+    pixel_wise(ramp.domain_with_border(), ramp) | [=] VPP_KERNEL(vint2 q, uint8_t& v) { v = (uint8_t)(4 * q[1] + 8); };
+    image2d<vint2> g(32, 32);
+    scharr(ramp, g);
+    for (auto q : g.domain()) assert(g(q) == vint2(0, 4));  // d/drow = 0, d/dcol = (3+10+3)*8/32
+  }
+  std::puts("ALL OK");
+  return 0;
+}

@@ -23,3 +23,5 @@ b1 = cv2.GaussianBlur(i1, (9, 9), sigmaX=3, sigmaY=5, borderType=cv2.BORDER_REPL
 b2 = cv2.GaussianBlur(i2, (9, 9), sigmaX=3, sigmaY=5, borderType=cv2.BORDER_REPLICATE)
 np.savez_compressed(os.path.join(os.path.dirname(__file__), "pyrlk_scene.npz"), i1=b1, i2=b2)
 print("wrote pyrlk_scene.npz", b1.max(), b2.max())
+b1.tofile(os.path.join(os.path.dirname(__file__), "pyrlk_i1_100x100.u8"))  # raw copies for the C++ test (tests/cpp/algo_tests.cu)
+b2.tofile(os.path.join(os.path.dirname(__file__), "pyrlk_i2_100x100.u8"))

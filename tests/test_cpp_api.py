@@ -1,0 +1,23 @@
+"""The C++14 host API (vpp_b200/include/vpp): the reference's own tests, rewritten with device kernels,
+are compiled by build.sh into tests/cpp/_build and run here on the GPU."""
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BUILD = os.path.join(ROOT, "tests", "cpp", "_build")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["core_tests", "algo_tests"])
+def test_cpp_binary(gpu, name):
+    exe = os.path.join(BUILD, name)
+    assert os.path.exists(exe), "build.sh did not produce %s" % exe
+    r = subprocess.run([exe, os.path.join(ROOT, "tests", "golden")], capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert r.returncode == 0 and "ALL OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_cpp_binaries_are_built(built):
+    for name in ("core_tests", "algo_tests"):
+        assert os.path.exists(os.path.join(BUILD, name))

@@ -1,0 +1,73 @@
+// fast9(A, th, [_local_maxima | _blockwise, _block_size =, _mask =, _scores = &vec])
+// (reference: vpp/algorithms/fast_detector/fast.hh:25-28, fast.hpp:931-955).  Keypoints come back in
+// raster order; `_ring = 1` (extension) selects the true Bresenham ring instead of the ring fast9()
+// actually samples (fast.hpp:367-368).
+#pragma once
+#include <vector>
+#include <vpp/core/image2d.hh>
+
+namespace vpp {
+
+namespace internals {
+struct device_array {
+  vppb_img img;
+  explicit device_array(size_t bytes) { vppb_check(vppb_alloc(&img, 1, (int)(bytes ? bytes : 1), 1, 0, 256)); }
+  ~device_array() { vppb_free(&img); }
+  void* ptr() const { return img.base; }
+  void to_host(void* dst, size_t bytes) const {
+    if (!bytes) return;
+    vppb_img v = img; v.ncols = (int)bytes;
+    vppb_check(vppb_download(&v, dst, (int64_t)bytes, 0, nullptr));
+    vppb_check(vppb_sync(nullptr));
+  }
+  void from_host(const void* src, size_t bytes) const {
+    if (!bytes) return;
+    vppb_img v = img; v.ncols = (int)bytes;
+    vppb_check(vppb_upload(&v, src, (int64_t)bytes, 0, nullptr));
+    vppb_check(vppb_sync(nullptr));
+  }
+};
+}  // namespace internals
+
+template <typename... OPTS>
+std::vector<vint2> fast9(const image2d<unsigned char>& A, int th, OPTS... opts_) {
+  auto opts = s::D(opts_...);
+  if (A.border() < 3) throw std::runtime_error("Image need a border of 3px at least for the FAST detector");  // fast.hpp:937-938
+  image2d<unsigned char> mask = opts.get(s::_mask, image2d<unsigned char>());
+  std::vector<int>* scores = opts.get(s::_scores, (std::vector<int>*)nullptr);
+  const int block_size = opts.get(s::_block_size, 10);
+  const int mode = opts.has(s::_local_maxima) ? VPPB_FAST_LOCAL_MAXIMA : (opts.has(s::_blockwise) ? VPPB_FAST_BLOCKWISE : VPPB_FAST_ALL);
+  const int ring = opts.get(s::_ring, 0);
+  internals::device_array ws((size_t)vppb_fast9_workspace_bytes(A.nrows(), A.ncols(), block_size));
+  int capacity = std::max(1024, A.nrows() * A.ncols() / 16), count = 0;
+  std::vector<vint2> kps;
+  for (;;) {
+    internals::device_array dk((size_t)capacity * sizeof(vppb_int2)), ds(scores ? (size_t)capacity * 4 : 0);
+    int rc = vppb_fast9_u8(A.device_read(), th, mask.has_data() ? mask.device_read() : nullptr, mode, block_size, ring, ws.ptr(),
+                           vppb_fast9_workspace_bytes(A.nrows(), A.ncols(), block_size), (vppb_int2*)dk.ptr(),
+                           scores ? (int32_t*)ds.ptr() : nullptr, capacity, &count, nullptr);
+    if (rc == VPPB_E_CAPACITY) { capacity = count; continue; }
+    vppb_check(rc);
+    kps.resize(count);
+    dk.to_host(kps.data(), (size_t)count * sizeof(vint2));
+    if (scores) { scores->resize(count); ds.to_host(scores->data(), (size_t)count * 4); }
+    return kps;
+  }
+}
+
+template <typename KPS>
+void fast9_scores(const image2d<unsigned char>& A, int th, const KPS& keypoints, std::vector<int>& scores) {  // fast.hpp:643-652
+  const size_t n = keypoints.size();
+  scores.resize(n);
+  internals::device_array dk(n * sizeof(vint2)), ds(n * 4);
+  dk.from_host(keypoints.data(), n * sizeof(vint2));
+  vppb_check(vppb_fast9_scores(A.device_read(), th, (const vppb_int2*)dk.ptr(), (int)n, (int32_t*)ds.ptr(), nullptr));
+  ds.to_host(scores.data(), n * 4);
+}
+inline int fast9_score(const image2d<unsigned char>& A, int th, vint2 p) {  // fast.hpp:655-660
+  std::vector<vint2> k(1, p); std::vector<int> s;
+  fast9_scores(A, th, k, s);
+  return s[0];
+}
+
+}  // namespace vpp
