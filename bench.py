@@ -123,23 +123,21 @@ def cpu_box_bench(h, w, steps, warmup, budget_s, want_ref=True):
     from tests import oracle as orc
 
     kind, lib, fn = "port", orc.load(omp=True), None
-    ref_path = os.path.join(ROOT, "oracle", "_ref", "libvppref.so")
+    ref_path = os.path.join(ROOT, "oracle", "_ref", "libvppref_omp.so")
     if want_ref and os.path.exists(ref_path):
-        try:
+        try:  # the reference's own headers (oracle/ref_shim/build_ref.sh), benchmark flags, OpenMP
             r = C.CDLL(ref_path)
             r.vppref_box5x5_u8c3.argtypes = [C.POINTER(orc.VoImg), C.POINTER(orc.VoImg)]
-            fn, kind = r.vppref_box5x5_u8c3, "reference"
-            cores = r.vppref_num_threads()
+            r.vo_set_num_threads = r.vppref_set_num_threads
+            fn, kind, lib = r.vppref_box5x5_u8c3, "reference", r
         except Exception:
             fn = None
     if fn is None:
         fn = lambda a, b: lib.vo_box5x5_u8(a, b, 3)
-        cores = lib.vo_num_threads()
     src = make_frames(h, w, 1)[0]
     hs = orc.HostImage(h, w, "vuchar3", border=2, aligned=32, data=src, fill_border="mirror")
     hd = orc.HostImage(h, w, "vuchar3", aligned=32)
-    if kind == "port":
-        cores = pick_threads(lib, lambda: fn(hs.ptr(), hd.ptr()))
+    cores = pick_threads(lib, lambda: fn(hs.ptr(), hd.ptr()))
     t0 = time.perf_counter()
     fn(hs.ptr(), hd.ptr())
     one = time.perf_counter() - t0
