@@ -248,7 +248,9 @@ def main():
     sp = C.c_void_p(stream.cuda_stream)
 
     # ---- row tile of this rank (whole frame at N=1)
-    r0, r1 = (H * rank) // world, (H * (rank + 1)) // world
+    from vpp_b200 import tiles
+
+    r0, r1 = tiles.tile_rows(H, rank, world)
     th = r1 - r0
     frames = make_frames(H, W, nframes)
     padded = [np.pad(f, ((2, 2), (2, 2), (0, 0)), mode="symmetric") for f in frames]
@@ -285,18 +287,12 @@ def main():
         stream = torch.cuda.current_stream()
         sp = C.c_void_p(stream.cuda_stream)
         if world > 1:
-            ops = []
             for i, s in enumerate(src):
                 if up >= 0:
                     capi.check(capi.lib.vppb_halo_pack(s.ptr(), halo, 0, C.c_void_p(send_up.data_ptr() + i * hb), sp)); n += 1
                 if down < world:
                     capi.check(capi.lib.vppb_halo_pack(s.ptr(), halo, 1, C.c_void_p(send_dn.data_ptr() + i * hb), sp)); n += 1
-            if up >= 0:
-                ops += [dist.P2POp(dist.isend, send_up, up), dist.P2POp(dist.irecv, recv_up, up)]
-            if down < world:
-                ops += [dist.P2POp(dist.isend, send_dn, down), dist.P2POp(dist.irecv, recv_dn, down)]
-            for w_ in dist.batch_isend_irecv(ops):
-                w_.wait()
+            tiles.exchange_halos(dist, rank, world, send_up, send_dn, recv_up, recv_dn)  # ONE grouped NCCL send/recv per step
             for i, s in enumerate(src):
                 if up >= 0:
                     capi.check(capi.lib.vppb_halo_unpack(s.ptr(), halo, 0, C.c_void_p(recv_up.data_ptr() + i * hb), sp)); n += 1

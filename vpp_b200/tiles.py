@@ -1,0 +1,30 @@
+"""Row-tile sharding of a frame over the ranks of one node and the single grouped halo exchange.
+
+Host logic only (no kernels): tile bounds, neighbour ranks, and one `batch_isend_irecv` that swaps the
+edge rows of every frame of a step with both neighbours.  Works with any torch.distributed backend:
+NCCL over NVLink on the GPUs (bench.py), gloo on CPU (tests/test_tiles_gloo.py)."""
+
+
+def tile_rows(nrows, rank, world):
+    """Rows [r0, r1) of the frame owned by `rank` (contiguous, floor split as SURVEY §8e)."""
+    return (nrows * rank) // world, (nrows * (rank + 1)) // world
+
+
+def neighbours(rank, world):
+    """(up, down) ranks or None at the frame edge (outer tiles keep their mirror border)."""
+    return (rank - 1 if rank > 0 else None), (rank + 1 if rank + 1 < world else None)
+
+
+def exchange_halos(dist, rank, world, send_up, send_dn, recv_up, recv_dn):
+    """One grouped exchange: my top edge rows go up, my bottom edge rows go down; the neighbours'
+    edge rows land in recv_up / recv_dn.  Tensors are flat staging buffers (all frames packed)."""
+    up, down = neighbours(rank, world)
+    ops = []
+    if up is not None:
+        ops += [dist.P2POp(dist.isend, send_up, up), dist.P2POp(dist.irecv, recv_up, up)]
+    if down is not None:
+        ops += [dist.P2POp(dist.isend, send_dn, down), dist.P2POp(dist.irecv, recv_dn, down)]
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    return up, down
