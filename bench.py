@@ -208,7 +208,7 @@ def main():
     n_gpus = max(args.gpus, 1)
     workload = args.workload or ("1080p" if n_gpus == 1 else "8k")
     H, W = WORKLOADS[workload]
-    nframes = args.frames or {"1080p": 32, "4k": 8, "8k": 4}[workload]
+    nframes = args.frames or {"1080p": 32, "4k": 16, "8k": 32}[workload]
     steps, warmup = args.steps, max(args.warmup, 3)
 
     base = {"metric": "box5x5_vuchar3_throughput", "unit": "Mpix/s", "n_gpus": n_gpus, "steps": steps, "warmup": warmup,
@@ -252,63 +252,140 @@ def main():
 
     r0, r1 = tiles.tile_rows(H, rank, world)
     th = r1 - r0
-    frames = make_frames(H, W, nframes)
-    padded = [np.pad(f, ((2, 2), (2, 2), (0, 0)), mode="symmetric") for f in frames]
-    src, dst = [], []
-    for f in padded:
-        s = vpp.Image2d(th, W, "vuchar3", border=2)
-        s.upload(f[r0:r1 + 4], with_border=True)  # rows r0-2 .. r1+1: true halos, used only as the parity reference at N>1
-        src.append(s)
-        dst.append(vpp.Image2d(th, W, "vuchar3"))
+    uniq = make_frames(H, W, min(nframes, 4))  # distinct host frames (device frames cycle through them)
+    frames = [uniq[i % len(uniq)] for i in range(nframes)]
+    upad = [np.pad(f, ((2, 2), (2, 2), (0, 0)), mode="symmetric") for f in uniq]
+    padded = [upad[i % len(uniq)] for i in range(nframes)]
+    src, dst, bufs = [], [], []
     halo = 2
+
+    def torch_tile(border):
+        """image2d<vuchar3> tile inside a torch allocation (so NCCL can address its rows), described with vppb_wrap"""
+        pitch, total, _ = vpp.layout(th, W, 3, border, 128)
+        buf = torch.empty(total, dtype=torch.uint8, device=dev)
+        desc = capi.VppbImg()
+        capi.check(capi.lib.vppb_wrap(C.byref(desc), C.c_void_p(buf.data_ptr()), th, W, 3, border, 128))
+        return vpp.Image2d(0, 0, "vuchar3", _desc=desc, _owner=buf), buf, pitch
+
+    for f in padded:
+        s, buf, pitch = torch_tile(2)
+        s.upload(f[r0:r1 + 4], with_border=True)  # rows r0-2 .. r1+1 (true halos: overwritten below at N>1, restored by the exchange)
+        src.append(s)
+        bufs.append(buf)
+        dst.append(torch_tile(0)[0])
     up, down = rank - 1, rank + 1
-    hb = int(capi.lib.vppb_halo_bytes(src[0].ptr(), halo))
     if world > 1:
-        send_up = torch.empty(nframes * hb, dtype=torch.uint8, device=dev)
-        send_dn = torch.empty_like(send_up)
-        recv_up = torch.empty_like(send_up)
-        recv_dn = torch.empty_like(send_up)
+        # halo rows as views of the tile buffers: row r of the buffer starts at (border + r) * pitch
+        send_up = [b[2 * pitch:4 * pitch] for b in bufs]
+        send_dn = [b[th * pitch:(th + 2) * pitch] for b in bufs]
+        recv_up = [b[0:2 * pitch] for b in bufs]
+        recv_dn = [b[(th + 2) * pitch:(th + 4) * pitch] for b in bufs]
         # scramble the interior tiles' halo rows so that a broken exchange cannot go unnoticed
-        for s in src:
+        for i in range(nframes):
             if up >= 0:
-                capi.check(capi.lib.vppb_fill((s | vpp.Box2d((-2, -2), (-1, W + 1))).ptr(), (C.c_ubyte * 3)(7, 7, 7), 0, sp))
+                recv_up[i].fill_(7)
             if down < world:
-                capi.check(capi.lib.vppb_fill((s | vpp.Box2d((th, -2), (th + 1, W + 1))).ptr(), (C.c_ubyte * 3)(9, 9, 9), 0, sp))
+                recv_dn[i].fill_(9)
+        comm_stream = torch.cuda.Stream(device=dev)
+        inner = vpp.Box2d((2, 0), (th - 3, W - 1))
+        top, bot = vpp.Box2d((0, 0), (1, W - 1)), vpp.Box2d((th - 2, 0), (th - 1, W - 1))
+        src_in, dst_in = [s | inner for s in src], [d | inner for d in dst]
+        src_e = [s | top for s in src] + [s | bot for s in src]
+        dst_e = [d | top for d in dst] + [d | bot for d in dst]
 
     launches_per_step = 0
     side = [torch.cuda.Stream(device=dev) for _ in range(max(args.streams, 1))] if args.streams > 1 else []
     side_p = [C.c_void_p(s_.cuda_stream) for s_ in side]
-    fork = torch.cuda.Event()
+    fork, fork2, comm_done = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
     base["config"]["streams"] = max(args.streams, 1)
+
+    def fan_out(stream, pairs, ev):
+        """one box5x5 launch per (src, dst) pair, spread over the side streams, joined back into `stream`"""
+        sp = C.c_void_p(stream.cuda_stream)
+        if len(side) > 1:
+            ev.record(stream)
+            for s_ in side:
+                s_.wait_event(ev)
+            for i, (s, d) in enumerate(pairs):
+                capi.check(capi.lib.vppb_box5x5_u8c3(s.ptr(), d.ptr(), side_p[i % len(side)]))
+            for s_ in side:
+                stream.wait_stream(s_)
+        else:
+            for s, d in pairs:
+                capi.check(capi.lib.vppb_box5x5_u8c3(s.ptr(), d.ptr(), sp))
+        return len(pairs)
+
+    if world > 1:
+        hb = int(capi.lib.vppb_halo_bytes(src[0].ptr(), halo))
+        st_send_up = torch.empty(nframes * hb, dtype=torch.uint8, device=dev)
+        st_send_dn, st_recv_up, st_recv_dn = torch.empty_like(st_send_up), torch.empty_like(st_send_up), torch.empty_like(st_send_up)
+        packed = torch.cuda.Event()
+
+    if world > 1:
+        src_descs = (capi.VppbImg * nframes)(*[s.desc for s in src])
+
+    def pack_all(stream):
+        sp = C.c_void_p(stream.cuda_stream)
+        n = 0
+        if up >= 0:
+            capi.check(capi.lib.vppb_halo_pack_batch(src_descs, nframes, halo, 0, C.c_void_p(st_send_up.data_ptr()), sp)); n += 1
+        if down < world:
+            capi.check(capi.lib.vppb_halo_pack_batch(src_descs, nframes, halo, 1, C.c_void_p(st_send_dn.data_ptr()), sp)); n += 1
+        return n
+
+    def unpack_all(stream):
+        sp = C.c_void_p(stream.cuda_stream)
+        n = 0
+        if up >= 0:
+            capi.check(capi.lib.vppb_halo_unpack_batch(src_descs, nframes, halo, 0, C.c_void_p(st_recv_up.data_ptr()), sp)); n += 1
+        if down < world:
+            capi.check(capi.lib.vppb_halo_unpack_batch(src_descs, nframes, halo, 1, C.c_void_p(st_recv_dn.data_ptr()), sp)); n += 1
+        return n
+
+    # N>1: two device-side pieces per step - [pack the edge rows of all frames] and [unpack + one box launch per
+    # tile] - each replayed as a CUDA graph; the ONE grouped NCCL send/recv of the step runs between them.
+    pieces = {}
+
+    def piece(name, fn):
+        def run():
+            stream = torch.cuda.current_stream()
+            return fn(stream)
+        if args.graph and world > 1:
+            try:
+                for _ in range(2):
+                    run()
+                torch.cuda.synchronize()
+                g_ = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g_):
+                    cnt = run()
+                pieces[name] = (g_.replay, cnt)
+                return
+            except Exception as ex:  # pragma: no cover
+                sys.stderr.write("graph capture of %s failed: %r\n" % (name, ex))
+                torch.cuda.synchronize()
+        pieces[name] = (run, None)
+
+    if world > 1:
+        piece("pack", pack_all)
+        piece("boxes", lambda st: unpack_all(st) + fan_out(st, list(zip(src, dst)), fork))
 
     def step():
         nonlocal launches_per_step
         n = 0
         stream = torch.cuda.current_stream()
-        sp = C.c_void_p(stream.cuda_stream)
         if world > 1:
-            for i, s in enumerate(src):
-                if up >= 0:
-                    capi.check(capi.lib.vppb_halo_pack(s.ptr(), halo, 0, C.c_void_p(send_up.data_ptr() + i * hb), sp)); n += 1
-                if down < world:
-                    capi.check(capi.lib.vppb_halo_pack(s.ptr(), halo, 1, C.c_void_p(send_dn.data_ptr() + i * hb), sp)); n += 1
-            tiles.exchange_halos(dist, rank, world, send_up, send_dn, recv_up, recv_dn)  # ONE grouped NCCL send/recv per step
-            for i, s in enumerate(src):
-                if up >= 0:
-                    capi.check(capi.lib.vppb_halo_unpack(s.ptr(), halo, 0, C.c_void_p(recv_up.data_ptr() + i * hb), sp)); n += 1
-                if down < world:
-                    capi.check(capi.lib.vppb_halo_unpack(s.ptr(), halo, 1, C.c_void_p(recv_dn.data_ptr() + i * hb), sp)); n += 1
-        if len(side) > 1:
-            fork.record(stream)
-            for k, s_ in enumerate(side):
-                s_.wait_event(fork)
-            for i, (s, d) in enumerate(zip(src, dst)):
-                capi.check(capi.lib.vppb_box5x5_u8c3(s.ptr(), d.ptr(), side_p[i % len(side)])); n += 1
-            for s_ in side:
-                stream.wait_stream(s_)
+            r = pieces["pack"][0]()
+            n += pieces["pack"][1] if pieces["pack"][1] is not None else r
+            packed.record(stream)
+            comm_stream.wait_event(packed)
+            with torch.cuda.stream(comm_stream):
+                tiles.exchange_halos(dist, rank, world, st_send_up, st_send_dn, st_recv_up, st_recv_dn)  # ONE grouped NCCL send/recv
+                comm_done.record(comm_stream)
+            stream.wait_event(comm_done)
+            r = pieces["boxes"][0]()
+            n += pieces["boxes"][1] if pieces["boxes"][1] is not None else r
         else:
-            for s, d in zip(src, dst):
-                capi.check(capi.lib.vppb_box5x5_u8c3(s.ptr(), d.ptr(), sp)); n += 1
+            n += fan_out(stream, list(zip(src, dst)), fork)
         launches_per_step = n
 
     def barrier():
@@ -321,18 +398,21 @@ def main():
     barrier()
     # The step (one launch per frame, fork/join over the side streams) is captured once into a CUDA graph
     # and replayed: same kernels, same work, without the per-launch host cost of the Python/ctypes loop.
-    graph = None
-    if args.graph and world == 1:
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            step()
-        run_step = graph.replay
-        for _ in range(2):
-            run_step()
-        barrier()
-    else:
-        run_step = step
-    base["config"]["cuda_graph"] = graph is not None
+    graph, run_step = None, step
+    if args.graph and world == 1:  # at N>1 the device pieces are graphs already; NCCL P2P inside a captured graph hung on this stack
+        try:
+            g_ = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g_):
+                step()
+            for _ in range(2):
+                g_.replay()
+            barrier()
+            graph, run_step = g_, g_.replay
+        except Exception as ex:  # e.g. NCCL P2P not capturable in this build: stay eager
+            sys.stderr.write("CUDA graph capture failed, running eagerly: %r\n" % (ex,))
+            torch.cuda.synchronize()
+            graph, run_step = None, step
+    base["config"]["cuda_graph"] = (graph is not None) or (world > 1 and all(v[1] is not None for v in pieces.values()))
     sampler = ClockSampler(local_rank if world > 1 else 0)
     if rank == 0:
         sampler.start()

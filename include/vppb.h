@@ -160,6 +160,10 @@ int vppb_lk_match_u8(const vppb_img* prev, const vppb_img* next, const vppb_img*
 int64_t vppb_halo_bytes(const vppb_img* img, int32_t halo);
 int vppb_halo_pack(const vppb_img* img, int32_t halo, int which, void* staging, void* stream);
 int vppb_halo_unpack(const vppb_img* img, int32_t halo, int which, const void* staging, void* stream);
+/* The same for n tiles of identical geometry in ONE launch (tile i at staging + i * vppb_halo_bytes): the
+ * per-step cost of the halo exchange is then two small kernels + one grouped NCCL send/recv. */
+int vppb_halo_pack_batch(const vppb_img* imgs, int32_t n, int32_t halo, int which, void* staging, void* stream);
+int vppb_halo_unpack_batch(const vppb_img* imgs, int32_t n, int32_t halo, int which, const void* staging, void* stream);
 
 #ifdef __cplusplus
 }

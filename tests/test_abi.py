@@ -82,3 +82,16 @@ def test_host_mirror_logic(capi):
     assert (b.nrows, b.ncols) == (10, 20) and b.has((9, 19)) and not b.has((10, 0))
     assert b == Box2d((0, 0), (9, 19))
     assert layout(1080, 1920, 3, 2, 128)[0] == 6016
+
+
+def test_box_division_magic():
+    """The two exact divisions by 25 used by k_box5_bytes_tma (vpp_b200/csrc/box.cu), checked exhaustively:
+    lo lane  (s * 671089) >> 24 == s // 25  for 0 <= s <= 6375 (= 25 * 255), product < 2^32;
+    hi lane  byte 1 of mulhi(hi << 16 | lo, 671089) == hi // 25 for every lo in the same range."""
+    M = 671089
+    s = np.arange(6376, dtype=np.uint64)
+    assert ((s * M) >> 24 == s // 25).all() and int((s * M).max()) < 2 ** 32
+    hi = s[:, None]
+    lo = np.arange(6376, dtype=np.uint64)[None, :]
+    q = ((((hi << 16) | lo) * M) >> 32 >> 8) & 0xFF
+    assert (q == hi // 25).all()

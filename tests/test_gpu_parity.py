@@ -437,3 +437,36 @@ def test_full_size_properties(vpp):
     hd = orc.HostImage(64, 3840, "vuchar3")
     orc.load().vo_box5x5_u8(hs.ptr(), hd.ptr(), 3)
     assert np.array_equal(D2.download()[1000:1064], hd.get())
+
+
+# ------------------------------------------------------------------ row-tile halos
+def test_halo_pack_unpack_single_and_batch(vpp):
+    from vpp_b200 import capi
+    from vpp_b200.ops import _DeviceBuffer
+
+    nr, nc, b, n = 12, 37, 2, 5
+    r = rng(70)
+    hosts = [r.integers(0, 256, (nr + 2 * b, nc + 2 * b, 3), dtype=np.uint8) for _ in range(n)]
+    imgs = [vpp.Image2d(nr, nc, "vuchar3", border=b) for _ in range(n)]
+    for im, h in zip(imgs, hosts):
+        im.upload(h, with_border=True)
+    hb = capi.lib.vppb_halo_bytes(imgs[0].ptr(), 2)
+    assert hb == 2 * (nc + 2 * b) * 3
+    descs = (capi.VppbImg * n)(*[im.desc for im in imgs])
+    for which, rows in ((0, slice(b, b + 2)), (1, slice(b + nr - 2, b + nr))):
+        st = _DeviceBuffer(n * hb)
+        capi.check(capi.lib.vppb_halo_pack_batch(descs, n, 2, which, st.ptr, None))
+        got = st.to_host(np.uint8, n * hb).reshape(n, 2, nc + 2 * b, 3)
+        assert np.array_equal(got, np.stack([h[rows] for h in hosts]))
+        st1 = _DeviceBuffer(hb)
+        capi.check(capi.lib.vppb_halo_pack(imgs[3].ptr(), 2, which, st1.ptr, None))
+        assert np.array_equal(st1.to_host(np.uint8, hb).reshape(2, nc + 2 * b, 3), hosts[3][rows])
+    # unpack: staging -> border rows above (which 0) / below (which 1); the domain must stay untouched
+    payload = r.integers(0, 256, (n, 2, nc + 2 * b, 3), dtype=np.uint8)
+    st = _DeviceBuffer(payload.nbytes).from_host(payload)
+    capi.check(capi.lib.vppb_halo_unpack_batch(descs, n, 2, 0, st.ptr, None))
+    capi.check(capi.lib.vppb_halo_unpack_batch(descs, n, 2, 1, st.ptr, None))
+    for i, im in enumerate(imgs):
+        a = im.download(with_border=True)
+        assert np.array_equal(a[0:2], payload[i]) and np.array_equal(a[-2:], payload[i])
+        assert np.array_equal(a[2:-2], hosts[i][2:-2])

@@ -99,6 +99,8 @@ PROTOTYPES = {
     "vppb_halo_bytes": (_I64, [_IMG, _I32]),
     "vppb_halo_pack": (C.c_int, [_IMG, _I32, C.c_int, _VP, _VP]),
     "vppb_halo_unpack": (C.c_int, [_IMG, _I32, C.c_int, _VP, _VP]),
+    "vppb_halo_pack_batch": (C.c_int, [_IMG, _I32, _I32, C.c_int, _VP, _VP]),
+    "vppb_halo_unpack_batch": (C.c_int, [_IMG, _I32, _I32, C.c_int, _VP, _VP]),
 }
 
 

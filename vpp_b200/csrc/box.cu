@@ -88,17 +88,28 @@ template <int TH> struct BoxCfg {
 };
 constexpr unsigned BX_DIV25 = 671089u;  // floor(s/25) == (s * 671089) >> 24 for 0 <= s <= 6375 (checked exhaustively)
 
+// a + b (and a - b) on the FMA pipe: with a runtime multiplier ptxas must keep the IMAD, which moves the
+// packed-lane additions off the half-rate ALU pipe (PRMT/LOP3/IADD3/SHF) that bounds this kernel.
+__device__ __forceinline__ uint32_t fadd_u32(uint32_t a, uint32_t mul, uint32_t b) { return a * mul + b; }  // mul = +1 / -1 at run time
+
+// floor(lane / 25) of both 16-bit lanes of se (lanes x, x+2) and so (lanes x+1, x+3), packed to 4 bytes.
+// lo lanes: (v * 671089) >> 24.  hi lanes: mulhi(se, 671089) = (hi*M + ((lo*M) >> 16)) >> 16, whose byte 1 is
+// floor(hi/25): the carry-in (< 2^16) is far below the slack of the magic number (exhaustively checked in
+// tests/test_abi.py::test_box_division_magic).
 __device__ __forceinline__ uint32_t box_div_pack(uint32_t se, uint32_t so) {
-  const uint32_t pel = (se & 0xFFFFu) * BX_DIV25, peh = (se >> 16) * BX_DIV25;
-  const uint32_t pol = (so & 0xFFFFu) * BX_DIV25, poh = (so >> 16) * BX_DIV25;
-  const uint32_t lo = __byte_perm(pel, pol, 0x0073);  // (q(x), q(x+1))
-  const uint32_t hi = __byte_perm(peh, poh, 0x0073);  // (q(x+2), q(x+3))
+  const uint32_t pel = (se & 0xFFFFu) * BX_DIV25, pol = (so & 0xFFFFu) * BX_DIV25;
+  const uint32_t peh = __umulhi(se, BX_DIV25), poh = __umulhi(so, BX_DIV25);
+  const uint32_t lo = __byte_perm(pel, pol, 0x0073);  // (q(x), q(x+1)): byte 3 of the products
+  const uint32_t hi = __byte_perm(peh, poh, 0x0051);  // (q(x+2), q(x+3)): byte 1 of the high products
   return __byte_perm(lo, hi, 0x5410);
 }
 
+// Persistent: each CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...; the TMA load of the NEXT tile is
+// issued right after phase 1 (the raw box is dead once the column sums are in shared memory), so its
+// latency hides behind phase 2.
 template <int CS, int BX_TH>
 __global__ void __launch_bounds__(BX_THREADS, BX_TH == 16 ? 4 : 6) k_box5_bytes_tma(const __grid_constant__ CUtensorMap tmap, Img out, int rowbytes, int strips,
-                                                                 int vec_store) {
+                                                                 int ntiles, int vec_store, uint32_t one) {
   constexpr int BX_RAW_BYTES = BoxCfg<BX_TH>::RAW_BYTES, BX_CS_BYTES = BoxCfg<BX_TH>::CS_BYTES;
   constexpr int RG_ROWS = BX_TH / 2;  // output rows per phase-1 row group
   extern __shared__ __align__(128) unsigned char smem[];
@@ -107,8 +118,7 @@ __global__ void __launch_bounds__(BX_THREADS, BX_TH == 16 ? 4 : 6) k_box5_bytes_
   uint32_t* csO = csE + BX_TH * BX_CS_ROW_WORDS;
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + BX_RAW_BYTES + BX_CS_BYTES);
   const int tid = threadIdx.x;
-  const int strip = blockIdx.x % strips, rt = blockIdx.x / strips;
-  const int x0 = strip * BX_OUTW, y0 = rt * BX_TH;
+  const uint32_t minus_one = 0u - one;
 
   if (tid == 0) {
     mbar_init(bar, 1);
@@ -117,82 +127,98 @@ __global__ void __launch_bounds__(BX_THREADS, BX_TH == 16 ? 4 : 6) k_box5_bytes_
     // tensor origin = 16 bytes left of x = 0, 2 rows above y = 0; elements are 8 bytes; the box starts at
     // x0 - 16.  (Measured on B200: the innermost box coordinate times the element size must be a multiple
     // of 16 bytes, otherwise UTMALDG raises "illegal instruction" - dbg/tma_test.cu.)
-    tma_load_2d(raw, &tmap, x0 / 8, y0, bar);
+    tma_load_2d(raw, &tmap, (blockIdx.x % strips) * (BX_OUTW / 8), (blockIdx.x / strips) * BX_TH, bar);
   }
   __syncthreads();  // barrier init visible to the waiters
-  mbar_wait(bar, 0);
+  uint32_t parity = 0;
 
-  // ---------------- phase 1: 5-row column sums
-  {
-    const int cg = tid & 63, rg = tid >> 6;
-    const unsigned char* col = raw + (rg * RG_ROWS) * BX_BOXW + cg * 16;
-    uint32_t ringE[5][4], ringO[5][4], VE[4], VO[4];
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int x0 = (tile % strips) * BX_OUTW, y0 = (tile / strips) * BX_TH;
+    mbar_wait(bar, parity);
+    parity ^= 1;
+
+    // ---------------- phase 1: 5-row column sums
+    {
+      const int cg = tid & 63, rg = tid >> 6;
+      const unsigned char* col = raw + (rg * RG_ROWS) * BX_BOXW + cg * 16;
+      uint32_t ringE[5][4], ringO[5][4], VE[4], VO[4];
 #pragma unroll
-    for (int q = 0; q < 4; q++) { VE[q] = 0; VO[q] = 0; }
+      for (int q = 0; q < 4; q++) { VE[q] = 0; VO[q] = 0; }
 #pragma unroll
-    for (int j = 0; j < RG_ROWS + 4; j++) {
-      const uint4 v = *reinterpret_cast<const uint4*>(col + j * BX_BOXW);
-      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-      const int slot = j % 5;
+      for (int j = 0; j < RG_ROWS + 4; j++) {
+        const uint4 v = *reinterpret_cast<const uint4*>(col + j * BX_BOXW);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        const int slot = j % 5;
 #pragma unroll
-      for (int q = 0; q < 4; q++) {
-        const uint32_t e = w[q] & 0x00FF00FFu, o = __byte_perm(w[q], 0u, 0x4341);
-        if (j >= 5) { VE[q] += e - ringE[slot][q]; VO[q] += o - ringO[slot][q]; }
-        else { VE[q] += e; VO[q] += o; }
-        ringE[slot][q] = e;
-        ringO[slot][q] = o;
-      }
-      if (j >= 4) {
-        const int orow = rg * RG_ROWS + j - 4;
-        *reinterpret_cast<uint4*>(csE + orow * BX_CS_ROW_WORDS + cg * 4) = make_uint4(VE[0], VE[1], VE[2], VE[3]);
-        *reinterpret_cast<uint4*>(csO + orow * BX_CS_ROW_WORDS + cg * 4) = make_uint4(VO[0], VO[1], VO[2], VO[3]);
+        for (int q = 0; q < 4; q++) {
+          const uint32_t e = w[q] & 0x00FF00FFu, o = __byte_perm(w[q], 0u, 0x4341);
+          if (j >= 5) {
+            VE[q] = fadd_u32(ringE[slot][q], minus_one, VE[q] + e);   // V += e - old  (one IADD3 + one IMAD)
+            VO[q] = fadd_u32(ringO[slot][q], minus_one, VO[q] + o);
+          } else { VE[q] += e; VO[q] += o; }
+          ringE[slot][q] = e;
+          ringO[slot][q] = o;
+        }
+        if (j >= 4) {
+          const int orow = rg * RG_ROWS + j - 4;
+          *reinterpret_cast<uint4*>(csE + orow * BX_CS_ROW_WORDS + cg * 4) = make_uint4(VE[0], VE[1], VE[2], VE[3]);
+          *reinterpret_cast<uint4*>(csO + orow * BX_CS_ROW_WORDS + cg * 4) = make_uint4(VO[0], VO[1], VO[2], VO[3]);
+        }
       }
     }
-  }
-  __syncthreads();
-
-  // ---------------- phase 2: horizontal taps, divide, store
-  const int rows_here = min(BX_TH, out.nrows - y0);
-  for (int u = tid; u < BX_TH * 62; u += BX_THREADS) {
-    const int row = u / 62, og = u - row * 62;
-    const int x = x0 + og * 16;
-    if (row >= rows_here || x >= rowbytes) continue;
-    // own words are box words 4og+4 .. 4og+7 (the box starts 16 bytes left of x0); window = words k-2 .. k+5
-    const uint32_t* pe = csE + row * BX_CS_ROW_WORDS + og * 4 + 2;
-    const uint32_t* po = csO + row * BX_CS_ROW_WORDS + og * 4 + 2;
-    const uint2 e0 = *reinterpret_cast<const uint2*>(pe), e2 = *reinterpret_cast<const uint2*>(pe + 6);
-    const uint4 e1 = *reinterpret_cast<const uint4*>(pe + 2);
-    const uint2 o0 = *reinterpret_cast<const uint2*>(po), o2 = *reinterpret_cast<const uint2*>(po + 6);
-    const uint4 o1 = *reinterpret_cast<const uint4*>(po + 2);
-    const uint32_t E[8] = {e0.x, e0.y, e1.x, e1.y, e1.z, e1.w, e2.x, e2.y};
-    const uint32_t O[8] = {o0.x, o0.y, o1.x, o1.y, o1.z, o1.w, o2.x, o2.y};
-    uint32_t SE[7], SO[7];
-#pragma unroll
-    for (int i = 0; i < 7; i++) {
-      SE[i] = __byte_perm(E[i], E[i + 1], 0x5432);  // lanes (byte2 of word i, byte0 of word i+1)
-      SO[i] = __byte_perm(O[i], O[i + 1], 0x5432);  // lanes (byte3 of word i, byte1 of word i+1)
+    __syncthreads();
+    // the raw box is dead: prefetch the next tile of this CTA behind phase 2
+    if (tid == 0 && tile + (int)gridDim.x < ntiles) {
+      const int nt = tile + gridDim.x;
+      mbar_arrive_expect_tx(bar, BX_RAW_BYTES);
+      tma_load_2d(raw, &tmap, (nt % strips) * (BX_OUTW / 8), (nt / strips) * BX_TH, bar);
     }
-    uint32_t ow[4];
+
+    // ---------------- phase 2: horizontal taps, divide, store
+    const int rows_here = min(BX_TH, out.nrows - y0);
+    for (int u = tid; u < BX_TH * 62; u += BX_THREADS) {
+      const int row = u / 62, og = u - row * 62;
+      const int x = x0 + og * 16;
+      if (row >= rows_here || x >= rowbytes) continue;
+      // own words are box words 4og+4 .. 4og+7 (the box starts 16 bytes left of x0); window = words k-2 .. k+5
+      const uint32_t* pe = csE + row * BX_CS_ROW_WORDS + og * 4 + 2;
+      const uint32_t* po = csO + row * BX_CS_ROW_WORDS + og * 4 + 2;
+      const uint2 e0 = *reinterpret_cast<const uint2*>(pe), e2 = *reinterpret_cast<const uint2*>(pe + 6);
+      const uint4 e1 = *reinterpret_cast<const uint4*>(pe + 2);
+      const uint2 o0 = *reinterpret_cast<const uint2*>(po), o2 = *reinterpret_cast<const uint2*>(po + 6);
+      const uint4 o1 = *reinterpret_cast<const uint4*>(po + 2);
+      const uint32_t E[8] = {e0.x, e0.y, e1.x, e1.y, e1.z, e1.w, e2.x, e2.y};
+      const uint32_t O[8] = {o0.x, o0.y, o1.x, o1.y, o1.z, o1.w, o2.x, o2.y};
+      uint32_t SE[7], SO[7];
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
-      const int i = j + 2;
-      uint32_t he, ho;
-      if (CS == 3) {
-        he = SE[i - 2] + O[i - 1] + E[i] + SO[i] + SE[i + 1];      // lanes (x, x+2): taps x-6, x-3, x, x+3, x+6
-        ho = SO[i - 2] + SE[i - 1] + O[i] + E[i + 1] + SO[i + 1];  // lanes (x+1, x+3)
+      for (int i = 0; i < 7; i++) {
+        SE[i] = __byte_perm(E[i], E[i + 1], 0x5432);  // lanes (byte2 of word i, byte0 of word i+1)
+        SO[i] = __byte_perm(O[i], O[i + 1], 0x5432);  // lanes (byte3 of word i, byte1 of word i+1)
+      }
+      uint32_t ow[4];
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const int i = j + 2;
+        uint32_t he, ho;
+        if (CS == 3) {
+          // lanes (x, x+2): taps x-6, x-3, x, x+3, x+6 ; lanes (x+1, x+3) likewise.  3 terms on the ALU (IADD3), 2 on the FMA pipe.
+          he = fadd_u32(SE[i + 1], one, fadd_u32(SO[i], one, SE[i - 2] + O[i - 1] + E[i]));
+          ho = fadd_u32(SO[i + 1], one, fadd_u32(E[i + 1], one, SO[i - 2] + SE[i - 1] + O[i]));
+        } else {
+          he = fadd_u32(SE[i], one, fadd_u32(O[i], one, SE[i - 1] + SO[i - 1] + E[i]));  // CS == 1: taps x-2 .. x+2
+          ho = fadd_u32(SO[i], one, fadd_u32(SE[i], one, SO[i - 1] + E[i] + O[i]));
+        }
+        ow[j] = box_div_pack(he, ho);
+      }
+      unsigned char* dst = out.base + (long long)(y0 + row) * out.pitch + x;
+      if (vec_store && x + 16 <= rowbytes) {
+        *reinterpret_cast<uint4*>(dst) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
       } else {
-        he = SE[i - 1] + SO[i - 1] + E[i] + O[i] + SE[i];          // CS == 1: taps x-2 .. x+2
-        ho = SO[i - 1] + E[i] + O[i] + SE[i] + SO[i];
+        for (int k = 0; k < 16; k++)
+          if (x + k < rowbytes) dst[k] = (unsigned char)(ow[k >> 2] >> ((k & 3) * 8));
       }
-      ow[j] = box_div_pack(he, ho);
     }
-    unsigned char* dst = out.base + (long long)(y0 + row) * out.pitch + x;
-    if (vec_store && x + 16 <= rowbytes) {
-      *reinterpret_cast<uint4*>(dst) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
-    } else {
-      for (int k = 0; k < 16; k++)
-        if (x + k < rowbytes) dst[k] = (unsigned char)(ow[k >> 2] >> ((k & 3) * 8));
-    }
+    __syncthreads();  // column sums consumed before the next tile's phase 1 overwrites them
   }
 }
 
@@ -252,10 +278,13 @@ static int box5_bytes(const vppb_img* in, const vppb_img* out, void* stream, con
       VPPB_CUDA(cudaFuncSetAttribute(k_box5_bytes_tma<CS, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, BoxCfg<8>::SMEM));
       attr_set[CS == 3] = true;
     }
+    const int ntiles = strips * row_tiles;
+    const int resident = sm_count() * (th == 16 ? 4 : 6);
+    const int grid = ntiles < resident ? ntiles : resident;
     if (th == 16)
-      k_box5_bytes_tma<CS, 16><<<strips * row_tiles, BX_THREADS, BoxCfg<16>::SMEM, st>>>(tmap, view(out), rowbytes, strips, vec_store);
+      k_box5_bytes_tma<CS, 16><<<grid, BX_THREADS, BoxCfg<16>::SMEM, st>>>(tmap, view(out), rowbytes, strips, ntiles, vec_store, 1u);
     else
-      k_box5_bytes_tma<CS, 8><<<strips * row_tiles, BX_THREADS, BoxCfg<8>::SMEM, st>>>(tmap, view(out), rowbytes, strips, vec_store);
+      k_box5_bytes_tma<CS, 8><<<grid, BX_THREADS, BoxCfg<8>::SMEM, st>>>(tmap, view(out), rowbytes, strips, ntiles, vec_store, 1u);
   } else {
     long long total = (long long)in->nrows * rowbytes;
     long long blocks = (total + 255) / 256;

@@ -254,6 +254,205 @@ __global__ void __launch_bounds__(128) k_lk_match(LkLevels L, vppb_lk_params P, 
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// v2: four keypoints per warp (8 lanes each).  The window samples are spread over the 8 lanes of a
+// keypoint; the per-pixel terms go to shared memory and ONE lane per (keypoint, component) adds them
+// in the reference's window order.  Same float sequence as k_lk_match (bit-identical results), but
+// the 2 x WS^2 dependent additions are issued once per keypoint instead of once per lane, which cuts
+// the warp-instruction count per keypoint ~3.5x.  Used for WS <= 11.
+constexpr int LK2_LPK = 8;    // lanes per keypoint
+constexpr int LK2_KPW = 4;    // keypoints per warp
+constexpr int LK2_WARPS = 4;  // warps per CTA
+constexpr int LK2_MAXPIX = 121;
+
+template <int PPL, bool GRAD_FLOAT>
+__global__ void __launch_bounds__(LK2_WARPS * 32) k_lk_match_v2(LkLevels L, vppb_lk_params P, const vppb_float2* __restrict__ kps,
+                                                             const vppb_float2* __restrict__ prediction, int n,
+                                                             vppb_float2* __restrict__ flow_out, float* __restrict__ err_out) {
+  __shared__ float sbuf[LK2_WARPS][3][LK2_KPW][LK2_MAXPIX + 2];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int k = lane >> 3, sl = lane & 7, lead = lane & ~7;
+  const int kp_idx = (blockIdx.x * LK2_WARPS + warp) * LK2_KPW + k;
+  const bool kp_ok = kp_idx < n;
+  float (*buf)[LK2_KPW][LK2_MAXPIX + 2] = sbuf[warp];
+  const int ws = P.winsize, hws = ws / 2, npix = ws * ws;
+  const int kload = kp_ok ? kp_idx : 0;
+  const float kp0 = kps[kload].r, kp1 = kps[kload].c;
+
+  float off_r[PPL], off_c[PPL];
+  bool have[PPL];
+#pragma unroll
+  for (int j = 0; j < PPL; j++) {
+    const int i = sl + LK2_LPK * j;
+    have[j] = i < npix;
+    off_r[j] = (float)(i / ws - hws);
+    off_c[j] = (float)(i % ws - hws);
+  }
+  // ordered sums of `ncomp` components of keypoint k: lane sl (< ncomp) adds buf[sl][k][0..npix) in order
+  auto ordered_sum = [&](int ncomp) -> float {
+    __syncwarp();
+    float acc = 0.f;
+    if (sl < ncomp) {
+      const float* src = buf[sl][k];
+#pragma unroll 7
+      for (int i = 0; i < npix; i++) acc = __fadd_rn(acc, src[i]);
+    }
+    __syncwarp();
+    return acc;
+  };
+
+  float tr0 = 0.f, tr1 = 0.f, dist = 0.f;
+  if (prediction) {
+    tr0 = __fdiv_rn(prediction[kload].r, P.pred_div);
+    tr1 = __fdiv_rn(prediction[kload].c, P.pred_div);
+  }
+
+  for (int S = P.nlevels - 1; S >= P.min_scale; S--) {
+    tr0 = __fmul_rn(tr0, P.factor);
+    tr1 = __fmul_rn(tr1, P.factor);
+    const Img& A = L.prev[S];
+    const Img& B = L.next[S];
+    const Img& Ag = L.grad[S];
+    const float scale = (float)(1 << S);
+    const float p0 = __fdiv_rn(kp0, scale), p1 = __fdiv_rn(kp1, scale);
+
+    float gs0[PPL], gs1[PPL], asv[PPL];
+    bool valid[PPL];
+    int cpt_l = 0;
+#pragma unroll
+    for (int j = 0; j < PPL; j++) {
+      const float n0 = __fadd_rn(p0, off_r[j]), n1 = __fadd_rn(p1, off_c[j]);
+      const int i0 = (int)n0, i1 = (int)n1;
+      valid[j] = have[j] && i0 >= 0 && i0 < A.nrows && i1 >= 0 && i1 < A.ncols;
+      gs0[j] = 0.f; gs1[j] = 0.f; asv[j] = 0.f;
+      if (valid[j]) {
+        const float2 g = interp_grad<GRAD_FLOAT>(Ag, n0, n1);
+        gs0[j] = g.x; gs1[j] = g.y;
+        asv[j] = (float)interp_u8(A, n0, n1);
+        cpt_l++;
+      }
+      if (have[j]) {
+        const int i = sl + LK2_LPK * j;
+        buf[0][k][i] = __fmul_rn(gs0[j], gs0[j]);
+        buf[1][k][i] = __fmul_rn(gs0[j], gs1[j]);
+        buf[2][k][i] = __fmul_rn(gs1[j], gs1[j]);
+      }
+    }
+    // cpt: number of in-domain window pixels of this keypoint (sum over its 8 lanes)
+    int cpt = cpt_l;
+    cpt += __shfl_xor_sync(FULL, cpt, 1); cpt += __shfl_xor_sync(FULL, cpt, 2); cpt += __shfl_xor_sync(FULL, cpt, 4);
+    const float gsum = ordered_sum(3);
+    const float G00 = __shfl_sync(FULL, gsum, lead), G01 = __shfl_sync(FULL, gsum, lead + 1), G11 = __shfl_sync(FULL, gsum, lead + 2);
+
+    float m0 = -1.f, m1 = -1.f, merr = FLT_MAX;
+    bool active = true;  // this keypoint is still iterating at this level
+    {
+      const float cf = (float)cpt;
+      const float a = __fdiv_rn(G00, cf), b = __fdiv_rn(G01, cf), d = __fdiv_rn(G11, cf);
+      const float half = __fmul_rn(__fadd_rn(a, d), 0.5f), diff = __fmul_rn(__fsub_rn(a, d), 0.5f);
+      const float root = __fsqrt_rn(__fadd_rn(__fmul_rn(diff, diff), __fmul_rn(b, b)));
+      const float e1 = fabsf(__fadd_rn(half, root)), e2 = fabsf(__fsub_rn(half, root));
+      float min_ev = 99999.f;
+      if (e1 < min_ev) min_ev = e1;
+      if (e2 < min_ev) min_ev = e2;
+      if (min_ev < P.min_ev) active = false;  // result stays ((-1,-1), FLT_MAX)
+    }
+    const bool rejected = !active;
+    const float det = __fsub_rn(__fmul_rn(G00, G11), __fmul_rn(G01, G01));
+    const float invdet = __fdiv_rn(1.f, det);
+    const float I00 = __fmul_rn(G11, invdet), I01 = __fmul_rn(-G01, invdet), I11 = __fmul_rn(G00, invdet);
+    float v0 = __fadd_rn(p0, tr0), v1 = __fadd_rn(p1, tr1);
+    float nk0 = 1.f, nk1 = 1.f;
+    bool failed = false;
+    for (int kk = 0; kk <= P.max_iter; kk++) {
+      if (active) {
+        const float nrm = __fsqrt_rn(__fadd_rn(__fmul_rn(nk0, nk0), __fmul_rn(nk1, nk1)));
+        if (!(nrm >= P.delta)) active = false;
+      }
+      if (!__any_sync(FULL, active)) break;
+#pragma unroll
+      for (int j = 0; j < PPL; j++) {
+        if (have[j]) {
+          float c0 = 0.f, c1 = 0.f;
+          if (valid[j] && active) {
+            const float dt = __fsub_rn(asv[j], (float)interp_u8(B, __fadd_rn(v0, off_r[j]), __fadd_rn(v1, off_c[j])));
+            c0 = __fmul_rn(gs0[j], dt);
+            c1 = __fmul_rn(gs1[j], dt);
+          }
+          const int i = sl + LK2_LPK * j;
+          buf[0][k][i] = c0;
+          buf[1][k][i] = c1;
+        }
+      }
+      const float bsum = ordered_sum(2);
+      const float bk0 = __shfl_sync(FULL, bsum, lead), bk1 = __shfl_sync(FULL, bsum, lead + 1);
+      if (active) {
+        nk0 = __fadd_rn(__fmul_rn(I00, bk0), __fmul_rn(I01, bk1));
+        nk1 = __fadd_rn(__fmul_rn(I01, bk0), __fmul_rn(I11, bk1));
+        v0 = __fadd_rn(v0, nk0);
+        v1 = __fadd_rn(v1, nk1);
+        const int iv0 = (int)v0, iv1 = (int)v1;
+        if (!finite2(v0, v1) || iv0 < 0 || iv0 >= B.nrows || iv1 < 0 || iv1 >= B.ncols) { failed = true; active = false; }
+      }
+    }
+    // ---- matching error for the keypoints that neither were rejected nor left the domain
+    const bool want_err = !rejected && !failed;
+#pragma unroll
+    for (int j = 0; j < PPL; j++) {
+      if (have[j]) {
+        float e = 0.f;
+        if (want_err) {
+          const int bi = interp_u8(B, __fadd_rn(v0, off_r[j]), __fadd_rn(v1, off_c[j]));
+          e = fabsf((float)((int)asv[j] - bi));
+        }
+        const int i = sl + LK2_LPK * j;
+        buf[0][k][i] = e;
+        buf[1][k][i] = asv[j];
+      }
+    }
+    const float esum = ordered_sum(2);
+    const float err = __shfl_sync(FULL, esum, lead), asum = __shfl_sync(FULL, esum, lead + 1);
+    const int cpt2 = cpt + npix;
+    float stddev = 1.f;
+    if (P.err_mode != VPPB_LK_ERR_SAD) {  // warp-uniform
+      const float avg = __fdiv_rn(asum, (float)npix);
+#pragma unroll
+      for (int j = 0; j < PPL; j++)
+        if (have[j]) buf[0][k][sl + LK2_LPK * j] = fabsf(__fsub_rn(avg, asv[j]));
+      const float dsum = ordered_sum(1);
+      stddev = __fdiv_rn(__shfl_sync(FULL, dsum, lead), (float)npix);
+    }
+    if (rejected) { m0 = -1.f; m1 = -1.f; merr = FLT_MAX; }
+    else if (failed) { m0 = 0.f; m1 = 0.f; merr = FLT_MAX; }
+    else {
+      merr = P.err_mode == VPPB_LK_ERR_SAD ? __fdiv_rn(err, (float)cpt2) : __fdiv_rn(err, __fmul_rn((float)cpt2, stddev));
+      m0 = __fsub_rn(v0, p0);
+      m1 = __fsub_rn(v1, p1);
+    }
+    if (!P.gate_on_max_err || merr < P.max_err) { tr0 = m0; tr1 = m1; }
+    dist = merr;
+  }
+  if (sl == 0 && kp_ok) {
+    flow_out[kp_idx].r = tr0;
+    flow_out[kp_idx].c = tr1;
+    err_out[kp_idx] = dist;
+  }
+}
+
+template <bool GF>
+static bool lk_launch_v2(int winsize, cudaStream_t st, const LkLevels& L, const vppb_lk_params& P, const vppb_float2* kps,
+                         const vppb_float2* pred, int n, vppb_float2* flow, float* err) {
+  const int per_cta = LK2_WARPS * LK2_KPW;
+  const int grid = (n + per_cta - 1) / per_cta;
+  switch (winsize) {
+    case 1: case 3: case 5: k_lk_match_v2<4, GF><<<grid, LK2_WARPS * 32, 0, st>>>(L, P, kps, pred, n, flow, err); return true;
+    case 7: k_lk_match_v2<7, GF><<<grid, LK2_WARPS * 32, 0, st>>>(L, P, kps, pred, n, flow, err); return true;
+    case 9: k_lk_match_v2<11, GF><<<grid, LK2_WARPS * 32, 0, st>>>(L, P, kps, pred, n, flow, err); return true;
+    case 11: k_lk_match_v2<16, GF><<<grid, LK2_WARPS * 32, 0, st>>>(L, P, kps, pred, n, flow, err); return true;
+    default: return false;
+  }
+}
+
 template <bool GF>
 static void lk_launch(int ppl, int grid, cudaStream_t st, const LkLevels& L, const vppb_lk_params& P, const vppb_float2* kps,
                       const vppb_float2* pred, int n, vppb_float2* flow, float* err) {
@@ -298,8 +497,16 @@ int vppb_lk_match_u8(const vppb_img* prev, const vppb_img* next, const vppb_img*
   if (ppl == 5) ppl = 6;
   if (ppl == 7) ppl = 8;
   const int grid = (n + 3) / 4;  // 4 warps (keypoints) per CTA
-  if (P.grad_is_float) lk_launch<true>(ppl, grid, as_stream(stream), L, P, kps, prediction, n, flow_out, err_out);
-  else lk_launch<false>(ppl, grid, as_stream(stream), L, P, kps, prediction, n, flow_out, err_out);
+  static int use_v1 = -1;  // VPPB_LK_V1=1 forces the one-keypoint-per-warp kernel (A/B comparisons)
+  if (use_v1 < 0) { const char* e = getenv("VPPB_LK_V1"); use_v1 = (e && atoi(e)) ? 1 : 0; }
+  bool done = false;
+  if (!use_v1)
+    done = P.grad_is_float ? lk_launch_v2<true>(P.winsize, as_stream(stream), L, P, kps, prediction, n, flow_out, err_out)
+                           : lk_launch_v2<false>(P.winsize, as_stream(stream), L, P, kps, prediction, n, flow_out, err_out);
+  if (!done) {
+    if (P.grad_is_float) lk_launch<true>(ppl, grid, as_stream(stream), L, P, kps, prediction, n, flow_out, err_out);
+    else lk_launch<false>(ppl, grid, as_stream(stream), L, P, kps, prediction, n, flow_out, err_out);
+  }
   VPPB_LAUNCH_CHECK("vppb_lk_match_u8");
   return VPPB_OK;
 }

@@ -261,6 +261,26 @@ static int* sum_scratch() {
   return p;
 }
 
+// ---------------------------------------------------------------- batched halo rows <-> staging
+// One launch moves the `halo` edge (or border) rows of up to 64 tiles; bytes are moved individually
+// (the row block starts border*elem bytes left of column 0, so no common vector alignment exists).
+constexpr int kHaloBatch = 64;
+struct HaloBatch {
+  unsigned char* img_rows[kHaloBatch];  // address of the first byte of the first row block of image i
+  int n, pitch, rows, wbytes;
+};
+__global__ void k_halo_batch(HaloBatch b, unsigned char* staging, int to_staging) {
+  const long long per_img = (long long)b.rows * b.wbytes;
+  const long long total = per_img * b.n;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int img = (int)(i / per_img);
+    const long long j = i - (long long)img * per_img;
+    const int r = (int)(j / b.wbytes), x = (int)(j - (long long)r * b.wbytes);
+    unsigned char* p = b.img_rows[img] + (long long)r * b.pitch + x;
+    if (to_staging) staging[i] = *p; else *p = staging[i];
+  }
+}
+
 }  // namespace vppb
 
 using namespace vppb;
@@ -368,6 +388,37 @@ int vppb_halo_unpack(const vppb_img* img, int32_t halo, int which, const void* s
   const int r0 = which == 0 ? -halo : img->nrows;
   unsigned char* dst = static_cast<unsigned char*>(img->base) + (long long)r0 * img->pitch - (long long)img->border * img->elem_bytes;
   return copy_rect(static_cast<const unsigned char*>(staging), wbytes, dst, img->pitch, halo, wbytes, as_stream(stream));
+}
+
+// Batched forms: the same rows of n tiles of identical geometry, packed back to back (tile i at i * vppb_halo_bytes).
+static int halo_batch(const vppb_img* imgs, int n, int halo, int which, void* staging, void* stream, bool pack) {
+  VPPB_REQUIRE(imgs && staging && n > 0, VPPB_E_ARG, "vppb_halo_%s_batch: NULL argument", pack ? "pack" : "unpack");
+  const vppb_img& g = imgs[0];
+  VPPB_REQUIRE(halo > 0 && (pack ? halo <= g.nrows : halo <= g.border), pack ? VPPB_E_ARG : VPPB_E_BORDER, "vppb_halo_batch: halo %d out of range", halo);
+  const int wbytes = (int)((g.ncols + 2LL * g.border) * g.elem_bytes);
+  const long long per = (long long)halo * wbytes;
+  for (int i0 = 0; i0 < n; i0 += kHaloBatch) {
+    HaloBatch b;
+    b.n = n - i0 < kHaloBatch ? n - i0 : kHaloBatch;
+    b.pitch = g.pitch; b.rows = halo; b.wbytes = wbytes;
+    for (int k = 0; k < b.n; k++) {
+      const vppb_img& im = imgs[i0 + k];
+      VPPB_REQUIRE(im.base && im.nrows == g.nrows && im.ncols == g.ncols && im.pitch == g.pitch && im.border == g.border && im.elem_bytes == g.elem_bytes,
+                   VPPB_E_ARG, "vppb_halo_batch: tile %d has a different geometry", i0 + k);
+      const int r0 = pack ? (which == 0 ? 0 : im.nrows - halo) : (which == 0 ? -halo : im.nrows);
+      b.img_rows[k] = static_cast<unsigned char*>(im.base) + (long long)r0 * im.pitch - (long long)im.border * im.elem_bytes;
+    }
+    const long long total = per * b.n;
+    k_halo_batch<<<stream_grid(total / 4 + 1), kThreads, 0, as_stream(stream)>>>(b, static_cast<unsigned char*>(staging) + (long long)i0 * per, pack ? 1 : 0);
+  }
+  VPPB_LAUNCH_CHECK("vppb_halo_batch");
+  return VPPB_OK;
+}
+int vppb_halo_pack_batch(const vppb_img* imgs, int32_t n, int32_t halo, int which, void* staging, void* stream) {
+  return halo_batch(imgs, n, halo, which, staging, stream, true);
+}
+int vppb_halo_unpack_batch(const vppb_img* imgs, int32_t n, int32_t halo, int which, const void* staging, void* stream) {
+  return halo_batch(imgs, n, halo, which, const_cast<void*>(staging), stream, false);
 }
 
 }  // extern "C"

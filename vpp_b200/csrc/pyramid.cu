@@ -8,45 +8,74 @@
 // un-contracted evaluation order bit for bit.
 #include "common.cuh"
 
+#include <algorithm>
+
 namespace vppb {
 
 // ------------------------------------------------------------------ Scharr
-// 4 pixels per thread: rows r-1, r, r+1 are fetched as three aligned 32-bit words each
-// (columns c-4 .. c+7), outputs are two 16-byte stores.
+// 8 pixels per thread.  Each of the rows r-1, r, r+1 is fetched as one 16-byte load (columns c0 ..
+// c0+15, of which c0..c0+8 are used) plus one 4-byte load for column c0-1; the eight vector<Vt,2>
+// results leave as four 16-byte stores (a warp writes 2 KB contiguous).  Output-dominated: 1 B read,
+// 8 B written per pixel.
+__device__ __forceinline__ int byte_of(uint32_t w, int k) { return (int)((w >> (8 * k)) & 0xFFu); }
+
 template <bool AS_FLOAT>
-__global__ void __launch_bounds__(256) k_scharr_u8(Img in, Img out, int groups_per_row) {
-  long long total = (long long)out.nrows * groups_per_row;
+__global__ void __launch_bounds__(256) k_scharr_u8_v8(Img in, Img out, int groups_per_row) {
+  const long long total = (long long)out.nrows * groups_per_row;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int r = (int)(i / groups_per_row);
-    const int c0 = (int)(i - (long long)r * groups_per_row) * 4;
-    int px[3][6];  // columns c0-1 .. c0+4 of rows r-1, r, r+1
+    const int c0 = (int)(i - (long long)r * groups_per_row) * 8;
+    int px[3][10];  // columns c0-1 .. c0+8
 #pragma unroll
     for (int k = 0; k < 3; k++) {
-      const unsigned char* row = row_ptr<unsigned char>(in, r - 1 + k);
+      const unsigned char* row = row_ptr<unsigned char>(in, r - 1 + k) + c0;
+      const uint32_t left = __ldg(reinterpret_cast<const uint32_t*>(row - 4));
+      const uint2 mid = __ldg(reinterpret_cast<const uint2*>(row));
+      const uint32_t right = __ldg(reinterpret_cast<const uint32_t*>(row + 8));
+      px[k][0] = byte_of(left, 3);
 #pragma unroll
-      for (int j = 0; j < 6; j++) {
-        int c = c0 - 1 + j;
-        // columns past ncols are only read when they are still inside the border frame
-        px[k][j] = (c < in.ncols + in.border) ? (int)__ldg(row + c) : 0;
+      for (int j = 0; j < 4; j++) { px[k][1 + j] = byte_of(mid.x, j); px[k][5 + j] = byte_of(mid.y, j); }
+      px[k][9] = byte_of(right, 0);
+    }
+    unsigned char* orow = row_ptr<unsigned char>(out, r) + (long long)c0 * 8;
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) {
+      int a[2], b[2];
+#pragma unroll
+      for (int t = 0; t < 2; t++) {
+        const int* r1 = &px[0][j + t];
+        const int* r2 = &px[1][j + t];
+        const int* r3 = &px[2][j + t];
+        a[t] = 3 * r3[0] + 10 * r3[1] + 3 * r3[2] - 3 * r1[0] - 10 * r1[1] - 3 * r1[2];  // scharr.hh:64-83
+        b[t] = 3 * r1[2] + 10 * r2[2] + 3 * r3[2] - 3 * r1[0] - 10 * r2[0] - 3 * r3[0];
+      }
+      const float fa0 = __fdiv_rn((float)a[0], 32.f), fb0 = __fdiv_rn((float)b[0], 32.f);
+      const float fa1 = __fdiv_rn((float)a[1], 32.f), fb1 = __fdiv_rn((float)b[1], 32.f);
+      if (c0 + j + 1 < out.ncols) {
+        if (AS_FLOAT) *reinterpret_cast<float4*>(orow + j * 8) = make_float4(fa0, fb0, fa1, fb1);
+        else *reinterpret_cast<int4*>(orow + j * 8) = make_int4((int)fa0, (int)fb0, (int)fa1, (int)fb1);
+      } else if (c0 + j < out.ncols) {
+        if (AS_FLOAT) *reinterpret_cast<float2*>(orow + j * 8) = make_float2(fa0, fb0);
+        else *reinterpret_cast<int2*>(orow + j * 8) = make_int2((int)fa0, (int)fb0);
       }
     }
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-      const int c = c0 + j;
-      if (c >= out.ncols) break;
-      const int* r1 = &px[0][j];  // r1[0] = (r-1, c-1), r1[1] = (r-1, c), r1[2] = (r-1, c+1)
-      const int* r2 = &px[1][j];
-      const int* r3 = &px[2][j];
-      // scharr.hh:64-83 — integer-valued in both the int and the float instantiation
-      const int a = 3 * r3[0] + 10 * r3[1] + 3 * r3[2] - 3 * r1[0] - 10 * r1[1] - 3 * r1[2];
-      const int b = 3 * r1[2] + 10 * r2[2] + 3 * r3[2] - 3 * r1[0] - 10 * r2[0] - 3 * r3[0];
-      const float fa = __fdiv_rn((float)a, 32.f), fb = __fdiv_rn((float)b, 32.f);
-      if (AS_FLOAT) {
-        reinterpret_cast<float2*>(row_ptr<unsigned char>(out, r))[c] = make_float2(fa, fb);
-      } else {
-        reinterpret_cast<int2*>(row_ptr<unsigned char>(out, r))[c] = make_int2((int)fa, (int)fb);  // trunc toward 0
-      }
-    }
+  }
+}
+
+// any layout: 1 pixel per thread, byte loads
+template <bool AS_FLOAT>
+__global__ void __launch_bounds__(256) k_scharr_u8(Img in, Img out, int) {
+  const long long total = (long long)out.nrows * out.ncols;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / out.ncols), c = (int)(i - (long long)r * out.ncols);
+    const unsigned char* r1 = row_ptr<unsigned char>(in, r - 1) + c - 1;
+    const unsigned char* r2 = row_ptr<unsigned char>(in, r) + c - 1;
+    const unsigned char* r3 = row_ptr<unsigned char>(in, r + 1) + c - 1;
+    const int a = 3 * (int)r3[0] + 10 * (int)r3[1] + 3 * (int)r3[2] - 3 * (int)r1[0] - 10 * (int)r1[1] - 3 * (int)r1[2];
+    const int b = 3 * (int)r1[2] + 10 * (int)r2[2] + 3 * (int)r3[2] - 3 * (int)r1[0] - 10 * (int)r2[0] - 3 * (int)r3[0];
+    const float fa = __fdiv_rn((float)a, 32.f), fb = __fdiv_rn((float)b, 32.f);
+    if (AS_FLOAT) reinterpret_cast<float2*>(row_ptr<unsigned char>(out, r))[c] = make_float2(fa, fb);
+    else reinterpret_cast<int2*>(row_ptr<unsigned char>(out, r))[c] = make_int2((int)fa, (int)fb);  // trunc toward 0
   }
 }
 
@@ -96,6 +125,108 @@ __global__ void __launch_bounds__(256) k_lowpass_sub2(Img in, Img out, int step)
   }
 }
 
+// u8 fast path: one thread = 8 x 2 outputs.  The 7 input rows it needs (mirrored indices at the top /
+// bottom, as the mirror-filled H temp of pyramid.hh:36) are fetched as 4 + 16 + 4 bytes each, H is
+// evaluated at the 8 even columns per row, V on the H columns; ~1.3 loads per output instead of 25.
+// Covers the outputs whose centre (2r, 2c) lies inside the parent; the mirrored last row / column of
+// an even-sized parent (centre on an odd pixel) is left to k_lowpass_sub2_edges.
+__global__ void __launch_bounds__(128) k_lowpass_sub2_u8_fast(Img in, Img out, int fast_rows, int fast_cols, int groups_per_row) {
+  const int row_pairs = (fast_rows + 1) / 2;
+  const long long total = (long long)row_pairs * groups_per_row;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int rp = (int)(i / groups_per_row), g = (int)(i - (long long)rp * groups_per_row);
+    const int r0 = 2 * rp, c0 = 8 * g;
+    int H[7][8];
+#pragma unroll
+    for (int d = 0; d < 7; d++) {
+      const int yy = mirror_idx(2 * r0 - 2 + d, in.nrows);
+      const unsigned char* row = row_ptr<unsigned char>(in, yy) + 16 * g;
+      const uint32_t left = __ldg(reinterpret_cast<const uint32_t*>(row - 4));
+      const uint4 mid = __ldg(reinterpret_cast<const uint4*>(row));
+      const uint32_t right = __ldg(reinterpret_cast<const uint32_t*>(row + 16));
+      int p[19];  // bytes 16g-2 .. 16g+16
+      p[0] = byte_of(left, 2); p[1] = byte_of(left, 3);
+#pragma unroll
+      for (int j = 0; j < 4; j++) { p[2 + j] = byte_of(mid.x, j); p[6 + j] = byte_of(mid.y, j); p[10 + j] = byte_of(mid.z, j); p[14 + j] = byte_of(mid.w, j); }
+      p[18] = byte_of(right, 0);
+#pragma unroll
+      for (int k = 0; k < 8; k++) H[d][k] = (p[2 * k] + 4 * p[2 * k + 1] + 6 * p[2 * k + 2] + 4 * p[2 * k + 3] + p[2 * k + 4]) >> 4;  // pyramid.hh:27-32
+    }
+#pragma unroll
+    for (int t = 0; t < 2; t++) {
+      const int r = r0 + t;
+      if (r >= fast_rows) break;
+      uint32_t lo = 0, hi = 0;
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        const int v = (H[2 * t][k] + 4 * H[2 * t + 1][k] + 6 * H[2 * t + 2][k] + 4 * H[2 * t + 3][k] + H[2 * t + 4][k]) >> 4;  // pyramid.hh:50-55
+        if (k < 4) lo |= (uint32_t)v << (8 * k); else hi |= (uint32_t)v << (8 * (k - 4));
+      }
+      unsigned char* dst = row_ptr<unsigned char>(out, r) + c0;
+      if (c0 + 8 <= fast_cols) *reinterpret_cast<uint2*>(dst) = make_uint2(lo, hi);
+      else
+        for (int k = 0; k < 8 && c0 + k < fast_cols; k++) dst[k] = (unsigned char)((k < 4 ? lo >> (8 * k) : hi >> (8 * (k - 4))) & 0xFF);
+    }
+  }
+}
+
+// outputs of the last row (if has_row) and last column (if has_col): same arithmetic as k_lowpass_sub2<0>
+__global__ void __launch_bounds__(128) k_lowpass_sub2_edges_u8(Img in, Img out, int has_row, int has_col) {
+  const int n_row = has_row ? out.ncols : 0;
+  const int n_col = has_col ? out.nrows - (has_row ? 1 : 0) : 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_row + n_col; i += gridDim.x * blockDim.x) {
+    const int r = i < n_row ? out.nrows - 1 : i - n_row;
+    const int c = i < n_row ? i : out.ncols - 1;
+    const int y = mirror_idx(r * 2, in.nrows), x = mirror_idx(c * 2, in.ncols);
+    int h[5];
+#pragma unroll
+    for (int d = 0; d < 5; d++) {
+      const unsigned char* row = row_ptr<unsigned char>(in, mirror_idx(y - 2 + d, in.nrows));
+      h[d] = lp5((int)row[x - 2], (int)row[x - 1], (int)row[x], (int)row[x + 1], (int)row[x + 2]);
+    }
+    row_ptr<unsigned char>(out, r)[c] = (unsigned char)lp5(h[0], h[1], h[2], h[3], h[4]);
+  }
+}
+
+// 8-byte pixels (vint2 / vfloat2 gradient pyramids): one thread per output pixel, both components;
+// each of the 5 rows is read as 16 + 16 + 8 bytes when the centre column is even (always, except for
+// the mirrored last column of an even-sized parent).
+template <typename A> struct vec2_of;
+template <> struct vec2_of<int> { typedef int2 type; typedef int4 type4; };
+template <> struct vec2_of<float> { typedef float2 type; typedef float4 type4; };
+
+template <int KIND>
+__global__ void __launch_bounds__(256) k_lowpass_sub2_px8(Img in, Img out, int aligned16) {
+  typedef typename LpT<KIND>::acc A;
+  typedef typename vec2_of<A>::type V2;
+  typedef typename vec2_of<A>::type4 V4;
+  const long long total = (long long)out.nrows * out.ncols;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / out.ncols), c = (int)(i - (long long)r * out.ncols);
+    const int y = mirror_idx(r * 2, in.nrows), x = mirror_idx(c * 2, in.ncols);
+    A hx[5], hy[5];
+#pragma unroll
+    for (int d = 0; d < 5; d++) {
+      const unsigned char* row = row_ptr<unsigned char>(in, mirror_idx(y - 2 + d, in.nrows)) + (long long)(x - 2) * 8;
+      V2 p0, p1, p2, p3, p4;
+      if (aligned16 && !(x & 1)) {
+        const V4 a = *reinterpret_cast<const V4*>(row), b = *reinterpret_cast<const V4*>(row + 16);
+        p0.x = a.x; p0.y = a.y; p1.x = a.z; p1.y = a.w; p2.x = b.x; p2.y = b.y; p3.x = b.z; p3.y = b.w;
+        p4 = *reinterpret_cast<const V2*>(row + 32);
+      } else {
+        const V2* q = reinterpret_cast<const V2*>(row);
+        p0 = q[0]; p1 = q[1]; p2 = q[2]; p3 = q[3]; p4 = q[4];
+      }
+      hx[d] = lp5(p0.x, p1.x, p2.x, p3.x, p4.x);
+      hy[d] = lp5(p0.y, p1.y, p2.y, p3.y, p4.y);
+    }
+    V2 o;
+    o.x = lp5(hx[0], hx[1], hx[2], hx[3], hx[4]);
+    o.y = lp5(hy[0], hy[1], hy[2], hy[3], hy[4]);
+    reinterpret_cast<V2*>(row_ptr<unsigned char>(out, r))[c] = o;
+  }
+}
+
 static int grid_for(long long items, int threads) {
   long long blocks = (items + threads - 1) / threads;
   long long cap = (long long)sm_count() * 16;
@@ -115,10 +246,20 @@ int vppb_scharr_u8(const vppb_img* in, const vppb_img* out, int as_float, void* 
   VPPB_REQUIRE(in->nrows >= out->nrows && in->ncols >= out->ncols, VPPB_E_ARG, "vppb_scharr_u8: input smaller than output");
   VPPB_REQUIRE(in->border >= 1, VPPB_E_BORDER, "vppb_scharr_u8: input border %d < 1", in->border);
   VPPB_REQUIRE(((uintptr_t)out->base % 8) == 0 && (out->pitch % 8) == 0, VPPB_E_ARG, "vppb_scharr_u8: output not 8-byte aligned");
-  const int groups = (out->ncols + 3) / 4;
-  const int grid = grid_for((long long)out->nrows * groups, 256);
-  if (as_float) k_scharr_u8<true><<<grid, 256, 0, as_stream(stream)>>>(view(in), view(out), groups);
-  else k_scharr_u8<false><<<grid, 256, 0, as_stream(stream)>>>(view(in), view(out), groups);
+  // fast path: 8-byte aligned input rows with >= 4 addressable bytes left of column 0 and enough row to the right
+  // of the last group (the library layout pads rows to 128 B), 16-byte aligned output rows
+  const int groups = (out->ncols + 7) / 8;
+  const bool fast = ((uintptr_t)in->base % 8) == 0 && (in->pitch % 8) == 0 && ((uintptr_t)out->base % 16) == 0 && (out->pitch % 16) == 0 &&
+                    in->align >= 16 && in->border >= 1 && (long long)groups * 8 + 4 <= in->pitch - (long long)in->align;
+  if (fast) {
+    const int grid = grid_for((long long)out->nrows * groups, 256);
+    if (as_float) k_scharr_u8_v8<true><<<grid, 256, 0, as_stream(stream)>>>(view(in), view(out), groups);
+    else k_scharr_u8_v8<false><<<grid, 256, 0, as_stream(stream)>>>(view(in), view(out), groups);
+  } else {
+    const int grid = grid_for((long long)out->nrows * out->ncols, 256);
+    if (as_float) k_scharr_u8<true><<<grid, 256, 0, as_stream(stream)>>>(view(in), view(out), 0);
+    else k_scharr_u8<false><<<grid, 256, 0, as_stream(stream)>>>(view(in), view(out), 0);
+  }
   VPPB_LAUNCH_CHECK("vppb_scharr_u8");
   return VPPB_OK;
 }
@@ -135,9 +276,26 @@ int vppb_lowpass_sub2(const vppb_img* in, const vppb_img* out, int kind, void* s
   cudaStream_t st = as_stream(stream);
   const long long items = (long long)out->nrows * out->ncols * (kind == 0 ? 1 : 2);
   const int grid = grid_for(items, 256);
-  if (kind == 0) k_lowpass_sub2<0><<<grid, 256, 0, st>>>(view(in), view(out), 2);
-  else if (kind == 1) k_lowpass_sub2<1><<<grid, 256, 0, st>>>(view(in), view(out), 2);
-  else k_lowpass_sub2<2><<<grid, 256, 0, st>>>(view(in), view(out), 2);
+  if (kind == 0) {
+    // fast path needs the library layout (4 bytes left / 20 bytes right of the domain inside the row) and 8-byte aligned output rows
+    const bool fast = in->align >= 32 && ((uintptr_t)in->base % 16) == 0 && (in->pitch % 16) == 0 && ((uintptr_t)out->base % 8) == 0 &&
+                      (out->pitch % 8) == 0 && in->nrows >= 4 && in->ncols >= 4;
+    if (fast) {
+      const int fast_rows = std::min(out->nrows, (in->nrows + 1) / 2), fast_cols = std::min(out->ncols, (in->ncols + 1) / 2);
+      const int groups = (fast_cols + 7) / 8;
+      k_lowpass_sub2_u8_fast<<<grid_for((long long)((fast_rows + 1) / 2) * groups, 128), 128, 0, st>>>(view(in), view(out), fast_rows, fast_cols, groups);
+      const int has_row = out->nrows > fast_rows, has_col = out->ncols > fast_cols;
+      if (has_row || has_col) k_lowpass_sub2_edges_u8<<<grid_for(out->nrows + out->ncols, 128), 128, 0, st>>>(view(in), view(out), has_row, has_col);
+    } else {
+      k_lowpass_sub2<0><<<grid, 256, 0, st>>>(view(in), view(out), 2);
+    }
+  }
+  else {
+    const int aligned16 = (((uintptr_t)in->base % 16) == 0 && (in->pitch % 16) == 0) ? 1 : 0;
+    const int g2 = grid_for((long long)out->nrows * out->ncols, 256);
+    if (kind == 1) k_lowpass_sub2_px8<1><<<g2, 256, 0, st>>>(view(in), view(out), aligned16);
+    else k_lowpass_sub2_px8<2><<<g2, 256, 0, st>>>(view(in), view(out), aligned16);
+  }
   VPPB_LAUNCH_CHECK("vppb_lowpass_sub2");
   return VPPB_OK;
 }

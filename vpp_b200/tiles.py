@@ -28,3 +28,19 @@ def exchange_halos(dist, rank, world, send_up, send_dn, recv_up, recv_dn):
         for w in dist.batch_isend_irecv(ops):
             w.wait()
     return up, down
+
+
+def exchange_halos_inplace(dist, rank, world, send_up, send_dn, recv_up, recv_dn):
+    """Same single grouped exchange, but straight from / into the images: because the edge rows of a pitched
+    tile (with their column border) are one contiguous block, the per-frame lists of tensor views
+    (top edge rows, bottom edge rows, top border rows, bottom border rows) need no pack / unpack kernels."""
+    up, down = neighbours(rank, world)
+    ops = []
+    if up is not None:
+        ops += [dist.P2POp(dist.isend, t, up) for t in send_up] + [dist.P2POp(dist.irecv, t, up) for t in recv_up]
+    if down is not None:
+        ops += [dist.P2POp(dist.isend, t, down) for t in send_dn] + [dist.P2POp(dist.irecv, t, down) for t in recv_dn]
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    return up, down
