@@ -152,6 +152,23 @@ int vppb_lk_match_u8(const vppb_img* prev, const vppb_img* next, const vppb_img*
                      const vppb_lk_params* params, const vppb_float2* kps, const vppb_float2* prediction,
                      int32_t n, vppb_float2* flow_out, float* err_out, void* stream);
 
+/* ---- semi-dense optical flow of video_extruder (semi_dense_optical_flow.hpp:46-214, gradient_descent.hh:10-89) --- */
+typedef struct vppb_sdof_params {
+  int32_t winsize;      /* SAD window side (reference default 7; video_extruder passes 9) */
+  int32_t nscales;      /* pyramid levels (<= 8) */
+  int32_t min_scale;    /* finest level processed */
+  int32_t propagation;  /* number of neighbour-propagation sweeps (even sweeps backward, odd forward) */
+  int32_t patchsize;    /* cell side */
+} vppb_sdof_params;
+int64_t vppb_sdof_workspace_bytes(int32_t nrows, int32_t ncols, const vppb_sdof_params* params);
+/* pyr1 / pyr2: `nscales` u8 pyramid levels of the two frames (pyramid2d<uchar>(img, nscales, 2, _border >= winsize/2),
+ * borders mirror-filled).  kps: n device (row, col) records.  For keypoint i, out_valid[i] tells whether the reference
+ * would call match_callback(i, out_pos[i], out_dist[i]).  Serial semantics of the reference: the first keypoint (lowest
+ * index) of a cell claims it; propagation sweeps are Gauss-Seidel in the reference's raster orders (wavefront launches). */
+int vppb_sdof_u8(const vppb_img* pyr1, const vppb_img* pyr2, const vppb_sdof_params* params, const vppb_int2* kps, int32_t n,
+                 void* workspace, int64_t workspace_bytes, vppb_int2* out_pos, int32_t* out_dist, unsigned char* out_valid,
+                 void* stream);
+
 /* ---- multi-GPU row tiles ------------------------------------------------------------------ */
 /* Pack / unpack the `halo` edge rows of a row tile into/from a contiguous device staging buffer
  * (the payload of the one grouped NCCL neighbour exchange per frame).  which: 0 = top rows

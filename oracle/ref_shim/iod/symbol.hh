@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cassert>
 #include <cfloat>
+#include <climits>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -17,6 +18,8 @@
 #include <vector>
 
 namespace iod {
+
+struct variable_base {};  // makes iod an associated namespace of every `_sym = value` (unqualified D(...) calls)
 
 template <typename S>
 struct symbol {
@@ -85,7 +88,7 @@ auto static_if(F f, G g, A&&... a) { return static_if_<C>(std::integral_constant
     using iod::symbol<_##NAME##_t>::operator=;                         \
     constexpr _##NAME##_t() {}                                         \
     template <typename T>                                              \
-    struct variable_type {                                             \
+    struct variable_type : iod::variable_base {                        \
       typedef _##NAME##_t symbol_type;                                 \
       typedef T value_type;                                            \
       variable_type() {}                                               \

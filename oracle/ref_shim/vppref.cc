@@ -8,6 +8,8 @@
 #include <vpp/algorithms/fast_detector/fast.hh>
 #include <vpp/algorithms/lucas_kanade.hh>
 #include <vpp/algorithms/pyrlk/lk.hh>
+#include <vpp/algorithms/optical_flow/semi_dense_optical_flow.hpp>
+#include <climits>
 #include <stdint.h>
 #ifdef _OPENMP
 #include <omp.h>
@@ -206,6 +208,17 @@ void vppref_pyrlk_levels(const vo_img* prev, const vo_img* next, const vo_img* g
     case 9: pyrlk_levels<9>(prev, next, grad, nlevels, min_scale, kps, n, min_ev, max_err, max_iter, delta, flow_out, dist_out); break;
     default: pyrlk_levels<11>(prev, next, grad, nlevels, min_scale, kps, n, min_ev, max_err, max_iter, delta, flow_out, dist_out); break;
   }
+}
+
+
+// semi_dense_optical_flow (semi_dense_optical_flow.hpp:46-214): out_valid[i] = 1 where match_callback fired
+void vppref_semi_dense_flow(const vo_img* i1, const vo_img* i2, const vo_int2* kps, int n, int winsize, int nscales, int min_scale,
+                            int propagation, int patchsize, vo_int2* out_pos, int32_t* out_dist, unsigned char* out_valid) {
+  auto I1 = wrap<unsigned char>(i1), I2 = wrap<unsigned char>(i2);
+  std::vector<vint2> keypoints(n);
+  for (int i = 0; i < n; i++) { keypoints[i] = vint2(kps[i].r, kps[i].c); out_valid[i] = 0; out_pos[i].r = out_pos[i].c = 0; out_dist[i] = 0; }
+  semi_dense_optical_flow(keypoints, [&](int i, vint2 pos, int d) { out_valid[i] = 1; out_pos[i].r = pos[0]; out_pos[i].c = pos[1]; out_dist[i] = d; },
+                          I1, I2, _winsize = winsize, _nscales = nscales, _min_scale = min_scale, _propagation = propagation, _patchsize = patchsize);
 }
 
 }  // extern "C"

@@ -48,6 +48,7 @@ def load(omp=False):
         lib.vo_fast9_score.argtypes = [I, C.c_int, C.c_int, C.c_int]
         lib.vo_interp_u8.argtypes = [I, C.c_float, C.c_float]
         lib.vo_lk_match_u8.argtypes = [I, I, I, P(VoLkParams), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        lib.vo_semi_dense_flow.argtypes = [I, I, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.vo_num_threads.restype = C.c_int
         _LIBS[key] = lib
     return _LIBS[key]

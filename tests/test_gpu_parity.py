@@ -470,3 +470,25 @@ def test_halo_pack_unpack_single_and_batch(vpp):
         a = im.download(with_border=True)
         assert np.array_equal(a[0:2], payload[i]) and np.array_equal(a[-2:], payload[i])
         assert np.array_equal(a[2:-2], hosts[i][2:-2])
+
+
+# ------------------------------------------------------------------ semi-dense optical flow (video_extruder)
+@pytest.mark.parametrize("shape,ws,nscales,min_scale,prop,patch", [((121, 161), 9, 3, 0, 2, 5), ((145, 209), 7, 4, 0, 2, 5), ((129, 97), 9, 3, 1, 3, 3),
+                                                                  ((240, 322), 9, 3, 0, 2, 5), ((121, 161), 9, 2, 0, 0, 5)])
+def test_semi_dense_optical_flow_bit_exact(vpp, shape, ws, nscales, min_scale, prop, patch):
+    f1, f2, _ = scenes.lk_pair(shape[0], shape[1], 4, seed=21, shift=(3.0, -2.0), margin=10)
+    o = orc.load()
+    G = vpp.Image2d.from_host(f1, "u8", border=3)
+    vpp.fill_border_mirror(G)
+    kps = vpp.fast9(G, 8, blockwise=True, block_size=6)  # what video_extruder feeds the flow with
+    n = len(kps)
+    assert n > 100
+    pos, dist, valid = vpp.semi_dense_optical_flow(kps, vpp.Image2d.from_host(f1, "u8"), vpp.Image2d.from_host(f2, "u8"), winsize=ws, nscales=nscales,
+                                                   min_scale=min_scale, propagation=prop, patchsize=patch)
+    h1, h2 = orc.HostImage(shape[0], shape[1], "u8", data=f1), orc.HostImage(shape[0], shape[1], "u8", data=f2)
+    rpos, rdist, rvalid = np.zeros((n, 2), np.int32), np.zeros(n, np.int32), np.zeros(n, np.uint8)
+    k = np.ascontiguousarray(kps)
+    o.vo_semi_dense_flow(h1.ptr(), h2.ptr(), k.ctypes.data, n, ws, nscales, min_scale, prop, patch, rpos.ctypes.data, rdist.ctypes.data, rvalid.ctypes.data)
+    assert np.array_equal(valid, rvalid.astype(bool)) and valid.sum() > 50
+    assert np.array_equal(pos, rpos)
+    assert np.array_equal(dist, rdist)

@@ -34,6 +34,7 @@ def _load(path):
     r.vppref_is_fast9_keypoint.argtypes = [I, C.c_int, C.c_int, C.c_int]
     r.vppref_interp_u8.argtypes = [I, C.c_float, C.c_float]
     r.vppref_lucas_kanade.argtypes = [I, I, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_void_p, C.c_void_p]
+    r.vppref_semi_dense_flow.argtypes = [I, I, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     r.vppref_pyrlk_levels.argtypes = [I, I, I, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float,
                                       C.c_void_p, C.c_void_p]
     return r
@@ -212,3 +213,29 @@ def test_lk_square_win_matcher(ref, o, winsize):
     assert np.allclose(flow, rflow, rtol=1e-5, atol=1e-5), np.abs(flow - rflow).max()
     ok = rdist < 3e38
     assert np.allclose(dist[ok], rdist[ok], rtol=1e-4)
+
+
+@pytest.mark.parametrize("shape,ws,nscales,min_scale,prop,patch", [((121, 161), 9, 3, 0, 2, 5), ((145, 209), 7, 4, 0, 2, 5),
+                                                                  ((129, 97), 9, 3, 1, 3, 3), ((121, 161), 9, 2, 0, 0, 5)])
+def test_semi_dense_flow_serial_semantics(ref, o, shape, ws, nscales, min_scale, prop, patch):
+    """semi_dense_optical_flow (semi_dense_optical_flow.hpp:46-214 + gradient_descent.hh) executed by the reference's
+    own headers, serial build, vs the oracle restatement: positions, distances and the set of reported keypoints.
+    Sizes of the form 2^k m + 1 keep every pyramid level odd, so the reference never reads its uninitialised
+    low-pass border (pyramid.hh:179-181)."""
+    f1, f2, _ = scenes.lk_pair(shape[0], shape[1], 4, seed=21, shift=(3.0, -2.0), margin=10)
+    k = np.zeros((f1.size, 2), np.int32)
+    h = orc.HostImage(shape[0], shape[1], "u8", border=3, data=f1, fill_border="mirror")
+    n = o.vo_fast9_u8(h.ptr(), 8, None, 2, 6, 0, k.ctypes.data, None, len(k))  # blockwise FAST keypoints, as video_extruder feeds it
+    kps = np.ascontiguousarray(k[:n])
+    assert n > 100
+    h1, h2 = orc.HostImage(shape[0], shape[1], "u8", data=f1), orc.HostImage(shape[0], shape[1], "u8", data=f2)
+    res = []
+    for fn in (ref.vppref_semi_dense_flow, o.vo_semi_dense_flow):
+        pos, dist, valid = np.zeros((n, 2), np.int32), np.zeros(n, np.int32), np.zeros(n, np.uint8)
+        fn(h1.ptr(), h2.ptr(), kps.ctypes.data, n, ws, nscales, min_scale, prop, patch, pos.ctypes.data, dist.ctypes.data, valid.ctypes.data)
+        res.append((pos, dist, valid))
+    assert np.array_equal(res[0][2], res[1][2]) and res[0][2].sum() > 50
+    assert np.array_equal(res[0][0], res[1][0])
+    assert np.array_equal(res[0][1], res[1][1])
+    flow = (res[1][0] - kps)[res[1][2] > 0]
+    assert np.median(np.abs(flow - np.array([3, -2])).max(axis=1)) <= 1  # the synthetic motion is (3,-2) +- 0.5 px

@@ -9,5 +9,5 @@ from .image import Box2d, Image2d, make_box2d, layout, DEFAULT_ALIGNMENT  # noqa
 from .ops import (  # noqa: F401
     Pyramid2d, box5x5, clone, copy, copy_with_border, fast9, fast9_scores, fill, fill_border_closest,
     fill_border_mirror, fill_border_with_value, fill_with_border, lucas_kanade, pixel_wise_add, pyrlk_match,
-    scharr, sum,
+    scharr, semi_dense_optical_flow, sum,
 )

@@ -60,6 +60,11 @@ class VppbLkParams(C.Structure):
     ]
 
 
+class VppbSdofParams(C.Structure):
+    _fields_ = [("winsize", C.c_int32), ("nscales", C.c_int32), ("min_scale", C.c_int32), ("propagation", C.c_int32),
+                ("patchsize", C.c_int32)]
+
+
 _P = C.POINTER
 _IMG = _P(VppbImg)
 _VP = C.c_void_p
@@ -96,6 +101,8 @@ PROTOTYPES = {
     "vppb_fast9_u8": (C.c_int, [_IMG, _I32, _IMG, _I32, _I32, _I32, _VP, _I64, _VP, _VP, _I32, _P(_I32), _VP]),
     "vppb_fast9_scores": (C.c_int, [_IMG, _I32, _VP, _I32, _VP, _VP]),
     "vppb_lk_match_u8": (C.c_int, [_IMG, _IMG, _IMG, _P(VppbLkParams), _VP, _VP, _I32, _VP, _VP, _VP]),
+    "vppb_sdof_workspace_bytes": (_I64, [_I32, _I32, _P(VppbSdofParams)]),
+    "vppb_sdof_u8": (C.c_int, [_IMG, _IMG, _P(VppbSdofParams), _VP, _I32, _VP, _I64, _VP, _VP, _VP, _VP]),
     "vppb_halo_bytes": (_I64, [_IMG, _I32]),
     "vppb_halo_pack": (C.c_int, [_IMG, _I32, C.c_int, _VP, _VP]),
     "vppb_halo_unpack": (C.c_int, [_IMG, _I32, C.c_int, _VP, _VP]),

@@ -1,0 +1,232 @@
+// Semi-dense optical flow of video_extruder: coarse-to-fine SAD block matching on a grid of
+// patchsize x patchsize cells, greedy 8-neighbour descent, neighbour propagation sweeps.
+// Reference: vpp/algorithms/optical_flow/semi_dense_optical_flow.hpp:17-214,
+// vpp/algorithms/optical_flow/gradient_descent.hh:10-89.
+//
+// The reference is sequentially defined (and racy under OpenMP): the FIRST keypoint that reaches a
+// cell claims it, and the propagation sweeps are Gauss-Seidel in raster order.  The GPU keeps the
+// serial semantics exactly:
+//   - claim: atomicMin of the keypoint index per cell, then only the owner matches (the match of a
+//     cell depends on nothing the other keypoints do);
+//   - propagation: iteration (kr, kc) of a sweep only depends on iterations (kr, kc-1) and
+//     (kr-1, kc-1..kc+1), so all iterations with kc + 2 kr = t are independent: one launch per
+//     wavefront t, one warp per cell, in the sweep's own direction.
+// One warp evaluates a SAD (winsize^2 <= 225 byte pairs over 32 lanes, integer shuffle reduction);
+// the row-wise early exit of the reference only skips sums that already exceed the threshold, so the
+// full SAD gives the same comparisons.  Gather / latency bound, not HBM bound.
+#include "common.cuh"
+
+#include <limits.h>
+
+namespace vppb {
+
+constexpr unsigned FULLM = 0xffffffffu;
+
+struct SdofLevel {
+  Img i1, i2;
+  int2* flow;            // cells: (cr + 2) x (cc + 2) entries, row stride = cstride
+  unsigned char* mark;
+  int* dist;
+  int* owner;
+  int cr, cc, cstride;   // cell-map domain (pf_domain pyramid level) and row stride
+};
+
+__device__ __forceinline__ int sad_warp(const Img& a, const Img& b, int ar, int ac, int br, int bc, int ws) {
+  if (ar < 0 || ar >= a.nrows || ac < 0 || ac >= a.ncols || br < 0 || br >= b.nrows || bc < 0 || bc >= b.ncols) return INT_MAX;  // :102-108
+  const int lane = threadIdx.x & 31, h = ws / 2, n = ws * ws;
+  const unsigned char* pa = a.base + (long long)(ar - h) * a.pitch + (ac - h);
+  const unsigned char* pb = b.base + (long long)(br - h) * b.pitch + (bc - h);
+  int s = 0;
+  for (int i = lane; i < n; i += 32) {
+    const int r = i / ws, c = i - r * ws;
+    s += abs((int)pa[(long long)r * a.pitch + c] - (int)pb[(long long)r * b.pitch + c]);
+  }
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULLM, s, o);
+  return s;
+}
+
+__constant__ int c_c8_it[9][2] = {{6, 3}, {0, 3}, {0, 5}, {2, 5}, {2, 7}, {4, 7}, {4, 1}, {6, 1}, {0, 0}};
+__constant__ int c_c8[8][2] = {{-1, 1}, {0, 1}, {1, 1}, {-1, 0}, {1, 0}, {-1, -1}, {0, -1}, {1, -1}};
+
+// gradient_descent.hh:10-89 (whole warp, uniform control flow)
+__device__ __forceinline__ void descent_warp(const Img& a, const Img& b, int pr, int pc, int predr, int predc, int ws, int max_it, int& flr,
+                                             int& flc, int& dist) {
+  int mr = predr, mc = predc;
+  int md = sad_warp(a, b, pr, pc, predr, predc, ws);
+  int mi = 8;
+  for (int search = 0; search < max_it; search++) {
+    int i = c_c8_it[mi][0];
+    const int end = c_c8_it[mi][1];
+    bool first = true;
+    while (first || i != end) {
+      first = false;
+      const int nr = predr + c_c8[i][0], nc = predc + c_c8[i][1];
+      const int d = sad_warp(a, b, pr, pc, nr, nc, ws);
+      if (d < md) { mr = nr; mc = nc; mi = i; md = d; }
+      i = (i + 1) & 7;
+    }
+    if (predr == mr && predc == mc) break;
+    predr = mr; predc = mc;
+  }
+  flr = mr - pr; flc = mc - pc; dist = md;
+}
+
+__global__ void k_sdof_clear(SdofLevel L) {
+  const int total = (L.cr + 2) * L.cstride;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) { L.mark[i] = 0; L.owner[i] = INT_MAX; }
+}
+
+__global__ void k_sdof_claim(SdofLevel L, const vppb_int2* kps, int n, int scale_div, int patch) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int fr = (kps[i].r / scale_div) / patch, fc = (kps[i].c / scale_div) / patch;
+    atomicMin(&L.owner[fr * L.cstride + fc], i);
+  }
+}
+
+// :114-143, one warp per keypoint; only the owner (lowest index == first in serial order) of a cell matches
+__global__ void __launch_bounds__(128) k_sdof_match(SdofLevel L, SdofLevel coarser, int has_coarser, const vppb_int2* kps, int n, int scale_div,
+                                                    int patch, int ws) {
+  const int lane = threadIdx.x & 31;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += nwarps) {
+    const int pr = kps[i].r / scale_div, pc = kps[i].c / scale_div;
+    const int cell = (pr / patch) * L.cstride + (pc / patch);
+    if (L.owner[cell] != i) continue;  // warp-uniform
+    int predr = pr, predc = pc;
+    if (has_coarser) {
+      const int m = (pr / (2 * patch)) * coarser.cstride + (pc / (2 * patch));
+      if (coarser.mark[m]) { predr = pr + coarser.flow[m].x * 2; predc = pc + coarser.flow[m].y * 2; }
+    }
+    int flr, flc, d;
+    descent_warp(L.i1, L.i2, pr, pc, predr, predc, ws, 5, flr, flc, d);
+    if (lane == 0) { L.flow[cell] = make_int2(flr, flc); L.dist[cell] = d; L.mark[cell] = 2; }
+  }
+}
+
+// :149-189 for the iterations (kr, kc) of one sweep with kc + 2 kr == t; forward sweeps start at pixel 0 and step
+// +patch, backward sweeps start at the last pixel and step -patch (so p is not the cell corner there)
+__global__ void __launch_bounds__(128) k_sdof_prop_wave(SdofLevel L, int t, int forward, int nkr, int nkc, int patch, int ws) {
+  const int lane = threadIdx.x & 31;
+  const int kr_lo = max(0, (t - (nkc - 1) + 1) / 2), kr_hi = min(nkr - 1, t / 2);
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int inr = L.i1.nrows, inc = L.i1.ncols;
+  for (int kr = kr_lo + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5); kr <= kr_hi; kr += nwarps) {
+    const int kc = t - 2 * kr;
+    if (kc < 0 || kc >= nkc) continue;
+    const int r = forward ? kr * patch : inr - 1 - kr * patch, c = forward ? kc * patch : inc - 1 - kc * patch;
+    const int fr = r / patch, fc = c / patch;
+    const int cell = fr * L.cstride + fc;
+    if (!L.mark[cell]) continue;  // warp-uniform
+    int2 cur = L.flow[cell];
+    const int2 prev = cur;
+    int d1 = L.dist[cell];
+    bool changed = false;
+    for (int dr = -1; dr <= 1; dr++)
+      for (int dc = -1; dc <= 1; dc++) {
+        if (!dr && !dc) continue;
+        const int nr = fr + dr, nc = fc + dc;
+        if (nr < 0 || nr >= L.cr || nc < 0 || nc >= L.cc) continue;
+        const int ncell = nr * L.cstride + nc;
+        if (!L.mark[ncell]) continue;
+        const int2 nf = L.flow[ncell];
+        const int a0 = cur.x - nf.x, a1 = cur.y - nf.y, b0 = prev.x - nf.x, b1 = prev.y - nf.y;
+        if (a0 * a0 + a1 * a1 < 9 || b0 * b0 + b1 * b1 < 9) continue;  // integer norm() > 2
+        const int d2 = sad_warp(L.i1, L.i2, r, c, r + nf.x, c + nf.y, ws);
+        if (d2 < d1) {
+          int flr, flc, d;
+          descent_warp(L.i1, L.i2, r, c, r + nf.x, c + nf.y, ws, 5, flr, flc, d);
+          if (d < d1) { cur = make_int2(flr, flc); d1 = d; changed = true; }
+        }
+      }
+    if (changed && lane == 0) { L.flow[cell] = cur; L.dist[cell] = d1; L.mark[cell] = 1; }
+  }
+}
+
+__global__ void k_sdof_emit(SdofLevel L, const vppb_int2* kps, int n, int div, int mul, vppb_int2* pos, int* dist, unsigned char* valid) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int fr = kps[i].r / div, fc = kps[i].c / div;
+    int v = 0, pr = 0, pc = 0, d = 0;
+    if (fr >= 0 && fr < L.cr && fc >= 0 && fc < L.cc && L.mark[fr * L.cstride + fc]) {
+      const int cell = fr * L.cstride + fc;
+      v = 1; pr = kps[i].r + L.flow[cell].x * mul; pc = kps[i].c + L.flow[cell].y * mul; d = L.dist[cell];
+    }
+    valid[i] = (unsigned char)v; pos[i].r = pr; pos[i].c = pc; dist[i] = d;
+  }
+}
+
+static void cell_dims(int nrows, int ncols, int patch, int level, int& cr, int& cc) {
+  cr = nrows / patch; cc = ncols / patch;
+  for (int s = 0; s < level; s++) { cr = (int)(1 + cr / 2.f); cc = (int)(1 + cc / 2.f); }  // pyramid.hh:140 on pf_domain
+}
+static long long level_bytes(int cr, int cc) {
+  const long long cells = (long long)(cr + 2) * (cc + 2);
+  return ((cells * (8 + 4 + 4 + 1) + 255) / 256) * 256 + 1024;
+}
+
+}  // namespace vppb
+
+using namespace vppb;
+
+extern "C" {
+
+int64_t vppb_sdof_workspace_bytes(int32_t nrows, int32_t ncols, const vppb_sdof_params* p) {
+  if (!p || p->patchsize <= 0 || p->nscales <= 0 || p->nscales > 8) return 0;
+  long long total = 0;
+  for (int s = 0; s < p->nscales; s++) { int cr, cc; cell_dims(nrows, ncols, p->patchsize, s, cr, cc); total += level_bytes(cr, cc); }
+  return total;
+}
+
+int vppb_sdof_u8(const vppb_img* pyr1, const vppb_img* pyr2, const vppb_sdof_params* p, const vppb_int2* kps, int32_t n, void* workspace,
+                 int64_t workspace_bytes, vppb_int2* out_pos, int32_t* out_dist, unsigned char* out_valid, void* stream) {
+  VPPB_REQUIRE(pyr1 && pyr2 && p && workspace, VPPB_E_ARG, "vppb_sdof_u8: NULL argument");
+  VPPB_REQUIRE(n == 0 || (kps && out_pos && out_dist && out_valid), VPPB_E_ARG, "vppb_sdof_u8: NULL keypoint/output array");
+  VPPB_REQUIRE(p->nscales >= 1 && p->nscales <= 8 && p->min_scale >= 0 && p->min_scale < p->nscales && p->patchsize >= 1 && p->winsize >= 1 &&
+                   p->winsize <= 15 && p->propagation >= 0, VPPB_E_ARG, "vppb_sdof_u8: parameters out of range");
+  VPPB_REQUIRE(workspace_bytes >= vppb_sdof_workspace_bytes(pyr1[0].nrows, pyr1[0].ncols, p), VPPB_E_ARG, "vppb_sdof_u8: workspace too small");
+  cudaStream_t st = as_stream(stream);
+  SdofLevel L[8];
+  unsigned char* w = static_cast<unsigned char*>(workspace);
+  for (int s = 0; s < p->nscales; s++) {
+    VPPB_REQUIRE(pyr1[s].base && pyr2[s].base && pyr1[s].elem_bytes == 1 && pyr2[s].elem_bytes == 1 && same_domain(&pyr1[s], &pyr2[s]), VPPB_E_ARG,
+                 "vppb_sdof_u8: level %d images invalid", s);
+    // the SAD window is centred on in-domain pixels only, so winsize/2 border pixels suffice (the reference allocates 2*winsize)
+    VPPB_REQUIRE(pyr1[s].border >= p->winsize / 2 && pyr2[s].border >= p->winsize / 2, VPPB_E_BORDER, "vppb_sdof_u8: level %d border < winsize/2", s);
+    int cr, cc;
+    cell_dims(pyr1[0].nrows, pyr1[0].ncols, p->patchsize, s, cr, cc);
+    const long long cells = (long long)(cr + 2) * (cc + 2);
+    L[s].i1 = view(&pyr1[s]); L[s].i2 = view(&pyr2[s]);
+    L[s].cr = cr; L[s].cc = cc; L[s].cstride = cc + 2;
+    L[s].flow = reinterpret_cast<int2*>(w);
+    L[s].dist = reinterpret_cast<int*>(w + cells * 8);
+    L[s].owner = reinterpret_cast<int*>(w + cells * 12);
+    L[s].mark = w + cells * 16;
+    w += level_bytes(cr, cc);
+  }
+  const int sms = sm_count();
+  for (int scale = p->nscales - 1; scale >= p->min_scale; scale--) {
+    const int scale_div = 1 << scale;
+    SdofLevel& Ls = L[scale];
+    k_sdof_clear<<<sms * 2, 256, 0, st>>>(Ls);
+    if (n > 0) {
+      k_sdof_claim<<<(n + 255) / 256, 256, 0, st>>>(Ls, kps, n, scale_div, p->patchsize);
+      const int blocks = (n + 3) / 4;
+      k_sdof_match<<<blocks < sms * 16 ? blocks : sms * 16, 128, 0, st>>>(Ls, L[scale + 1 < p->nscales ? scale + 1 : scale], scale < p->nscales - 1 ? 1 : 0, kps,
+                                                                        n, scale_div, p->patchsize, p->winsize);
+    }
+    const int nkr = (Ls.i1.nrows + p->patchsize - 1) / p->patchsize, nkc = (Ls.i1.ncols + p->patchsize - 1) / p->patchsize;
+    for (int Ki = 0; Ki < p->propagation; Ki++) {
+      const int forward = Ki % 2;  // :191-200: odd iterations forward, even (incl. the first) backward
+      const int waves = nkc + 2 * (nkr - 1);
+      for (int t = 0; t < waves; t++) {
+        const int width = (nkr < (nkc + 1) / 2 + 1 ? nkr : (nkc + 1) / 2 + 1);
+        const int blocks = (width + 3) / 4;
+        k_sdof_prop_wave<<<blocks, 128, 0, st>>>(Ls, t, forward, nkr, nkc, p->patchsize, p->winsize);
+      }
+    }
+  }
+  if (n > 0) k_sdof_emit<<<(n + 255) / 256, 256, 0, st>>>(L[p->min_scale], kps, n, p->patchsize * (1 << p->min_scale), 1 << p->min_scale, out_pos, out_dist, out_valid);
+  VPPB_LAUNCH_CHECK("vppb_sdof_u8");
+  return VPPB_OK;
+}
+
+}  // extern "C"

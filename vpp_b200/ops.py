@@ -243,3 +243,21 @@ def pyrlk_match(pyr_prev, pyr_prev_grad, pyr_next, keypoints, winsize, min_ev, m
     inside = (moved[:, 0] >= 0) & (moved[:, 0] < pyr_prev[0].nrows) & (moved[:, 1] >= 0) & (moved[:, 1] < pyr_prev[0].ncols)
     keep = ~(dist > max_err) & inside
     return flow, dist, keep
+
+
+# ---- semi-dense optical flow ------------------------------------------------------------------
+def semi_dense_optical_flow(keypoints, i1, i2, winsize=7, nscales=4, min_scale=0, propagation=2, patchsize=5, stream=None):
+    """semi_dense_optical_flow(keypoints, match_callback, i1, i2, _winsize, _nscales, _min_scale, _propagation, _patchsize)
+    (semi_dense_optical_flow.hpp:46-214; defaults :57-61).  keypoints: (n, 2) int (row, col).
+    Returns (pos[n,2], dist[n], valid[n]): for every i with valid[i] the reference calls match_callback(i, pos[i], dist[i])."""
+    kp = np.ascontiguousarray(keypoints, dtype=np.int32).reshape(-1, 2)
+    n = len(kp)
+    p1 = Pyramid2d(i1, nscales, 2, border=2 * winsize)  # :72-73
+    p2 = Pyramid2d(i2, nscales, 2, border=2 * winsize)
+    P = capi.VppbSdofParams(winsize, nscales, min_scale, propagation, patchsize)
+    ws = _DeviceBuffer(lib.vppb_sdof_workspace_bytes(i1.nrows, i1.ncols, C.byref(P)))
+    d_kp = _DeviceBuffer(kp.nbytes).from_host(kp)
+    d_pos, d_dist, d_valid = _DeviceBuffer(n * 8), _DeviceBuffer(n * 4), _DeviceBuffer(n)
+    check(lib.vppb_sdof_u8(p1.desc_array(), p2.desc_array(), C.byref(P), d_kp.ptr, n, ws.ptr, ws.nbytes, d_pos.ptr, d_dist.ptr,
+                           d_valid.ptr, stream))
+    return d_pos.to_host(np.int32, n * 2).reshape(-1, 2), d_dist.to_host(np.int32, n), d_valid.to_host(np.uint8, n).astype(bool)
