@@ -8,6 +8,7 @@
 #include <vpp/algorithms/fast_detector/fast.hh>
 #include <vpp/algorithms/filters/scharr.hh>
 #include <vpp/algorithms/lucas_kanade.hh>
+#include <vpp/algorithms/optical_flow.hh>
 #include <vpp/algorithms/pyrlk/pyrlk_match.hh>
 
 using namespace vpp;
@@ -89,6 +90,23 @@ int main(int argc, char** argv) {
     image2d<vint2> g(32, 32);
     scharr(ramp, g);
     for (auto q : g.domain()) assert(g(q) == vint2(0, 4));  // d/drow = 0, d/dcol = (3+10+3)*8/32
+  }
+  {  // semi_dense_optical_flow: a textured frame shifted by (3,-2) -> most cells report that flow
+    image2d<uint8_t> f1(121, 161), f2(121, 161);
+    for (auto p : f1.domain()) {
+      auto tex = [](int r, int c) { return (uint8_t)(128 + 60 * std::sin(r * 0.37) * std::cos(c * 0.29) + 50 * std::sin((r + 2 * c) * 0.11)); };
+      f1(p) = tex(p[0], p[1]);
+      f2(p) = tex(p[0] - 3, p[1] + 2);
+    }
+    image2d<uint8_t> g = clone(f1, _border = 3);
+    fill_border_mirror(g);
+    auto kps = fast9(g, 5, _blockwise, _block_size = 6);
+    assert(kps.size() > 50);
+    int calls = 0, good = 0, last = -1;
+    semi_dense_optical_flow(kps, [&](int i, vint2 pos, int d) { assert(i > last); last = i; calls++; vint2 f = pos - kps[i]; good += (f == vint2(3, -2)); (void)d; },
+                            f1, f2, _winsize = 9, _nscales = 3, _patchsize = 5, _propagation = 2);
+    std::printf("semi_dense_optical_flow: %d callbacks, %d with flow (3,-2)\n", calls, good);
+    assert(calls > 50 && good * 10 >= calls * 7);
   }
   std::puts("ALL OK");
   return 0;

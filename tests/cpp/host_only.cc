@@ -3,6 +3,7 @@
 #include <vpp/vpp.hh>
 #include <vpp/algorithms/fast_detector/fast.hh>
 #include <vpp/algorithms/lucas_kanade.hh>
+#include <vpp/algorithms/optical_flow.hh>
 #include <vpp/algorithms/pyrlk/pyrlk_match.hh>
 
 int host_only_demo() {
