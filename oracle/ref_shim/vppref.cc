@@ -10,6 +10,7 @@
 #include <vpp/algorithms/pyrlk/lk.hh>
 #include <vpp/algorithms/optical_flow/semi_dense_optical_flow.hpp>
 #include <climits>
+#include <vpp/algorithms/video_extruder.hh>
 #include <stdint.h>
 #ifdef _OPENMP
 #include <omp.h>
@@ -145,6 +146,16 @@ int vppref_fast9_u8(const vo_img* img, int th, const vo_img* mask, int mode, int
   }
   return n <= capacity ? n : -n;
 }
+// blockwise FAST in the order the reference returns it (meaningful in the serial build: cells in raster order)
+int vppref_fast9_blockwise_native_order(const vo_img* img, int th, const vo_img* mask, int block_size, vo_int2* kps, int capacity) {
+  auto A = wrap<unsigned char>(img);
+  image2d<unsigned char> M;
+  if (mask && mask->base) M = wrap<unsigned char>(mask);
+  auto k = fast9(A, th, _blockwise, _block_size = block_size, _mask = M);
+  int n = (int)k.size();
+  for (int i = 0; i < n && i < capacity; i++) { kps[i].r = k[i][0]; kps[i].c = k[i][1]; }
+  return n;
+}
 int vppref_fast9_score(const vo_img* img, int th, int r, int c) { auto A = wrap<unsigned char>(img); return fast9_score(A, th, vint2(r, c)); }
 // the scalar detector with the TRUE ring (fast.hpp:79-112)
 int vppref_is_fast9_keypoint(const vo_img* img, int th, int r, int c) {
@@ -219,6 +230,26 @@ void vppref_semi_dense_flow(const vo_img* i1, const vo_img* i2, const vo_int2* k
   for (int i = 0; i < n; i++) { keypoints[i] = vint2(kps[i].r, kps[i].c); out_valid[i] = 0; out_pos[i].r = out_pos[i].c = 0; out_dist[i] = 0; }
   semi_dense_optical_flow(keypoints, [&](int i, vint2 pos, int d) { out_valid[i] = 1; out_pos[i].r = pos[0]; out_pos[i].c = pos[1]; out_dist[i] = d; },
                           I1, I2, _winsize = winsize, _nscales = nscales, _min_scale = min_scale, _propagation = propagation, _patchsize = patchsize);
+}
+
+
+// video_extruder_init + nframes-1 x video_extruder_update (video_extruder.hpp:15-135) over a frame sequence
+// (frames[i]: u8, border >= 3, mirror-filled).  Dumps the final keypoints as rows of 6 ints
+// (row, col, age, trajectory start frame, trajectory length, trajectory alive); returns their count.
+int vppref_video_extruder(const vo_img* frames, int nframes, int detector_th, int keypoint_spacing, int detector_period, int max_traj, int nscales,
+                          int winsize, int propagation, int32_t* out, int capacity) {
+  auto ctx = video_extruder_init(make_box2d(frames[0].nrows, frames[0].ncols));
+  for (int f = 1; f < nframes; f++) {
+    auto f1 = wrap<unsigned char>(&frames[f - 1]), f2 = wrap<unsigned char>(&frames[f]);
+    video_extruder_update(ctx, f1, f2, _detector_th = detector_th, _keypoint_spacing = keypoint_spacing, _detector_period = detector_period,
+                          _max_trajectory_length = max_traj, _nscales = nscales, _winsize = winsize, _propagation = propagation);
+  }
+  const int n = ctx.keypoints.size();
+  for (int i = 0; i < n && i < capacity; i++) {
+    out[6 * i + 0] = ctx.keypoints[i].position[0]; out[6 * i + 1] = ctx.keypoints[i].position[1]; out[6 * i + 2] = ctx.keypoints[i].age;
+    out[6 * i + 3] = ctx.trajectories[i].start_frame(); out[6 * i + 4] = ctx.trajectories[i].size(); out[6 * i + 5] = ctx.trajectories[i].alive() ? 1 : 0;
+  }
+  return n;
 }
 
 }  // extern "C"

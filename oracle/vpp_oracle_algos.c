@@ -112,17 +112,29 @@ int vo_fast9_u8(const vo_img* img, int th, const vo_img* mask, int mode, int blo
     }
   }
   int n = 0;
-  for (int r = 0; r < nr; r++)
-    for (int c = 0; c < nc; c++)
-      if (keep[(size_t)r * nc + c]) {
-        if (n < capacity) {
-          kps[n].r = r;
-          kps[n].c = c;
-          /* fast.hpp:670-671 raw score; :698-704 the u8 score image entry for the maxima modes */
-          if (scores) scores[n] = mode == 0 ? vo_fast9_score(img, th, r, c) : (int)SC(r, c);
+  if (mode == 2) {
+    /* serial order of fast.hpp:763-790: cells in raster order, at most one keypoint per cell */
+    for (int r0 = 0; r0 < nr; r0 += block_size)
+      for (int c0 = 0; c0 < nc; c0 += block_size)
+        for (int r = r0; r < r0 + block_size && r < nr; r++)
+          for (int c = c0; c < c0 + block_size && c < nc; c++)
+            if (keep[(size_t)r * nc + c]) {
+              if (n < capacity) { kps[n].r = r; kps[n].c = c; if (scores) scores[n] = (int)SC(r, c); }
+              n++;
+            }
+  } else {
+    for (int r = 0; r < nr; r++)
+      for (int c = 0; c < nc; c++)
+        if (keep[(size_t)r * nc + c]) {
+          if (n < capacity) {
+            kps[n].r = r;
+            kps[n].c = c;
+            /* fast.hpp:670-671 raw score; :698-704 the u8 score image entry for the maxima modes */
+            if (scores) scores[n] = mode == 0 ? vo_fast9_score(img, th, r, c) : (int)SC(r, c);
+          }
+          n++;
         }
-        n++;
-      }
+  }
 #undef SC
   if (keep != det) free(keep);
   free(det);

@@ -492,3 +492,22 @@ def test_semi_dense_optical_flow_bit_exact(vpp, shape, ws, nscales, min_scale, p
     assert np.array_equal(valid, rvalid.astype(bool)) and valid.sum() > 50
     assert np.array_equal(pos, rpos)
     assert np.array_equal(dist, rdist)
+
+
+# ------------------------------------------------------------------ video_extruder (semi-dense flow + FAST orchestration)
+def test_video_extruder_gpu_equals_oracle(vpp):
+    from vpp_b200 import video_extruder as ve
+    from tests.oracle_video import OracleOps
+    from tests.test_oracle_vs_ref import _moving_frames
+
+    nr, nc, nf = 161, 241, 6
+    frames = _moving_frames(nr, nc, nf)
+    kw = dict(detector_th=6, keypoint_spacing=10, detector_period=3, max_trajectory_length=5, nscales=3, winsize=9, propagation=2)
+    g, c = ve.video_extruder_init(nr, nc), ve.video_extruder_init(nr, nc)
+    gops, cops = ve.GpuOps(), OracleOps()
+    for f in range(1, nf):
+        ve.video_extruder_update(g, frames[f - 1], frames[f], gops, **kw)
+        ve.video_extruder_update(c, frames[f - 1], frames[f], cops, **kw)
+        assert np.array_equal(ve.state_table(g), ve.state_table(c)), "frame %d" % f
+    t = ve.state_table(g)
+    assert len(t) > 20 and (t[:, 2] > 1).sum() > 5

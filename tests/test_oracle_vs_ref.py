@@ -30,10 +30,12 @@ def _load(path):
     r.vppref_lowpass_u8.argtypes = [I, I]
     r.vppref_pyramid.argtypes = [I, C.c_int, I, C.c_int]
     r.vppref_fast9_u8.argtypes = [I, C.c_int, I, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+    r.vppref_fast9_blockwise_native_order.argtypes = [I, C.c_int, I, C.c_int, C.c_void_p, C.c_int]
     r.vppref_fast9_score.argtypes = [I, C.c_int, C.c_int, C.c_int]
     r.vppref_is_fast9_keypoint.argtypes = [I, C.c_int, C.c_int, C.c_int]
     r.vppref_interp_u8.argtypes = [I, C.c_float, C.c_float]
     r.vppref_lucas_kanade.argtypes = [I, I, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_void_p, C.c_void_p]
+    r.vppref_video_extruder.argtypes = [I, C.c_int] + [C.c_int] * 7 + [C.c_void_p, C.c_int]
     r.vppref_semi_dense_flow.argtypes = [I, I, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     r.vppref_pyrlk_levels.argtypes = [I, I, I, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float,
                                       C.c_void_p, C.c_void_p]
@@ -149,7 +151,15 @@ def test_fast9_reference_ring(o, built, lib_path):
                 n1 = r.vppref_fast9_u8(h.ptr(), th, hm.ptr() if hm else None, mode, 10, k1.ctypes.data, s1.ctypes.data, img.size)
                 n2 = o.vo_fast9_u8(h.ptr(), th, hm.ptr() if hm else None, mode, 10, 0, k2.ctypes.data, s2.ctypes.data, img.size)
                 assert n1 == n2, (th, mode, maskval, n1, n2)
+                if mode == 2:  # the oracle emits blockwise keypoints in cell order (the reference's serial order); the wrapper sorts by pixel
+                    order = np.lexsort((k2[:n2, 1], k2[:n2, 0]))
+                    k2[:n2], s2[:n2] = k2[:n2][order], s2[:n2][order]
                 assert np.array_equal(k1[:n1], k2[:n2]) and np.array_equal(s1[:n1], s2[:n2]), (th, mode, maskval)
+                if mode == 2 and lib_path == REF:  # serial build: the reference's own output order == the oracle's
+                    k3, k4 = np.zeros((img.size, 2), np.int32), np.zeros((img.size, 2), np.int32)
+                    n3 = r.vppref_fast9_blockwise_native_order(h.ptr(), th, hm.ptr() if hm else None, 10, k3.ctypes.data, img.size)
+                    n4 = o.vo_fast9_u8(h.ptr(), th, hm.ptr() if hm else None, 2, 10, 0, k4.ctypes.data, None, img.size)
+                    assert n3 == n4 and np.array_equal(k3[:n3], k4[:n4])
         assert n1 >= 0
 
 
@@ -239,3 +249,45 @@ def test_semi_dense_flow_serial_semantics(ref, o, shape, ws, nscales, min_scale,
     assert np.array_equal(res[0][1], res[1][1])
     flow = (res[1][0] - kps)[res[1][2] > 0]
     assert np.median(np.abs(flow - np.array([3, -2])).max(axis=1)) <= 1  # the synthetic motion is (3,-2) +- 0.5 px
+
+
+def _moving_frames(nr, nc, nframes, seed=31):
+    """a textured scene translating by (2,-1) px per frame (+ a little per-frame noise)"""
+    base = scenes.rectangles_scene(nr + 64, nc + 64, seed=seed, noise=2)
+    rngf = np.random.default_rng(seed)
+    out = []
+    for f in range(nframes):
+        a = base[32 - 2 * f:32 - 2 * f + nr, 32 + f:32 + f + nc].astype(np.int32) + rngf.integers(-1, 2, (nr, nc))
+        out.append(np.clip(a, 0, 255).astype(np.uint8))
+    return out
+
+
+def test_video_extruder_orchestration(ref, o):
+    """video_extruder_update (video_extruder.hpp:24-135) run by the reference's own headers over 7 frames vs the
+    Python orchestration of vpp_b200.video_extruder on the oracle backend: identical keypoints, ages and trajectories."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("video_extruder", os.path.join(ROOT, "vpp_b200", "video_extruder.py"))
+    ve = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ve)
+    from tests.oracle_video import OracleOps
+
+    # the -DNDEBUG build (the flags of the reference's examples / benchmarks), single thread = serial semantics: with
+    # asserts on, keypoint_container.hpp:82 aborts as soon as a dead keypoint is revived by move() - which the
+    # reference's own update loop does (video_extruder.hpp:48-51 on entries that died but were not compacted yet)
+    ref = _load(REF_OMP)
+    ref.vppref_set_num_threads(1)
+    nr, nc, nf = 161, 241, 7
+    frames = _moving_frames(nr, nc, nf)
+    hosts = [orc.HostImage(nr, nc, "u8", border=10, aligned=32, data=f, fill_border="mirror") for f in frames]
+    out = np.zeros((nr * nc, 6), np.int32)
+    n = ref.vppref_video_extruder(orc.desc_array(hosts), nf, 6, 10, 3, 5, 3, 9, 2, out.ctypes.data, len(out))
+    assert n > 20
+    ctx = ve.video_extruder_init(nr, nc)
+    ops = OracleOps(o)
+    for f in range(1, nf):
+        ve.video_extruder_update(ctx, frames[f - 1], frames[f], ops, detector_th=6, keypoint_spacing=10, detector_period=3,
+                                 max_trajectory_length=5, nscales=3, winsize=9, propagation=2)
+    mine = ve.state_table(ctx)
+    assert len(mine) == n
+    assert np.array_equal(mine, out[:n])
+    assert (mine[:, 2] > 1).sum() > 5  # some keypoints really were tracked across frames

@@ -11,3 +11,4 @@ from .ops import (  # noqa: F401
     fill_border_mirror, fill_border_with_value, fill_with_border, lucas_kanade, pixel_wise_add, pyrlk_match,
     scharr, semi_dense_optical_flow, sum,
 )
+from . import video_extruder  # noqa: F401,E402

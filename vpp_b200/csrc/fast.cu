@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(256) k_fast9_local_max(Img im, int th, const u
 
 // blockwise maxima (fast.hpp:745-799): per block_size x block_size cell anchored at (0,0), raster
 // scan, strict '>' (first maximum wins), kept iff max > 0.  One thread per cell; bits_out zeroed by caller.
-__global__ void __launch_bounds__(128) k_fast9_block_max(Img im, int th, int bs, const uint32_t* bits, uint32_t* bits_out, int wpr,
+__global__ void __launch_bounds__(128) k_fast9_block_max(Img im, int th, int bs, const uint32_t* bits, int* cellkp, int wpr,
                                                         int* rowcount, int cells_r, int cells_c) {
   const long long total = (long long)cells_r * cells_c;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -157,10 +157,8 @@ __global__ void __launch_bounds__(128) k_fast9_block_max(Img im, int th, int bs,
         c += span;
       }
     }
-    if (vmax > 0) {
-      atomicOr(&bits_out[(long long)pr * wpr + (pc >> 5)], 1u << (pc & 31));
-      atomicAdd(&rowcount[pr], 1);
-    }
+    cellkp[i] = vmax > 0 ? ((pr << 16) | pc) : -1;  // one keypoint at most per cell; emitted in CELL raster order
+    if (vmax > 0) atomicAdd(&rowcount[(int)(i / cells_c)], 1);
   }
 }
 
@@ -237,6 +235,32 @@ __global__ void __launch_bounds__(256) k_fast9_emit(Img im, int th, const uint32
   }
 }
 
+// blockwise emit: one warp per row of cells, keypoints leave in cell raster order (the serial order of fast.hpp:763-790)
+__global__ void __launch_bounds__(256) k_fast9_emit_cells(Img im, int th, const int* cellkp, int cells_r, int cells_c, const int* rowoff, vppb_int2* kps,
+                                                         int* scores, int capacity) {
+  const int lane = threadIdx.x & 31;
+  const int warp0 = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int nwarps = (int)(((long long)gridDim.x * blockDim.x) >> 5);
+  for (int cr = warp0; cr < cells_r; cr += nwarps) {
+    int off = rowoff[cr];
+    if (rowoff[cr + 1] == off) continue;
+    for (int c0 = 0; c0 < cells_c; c0 += 32) {
+      const int cc = c0 + lane;
+      const int v = cc < cells_c ? cellkp[(long long)cr * cells_c + cc] : -1;
+      const unsigned m = __ballot_sync(0xffffffffu, v >= 0);
+      if (v >= 0) {
+        const int pos = off + __popc(m & ((1u << lane) - 1u));
+        if (pos < capacity) {
+          const int r = v >> 16, c = v & 0xFFFF;
+          kps[pos].r = r; kps[pos].c = c;
+          if (scores) scores[pos] = (fast9_score_at(im, r, c, th) / 16) & 255;
+        }
+      }
+      off += __popc(m);
+    }
+  }
+}
+
 __global__ void k_fast9_scores(Img im, int th, const vppb_int2* kps, int n, int* scores) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
     scores[i] = fast9_score_at(im, kps[i].r, kps[i].c, th);
@@ -247,10 +271,11 @@ struct FastWs {
   uint32_t* bits_b;
   int* rowcount;
   int* rowoff;
+  int* cellkp;
   long long bytes;
 };
 
-static FastWs fast_ws_layout(void* base, int nrows, int ncols) {
+static FastWs fast_ws_layout(void* base, int nrows, int ncols, int block_size) {
   FastWs w;
   const long long wpr = (ncols + 31) / 32;
   const long long bits_bytes = ((long long)nrows * wpr * 4 + 255) / 256 * 256;
@@ -260,7 +285,10 @@ static FastWs fast_ws_layout(void* base, int nrows, int ncols) {
   w.bits_b = reinterpret_cast<uint32_t*>(p + bits_bytes);
   w.rowcount = reinterpret_cast<int*>(p + 2 * bits_bytes);
   w.rowoff = reinterpret_cast<int*>(p + 2 * bits_bytes + rows_bytes);
-  w.bytes = 2 * bits_bytes + 2 * rows_bytes;
+  w.cellkp = reinterpret_cast<int*>(p + 2 * bits_bytes + 2 * rows_bytes);
+  const int bs = block_size > 0 ? block_size : 10;
+  const long long cells = (long long)((nrows + bs - 1) / bs) * ((ncols + bs - 1) / bs);
+  w.bytes = 2 * bits_bytes + 2 * rows_bytes + ((cells * 4 + 255) / 256) * 256;
   return w;
 }
 
@@ -271,9 +299,8 @@ using namespace vppb;
 extern "C" {
 
 int64_t vppb_fast9_workspace_bytes(int32_t nrows, int32_t ncols, int32_t block_size) {
-  (void)block_size;
   if (nrows <= 0 || ncols <= 0) return 0;
-  return fast_ws_layout(nullptr, nrows, ncols).bytes;
+  return fast_ws_layout(nullptr, nrows, ncols, block_size).bytes;
 }
 
 int vppb_fast9_u8(const vppb_img* img, int32_t th, const vppb_img* mask, int32_t mode, int32_t block_size, int32_t ring,
@@ -290,7 +317,8 @@ int vppb_fast9_u8(const vppb_img* img, int32_t th, const vppb_img* mask, int32_t
   if (has_mask)
     VPPB_REQUIRE(mask->elem_bytes == 1 && mask->nrows >= img->nrows && mask->ncols >= img->ncols, VPPB_E_ARG,
                  "vppb_fast9_u8: mask must be u8 and cover the image");
-  FastWs ws = fast_ws_layout(workspace, img->nrows, img->ncols);
+  VPPB_REQUIRE(img->nrows < 65536 && img->ncols < 65536, VPPB_E_ARG, "vppb_fast9_u8: image larger than 65535 in one dimension");
+  FastWs ws = fast_ws_layout(workspace, img->nrows, img->ncols, mode == VPPB_FAST_BLOCKWISE ? block_size : 10);
   VPPB_REQUIRE(workspace_bytes >= ws.bytes, VPPB_E_ARG, "vppb_fast9_u8: workspace %lld < %lld bytes", (long long)workspace_bytes, ws.bytes);
   cudaStream_t st = as_stream(stream);
   const int wpr = (img->ncols + 31) / 32;
@@ -313,12 +341,22 @@ int vppb_fast9_u8(const vppb_img* img, int32_t th, const vppb_img* mask, int32_t
       int grid = (int)(blocks < (long long)sms * 8 ? blocks : (long long)sms * 8);
       k_fast9_local_max<<<grid, 256, 0, st>>>(im, th, ws.bits_a, ws.bits_b, wpr, ws.rowcount);
     } else {
-      VPPB_CUDA(cudaMemsetAsync(ws.bits_b, 0, (size_t)words * 4, st));
       const int cells_r = (img->nrows + block_size - 1) / block_size, cells_c = (img->ncols + block_size - 1) / block_size;
       long long cells = (long long)cells_r * cells_c;
       long long blocks = (cells + 127) / 128;
       int grid = (int)(blocks < (long long)sms * 16 ? blocks : (long long)sms * 16);
-      k_fast9_block_max<<<grid, 128, 0, st>>>(im, th, block_size, ws.bits_a, ws.bits_b, wpr, ws.rowcount, cells_r, cells_c);
+      k_fast9_block_max<<<grid, 128, 0, st>>>(im, th, block_size, ws.bits_a, ws.cellkp, wpr, ws.rowcount, cells_r, cells_c);
+      k_fast9_scan<<<1, 1024, 0, st>>>(ws.rowcount, ws.rowoff, cells_r);
+      long long eb = ((long long)cells_r + 7) / 8;
+      k_fast9_emit_cells<<<(int)(eb < (long long)sms * 8 ? eb : (long long)sms * 8), 256, 0, st>>>(im, th, ws.cellkp, cells_r, cells_c, ws.rowoff, kps_out, scores_out,
+                                                                                                 capacity);
+      VPPB_LAUNCH_CHECK("vppb_fast9_u8");
+      int total = 0;
+      VPPB_CUDA(cudaMemcpyAsync(&total, ws.rowoff + cells_r, sizeof(int), cudaMemcpyDeviceToHost, st));
+      VPPB_CUDA(cudaStreamSynchronize(st));
+      *count_out = total;
+      VPPB_REQUIRE(total <= capacity, VPPB_E_CAPACITY, "vppb_fast9_u8: %d keypoints exceed the capacity %d", total, capacity);
+      return VPPB_OK;
     }
     final_bits = ws.bits_b;
   }

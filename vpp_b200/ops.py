@@ -164,7 +164,8 @@ class _DeviceBuffer:
 def fast9(img, th, local_maxima=False, blockwise=False, block_size=10, mask=None, scores=None, ring="reference",
           capacity=None, stream=None):
     """std::vector<vint2> fast9(A, th, [_local_maxima | _blockwise, _block_size=, _mask=, _scores=&vec])
-    (fast.hpp:931-955).  Returns an (n, 2) int32 array of (row, col) in raster order; if `scores` is a
+    (fast.hpp:931-955).  Returns an (n, 2) int32 array of (row, col) in raster order (blockwise: cell raster order, the
+    reference's serial order); if `scores` is a
     list it is replaced by the matching scores.  Raises RuntimeError if A.border() < 3 (fast.hpp:937-938)."""
     mode = capi.FAST_LOCAL_MAXIMA if local_maxima else (capi.FAST_BLOCKWISE if blockwise else capi.FAST_ALL)
     ring_id = capi.FAST_REFERENCE_RING if ring == "reference" else capi.FAST_TRUE_RING
