@@ -141,7 +141,7 @@ def cpu_box_bench(h, w, steps, warmup, budget_s, want_ref=True):
     t0 = time.perf_counter()
     fn(hs.ptr(), hd.ptr())
     one = time.perf_counter() - t0
-    per_step = max(1, min(64, int(budget_s / max(one, 1e-4) / max(steps + warmup, 1))))
+    per_step = max(1, min(4096, int(budget_s / max(one, 1e-4) / max(steps + warmup, 1))))  # ~budget_s seconds of CPU work in total
     for _ in range(warmup):
         for _ in range(per_step):
             fn(hs.ptr(), hd.ptr())
