@@ -69,11 +69,18 @@ struct FillVal { unsigned char b[64]; };
 // power-of-two element sizes <= 16: one 16-byte pattern for every aligned vector of a row range.
 // Range = bytes [x0, x0+wbytes) relative to row pointer `base + r*pitch`, rows [r0, r0+rows).
 __global__ void __launch_bounds__(kThreads) k_fill_vec(unsigned char* base, long long pitch, int rows, int nvec, int4 pat) {
-  long long total = (long long)rows * nvec;
-  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
-    long long r = i / nvec;
-    int v = (int)(i - r * nvec);
-    st_stream(reinterpret_cast<int4*>(base + r * pitch + (long long)v * 16), pat);
+  const long long total = (long long)rows * nvec;
+  const long long stride = (long long)gridDim.x * kThreads * kUnroll;
+  for (long long i0 = (long long)blockIdx.x * kThreads * kUnroll + threadIdx.x; i0 < total; i0 += stride) {
+#pragma unroll
+    for (int u = 0; u < kUnroll; u++) {  // kUnroll independent 16-byte stores in flight per thread
+      const long long i = i0 + (long long)u * kThreads;
+      if (i < total) {
+        const long long r = i / nvec;
+        const int v = (int)(i - r * nvec);
+        st_stream(reinterpret_cast<int4*>(base + r * pitch + (long long)v * 16), pat);
+      }
+    }
   }
 }
 
@@ -115,8 +122,8 @@ static int fill_rect(unsigned char* base, long long pitch, int rows, int cols, i
       }
       if (nvec > 0) {
         long long total = (long long)rows * nvec;
-        int grid = stream_grid(total * kUnroll);
-        k_fill_vec<<<grid, kThreads, 0, st>>>(base + head_b, pitch, rows, nvec, pat);
+        if (pitch == body_b && head_b == 0 && total < 0x7fffffffLL) { nvec = (int)total; rows = 1; }  // gap-free: one long row
+        k_fill_vec<<<stream_grid(total), kThreads, 0, st>>>(base + head_b, pitch, rows, nvec, pat);
       }
       if (tail_e > 0) {
         k_fill_elem<<<stream_grid((long long)rows * tail_e), kThreads, 0, st>>>(base + head_b + body_b, pitch, rows, tail_e, elem, val);
