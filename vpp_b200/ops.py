@@ -216,7 +216,9 @@ def lucas_kanade(i1, i2, keypoints, niterations=21, winsize=11, nscales=3, min_e
     """lucas_kanade(i1, i2, _keypoints=, _flow=, ...) (lucas_kanade.hpp:135-184).
     Returns (flow[n,2], dist[n]) — the values the reference hands to the _flow callback.
     As in the reference, min_ev and delta are stored in `int` (lucas_kanade.hpp:143-144) and so
-    truncate (0.0001 -> 0, 0.1 -> 0); pyramids and the vint2 Scharr gradient pyramid are built here."""
+    truncate (0.0001 -> 0, 0.1 -> 0); pyramids and the vint2 Scharr gradient pyramid are built here.
+    winsize < 5 gives the pyramids a border < 2, which the reference's 5-tap low-pass reads past (undefined values
+    there); here that raises VppbError(VPPB_E_BORDER) instead."""
     border = winsize // 2
     prev = Pyramid2d(i1, nscales, 2, border=border)
     nxt = Pyramid2d(i2, nscales, 2, border=border)
