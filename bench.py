@@ -641,8 +641,7 @@ def gpu_extras(vpp, capi, torch, stream, sp):
 
     def build():
         prev.update(I1, sp); nxt.update(I2, sp)
-        vpp.scharr(prev[0], grad[0], sp)
-        grad.propagate_level0(sp)
+        grad.update_from_scharr(prev[0], sp)
 
     def lk():
         capi.check(capi.lib.vppb_lk_match_u8(pa, na, ga, C.byref(P), d_kp.ptr, None, len(pts), d_flow.ptr, d_err.ptr, sp))

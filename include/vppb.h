@@ -87,6 +87,9 @@ int vppb_pw_add_i32(const vppb_img* a, const vppb_img* b, const vppb_img* c, voi
 int vppb_fill(const vppb_img* img, const void* value, int with_border, void* stream);
 /* copy(src,dst) copy.hh:10-19 (with_border=0) / copy_with_border copy.hh:22-27 (with_border=1) */
 int vppb_copy2d(const vppb_img* src, const vppb_img* dst, int with_border, void* stream);
+/* copy(src, dst) + fill_border_mirror(dst) in one launch (pyramid2d::update: copy then mirror, pyramid.hh:170,196).
+ * Equal domains; dst->border <= dst size. */
+int vppb_copy2d_mirror(const vppb_img* src, const vppb_img* dst, void* stream);
 /* fill_border_with_value fill.hh:32-45 / fill_border_mirror :48-83 / fill_border_closest :86-121 */
 int vppb_fill_border_value(const vppb_img* img, const void* value, void* stream);
 int vppb_fill_border_mirror(const vppb_img* img, void* stream);
@@ -106,10 +109,17 @@ int vppb_box5x5_u8(const vppb_img* in, const vppb_img* out, void* stream);
 /* ---- Scharr + pyramid (scharr.hh:46-87, pyramid.hh:12-81,133-198) ------------------------- */
 /* scharr(in u8, out vector<Vt,2>): out elem 8 bytes; as_float=0 -> vint2 (truncated), 1 -> vfloat2 */
 int vppb_scharr_u8(const vppb_img* in, const vppb_img* out, int as_float, void* stream);
+/* scharr + fill_border_mirror(out) in one launch (the gradient level 0 of lucas_kanade.hpp:156-157 /
+ * video_extruder.hpp: scharr, then pyramid2d::propagate_level0 mirrors it first).  out->border <= out size. */
+int vppb_scharr_u8_mirror(const vppb_img* in, const vppb_img* out, int as_float, void* stream);
 /* One pyramid step: out(r,c) = lowpass5x5sep(in)(2r,2c)  (antialiasing_lowpass_filter + subsample2,
  * fused; the mirror-filled H temp of pyramid.hh:36 is reproduced by index mirroring).
  * kind: 0 = u8, 1 = vint2 (integer /16 per component), 2 = vfloat2.  `in` needs border >= 2, filled. */
 int vppb_lowpass_sub2(const vppb_img* in, const vppb_img* out, int kind, void* stream);
+/* The same step followed by fill_border_mirror(out) (what pyramid2d::propagate_level0 does for every level,
+ * pyramid.hh:169-192), in ONE launch: the thread that produces out(r,c) also writes the <= 8 border pixels
+ * that mirror it.  Needs out->border <= min(out->nrows, out->ncols) (VPPB_E_BORDER otherwise). */
+int vppb_lowpass_sub2_mirror(const vppb_img* in, const vppb_img* out, int kind, void* stream);
 
 /* ---- FAST9 (fast.hpp:253-508, 643-799, 889-955) ------------------------------------------- */
 enum { VPPB_FAST_REFERENCE_RING = 0, VPPB_FAST_TRUE_RING = 1 };

@@ -268,6 +268,40 @@ def test_gradient_pyramid(vpp, gpix):
         assert np.array_equal(got.view(np.int32), exp.view(np.int32)), "level %d" % l
 
 
+@pytest.mark.parametrize("pix,kind", [("u8", 0), ("vint2", 1), ("vfloat2", 2)])
+def test_fused_level_equals_lowpass_then_mirror(vpp, pix, kind):
+    """vppb_lowpass_sub2_mirror == vppb_lowpass_sub2 + vppb_fill_border_mirror on every geometry: even / odd parents
+    (tail work items of the u8 launch), tiny levels where one pixel mirrors into both borders, prefixes of the level,
+    unaligned parents (generic kernel), borders 0..5."""
+    from vpp_b200 import capi
+
+    dt, ch = orc.PIXEL_TYPES[pix]
+    cases = [(4, 4, 2, 128), (5, 9, 3, 128), (8, 8, 4, 128), (9, 6, 2, 128), (16, 40, 5, 128), (33, 70, 3, 128), (64, 65, 0, 128), (97, 130, 4, 128),
+             (270, 481, 3, 128), (21, 30, 3, 1), (40, 41, 2, 4), (12, 200, 5, 128), (200, 12, 5, 128)]
+    for nr, nc, b, al in cases:
+        shape = (nr, nc) + ((ch,) if ch > 1 else ())
+        data = rng(nr * 1000 + nc).integers(0, 256, shape).astype(dt)
+        parent = vpp.Image2d.from_host(data, pix, border=2, aligned=al)
+        vpp.fill_border_mirror(parent)
+        for onr, onc in ((1 + nr // 2, 1 + nc // 2), (max(nr // 2, b, 1), max(nc // 2 - 1, b, 1))):
+            if b > onr or b > onc:
+                continue
+            a = vpp.Image2d(onr, onc, pix, border=b, aligned=al)
+            f = vpp.Image2d(onr, onc, pix, border=b, aligned=al)
+            for im in (a, f):
+                vpp.fill(im, 77 if ch == 1 else [77] * ch)
+                vpp.fill_border_with_value(im, 33 if ch == 1 else [33] * ch)
+            capi.check(capi.lib.vppb_lowpass_sub2(parent.ptr(), a.ptr(), kind, None))
+            vpp.fill_border_mirror(a)
+            capi.check(capi.lib.vppb_lowpass_sub2_mirror(parent.ptr(), f.ptr(), kind, None))
+            x, y = a.download(with_border=True), f.download(with_border=True)
+            assert np.array_equal(x.view(np.uint8), y.view(np.uint8)), (nr, nc, b, al, onr, onc)
+    # a border wider than the level cannot be mirrored
+    small = vpp.Image2d(3, 3, pix, border=4)
+    big = vpp.Image2d.from_host(rng(1).integers(0, 256, (5, 5) + ((ch,) if ch > 1 else ())).astype(dt), pix, border=2)
+    assert capi.lib.vppb_lowpass_sub2_mirror(big.ptr(), small.ptr(), kind, None) == capi.VPPB_E_BORDER
+
+
 # ------------------------------------------------------------------ FAST9
 def _oracle_fast(img, th, mask=None, mode=0, bs=10, ring=0, want_scores=False):
     o = orc.load()

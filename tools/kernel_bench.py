@@ -88,7 +88,12 @@ for (H, W, tag) in [(1080, 1920, "1080p"), (2160, 3840, "4k")]:
         vpp.fill_border_mirror(x)
     G1 = [vpp.Image2d(h2, w2, "vint2", border=3) for _ in range(n)]
     report("lowpass_sub2_vint2_" + tag, timed(lambda i: capi.lib.vppb_lowpass_sub2(Gi[i].ptr(), G1[i].ptr(), 1, sp), n), 8.0 * H * W + 8.0 * h2 * w2)
-    del Gi, G1, L1, U2
+    report("lowpass_sub2_mirror_u8_" + tag, timed(lambda i: capi.lib.vppb_lowpass_sub2_mirror(U[i].ptr(), L1[i].ptr(), 0, sp), n), 1.0 * H * W + h2 * w2)
+    report("lowpass_sub2_mirror_vint2_" + tag, timed(lambda i: capi.lib.vppb_lowpass_sub2_mirror(Gi[i].ptr(), G1[i].ptr(), 1, sp), n), 8.0 * H * W + 8.0 * h2 * w2)
+    report("scharr_u8_vint2_mirror_" + tag, timed(lambda i: capi.lib.vppb_scharr_u8_mirror(U[i].ptr(), Gi[i].ptr(), 0, sp), n), 9.0 * H * W)
+    P3 = [vpp.Pyramid2d((H, W), 3, 2, pixel="u8", border=3) for _ in range(min(n, 4))]
+    report("pyramid3_u8_update_" + tag, timed(lambda i: P3[i % len(P3)].update(U[i], sp), n), 2.0 * H * W + 1.25 * (H * W + h2 * w2), "copy+mirror, 2 x level+mirror: 3 launches")
+    del Gi, G1, L1, U2, P3
     # fast9: whole call (detect + scan + emit + count read-back) through the C-ABI with preallocated buffers
     from vpp_b200.ops import _DeviceBuffer
 

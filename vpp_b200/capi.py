@@ -88,6 +88,7 @@ PROTOTYPES = {
     "vppb_pw_add_i32": (C.c_int, [_IMG, _IMG, _IMG, _VP]),
     "vppb_fill": (C.c_int, [_IMG, _VP, C.c_int, _VP]),
     "vppb_copy2d": (C.c_int, [_IMG, _IMG, C.c_int, _VP]),
+    "vppb_copy2d_mirror": (C.c_int, [_IMG, _IMG, _VP]),
     "vppb_fill_border_value": (C.c_int, [_IMG, _VP, _VP]),
     "vppb_fill_border_mirror": (C.c_int, [_IMG, _VP]),
     "vppb_fill_border_closest": (C.c_int, [_IMG, _VP]),
@@ -96,7 +97,9 @@ PROTOTYPES = {
     "vppb_box5x5_i32": (C.c_int, [_IMG, _IMG, _VP]),
     "vppb_box5x5_u8": (C.c_int, [_IMG, _IMG, _VP]),
     "vppb_scharr_u8": (C.c_int, [_IMG, _IMG, C.c_int, _VP]),
+    "vppb_scharr_u8_mirror": (C.c_int, [_IMG, _IMG, C.c_int, _VP]),
     "vppb_lowpass_sub2": (C.c_int, [_IMG, _IMG, C.c_int, _VP]),
+    "vppb_lowpass_sub2_mirror": (C.c_int, [_IMG, _IMG, C.c_int, _VP]),
     "vppb_fast9_workspace_bytes": (_I64, [_I32, _I32, _I32]),
     "vppb_fast9_u8": (C.c_int, [_IMG, _I32, _IMG, _I32, _I32, _I32, _VP, _I64, _VP, _VP, _I32, _P(_I32), _VP]),
     "vppb_fast9_scores": (C.c_int, [_IMG, _I32, _VP, _I32, _VP, _VP]),

@@ -6,6 +6,8 @@
 // horizontal taps sit CS = 3 bytes apart.  Tiles are staged in shared memory by TMA
 // (cp.async.bulk.tensor.2d + mbarrier); see k_box5_bytes_tma below for the two-phase scheme.
 #include "common.cuh"
+
+#include <atomic>
 #include "tma.cuh"
 
 namespace vppb {
@@ -17,7 +19,8 @@ typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuin
 
 int encode_tensor_map_2d(CUtensorMap* map, void* origin, CUtensorMapDataType elem, int elem_bytes, uint64_t width,
                          uint64_t height, uint64_t pitch, uint32_t box_w, uint32_t box_h) {
-  static PFN_tmapEncodeTiled fn = nullptr;
+  static std::atomic<PFN_tmapEncodeTiled> cached{nullptr};
+  PFN_tmapEncodeTiled fn = cached.load(std::memory_order_acquire);
   if (!fn) {
     void* p = nullptr;
     cudaDriverEntryPointQueryResult q;
@@ -27,6 +30,7 @@ int encode_tensor_map_2d(CUtensorMap* map, void* origin, CUtensorMapDataType ele
       return VPPB_E_CUDA;
     }
     fn = reinterpret_cast<PFN_tmapEncodeTiled>(p);
+    cached.store(fn, std::memory_order_release);
   }
   (void)elem_bytes;
   cuuint64_t gdim[2] = {width, height};
@@ -272,11 +276,15 @@ static int box5_bytes(const vppb_img* in, const vppb_img* out, void* stream, con
     const int strips = (rowbytes + BX_OUTW - 1) / BX_OUTW;
     const int row_tiles = (in->nrows + th - 1) / th;
     const int vec_store = (((uintptr_t)out->base % 16) == 0 && (out->pitch % 16) == 0) ? 1 : 0;
-    static bool attr_set[2] = {false, false};
-    if (!attr_set[CS == 3]) {
+    // the opt-in shared-memory size is a per-device function attribute: set it once per device (bit = device ordinal)
+    static std::atomic<unsigned long long> attr_done{0};
+    int dev = 0;
+    VPPB_CUDA(cudaGetDevice(&dev));
+    const unsigned long long bit = 1ULL << (dev & 63);
+    if (!(attr_done.load(std::memory_order_acquire) & bit)) {
       VPPB_CUDA(cudaFuncSetAttribute(k_box5_bytes_tma<CS, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, BoxCfg<16>::SMEM));
       VPPB_CUDA(cudaFuncSetAttribute(k_box5_bytes_tma<CS, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, BoxCfg<8>::SMEM));
-      attr_set[CS == 3] = true;
+      attr_done.fetch_or(bit, std::memory_order_release);
     }
     const int ntiles = strips * row_tiles;
     const int resident = sm_count() * (th == 16 ? 4 : 6);

@@ -1,6 +1,7 @@
 // Library plumbing: error text, device selection, image2d<V> storage in pitched HBM.
 // Layout follows imageNd<V,N>::allocate (reference vpp/core/imageNd.hpp:151-196) with the row
 // alignment raised to 128 B (one L2 line / TMA-friendly) instead of the CPU's 16/32 B.
+#include <atomic>
 #include "common.cuh"
 
 #include <stdarg.h>
@@ -22,16 +23,17 @@ int cuda_fail(cudaError_t e, const char* what) {
 }
 
 int sm_count() {
-  static int cached = 0;
-  if (cached == 0) {
-    int dev = 0, n = 0;
+  static std::atomic<int> cached{0};
+  int n = cached.load(std::memory_order_relaxed);
+  if (n == 0) {
+    int dev = 0;
     if (cudaGetDevice(&dev) == cudaSuccess &&
         cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
-      cached = n;
+      cached.store(n, std::memory_order_relaxed);
     else
       return 148;
   }
-  return cached;
+  return n;
 }
 
 }  // namespace vppb

@@ -345,6 +345,64 @@ int vppb_copy2d(const vppb_img* src, const vppb_img* dst, int with_border, void*
   return copy_rect(s, src->pitch, d, dst->pitch, src->nrows + 2 * b, (long long)(src->ncols + 2 * b) * e, as_stream(stream));
 }
 
+// copy(src, dst) + fill_border_mirror(dst) in one launch: the border pixels of dst are read straight from the
+// mirrored position in src (the same value dst's domain receives), so nothing depends on the copy having landed.
+// Work items: rows*nvec 16-byte vectors, then rows*tail single bytes, then one item per border pixel of dst.
+__global__ void __launch_bounds__(kThreads) k_copy_mirror(Img src, Img dst, int nvec, int tail, int elem) {
+  const int b = dst.border, nr = dst.nrows, nc = dst.ncols;
+  const long long n_vec = (long long)nr * nvec, n_tail = (long long)nr * tail;
+  const long long wfull = nc + 2LL * b, n_top = (long long)b * wfull, n_side = (long long)nr * b;
+  const long long total = n_vec + n_tail + 2 * n_top + 2 * n_side;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    if (i < n_vec) {
+      const long long r = i / nvec;
+      const int k = (int)(i - r * nvec);
+      st_stream(reinterpret_cast<int4*>(dst.base + r * dst.pitch + (long long)k * 16),
+                ld_stream(reinterpret_cast<const int4*>(src.base + r * src.pitch + (long long)k * 16)));
+    } else if (i < n_vec + n_tail) {
+      const long long j = i - n_vec, r = j / tail;
+      const long long off = (long long)nvec * 16 + (j - r * tail);
+      dst.base[r * dst.pitch + off] = src.base[r * src.pitch + off];
+    } else {
+      long long j = i - n_vec - n_tail;
+      int r, c;
+      if (j < n_top) { r = (int)(j / wfull) - b; c = (int)(j % wfull) - b; }
+      else if (j < 2 * n_top) { j -= n_top; r = nr + (int)(j / wfull); c = (int)(j % wfull) - b; }
+      else if (j < 2 * n_top + n_side) { j -= 2 * n_top; r = (int)(j / b); c = (int)(j % b) - b; }
+      else { j -= 2 * n_top + n_side; r = (int)(j / b); c = nc + (int)(j % b); }
+      const int sr = r < 0 ? -r - 1 : (r >= nr ? 2 * nr - r - 1 : r);  // fill.hh:59-82
+      const int sc = c < 0 ? -c - 1 : (c >= nc ? 2 * nc - c - 1 : c);
+      const unsigned char* s = src.base + (long long)sr * src.pitch + (long long)sc * elem;
+      unsigned char* d = dst.base + (long long)r * dst.pitch + (long long)c * elem;
+      for (int k = 0; k < elem; k++) d[k] = s[k];
+    }
+  }
+}
+
+int vppb_copy2d_mirror(const vppb_img* src, const vppb_img* dst, void* stream) {
+  VPPB_REQUIRE(src && dst && src->base && dst->base, VPPB_E_ARG, "vppb_copy2d_mirror: NULL image");
+  VPPB_REQUIRE(src->elem_bytes == dst->elem_bytes && src->elem_bytes <= 64, VPPB_E_ARG, "vppb_copy2d_mirror: element sizes differ");
+  VPPB_REQUIRE(same_domain(src, dst), VPPB_E_ARG, "vppb_copy2d_mirror: needs equal domains");
+  VPPB_REQUIRE(dst->border <= dst->nrows && dst->border <= dst->ncols, VPPB_E_BORDER, "vppb_copy2d_mirror: border %d larger than the image",
+               dst->border);
+  const long long wbytes = (long long)src->ncols * src->elem_bytes;
+  const bool al = ((uintptr_t)src->base % 16) == 0 && ((uintptr_t)dst->base % 16) == 0 && (src->pitch % 16) == 0 && (dst->pitch % 16) == 0;
+  if (!al || src->base == dst->base) {  // views / odd alignments: the two separate steps
+    if (src->base != dst->base) {
+      int rc = vppb_copy2d(src, dst, 0, stream);
+      if (rc != VPPB_OK) return rc;
+    }
+    return fill_border(dst, 1, nullptr, stream);
+  }
+  const int nvec = (int)(wbytes / 16), tail = (int)(wbytes - (long long)nvec * 16);
+  const long long b = dst->border;
+  const long long total = (long long)src->nrows * (nvec + tail) + 2 * b * (dst->ncols + 2 * b) + 2 * b * dst->nrows;
+  if (total <= 0) return VPPB_OK;
+  k_copy_mirror<<<stream_grid(total), kThreads, 0, as_stream(stream)>>>(view(src), view(dst), nvec, tail, src->elem_bytes);
+  VPPB_LAUNCH_CHECK("vppb_copy2d_mirror");
+  return VPPB_OK;
+}
+
 int vppb_fill_border_value(const vppb_img* img, const void* value, void* stream) {
   VPPB_REQUIRE(value, VPPB_E_ARG, "vppb_fill_border_value: NULL value");
   return fill_border(img, 0, value, stream);

@@ -18,11 +18,42 @@ namespace vppb {
 // results leave as four 16-byte stores (a warp writes 2 KB contiguous).  Output-dominated: 1 B read,
 // 8 B written per pixel.
 __device__ __forceinline__ int byte_of(uint32_t w, int k) { return (int)((w >> (8 * k)) & 0xFFu); }
+__device__ __forceinline__ int mirror_idx(int i, int n) { return i < 0 ? -i - 1 : (i >= n ? 2 * n - i - 1 : i); }
+
+// one pixel, byte loads (scharr.hh:64-83), stored at out(orow, ocol)
+template <bool AS_FLOAT>
+__device__ __forceinline__ void scharr_px(const Img& in, const Img& out, int r, int c, int orow, int ocol) {
+  const unsigned char* r1 = row_ptr<unsigned char>(in, r - 1) + c - 1;
+  const unsigned char* r2 = row_ptr<unsigned char>(in, r) + c - 1;
+  const unsigned char* r3 = row_ptr<unsigned char>(in, r + 1) + c - 1;
+  const int a = 3 * (int)r3[0] + 10 * (int)r3[1] + 3 * (int)r3[2] - 3 * (int)r1[0] - 10 * (int)r1[1] - 3 * (int)r1[2];
+  const int b = 3 * (int)r1[2] + 10 * (int)r2[2] + 3 * (int)r3[2] - 3 * (int)r1[0] - 10 * (int)r2[0] - 3 * (int)r3[0];
+  const float fa = __fdiv_rn((float)a, 32.f), fb = __fdiv_rn((float)b, 32.f);
+  if (AS_FLOAT) reinterpret_cast<float2*>(row_ptr<unsigned char>(out, orow))[ocol] = make_float2(fa, fb);
+  else reinterpret_cast<int2*>(row_ptr<unsigned char>(out, orow))[ocol] = make_int2((int)fa, (int)fb);  // trunc toward 0
+}
+
+// Border pixel number j of `out` (frame of width mb), filled as fill_border_mirror would: the gradient at the
+// mirrored domain position, recomputed from `in` so the item does not depend on any other thread's store.
+template <bool AS_FLOAT>
+__device__ __forceinline__ void scharr_border_item(const Img& in, const Img& out, long long j, int mb) {
+  const int nr = out.nrows, nc = out.ncols;
+  const long long wfull = nc + 2LL * mb, n_top = (long long)mb * wfull, n_side = (long long)nr * mb;
+  int r, c;
+  if (j < n_top) { r = (int)(j / wfull) - mb; c = (int)(j % wfull) - mb; }
+  else if (j < 2 * n_top) { j -= n_top; r = nr + (int)(j / wfull); c = (int)(j % wfull) - mb; }
+  else if (j < 2 * n_top + n_side) { j -= 2 * n_top; r = (int)(j / mb); c = (int)(j % mb) - mb; }
+  else { j -= 2 * n_top + n_side; r = (int)(j / mb); c = nc + (int)(j % mb); }
+  scharr_px<AS_FLOAT>(in, out, mirror_idx(r, nr), mirror_idx(c, nc), r, c);
+}
+__host__ __device__ __forceinline__ long long border_items(int nr, int nc, int mb) { return 2LL * mb * (nc + 2LL * mb) + 2LL * nr * mb; }
 
 template <bool AS_FLOAT>
-__global__ void __launch_bounds__(256) k_scharr_u8_v8(Img in, Img out, int groups_per_row) {
+__global__ void __launch_bounds__(256) k_scharr_u8_v8(Img in, Img out, int groups_per_row, int mb) {
   const long long total = (long long)out.nrows * groups_per_row;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+  const long long n_border = border_items(out.nrows, out.ncols, mb);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total + n_border; i += (long long)gridDim.x * blockDim.x) {
+    if (i >= total) { scharr_border_item<AS_FLOAT>(in, out, i - total, mb); continue; }
     const int r = (int)(i / groups_per_row);
     const int c0 = (int)(i - (long long)r * groups_per_row) * 8;
     int px[3][10];  // columns c0-1 .. c0+8
@@ -64,18 +95,13 @@ __global__ void __launch_bounds__(256) k_scharr_u8_v8(Img in, Img out, int group
 
 // any layout: 1 pixel per thread, byte loads
 template <bool AS_FLOAT>
-__global__ void __launch_bounds__(256) k_scharr_u8(Img in, Img out, int) {
+__global__ void __launch_bounds__(256) k_scharr_u8(Img in, Img out, int mb) {
   const long long total = (long long)out.nrows * out.ncols;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+  const long long n_border = border_items(out.nrows, out.ncols, mb);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total + n_border; i += (long long)gridDim.x * blockDim.x) {
+    if (i >= total) { scharr_border_item<AS_FLOAT>(in, out, i - total, mb); continue; }
     const int r = (int)(i / out.ncols), c = (int)(i - (long long)r * out.ncols);
-    const unsigned char* r1 = row_ptr<unsigned char>(in, r - 1) + c - 1;
-    const unsigned char* r2 = row_ptr<unsigned char>(in, r) + c - 1;
-    const unsigned char* r3 = row_ptr<unsigned char>(in, r + 1) + c - 1;
-    const int a = 3 * (int)r3[0] + 10 * (int)r3[1] + 3 * (int)r3[2] - 3 * (int)r1[0] - 10 * (int)r1[1] - 3 * (int)r1[2];
-    const int b = 3 * (int)r1[2] + 10 * (int)r2[2] + 3 * (int)r3[2] - 3 * (int)r1[0] - 10 * (int)r2[0] - 3 * (int)r3[0];
-    const float fa = __fdiv_rn((float)a, 32.f), fb = __fdiv_rn((float)b, 32.f);
-    if (AS_FLOAT) reinterpret_cast<float2*>(row_ptr<unsigned char>(out, r))[c] = make_float2(fa, fb);
-    else reinterpret_cast<int2*>(row_ptr<unsigned char>(out, r))[c] = make_int2((int)fa, (int)fb);  // trunc toward 0
+    scharr_px<AS_FLOAT>(in, out, r, c, r, c);
   }
 }
 
@@ -95,13 +121,34 @@ __device__ __forceinline__ float lp5(float a, float b, float c, float d, float e
   return __fdiv_rn(s, 16.f);
 }
 
-__device__ __forceinline__ int mirror_idx(int i, int n) { return i < 0 ? -i - 1 : (i >= n ? 2 * n - i - 1 : i); }
+
+// Store out(r, c) = v and, when mb > 0, every border pixel that fill_border_mirror (border.hh mirror rule:
+// border(-1-k) = image(k), border(n+k) = image(n-1-k)) would copy from (r, c): up to 3 rows x 3 columns.
+// Every border pixel has exactly one source pixel, so a kernel in which each output pixel is produced by one
+// thread fills the whole mirror border without races.  `comps`/`k` address one component of a COMPS-vector.
+template <typename T>
+__device__ __forceinline__ void store_mirrored(const Img& out, int r, int c, T v, int mb, int comps = 1, int k = 0) {
+  row_ptr<T>(out, r)[c * comps + k] = v;
+  if (mb <= 0) return;
+  const bool rt = r < mb, rb = r >= out.nrows - mb, cl = c < mb, cr = c >= out.ncols - mb;
+  if (!(rt | rb | cl | cr)) return;  // interior pixel: no border pixel mirrors it
+#pragma unroll
+  for (int a = 0; a < 3; a++) {      // a / b: 0 = the pixel's own row / column, 1 = mirrored above / left, 2 = below / right
+    if (!(a == 0 || (a == 1 ? rt : rb))) continue;
+    T* row = row_ptr<T>(out, a == 0 ? r : (a == 1 ? -1 - r : 2 * out.nrows - 1 - r));
+#pragma unroll
+    for (int b = 0; b < 3; b++) {
+      if (!(b == 0 || (b == 1 ? cl : cr)) || (a == 0 && b == 0)) continue;
+      row[(b == 0 ? c : (b == 1 ? -1 - c : 2 * out.ncols - 1 - c)) * comps + k] = v;
+    }
+  }
+}
 
 // One thread per output pixel component.  out(r,c) = LP(mirror(2r), mirror(2c)); LP's V pass reads
 // H rows with mirrored indices (the mirror-filled temp of pyramid.hh:36), H reads in(row, x-2..x+2)
 // from the image's own (caller-filled) column border.
 template <int KIND>
-__global__ void __launch_bounds__(256) k_lowpass_sub2(Img in, Img out, int step) {
+__global__ void __launch_bounds__(256) k_lowpass_sub2(Img in, Img out, int step, int mb) {
   typedef typename LpT<KIND>::elem E;
   typedef typename LpT<KIND>::acc A;
   constexpr int COMPS = LpT<KIND>::comps;
@@ -121,7 +168,7 @@ __global__ void __launch_bounds__(256) k_lowpass_sub2(Img in, Img out, int step)
       h[d] = (A)(E)lp5((A)row[(x - 2) * COMPS + k], (A)row[(x - 1) * COMPS + k], (A)row[x * COMPS + k], (A)row[(x + 1) * COMPS + k],
                        (A)row[(x + 2) * COMPS + k]);
     }
-    row_ptr<E>(out, r)[c * COMPS + k] = (E)lp5(h[0], h[1], h[2], h[3], h[4]);
+    store_mirrored<E>(out, r, c, (E)lp5(h[0], h[1], h[2], h[3], h[4]), mb, COMPS, k);
   }
 }
 
@@ -129,11 +176,46 @@ __global__ void __launch_bounds__(256) k_lowpass_sub2(Img in, Img out, int step)
 // bottom, as the mirror-filled H temp of pyramid.hh:36) are fetched as 4 + 16 + 4 bytes each, H is
 // evaluated at the 8 even columns per row, V on the H columns; ~1.3 loads per output instead of 25.
 // Covers the outputs whose centre (2r, 2c) lies inside the parent; the mirrored last row / column of
-// an even-sized parent (centre on an odd pixel) is left to k_lowpass_sub2_edges.
-__global__ void __launch_bounds__(128) k_lowpass_sub2_u8_fast(Img in, Img out, int fast_rows, int fast_cols, int groups_per_row) {
+// an even-sized parent (centre on an odd pixel) is handled by the tail work items of the same launch.
+// One 8-byte group of row `tr` (a domain row or one of its mirrored border rows) + the mirrored border columns.
+__device__ __forceinline__ void put_u8x8(const Img& out, int tr, int c0, uint32_t lo, uint32_t hi, int valid_cols, int mb) {
+  unsigned char* rowp = row_ptr<unsigned char>(out, tr);
+  if (c0 + 8 <= valid_cols) *reinterpret_cast<uint2*>(rowp + c0) = make_uint2(lo, hi);
+  else
+    for (int k = 0; k < 8 && c0 + k < valid_cols; k++) rowp[c0 + k] = (unsigned char)((k < 4 ? lo >> (8 * k) : hi >> (8 * (k - 4))) & 0xFF);
+  if (mb > 0 && (c0 < mb || c0 + 8 > out.ncols - mb)) {
+    for (int k = 0; k < 8 && c0 + k < valid_cols; k++) {
+      const int c = c0 + k;
+      const unsigned char v = (unsigned char)((k < 4 ? lo >> (8 * k) : hi >> (8 * (k - 4))) & 0xFF);
+      if (c < mb) rowp[-1 - c] = v;
+      if (c >= out.ncols - mb) rowp[2 * out.ncols - 1 - c] = v;
+    }
+  }
+}
+
+// Work items [0, total) are 8 x 2 output groups; items [total, total + n_row + n_col) are the outputs of the
+// mirrored last row / last column of an even-sized parent (centre on an odd pixel), one per thread, with the
+// arithmetic of k_lowpass_sub2<0>.  mb > 0: the mirror border of `out` is written too (store_mirrored).
+__global__ void __launch_bounds__(128) k_lowpass_sub2_u8_fast(Img in, Img out, int fast_rows, int fast_cols, int groups_per_row, int mb) {
   const int row_pairs = (fast_rows + 1) / 2;
   const long long total = (long long)row_pairs * groups_per_row;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+  const int n_row = out.nrows > fast_rows ? out.ncols : 0;
+  const int n_col = out.ncols > fast_cols ? out.nrows - (n_row ? 1 : 0) : 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total + n_row + n_col; i += (long long)gridDim.x * blockDim.x) {
+    if (i >= total) {
+      const int e = (int)(i - total);
+      const int r = e < n_row ? out.nrows - 1 : e - n_row;
+      const int c = e < n_row ? e : out.ncols - 1;
+      const int y = mirror_idx(r * 2, in.nrows), x = mirror_idx(c * 2, in.ncols);
+      int h[5];
+#pragma unroll
+      for (int d = 0; d < 5; d++) {
+        const unsigned char* row = row_ptr<unsigned char>(in, mirror_idx(y - 2 + d, in.nrows));
+        h[d] = lp5((int)row[x - 2], (int)row[x - 1], (int)row[x], (int)row[x + 1], (int)row[x + 2]);
+      }
+      store_mirrored<unsigned char>(out, r, c, (unsigned char)lp5(h[0], h[1], h[2], h[3], h[4]), mb);
+      continue;
+    }
     const int rp = (int)(i / groups_per_row), g = (int)(i - (long long)rp * groups_per_row);
     const int r0 = 2 * rp, c0 = 8 * g;
     int H[7][8];
@@ -162,29 +244,12 @@ __global__ void __launch_bounds__(128) k_lowpass_sub2_u8_fast(Img in, Img out, i
         const int v = (H[2 * t][k] + 4 * H[2 * t + 1][k] + 6 * H[2 * t + 2][k] + 4 * H[2 * t + 3][k] + H[2 * t + 4][k]) >> 4;  // pyramid.hh:50-55
         if (k < 4) lo |= (uint32_t)v << (8 * k); else hi |= (uint32_t)v << (8 * (k - 4));
       }
-      unsigned char* dst = row_ptr<unsigned char>(out, r) + c0;
-      if (c0 + 8 <= fast_cols) *reinterpret_cast<uint2*>(dst) = make_uint2(lo, hi);
-      else
-        for (int k = 0; k < 8 && c0 + k < fast_cols; k++) dst[k] = (unsigned char)((k < 4 ? lo >> (8 * k) : hi >> (8 * (k - 4))) & 0xFF);
+      put_u8x8(out, r, c0, lo, hi, fast_cols, mb);
+      if (mb > 0) {
+        if (r < mb) put_u8x8(out, -1 - r, c0, lo, hi, fast_cols, mb);
+        if (r >= out.nrows - mb) put_u8x8(out, 2 * out.nrows - 1 - r, c0, lo, hi, fast_cols, mb);
+      }
     }
-  }
-}
-
-// outputs of the last row (if has_row) and last column (if has_col): same arithmetic as k_lowpass_sub2<0>
-__global__ void __launch_bounds__(128) k_lowpass_sub2_edges_u8(Img in, Img out, int has_row, int has_col) {
-  const int n_row = has_row ? out.ncols : 0;
-  const int n_col = has_col ? out.nrows - (has_row ? 1 : 0) : 0;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_row + n_col; i += gridDim.x * blockDim.x) {
-    const int r = i < n_row ? out.nrows - 1 : i - n_row;
-    const int c = i < n_row ? i : out.ncols - 1;
-    const int y = mirror_idx(r * 2, in.nrows), x = mirror_idx(c * 2, in.ncols);
-    int h[5];
-#pragma unroll
-    for (int d = 0; d < 5; d++) {
-      const unsigned char* row = row_ptr<unsigned char>(in, mirror_idx(y - 2 + d, in.nrows));
-      h[d] = lp5((int)row[x - 2], (int)row[x - 1], (int)row[x], (int)row[x + 1], (int)row[x + 2]);
-    }
-    row_ptr<unsigned char>(out, r)[c] = (unsigned char)lp5(h[0], h[1], h[2], h[3], h[4]);
   }
 }
 
@@ -196,7 +261,7 @@ template <> struct vec2_of<int> { typedef int2 type; typedef int4 type4; };
 template <> struct vec2_of<float> { typedef float2 type; typedef float4 type4; };
 
 template <int KIND>
-__global__ void __launch_bounds__(256) k_lowpass_sub2_px8(Img in, Img out, int aligned16) {
+__global__ void __launch_bounds__(256) k_lowpass_sub2_px8(Img in, Img out, int aligned16, int mb) {
   typedef typename LpT<KIND>::acc A;
   typedef typename vec2_of<A>::type V2;
   typedef typename vec2_of<A>::type4 V4;
@@ -223,7 +288,7 @@ __global__ void __launch_bounds__(256) k_lowpass_sub2_px8(Img in, Img out, int a
     V2 o;
     o.x = lp5(hx[0], hx[1], hx[2], hx[3], hx[4]);
     o.y = lp5(hy[0], hy[1], hy[2], hy[3], hy[4]);
-    reinterpret_cast<V2*>(row_ptr<unsigned char>(out, r))[c] = o;
+    store_mirrored<V2>(out, r, c, o, mb);
   }
 }
 
@@ -240,7 +305,7 @@ using namespace vppb;
 
 extern "C" {
 
-int vppb_scharr_u8(const vppb_img* in, const vppb_img* out, int as_float, void* stream) {
+static int scharr_u8(const vppb_img* in, const vppb_img* out, int as_float, int mirror, void* stream) {
   VPPB_REQUIRE(in && out && in->base && out->base, VPPB_E_ARG, "vppb_scharr_u8: NULL image");
   VPPB_REQUIRE(in->elem_bytes == 1 && out->elem_bytes == 8, VPPB_E_ARG, "vppb_scharr_u8: needs u8 input and 8-byte output elements");
   VPPB_REQUIRE(in->nrows >= out->nrows && in->ncols >= out->ncols, VPPB_E_ARG, "vppb_scharr_u8: input smaller than output");
@@ -248,23 +313,29 @@ int vppb_scharr_u8(const vppb_img* in, const vppb_img* out, int as_float, void* 
   VPPB_REQUIRE(((uintptr_t)out->base % 8) == 0 && (out->pitch % 8) == 0, VPPB_E_ARG, "vppb_scharr_u8: output not 8-byte aligned");
   // fast path: 8-byte aligned input rows with >= 4 addressable bytes left of column 0 and enough row to the right
   // of the last group (the library layout pads rows to 128 B), 16-byte aligned output rows
+  const int mb = mirror ? out->border : 0;
+  VPPB_REQUIRE(mb <= out->nrows && mb <= out->ncols, VPPB_E_BORDER, "vppb_scharr_u8_mirror: border %d larger than the output image", mb);
+  const long long nb = border_items(out->nrows, out->ncols, mb);
   const int groups = (out->ncols + 7) / 8;
   const bool fast = ((uintptr_t)in->base % 8) == 0 && (in->pitch % 8) == 0 && ((uintptr_t)out->base % 16) == 0 && (out->pitch % 16) == 0 &&
                     in->align >= 16 && in->border >= 1 && (long long)groups * 8 + 4 <= in->pitch - (long long)in->align;
   if (fast) {
-    const int grid = grid_for((long long)out->nrows * groups, 256);
-    if (as_float) k_scharr_u8_v8<true><<<grid, 256, 0, as_stream(stream)>>>(view(in), view(out), groups);
-    else k_scharr_u8_v8<false><<<grid, 256, 0, as_stream(stream)>>>(view(in), view(out), groups);
+    const int grid = grid_for((long long)out->nrows * groups + nb, 256);
+    if (as_float) k_scharr_u8_v8<true><<<grid, 256, 0, as_stream(stream)>>>(view(in), view(out), groups, mb);
+    else k_scharr_u8_v8<false><<<grid, 256, 0, as_stream(stream)>>>(view(in), view(out), groups, mb);
   } else {
-    const int grid = grid_for((long long)out->nrows * out->ncols, 256);
-    if (as_float) k_scharr_u8<true><<<grid, 256, 0, as_stream(stream)>>>(view(in), view(out), 0);
-    else k_scharr_u8<false><<<grid, 256, 0, as_stream(stream)>>>(view(in), view(out), 0);
+    const int grid = grid_for((long long)out->nrows * out->ncols + nb, 256);
+    if (as_float) k_scharr_u8<true><<<grid, 256, 0, as_stream(stream)>>>(view(in), view(out), mb);
+    else k_scharr_u8<false><<<grid, 256, 0, as_stream(stream)>>>(view(in), view(out), mb);
   }
   VPPB_LAUNCH_CHECK("vppb_scharr_u8");
   return VPPB_OK;
 }
 
-int vppb_lowpass_sub2(const vppb_img* in, const vppb_img* out, int kind, void* stream) {
+int vppb_scharr_u8(const vppb_img* in, const vppb_img* out, int as_float, void* stream) { return scharr_u8(in, out, as_float, 0, stream); }
+int vppb_scharr_u8_mirror(const vppb_img* in, const vppb_img* out, int as_float, void* stream) { return scharr_u8(in, out, as_float, 1, stream); }
+
+static int lowpass_sub2(const vppb_img* in, const vppb_img* out, int kind, int mirror, void* stream) {
   VPPB_REQUIRE(in && out && in->base && out->base, VPPB_E_ARG, "vppb_lowpass_sub2: NULL image");
   VPPB_REQUIRE(kind >= 0 && kind <= 2, VPPB_E_ARG, "vppb_lowpass_sub2: kind %d", kind);
   const int e = kind == 0 ? 1 : 8;
@@ -273,6 +344,8 @@ int vppb_lowpass_sub2(const vppb_img* in, const vppb_img* out, int kind, void* s
   // pyramid.hh:140,154: level size 1 + n/2; any smaller output is a prefix of it
   VPPB_REQUIRE(out->nrows <= 1 + in->nrows / 2 && out->ncols <= 1 + in->ncols / 2, VPPB_E_ARG,
                "vppb_lowpass_sub2: output %dx%d larger than 1+n/2 of input %dx%d", out->nrows, out->ncols, in->nrows, in->ncols);
+  const int mb = mirror ? out->border : 0;
+  VPPB_REQUIRE(mb <= out->nrows && mb <= out->ncols, VPPB_E_BORDER, "vppb_lowpass_sub2_mirror: border %d larger than the output image", mb);
   cudaStream_t st = as_stream(stream);
   const long long items = (long long)out->nrows * out->ncols * (kind == 0 ? 1 : 2);
   const int grid = grid_for(items, 256);
@@ -283,21 +356,23 @@ int vppb_lowpass_sub2(const vppb_img* in, const vppb_img* out, int kind, void* s
     if (fast) {
       const int fast_rows = std::min(out->nrows, (in->nrows + 1) / 2), fast_cols = std::min(out->ncols, (in->ncols + 1) / 2);
       const int groups = (fast_cols + 7) / 8;
-      k_lowpass_sub2_u8_fast<<<grid_for((long long)((fast_rows + 1) / 2) * groups, 128), 128, 0, st>>>(view(in), view(out), fast_rows, fast_cols, groups);
-      const int has_row = out->nrows > fast_rows, has_col = out->ncols > fast_cols;
-      if (has_row || has_col) k_lowpass_sub2_edges_u8<<<grid_for(out->nrows + out->ncols, 128), 128, 0, st>>>(view(in), view(out), has_row, has_col);
+      const long long work = (long long)((fast_rows + 1) / 2) * groups + out->nrows + out->ncols;
+      k_lowpass_sub2_u8_fast<<<grid_for(work, 128), 128, 0, st>>>(view(in), view(out), fast_rows, fast_cols, groups, mb);
     } else {
-      k_lowpass_sub2<0><<<grid, 256, 0, st>>>(view(in), view(out), 2);
+      k_lowpass_sub2<0><<<grid, 256, 0, st>>>(view(in), view(out), 2, mb);
     }
   }
   else {
     const int aligned16 = (((uintptr_t)in->base % 16) == 0 && (in->pitch % 16) == 0) ? 1 : 0;
     const int g2 = grid_for((long long)out->nrows * out->ncols, 256);
-    if (kind == 1) k_lowpass_sub2_px8<1><<<g2, 256, 0, st>>>(view(in), view(out), aligned16);
-    else k_lowpass_sub2_px8<2><<<g2, 256, 0, st>>>(view(in), view(out), aligned16);
+    if (kind == 1) k_lowpass_sub2_px8<1><<<g2, 256, 0, st>>>(view(in), view(out), aligned16, mb);
+    else k_lowpass_sub2_px8<2><<<g2, 256, 0, st>>>(view(in), view(out), aligned16, mb);
   }
   VPPB_LAUNCH_CHECK("vppb_lowpass_sub2");
   return VPPB_OK;
 }
+
+int vppb_lowpass_sub2(const vppb_img* in, const vppb_img* out, int kind, void* stream) { return lowpass_sub2(in, out, kind, 0, stream); }
+int vppb_lowpass_sub2_mirror(const vppb_img* in, const vppb_img* out, int kind, void* stream) { return lowpass_sub2(in, out, kind, 1, stream); }
 
 }  // extern "C"

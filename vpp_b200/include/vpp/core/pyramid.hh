@@ -36,12 +36,18 @@ struct pyramid {
 
   void propagate_level0() {  // pyramid.hh:169-192
     fill_border_mirror(levels_[0]);
-    for (size_t i = 1; i < levels_.size(); i++) {
-      vppb_check(vppb_lowpass_sub2(levels_[i - 1].device_read(), levels_[i].device_write(), internals::lowpass_kind<V>::value, nullptr));
-      fill_border_mirror(levels_[i]);
-    }
+    propagate_from_mirrored_level0();
   }
-  void update(const image_type& in) { copy(in, levels_[0]); propagate_level0(); }  // pyramid.hh:194-198
+  // levels 1.. from a level 0 whose mirror border is already in place: low-pass + subsample + mirror border of
+  // each new level in one launch
+  void propagate_from_mirrored_level0() {
+    for (size_t i = 1; i < levels_.size(); i++)
+      vppb_check(vppb_lowpass_sub2_mirror(levels_[i - 1].device_read(), levels_[i].device_write(), internals::lowpass_kind<V>::value, nullptr));
+  }
+  void update(const image_type& in) {  // pyramid.hh:194-198: copy, mirror, levels
+    vppb_check(vppb_copy2d_mirror(in.device_read(), levels_[0].device_write(), nullptr));
+    propagate_from_mirrored_level0();
+  }
   float factor() const { return factor_; }
   int size() const { return (int)levels_.size(); }
   void swap(pyramid& o) { levels_.swap(o.levels_); std::swap(factor_, o.factor_); }

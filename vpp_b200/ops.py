@@ -106,15 +106,22 @@ class Pyramid2d:
 
     size = __len__
 
-    def propagate_level0(self, stream=None):  # pyramid.hh:169-192
-        fill_border_mirror(self.levels[0], stream)
+    def propagate_level0(self, stream=None, level0_mirrored=False):  # pyramid.hh:169-192
+        if not level0_mirrored:
+            fill_border_mirror(self.levels[0], stream)
         for i in range(1, len(self.levels)):
-            check(lib.vppb_lowpass_sub2(self.levels[i - 1].ptr(), self.levels[i].ptr(), _LP_KIND[self.pixel], stream))
-            fill_border_mirror(self.levels[i], stream)
+            # low-pass + subsample + mirror border of the new level: one launch
+            check(lib.vppb_lowpass_sub2_mirror(self.levels[i - 1].ptr(), self.levels[i].ptr(), _LP_KIND[self.pixel], stream))
 
-    def update(self, img, stream=None):  # pyramid.hh:194-198
-        copy(img, self.levels[0], stream)
-        self.propagate_level0(stream)
+    def update(self, img, stream=None):  # pyramid.hh:194-198: copy, mirror, levels
+        check(lib.vppb_copy2d_mirror(img.ptr(), self.levels[0].ptr(), stream))
+        self.propagate_level0(stream, level0_mirrored=True)
+
+    def update_from_scharr(self, src, stream=None):
+        """scharr(src, pyr[0]); pyr.propagate_level0() — the gradient pyramid of lucas_kanade.hpp:156-157 and
+        video_extruder.hpp:60-61 — with level 0's mirror border written by the Scharr launch itself."""
+        check(lib.vppb_scharr_u8_mirror(src.ptr(), self.levels[0].ptr(), 1 if self.pixel == "vfloat2" else 0, stream))
+        self.propagate_level0(stream, level0_mirrored=True)
 
     def desc_array(self):
         arr = (capi.VppbImg * len(self.levels))()
@@ -223,8 +230,7 @@ def lucas_kanade(i1, i2, keypoints, niterations=21, winsize=11, nscales=3, min_e
     prev = Pyramid2d(i1, nscales, 2, border=border)
     nxt = Pyramid2d(i2, nscales, 2, border=border)
     grad = Pyramid2d((i1.nrows, i1.ncols), nscales, 2, pixel="vint2", border=border)
-    scharr(prev[0], grad[0], stream)
-    grad.propagate_level0(stream)
+    grad.update_from_scharr(prev[0], stream)
     P = capi.VppbLkParams(nlevels=nscales, min_scale=0, winsize=winsize, max_iter=niterations, grad_is_float=0,
                           err_mode=capi.LK_ERR_SAD, gate_on_max_err=0, min_ev=float(int(min_ev)), delta=float(int(delta)),
                           max_err=0.0, factor=2.0, pred_div=float(2 ** nscales))
