@@ -1,0 +1,87 @@
+// box_nbh2d<V, R, C>: the reference's tests/box_nbh2d.cc (point form) and the pixel_wise range form of
+// benchmarks/box_5x5_filter.cc:163-172, against vpp_b200/include/vpp.  Exit code 0 = all asserts held.
+#undef NDEBUG
+#include <cassert>
+#include <cstdio>
+#include <vpp/vpp.hh>
+
+using namespace vpp;
+
+static void test_point_form() {  // tests/box_nbh2d.cc:8-29, statement for statement
+  image2d<int> A(3, 3);
+  auto nbh = box_nbh2d<int, 3, 3>(A, vint2{1, 1});
+
+  fill(A, 1);  // device write after the accessor was made: the accessor must see it
+
+  nbh.for_all([](int& p) { p = 2; });
+  nbh.north() = 3;
+  nbh.east() = 4;
+  nbh.south() = 5;
+  nbh.west() = 6;
+
+  assert(A(0, 0) == 2);
+  assert(A(0, 1) == 3);
+  assert(A(0, 2) == 2);
+
+  assert(A(1, 0) == 6);
+  assert(A(1, 1) == 2);
+  assert(A(1, 2) == 4);
+
+  assert(A(2, 0) == 2);
+  assert(A(2, 1) == 5);
+  assert(A(2, 2) == 2);
+
+  // and the device sees what the accessor wrote on the host
+  image2d<int> B(3, 3);
+  pixel_wise(B, A) | [=] VPP_KERNEL(int& b, int& a) { b = a * 10; };
+  assert(B(1, 2) == 40 && B(2, 1) == 50 && B(0, 0) == 20);
+}
+
+static void test_range_form() {  // benchmarks/box_5x5_filter.cc:163-172
+  image2d<int> A(40, 50, _border = 2), B(40, 50), B2(40, 50), N4(40, 50), V(40, 50);
+  for (auto p : A.domain()) A(p) = (p[0] * 31 + p[1] * 17) % 1000;
+  fill_border_mirror(A);
+
+  auto Anbh = box_nbh2d<int, 5, 5>(A);
+  pixel_wise(B, Anbh) | [=] VPP_KERNEL(int& b, box_nbh2d_kernel<int, 5, 5>& a_nbh) {
+    int sum = 0;
+    a_nbh.for_all([&sum](int& n) { sum += n; });
+    b = sum / 25;
+  };
+  // the same filter through relative_access (benchmarks/box_5x5_filter2.cc:71-81): identical, border pixels included
+  pixel_wise(B2, relative_access(A)) | [=] VPP_KERNEL(int& b, relative_access_kernel<int> a) {
+    int sum = 0;
+    for (int i = -2; i <= 2; i++)
+      for (int j = -2; j <= 2; j++) sum += a(i, j);
+    b = sum / 25;
+  };
+  for (auto p : B.domain()) assert(B(p) == B2(p));
+  for (int r = 0; r < 40; r++)
+    for (int c = 0; c < 50; c++) {
+      int sum = 0;
+      for (int d = -2; d <= 2; d++)
+        for (int e = -2; e <= 2; e++) sum += A(r + d, c + e);  // border rows / columns are addressable on the host mirror
+      assert(B(r, c) == sum / 25);
+    }
+
+  // named neighbours, accessor taken by value, 3x3 window
+  pixel_wise(N4, box_nbh2d<int, 3, 3>(A)) | [=] VPP_KERNEL(int& o, box_nbh2d_kernel<int, 3, 3> n) {
+    o = n.north() * 1000 + n.south() * 100 + n.east() * 10 + n.west() - n(0, 0);
+  };
+  for (int r = 0; r < 40; r++)
+    for (int c = 0; c < 50; c++) assert(N4(r, c) == A(r - 1, c) * 1000 + A(r + 1, c) * 100 + A(r, c + 1) * 10 + A(r, c - 1) - A(r, c));
+
+  // writing through the accessor: every pixel stamps itself (window 1x1 reaches only the centre)
+  fill(V, 0);
+  pixel_wise(box_nbh2d<int, 1, 1>(V), V.domain()) | [=] VPP_KERNEL(box_nbh2d_kernel<int, 1, 1>& n, vint2 p) {
+    n.for_all([p](int& v) { v = p[0] * 100 + p[1]; });
+  };
+  for (auto p : V.domain()) assert(V(p) == p[0] * 100 + p[1]);
+}
+
+int main() {
+  test_point_form();
+  test_range_form();
+  std::printf("ALL OK\n");
+  return 0;
+}

@@ -10,7 +10,7 @@ BUILD = os.path.join(ROOT, "tests", "cpp", "_build")
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ["core_tests", "algo_tests"])
+@pytest.mark.parametrize("name", ["core_tests", "algo_tests", "nbh_tests"])
 def test_cpp_binary(gpu, name):
     exe = os.path.join(BUILD, name)
     assert os.path.exists(exe), "build.sh did not produce %s" % exe
@@ -19,5 +19,5 @@ def test_cpp_binary(gpu, name):
 
 
 def test_cpp_binaries_are_built(built):
-    for name in ("core_tests", "algo_tests"):
+    for name in ("core_tests", "algo_tests", "nbh_tests"):
         assert os.path.exists(os.path.join(BUILD, name))

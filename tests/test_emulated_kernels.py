@@ -45,6 +45,7 @@ def emu(built):
     for f in glob.glob(UBSAN_LOG + "*"):
         os.remove(f)
     os.environ["UBSAN_OPTIONS"] = "log_path=%s" % UBSAN_LOG  # read when the sanitizer runtime inside the .so initialises
+    os.environ.setdefault("VPPB_EMU_LOG", os.path.join(ROOT, "tests", "emu", "_build", "emu_fail.log"))  # why the emulator aborted, if it does
     lib = C.CDLL(path)
     I, VP = C.POINTER(EImg), C.c_void_p
     for name, args in {"vppb_pw_add_i32": [I, I, I, VP], "vppb_fill": [I, VP, C.c_int, VP], "vppb_copy2d": [I, I, C.c_int, VP],

@@ -36,6 +36,56 @@ struct relative_access_kernel {
   VPP_HD V& operator()(vint2 d) const { return (*this)(d[0], d[1]); }
 };
 
+// ---- box_nbh2d<V, R, C>: the legacy neighbourhood accessor (its header is gone from the reference at this commit,
+// superseded by relative_access; the API is the one its users still spell: tests/box_nbh2d.cc:8-29,
+// benchmarks/box_5x5_filter.cc:163-172).  Here it is a thin alias over the same accessor as relative_access.
+//   range form:  auto Anbh = box_nbh2d<int, 5, 5>(A);
+//                pixel_wise(B, Anbh) | [=] VPP_KERNEL (int& b, box_nbh2d_kernel<int, 5, 5>& n) { int s = 0; n.for_all([&s](int& v) { s += v; }); b = s / 25; };
+//   point form:  auto n = box_nbh2d<int, 3, 3>(A, vint2(1, 1)); n.for_all(f); n.north() = 3;   (host access, lazy mirror)
+// As in the reference nothing checks bounds: the image needs a border >= R/2, C/2 (filled by the caller).
+template <typename V, int R, int C>
+struct box_nbh2d_kernel {  // what a pixel_wise kernel receives for a box_nbh2d range
+  V* p;
+  int pitch;
+  VPP_HD V& operator()(int dr, int dc) const { return *(V*)((char*)p + (long long)dr * pitch + (long long)dc * (long long)sizeof(V)); }
+  VPP_HD V& operator()(vint2 d) const { return (*this)(d[0], d[1]); }
+  VPP_HD V& north() const { return (*this)(-1, 0); }
+  VPP_HD V& south() const { return (*this)(1, 0); }
+  VPP_HD V& east() const { return (*this)(0, 1); }
+  VPP_HD V& west() const { return (*this)(0, -1); }
+  template <typename F>
+  VPP_HD void for_all(F f) const {  // row-major over the R x C window centred on the pixel
+    for (int dr = -(R / 2); dr <= R / 2; dr++)
+      for (int dc = -(C / 2); dc <= C / 2; dc++) f((*this)(dr, dc));
+  }
+};
+template <typename V, int R, int C>
+struct box_nbh2d_range {
+  vint2 first_point_coordinates() const { return img.first_point_coordinates(); }
+  vint2 last_point_coordinates() const { return img.last_point_coordinates(); }
+  imageNd<V, 2> img;  // shares the buffer
+};
+template <typename V, int R, int C>
+struct box_nbh2d_point {  // host-side accessor around one pixel; every access goes through the image's lazy host mirror
+  imageNd<V, 2> img;
+  vint2 p;
+  V& operator()(int dr, int dc) { return img(p[0] + dr, p[1] + dc); }
+  V& operator()(vint2 d) { return (*this)(d[0], d[1]); }
+  V& north() { return (*this)(-1, 0); }
+  V& south() { return (*this)(1, 0); }
+  V& east() { return (*this)(0, 1); }
+  V& west() { return (*this)(0, -1); }
+  template <typename F>
+  void for_all(F f) {
+    for (int dr = -(R / 2); dr <= R / 2; dr++)
+      for (int dc = -(C / 2); dc <= C / 2; dc++) f((*this)(dr, dc));
+  }
+};
+template <typename V, int R, int C>
+box_nbh2d_range<V, R, C> box_nbh2d(const imageNd<V, 2>& img) { return box_nbh2d_range<V, R, C>{img}; }
+template <typename V, int R, int C>
+box_nbh2d_point<V, R, C> box_nbh2d(const imageNd<V, 2>& img, vint2 p) { return box_nbh2d_point<V, R, C>{img, p}; }
+
 namespace pixel_wise_internals {
 
 // device-side views of the pixel_wise arguments
@@ -59,6 +109,20 @@ template <typename V> image_view<V> make_view(const imageNd<V, 2>& i) { const vp
 inline box_view make_view(const box2d&) { return box_view(); }
 template <typename V> relative_view<V> make_view(const relative_access_<imageNd<V, 2>>& r) {
   const vppb_img* d = r.img.device_write(); return relative_view<V>{(unsigned char*)d->base, d->pitch}; }
+template <typename V, int R, int C>
+struct nbh_view {
+  unsigned char* base; int pitch;
+  VPP_HD box_nbh2d_kernel<V, R, C> at(int r, int c) const {
+    return box_nbh2d_kernel<V, R, C>{(V*)(base + (long long)r * pitch + (long long)c * (long long)sizeof(V)), pitch};
+  }
+};
+template <typename V, int R, int C> nbh_view<V, R, C> make_view(const box_nbh2d_range<V, R, C>& r) {
+  const vppb_img* d = r.img.device_write(); return nbh_view<V, R, C>{(unsigned char*)d->base, d->pitch}; }
+
+// The kernel's arguments are handed over as lvalues, so that it may take an accessor by value, by const& or - as the
+// reference's users of box_nbh2d do (`auto& a_nbh`) - by non-const reference; pixel references stay references.
+template <typename F, typename... A>
+VPP_HD void invoke_lv(F& fun, A&&... a) { fun(a...); }
 
 #if defined(__CUDACC__)
 enum { MODE_PARALLEL = 0, MODE_ROW_THREADS = 1, MODE_COL_THREADS = 2, MODE_SERIAL = 3 };
@@ -70,26 +134,26 @@ __global__ void pixel_wise_kernel(F fun, int r0, int c0, int nr, int nc, int mod
   if (mode == MODE_PARALLEL) {
     for (long long i = tid; i < (long long)nr * nc; i += stride) {
       const int r = r0 + (int)(i / nc), c = c0 + (int)(i % nc);
-      fun(views.at(r, c)...);
+      invoke_lv(fun, views.at(r, c)...);
     }
   } else if (mode == MODE_ROW_THREADS) {  // rows independent, columns in order (process_row, pixel_wise.hpp:69-81)
     for (long long i = tid; i < nr; i += stride)
       for (int k = 0; k < nc; k++) {
         const int c = cols_desc ? c0 + nc - 1 - k : c0 + k;
-        fun(views.at(r0 + (int)i, c)...);
+        invoke_lv(fun, views.at(r0 + (int)i, c)...);
       }
   } else if (mode == MODE_COL_THREADS) {  // columns independent, rows in order
     for (long long i = tid; i < nc; i += stride)
       for (int k = 0; k < nr; k++) {
         const int r = rows_desc ? r0 + nr - 1 - k : r0 + k;
-        fun(views.at(r, c0 + (int)i)...);
+        invoke_lv(fun, views.at(r, c0 + (int)i)...);
       }
   } else if (tid == 0) {  // pixel_wise_row_first_serial_2d (pixel_wise.hpp:105-126)
     for (int kr = 0; kr < nr; kr++)
       for (int kc = 0; kc < nc; kc++) {
         const int r = rows_desc ? r0 + nr - 1 - kr : r0 + kr;
         const int c = cols_desc ? c0 + nc - 1 - kc : c0 + kc;
-        fun(views.at(r, c)...);
+        invoke_lv(fun, views.at(r, c)...);
       }
   }
 }
@@ -99,6 +163,7 @@ template <typename P> struct arg_value;  // what the kernel receives for a range
 template <typename V> struct arg_value<imageNd<V, 2>> { typedef V& type; };
 template <> struct arg_value<box2d> { typedef vint2 type; };
 template <typename V> struct arg_value<relative_access_<imageNd<V, 2>>> { typedef relative_access_kernel<V> type; };
+template <typename V, int R, int C> struct arg_value<box_nbh2d_range<V, R, C>> { typedef box_nbh2d_kernel<V, R, C>& type; };
 template <typename P> using arg_value_t = typename arg_value<typename std::decay<P>::type>::type;
 
 }  // namespace pixel_wise_internals
