@@ -1,7 +1,9 @@
 """The C++14 host API (vpp_b200/include/vpp): the reference's own tests, rewritten with device kernels,
-are compiled by build.sh into tests/cpp/_build and run here on the GPU."""
+are compiled by build.sh into tests/cpp/_build and run here on the GPU — and, without a GPU, compiled by g++ against
+the CPU block/warp emulator of tests/emu/ (same headers, same test sources, kernels executed thread by thread)."""
 import os
 import subprocess
+import sys
 
 import pytest
 
@@ -21,3 +23,14 @@ def test_cpp_binary(gpu, name):
 def test_cpp_binaries_are_built(built):
     for name in ("core_tests", "algo_tests", "nbh_tests"):
         assert os.path.exists(os.path.join(BUILD, name))
+
+
+@pytest.mark.parametrize("name", ["core_tests", "algo_tests", "nbh_tests"])
+def test_cpp_binary_on_the_cpu_emulator(built, name):
+    sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
+    import build_emu
+
+    exe = build_emu.build_cpp_test(name)
+    env = dict(os.environ, VPPB_EMU_LOG=os.path.join(ROOT, "tests", "emu", "_build", "emu_fail.log"))
+    r = subprocess.run([exe, os.path.join(ROOT, "tests", "golden")], capture_output=True, text=True, timeout=900, cwd=ROOT, env=env)
+    assert r.returncode == 0 and "ALL OK" in r.stdout and "runtime error" not in r.stderr, r.stdout[-2000:] + r.stderr[-3000:]
