@@ -10,7 +10,7 @@ gcc -O2 -ffp-contract=off -fno-fast-math -fPIC -shared -o oracle/_build/libvpp_o
 gcc -O3 -march=native -fopenmp -DNDEBUG -ffp-contract=off -fPIC -shared -o oracle/_build/libvpp_oracle_omp.so oracle/*.c -lm
 # C++14 host API tests (the reference's own tests rewritten with device kernels), run by tests/test_cpp_api.py on the GPU box
 mkdir -p tests/cpp/_build
-for t in core_tests algo_tests nbh_tests; do
+for t in core_tests algo_tests nbh_tests extruder_tests; do
   nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -std=c++17 --extended-lambda -O1 -fmad=false -I vpp_b200/include \
        -o tests/cpp/_build/$t tests/cpp/$t.cu -L vpp_b200/lib -lvppb -Xlinker -rpath -Xlinker '$ORIGIN/../../../vpp_b200/lib'
 done

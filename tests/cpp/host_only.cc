@@ -5,6 +5,7 @@
 #include <vpp/algorithms/lucas_kanade.hh>
 #include <vpp/algorithms/optical_flow.hh>
 #include <vpp/algorithms/pyrlk/pyrlk_match.hh>
+#include <vpp/algorithms/video_extruder.hh>
 
 int host_only_demo() {
   using namespace vpp;
@@ -14,5 +15,9 @@ int host_only_demo() {
   vppb_check(vppb_box5x5_u8c3(a.device_read(), b.device_write(), nullptr));
   image2d<int> x(512, 512), y(512, 512), z(512, 512);
   vppb_check(vppb_pw_add_i32(x.device_write(), y.device_read(), z.device_read(), nullptr));
-  return b(0, 0)[0] + sum(x);
+  // the whole video_extruder is host-callable C++14: no device lambda in user code
+  image2d<unsigned char> f1(270, 480, _border = 3), f2(270, 480, _border = 3);
+  auto ctx = video_extruder_init(f1.domain());
+  video_extruder_update(ctx, f1, f2, _detector_th = 10, _keypoint_spacing = 10);
+  return b(0, 0)[0] + sum(x) + ctx.keypoints.size();
 }

@@ -12,7 +12,7 @@ BUILD = os.path.join(ROOT, "tests", "cpp", "_build")
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ["core_tests", "algo_tests", "nbh_tests"])
+@pytest.mark.parametrize("name", ["core_tests", "algo_tests", "nbh_tests", "extruder_tests"])
 def test_cpp_binary(gpu, name):
     exe = os.path.join(BUILD, name)
     assert os.path.exists(exe), "build.sh did not produce %s" % exe
@@ -21,11 +21,11 @@ def test_cpp_binary(gpu, name):
 
 
 def test_cpp_binaries_are_built(built):
-    for name in ("core_tests", "algo_tests", "nbh_tests"):
+    for name in ("core_tests", "algo_tests", "nbh_tests", "extruder_tests"):
         assert os.path.exists(os.path.join(BUILD, name))
 
 
-@pytest.mark.parametrize("name", ["core_tests", "algo_tests", "nbh_tests"])
+@pytest.mark.parametrize("name", ["core_tests", "algo_tests", "nbh_tests", "extruder_tests"])
 def test_cpp_binary_on_the_cpu_emulator(built, name):
     sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
     import build_emu

@@ -53,6 +53,12 @@ struct buffer_state {
     }
   }
   void host_written() { dev_valid = false; }
+  // the caller is about to overwrite EVERY byte of the mirror on the host: no need to fetch the device copy first
+  void host_overwrite_all() {
+    if (!host0) { host_valid = true; ensure_host(); }  // allocates the mirror; nothing to download
+    host_valid = true;
+    dev_valid = false;
+  }
   void ensure_device() {
     if (!dev_valid) {
       vppb_check(vppb_upload(&dev, host0, host_pitch, 1, nullptr));
@@ -150,6 +156,17 @@ class imageNd<V, 2> {
   // ---- device side (used by the operators of this library)
   const vppb_img* device_read() const { buf_->ensure_device(); return &view_; }
   const vppb_img* device_write() const { buf_->ensure_device(); buf_->device_written(); return &view_; }
+  // fill(img, v) + border, done on the host mirror (host-side bookkeeping images: keypoint index, detector mask):
+  // no kernel launch and no device -> host copy; the device copy is refreshed lazily if a device operator reads it
+  void host_fill_with_border(const V& v) {
+    assert(buf_ && r0_ == 0 && c0_ == 0 && view_.nrows == buf_->dev.nrows && view_.ncols == buf_->dev.ncols);  // whole images only
+    buf_->host_overwrite_all();
+    const int b = border();
+    for (int r = -b; r < nrows() + b; r++) {
+      V* row = (V*)(buf_->host0 + (long long)r * buf_->host_pitch);
+      for (int c = -b; c < ncols() + b; c++) row[c] = v;
+    }
+  }
   // flush device results back into caller-owned host memory (`_data=` images)
   void sync_host() const { buf_->ensure_host(); }
 
