@@ -106,6 +106,16 @@ int vppb_box5x5_i32(const vppb_img* in, const vppb_img* out, void* stream);
 /* same on single-channel u8 (image2d<unsigned char>) */
 int vppb_box5x5_u8(const vppb_img* in, const vppb_img* out, void* stream);
 
+/* ---- frame ingest: rgb_to_graylevel (colorspace_conversions.hh:10-47), SURVEY 8(f) N1 ------------------- */
+/* out(p) = (in(p)[0] + in(p)[1] + in(p)[2]) / 3 (int, truncating) over out's domain_with_border, as
+ * rgb_to_graylevel<unsigned char>(image2d<vuchar3 | vuchar4>) does; in: 3- or 4-byte pixels (4th channel ignored),
+ * out: u8, same domain, in->border >= out->border (the reference builds `out` with the input's border). */
+int vppb_rgb_to_graylevel_u8(const vppb_img* in, const vppb_img* out, void* stream);
+/* The ingest every caller performs before the path - clone(frame, _border = b); fill_border_mirror;
+ * rgb_to_graylevel (examples/video_extruder.cc:46-48) - in one launch: converts the domain and writes out's mirror
+ * border from the mirrored domain pixels.  `in` needs no border (a decoder surface: tight rows are fine). */
+int vppb_rgb_to_graylevel_u8_mirror(const vppb_img* in, const vppb_img* out, void* stream);
+
 /* ---- Scharr + pyramid (scharr.hh:46-87, pyramid.hh:12-81,133-198) ------------------------- */
 /* scharr(in u8, out vector<Vt,2>): out elem 8 bytes; as_float=0 -> vint2 (truncated), 1 -> vfloat2 */
 int vppb_scharr_u8(const vppb_img* in, const vppb_img* out, int as_float, void* stream);

@@ -5,6 +5,7 @@
 // with the reference's `_data = , _pitch = ` constructor (imageNd.hpp:99-141).
 #include <vpp/vpp.hh>
 #include <vpp/algorithms/filters/scharr.hh>
+#include <vpp/core/colorspace_conversions.hh>
 #include <vpp/algorithms/fast_detector/fast.hh>
 #include <vpp/algorithms/lucas_kanade.hh>
 #include <vpp/algorithms/pyrlk/lk.hh>
@@ -90,6 +91,19 @@ void vppref_box5x5_u8c3(const vo_img* in, const vo_img* out) {
       for (int j = -2; j <= 2; j++) sum += a(i, j).template cast<int>();
     b = (sum / 25).cast<unsigned char>();
   };
+}
+
+// rgb_to_graylevel<unsigned char>(image2d<vuchar3 | vuchar4>) (colorspace_conversions.hh:22-47): returns a new image with
+// the input's border, converted over domain_with_border(); copied out with `out`'s border (<= the input's).
+void vppref_rgb_to_graylevel(const vo_img* in, const vo_img* out) {
+  if (in->elem == 3) { auto A = wrap<vuchar3>(in); auto G = rgb_to_graylevel<unsigned char>(A); copy_out_with_border(G, out); }
+  else { auto A = wrap<vuchar4>(in); auto G = rgb_to_graylevel<unsigned char>(A); copy_out_with_border(G, out); }
+}
+// the same through the vuchar1 overload the reference's own test uses (tests/colorspace_conversions.cc:18)
+void vppref_rgb_to_graylevel_v1(const vo_img* in, const vo_img* out) {
+  auto A = wrap<vuchar3>(in);
+  image2d<vuchar1> G = rgb_to_graylevel<vuchar1>(A);
+  copy_out_with_border(G, out);
 }
 
 void vppref_scharr_u8(const vo_img* in, const vo_img* out, int as_float) {

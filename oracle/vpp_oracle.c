@@ -80,6 +80,19 @@ void vo_copy(const vo_img* src, const vo_img* dst, int with_border) {
     memcpy(ROW(dst, r) - (int64_t)b * e, ROW(src, r) - (int64_t)b * e, (size_t)(src->ncols + 2 * b) * e);
 }
 
+/* colorspace_conversions.hh:10-47: o = (i[0] + i[1] + i[2]) / 3 (int arithmetic, truncating; a 4th channel is ignored),
+ * for every pixel of in.domain_with_border(); `out` is built with the same border.  Here the frame converted is
+ * out's domain + min(in, out) border. */
+void vo_rgb_to_graylevel(const vo_img* in, const vo_img* out) {
+  const int b = in->border < out->border ? in->border : out->border, e = in->elem;
+#pragma omp parallel for
+  for (int r = -b; r < out->nrows + b; r++) {
+    const unsigned char* i = ROW(in, r);
+    unsigned char* o = ROW(out, r);
+    for (int c = -b; c < out->ncols + b; c++) o[c] = (unsigned char)(((int)i[(int64_t)c * e] + (int)i[(int64_t)c * e + 1] + (int)i[(int64_t)c * e + 2]) / 3);
+  }
+}
+
 static inline unsigned char* px(const vo_img* img, int r, int c) { return ROW(img, r) + (int64_t)c * img->elem; }
 
 /* fill.hh:32-45: four strips top / bottom / left / right */

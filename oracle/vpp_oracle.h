@@ -45,6 +45,8 @@ int vo_layout(int nrows, int ncols, int elem, int border, int align, int* pitch,
 void vo_pw_add_i32(const vo_img* a, const vo_img* b, const vo_img* c);
 void vo_fill(const vo_img* img, const void* value, int with_border);
 void vo_copy(const vo_img* src, const vo_img* dst, int with_border);
+/* rgb_to_graylevel (colorspace_conversions.hh:10-47): in elem 3 or 4 (u8 channels), out u8 */
+void vo_rgb_to_graylevel(const vo_img* in, const vo_img* out);
 void vo_fill_border_value(const vo_img* img, const void* value);
 void vo_fill_border_mirror(const vo_img* img);
 void vo_fill_border_closest(const vo_img* img);

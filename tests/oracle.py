@@ -42,6 +42,7 @@ def load(omp=False):
         lib.vo_box5x5_u8.argtypes = [I, I, C.c_int]
         lib.vo_box5x5_i32.argtypes = [I, I]
         lib.vo_scharr_u8.argtypes = [I, I, C.c_int]
+        lib.vo_rgb_to_graylevel.argtypes = [I, I]
         lib.vo_lowpass_sub2.argtypes = [I, I, C.c_int]
         lib.vo_lowpass.argtypes = [I, I, C.c_int]
         lib.vo_fast9_u8.argtypes = [I, C.c_int, I, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
@@ -54,7 +55,7 @@ def load(omp=False):
     return _LIBS[key]
 
 
-PIXEL_TYPES = {"u8": (np.uint8, 1), "i8": (np.int8, 1), "vuchar3": (np.uint8, 3), "i32": (np.int32, 1),
+PIXEL_TYPES = {"u8": (np.uint8, 1), "i8": (np.int8, 1), "vuchar3": (np.uint8, 3), "vuchar4": (np.uint8, 4), "i32": (np.int32, 1),
                "f32": (np.float32, 1), "vint2": (np.int32, 2), "vfloat2": (np.float32, 2)}
 
 

@@ -95,3 +95,13 @@ def test_box_division_magic():
     lo = np.arange(6376, dtype=np.uint64)[None, :]
     q = ((((hi << 16) | lo) * M) >> 32 >> 8) & 0xFF
     assert (q == hi // 25).all()
+
+
+def test_gray_division_magic():
+    """colorspace.cu divides the channel sum by 3 with (s * 43691) >> 17: exact for every s = r + g + b in 0..765
+    (the tempting (s * 171) >> 9 is not: it is off by one from s = 512 on)."""
+    import numpy as np
+
+    s = np.arange(0, 766, dtype=np.int64)
+    assert np.array_equal((s * 43691) >> 17, s // 3)
+    assert not np.array_equal((s * 171) >> 9, s // 3)

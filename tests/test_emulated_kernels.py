@@ -50,7 +50,7 @@ def emu(built):
     I, VP = C.POINTER(EImg), C.c_void_p
     for name, args in {"vppb_pw_add_i32": [I, I, I, VP], "vppb_fill": [I, VP, C.c_int, VP], "vppb_copy2d": [I, I, C.c_int, VP],
                        "vppb_copy2d_mirror": [I, I, VP], "vppb_fill_border_value": [I, VP, VP], "vppb_fill_border_mirror": [I, VP],
-                       "vppb_fill_border_closest": [I, VP], "vppb_scharr_u8": [I, I, C.c_int, VP], "vppb_scharr_u8_mirror": [I, I, C.c_int, VP],
+                       "vppb_fill_border_closest": [I, VP], "vppb_rgb_to_graylevel_u8": [I, I, VP], "vppb_rgb_to_graylevel_u8_mirror": [I, I, VP], "vppb_scharr_u8": [I, I, C.c_int, VP], "vppb_scharr_u8_mirror": [I, I, C.c_int, VP],
                        "vppb_lowpass_sub2": [I, I, C.c_int, VP], "vppb_lowpass_sub2_mirror": [I, I, C.c_int, VP],
                        "vppb_halo_pack": [I, C.c_int32, C.c_int, VP, VP], "vppb_halo_unpack": [I, C.c_int32, C.c_int, VP, VP],
                        "vppb_halo_pack_batch": [I, C.c_int32, C.c_int32, C.c_int, VP, VP], "vppb_halo_unpack_batch": [I, C.c_int32, C.c_int32, C.c_int, VP, VP]}.items():
@@ -286,3 +286,32 @@ def test_halo_pack_unpack_roundtrip(emu):
             single = twin(tiles[i])
             assert emu.vppb_halo_unpack(E(single), halo, 0, staging[i * per:].ctypes.data, None) == 0
             assert np.array_equal(outs[i].buf, single.buf), i
+
+
+@pytest.mark.parametrize("aligned", [128, 16, 4, 1])
+@pytest.mark.parametrize("pix", ["vuchar3", "vuchar4"])
+def test_rgb_to_graylevel_and_ingest(emu, pix, aligned):
+    o = orc.load()
+    for nr, nc in GEOMS + [(3, 16), (5, 32), (2, 47), (7, 129)]:
+        data = data_for(pix, nr, nc, nr * 5 + nc)
+        for b in (0, 1, 3):
+            if b > nr or b > nc:
+                continue
+            src = guarded(nr, nc, pix, border=b, aligned=aligned, data=data, seed=3)
+            if b:
+                o.vo_fill_border_mirror(src.ptr())
+            exp = guarded(nr, nc, "u8", border=b, aligned=aligned)
+            o.vo_rgb_to_graylevel(src.ptr(), exp.ptr())
+            for rev in both_orders(emu):
+                got = guarded(nr, nc, "u8", border=b, aligned=aligned)
+                assert emu.vppb_rgb_to_graylevel_u8(E(src), E(got), None) == 0, emu.vppb_last_error()
+                assert np.array_equal(got.buf, exp.buf) and guards_ok(got, src), ("gray", pix, nr, nc, b, aligned, rev)
+            # ingest: the source border is never read (random bytes there), the result carries the mirror border
+            tight = guarded(nr, nc, pix, border=0, aligned=aligned, data=data)
+            exp = guarded(nr, nc, "u8", border=b, aligned=aligned)
+            o.vo_rgb_to_graylevel(tight.ptr(), exp.ptr())
+            o.vo_fill_border_mirror(exp.ptr())
+            for rev in both_orders(emu):
+                got = guarded(nr, nc, "u8", border=b, aligned=aligned)
+                assert emu.vppb_rgb_to_graylevel_u8_mirror(E(tight), E(got), None) == 0, emu.vppb_last_error()
+                assert np.array_equal(got.buf, exp.buf) and guards_ok(got, tight), ("ingest", pix, nr, nc, b, aligned, rev)

@@ -1,6 +1,6 @@
 """The `-m gpu` parity tests of tests/test_gpu_parity.py, run a second time WITHOUT a GPU: the same Python host code
 (vpp_b200.ops / image / video_extruder) drives tests/emu/_build/libvppb_emu.so — the library's own .cu sources
-(core, pixelwise, pyramid, box, fast, lk, sdof) compiled by g++ and executed by the fiber-per-thread block/warp emulator
+(core, pixelwise, pyramid, colorspace, box, fast, lk, sdof) compiled by g++ and executed by the fiber-per-thread block/warp emulator
 of tests/emu/ — and every result is compared with the oracle exactly as on the GPU.
 
 This checks the kernels' logic (indexing, warp collectives, barriers, atomics' results, float evaluation order) and
@@ -66,6 +66,8 @@ test_box5x5_extremes_and_u8 = G.test_box5x5_extremes_and_u8
 test_box5x5_direct_path_on_views_matches = G.test_box5x5_direct_path_on_views_matches
 test_box5x5_i32 = G.test_box5x5_i32
 test_box_border_too_small_is_an_error = G.test_box_border_too_small_is_an_error
+# frame ingest (rgb_to_graylevel, fused with the mirror border)
+test_rgb_to_graylevel_and_frame_ingest = G.test_rgb_to_graylevel_and_frame_ingest
 # Scharr, pyramids (fused level launches)
 test_scharr = G.test_scharr
 test_pyramid_u8 = G.test_pyramid_u8

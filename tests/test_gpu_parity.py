@@ -302,6 +302,47 @@ def test_fused_level_equals_lowpass_then_mirror(vpp, pix, kind):
     assert capi.lib.vppb_lowpass_sub2_mirror(big.ptr(), small.ptr(), kind, None) == capi.VPPB_E_BORDER
 
 
+@pytest.mark.parametrize("pix", ["vuchar3", "vuchar4"])
+@pytest.mark.parametrize("shape", [(45, 67), (270, 480), (1, 1), (33, 16), (64, 1000)])
+def test_rgb_to_graylevel_and_frame_ingest(vpp, pix, shape):
+    """vppb_rgb_to_graylevel_u8 (domain_with_border form of colorspace_conversions.hh:22-47) and the fused ingest
+    clone(_border) + fill_border_mirror + rgb_to_graylevel (examples/video_extruder.cc:46-48) vs the oracle"""
+    from vpp_b200 import capi
+
+    o = orc.load()
+    ch = 3 if pix == "vuchar3" else 4
+    data = rng(shape[0] * 7 + shape[1]).integers(0, 256, shape + (ch,), dtype=np.uint8)
+    for b in (0, 2):
+        if b > min(shape):
+            continue
+        for al in (128, 16, 4):
+            hs = orc.HostImage(shape[0], shape[1], pix, border=b, aligned=al, data=data, fill_border="mirror" if b else None)
+            exp = orc.HostImage(shape[0], shape[1], "u8", border=b, aligned=al)
+            o.vo_rgb_to_graylevel(hs.ptr(), exp.ptr())
+            src = vpp.Image2d.from_host(data, pix, border=b, aligned=al)
+            if b:
+                vpp.fill_border_mirror(src)
+            got = vpp.rgb_to_graylevel(src)
+            assert (got.border, got.nrows, got.ncols) == (b, shape[0], shape[1])
+            assert np.array_equal(got.download(with_border=True), exp.get(True)), (b, al)
+    # ingest: tight source without border -> gray with a mirror border of 3 (what fast9 / the pyramids want)
+    for bb in (0, 1, 3):
+        if bb > min(shape):
+            continue
+        hs = orc.HostImage(shape[0], shape[1], pix, data=data)
+        exp = orc.HostImage(shape[0], shape[1], "u8", border=bb)
+        o.vo_rgb_to_graylevel(hs.ptr(), exp.ptr())
+        o.vo_fill_border_mirror(exp.ptr())
+        for al in (128, 1):
+            got = vpp.ingest_rgb_frame(vpp.Image2d.from_host(data, pix, aligned=al), bb)
+            assert np.array_equal(got.download(with_border=True), exp.get(True)), (bb, al)
+    # errors: output border wider than the input's (plain form), border wider than the image (ingest form)
+    a, g = vpp.Image2d(8, 8, pix), vpp.Image2d(8, 8, "u8", border=2)
+    assert capi.lib.vppb_rgb_to_graylevel_u8(a.ptr(), g.ptr(), None) == capi.VPPB_E_BORDER
+    g9 = vpp.Image2d(8, 8, "u8", border=9)
+    assert capi.lib.vppb_rgb_to_graylevel_u8_mirror(a.ptr(), g9.ptr(), None) == capi.VPPB_E_BORDER
+
+
 # ------------------------------------------------------------------ FAST9
 def _oracle_fast(img, th, mask=None, mode=0, bs=10, ring=0, want_scores=False):
     o = orc.load()

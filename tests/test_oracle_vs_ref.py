@@ -27,6 +27,8 @@ def _load(path):
     r.vppref_box5x5_i32.argtypes = [I, I]
     r.vppref_box5x5_u8c3.argtypes = [I, I]
     r.vppref_scharr_u8.argtypes = [I, I, C.c_int]
+    r.vppref_rgb_to_graylevel.argtypes = [I, I]
+    r.vppref_rgb_to_graylevel_v1.argtypes = [I, I]
     r.vppref_lowpass_u8.argtypes = [I, I]
     r.vppref_pyramid.argtypes = [I, C.c_int, I, C.c_int]
     r.vppref_fast9_u8.argtypes = [I, C.c_int, I, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
@@ -291,3 +293,27 @@ def test_video_extruder_orchestration(ref, o):
     assert len(mine) == n
     assert np.array_equal(mine, out[:n])
     assert (mine[:, 2] > 1).sum() > 5  # some keypoints really were tracked across frames
+
+
+@pytest.mark.parametrize("pix", ["vuchar3", "vuchar4"])
+def test_rgb_to_graylevel(ref, o, pix):
+    """rgb_to_graylevel<unsigned char> of the reference (colorspace_conversions.hh:22-47) vs the oracle: domain and border,
+    every channel sum 0..765 occurs; + the reference's own KAT (tests/colorspace_conversions.cc:8-23): gray(i,i,i) == i."""
+    ch = 3 if pix == "vuchar3" else 4
+    data = rng(77).integers(0, 256, (45, 67, ch), dtype=np.uint8)
+    data[0, :, :3] = 255
+    data[1, :, :3] = 0
+    for b in (0, 3):
+        src = orc.HostImage(45, 67, pix, border=b, aligned=32, data=data, fill_border="mirror" if b else None)
+        g1, g2 = orc.HostImage(45, 67, "u8", border=b, aligned=32), orc.HostImage(45, 67, "u8", border=b, aligned=32)
+        ref.vppref_rgb_to_graylevel(src.ptr(), g1.ptr())
+        o.vo_rgb_to_graylevel(src.ptr(), g2.ptr())
+        assert np.array_equal(g1.get(True), g2.get(True))
+        assert np.array_equal(g2.get(), (data[..., :3].astype(np.int32).sum(axis=2) // 3).astype(np.uint8))
+    if pix == "vuchar3":
+        kat = (np.arange(100 * 100) % 256).astype(np.uint8).reshape(100, 100)
+        src = orc.HostImage(100, 100, "vuchar3", data=np.repeat(kat[..., None], 3, axis=2))
+        for fn in (ref.vppref_rgb_to_graylevel_v1, o.vo_rgb_to_graylevel):
+            g = orc.HostImage(100, 100, "u8")
+            fn(src.ptr(), g.ptr())
+            assert np.array_equal(g.get(), kat)

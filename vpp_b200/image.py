@@ -15,6 +15,7 @@ PIXEL_TYPES = {
     "u8": (np.uint8, 1),       # image2d<unsigned char>
     "i8": (np.int8, 1),        # image2d<char>
     "vuchar3": (np.uint8, 3),  # image2d<vuchar3>
+    "vuchar4": (np.uint8, 4),  # image2d<vuchar4> (RGBA / BGRA surfaces)
     "i32": (np.int32, 1),      # image2d<int>
     "f32": (np.float32, 1),    # image2d<float>
     "vint2": (np.int32, 2),    # image2d<vint2>

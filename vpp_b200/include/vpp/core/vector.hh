@@ -26,6 +26,8 @@ struct vector {
   VPP_HD vector(A a, B b) { static_assert(N == 2, "2 components"); v[0] = T(a); v[1] = T(b); }
   template <typename A, typename B, typename C>
   VPP_HD vector(A a, B b, C c) { static_assert(N == 3, "3 components"); v[0] = T(a); v[1] = T(b); v[2] = T(c); }
+  template <typename A, typename B, typename C, typename D>
+  VPP_HD vector(A a, B b, C c, D d) { static_assert(N == 4, "4 components"); v[0] = T(a); v[1] = T(b); v[2] = T(c); v[3] = T(d); }
   VPP_HD T& operator[](int i) { return v[i]; }
   VPP_HD const T& operator[](int i) const { return v[i]; }
   VPP_HD static vector Zero() { vector r; for (unsigned i = 0; i < N; i++) r.v[i] = T(0); return r; }

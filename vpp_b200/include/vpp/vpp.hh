@@ -2,6 +2,7 @@
 #pragma once
 #include <vpp/core/boxNd.hh>
 #include <vpp/core/clone.hh>
+#include <vpp/core/colorspace_conversions.hh>
 #include <vpp/core/copy.hh>
 #include <vpp/core/fill.hh>
 #include <vpp/core/image2d.hh>

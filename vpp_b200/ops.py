@@ -67,6 +67,26 @@ def sum(img, stream=None):  # sum.hh:12-19 (char / uchar / int images; accumulat
     return out.value
 
 
+# ---- frame ingest -----------------------------------------------------------------------------
+def rgb_to_graylevel(src, dst=None, stream=None):
+    """rgb_to_graylevel<unsigned char>(image2d<vuchar3 | vuchar4>) (colorspace_conversions.hh:10-47): (r + g + b) / 3,
+    truncating, over domain_with_border; without `dst` the result has the input's border and alignment, as there."""
+    if dst is None:
+        dst = Image2d(src.nrows, src.ncols, "u8", border=src.border, aligned=src.alignment or DEFAULT_ALIGNMENT)
+    check(lib.vppb_rgb_to_graylevel_u8(src.ptr(), dst.ptr(), stream))
+    return dst
+
+
+def ingest_rgb_frame(src, border, dst=None, stream=None):
+    """clone(frame, _border = border); fill_border_mirror; rgb_to_graylevel<unsigned char> - what every caller of the
+    path does with a decoded frame (examples/video_extruder.cc:46-48) - as ONE launch: gray level of the domain plus
+    the mirror border of the result.  `src` may have any border (it is not read)."""
+    if dst is None:
+        dst = Image2d(src.nrows, src.ncols, "u8", border=border)
+    check(lib.vppb_rgb_to_graylevel_u8_mirror(src.ptr(), dst.ptr(), stream))
+    return dst
+
+
 # ---- stencils -------------------------------------------------------------------------------
 def box5x5(src, dst, stream=None):
     """pixel_wise(dst, relative_access(src)) | sum of the 5x5 neighbourhood / 25
