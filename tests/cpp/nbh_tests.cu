@@ -79,7 +79,47 @@ static void test_range_form() {  // benchmarks/box_5x5_filter.cc:163-172
   for (auto p : V.domain()) assert(V(p) == p[0] * 100 + p[1]);
 }
 
+static void test_windows() {  // vpp/core/window.hh:11-62
+  assert(c9.size() == 9 && c8.size() == 8 && c5.size() == 5 && c4.size() == 4);
+  // the reference's member order (raster)
+  const int e8[8][2] = {{-1, -1}, {-1, 0}, {-1, 1}, {0, -1}, {0, 1}, {1, -1}, {1, 0}, {1, 1}};
+  const int e5[5][2] = {{-1, 0}, {0, -1}, {0, 0}, {0, 1}, {1, 0}};
+  const int e4[4][2] = {{-1, 0}, {0, -1}, {0, 1}, {1, 0}};
+  for (int i = 0; i < 8; i++) assert(c8[i][0] == e8[i][0] && c8[i][1] == e8[i][1]);
+  for (int i = 0; i < 5; i++) assert(c5[i][0] == e5[i][0] && c5[i][1] == e5[i][1]);
+  for (int i = 0; i < 4; i++) assert(c4[i][0] == e4[i][0] && c4[i][1] == e4[i][1]);
+  for (int i = 0; i < 9; i++) assert(c9[i][0] == i / 3 - 1 && c9[i][1] == i % 3 - 1);
+  int host_sum = 0;
+  foreach(c9, [&](vint2 n) { host_sum += 10 * n[0] + n[1] + 11; });
+  assert(host_sum == 9 * 11);
+
+  image2d<int> A(20, 30, _border = 1), S4(20, 30), S8(20, 30);
+  for (auto p : A.domain()) A(p) = p[0] * 37 + p[1] * 3;
+  fill_border_mirror(A);
+  pixel_wise(S4, relative_access(A)) | [=] VPP_KERNEL(int& s, relative_access_kernel<int> a) {
+    int acc = 0;
+    foreach(c4, [&](vint2 n) { acc += a(n); });
+    s = acc;
+  };
+  pixel_wise(S8, relative_access(A)) | [=] VPP_KERNEL(int& s, relative_access_kernel<int> a) {
+    int acc = 0, k = 0;
+    foreach(c8, [&](vint2 n) { acc += a(n) * (++k); });  // order-sensitive
+    s = acc;
+  };
+  for (int r = 0; r < 20; r++)
+    for (int c = 0; c < 30; c++) {
+      assert(S4(r, c) == A(r - 1, c) + A(r, c - 1) + A(r, c + 1) + A(r + 1, c));
+      int acc = 0;
+      for (int i = 0; i < 8; i++) acc += A(r + e8[i][0], c + e8[i][1]) * (i + 1);
+      assert(S8(r, c) == acc);
+    }
+  static_assert(std::is_same<cast_to_float<int>, float>::value && std::is_same<cast_to_float<vuchar3>, vfloat3>::value, "cast_to_float");
+  vint2 z = zero<vint2>();
+  assert(z[0] == 0 && z[1] == 0 && (int)zero<int>() == 0);
+}
+
 int main() {
+  test_windows();
   test_point_form();
   test_range_form();
   std::printf("ALL OK\n");
