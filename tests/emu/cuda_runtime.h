@@ -74,6 +74,7 @@ inline cudaError_t cudaMemcpy2DAsync(void* d, size_t dp, const void* s, size_t s
 // A full round over the block in which nothing progressed is a deadlock and aborts the process with a message.
 namespace emu {
 extern bool reverse_order;
+extern unsigned shuffle_seed;
 void run_block(unsigned nthreads, void (*entry)(void*), void* arg);
 void block_barrier();
 int lane_id();

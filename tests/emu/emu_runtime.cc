@@ -15,6 +15,7 @@ thread_local dim3 threadIdx, blockIdx, blockDim, gridDim;
 namespace emu {
 
 bool reverse_order = false;
+unsigned shuffle_seed = 0;  // != 0: every scheduler round visits the threads of the block in a fresh pseudo-random order
 
 namespace {
 constexpr size_t kStack = 512 * 1024;
@@ -45,6 +46,7 @@ struct Block {
   void* arg = nullptr;
   struct MBar { uint32_t phase = 0, init = 0; int pending = 0; long long tx = 0; };
   std::map<uint64_t*, MBar> mbars;
+  std::vector<unsigned> order;
 };
 Block g;
 void* g_smem = nullptr;
@@ -192,8 +194,15 @@ void run_block(unsigned nthreads, void (*entry)(void*), void* arg) {
   }
   while (g.alive > 0) {
     const unsigned long long before = g.progress;
+    if (shuffle_seed) {
+      if (g.order.size() != nthreads) { g.order.resize(nthreads); for (unsigned k = 0; k < nthreads; k++) g.order[k] = k; }
+      for (unsigned k = nthreads; k > 1; k--) {  // Fisher-Yates with an xorshift generator
+        shuffle_seed ^= shuffle_seed << 13; shuffle_seed ^= shuffle_seed >> 17; shuffle_seed ^= shuffle_seed << 5;
+        std::swap(g.order[k - 1], g.order[shuffle_seed % k]);
+      }
+    }
     for (unsigned k = 0; k < nthreads; k++) {
-      const unsigned t = reverse_order ? nthreads - 1 - k : k;
+      const unsigned t = shuffle_seed ? g.order[k] : (reverse_order ? nthreads - 1 - k : k);
       if (g.fibers[t].done) continue;
       g.current = t;
       threadIdx = dim3{t, 0, 0};
@@ -228,3 +237,4 @@ cudaError_t cudaGetDriverEntryPoint(const char* symbol, void** fn, unsigned long
 }
 
 extern "C" void vppb_emu_set_reverse(int on) { emu::reverse_order = on != 0; }
+extern "C" void vppb_emu_set_shuffle(unsigned seed) { emu::shuffle_seed = seed; }

@@ -22,8 +22,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 UBSAN_LOG = os.path.join(ROOT, "tests", "emu", "_build", "ubsan.log")
 
 
-@pytest.fixture(scope="module")
-def vpp(built):
+@pytest.fixture(scope="module", params=["forward", "reversed", "shuffled"])
+def vpp(built, request):
+    """`reversed`: blocks and the threads inside a block are scheduled last to first - a result that depends on which
+    thread / block gets somewhere first (an unordered atomic append, a missing barrier) changes and fails the comparison;
+    `shuffled`: every scheduler round visits the threads of the block in a fresh pseudo-random order (seeded)"""
     sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
     import build_emu
 
@@ -39,10 +42,14 @@ def vpp(built):
     for name, (res, args) in capi.PROTOTYPES.items():
         fn = getattr(emu, name)
         fn.restype, fn.argtypes = res, args
+    emu.vppb_emu_set_reverse(1 if request.param == "reversed" else 0)
+    emu.vppb_emu_set_shuffle(12345 if request.param == "shuffled" else 0)
     mp = pytest.MonkeyPatch()
     mp.setattr(capi, "lib", emu)
     mp.setattr(ops, "lib", emu)
     yield vpp_b200
+    emu.vppb_emu_set_reverse(0)
+    emu.vppb_emu_set_shuffle(0)
     gc.collect()  # images allocated by the emulated library must be freed by it
     mp.undo()
     logs = glob.glob(UBSAN_LOG + "*")
