@@ -18,7 +18,14 @@ bool reverse_order = false;
 unsigned shuffle_seed = 0;  // != 0: every scheduler round visits the threads of the block in a fresh pseudo-random order
 
 namespace {
-constexpr size_t kStack = 512 * 1024;
+size_t stack_bytes() {  // per-fiber stack; VPPB_EMU_STACK_KB overrides (the ASan run uses small stacks: its swapcontext
+  static size_t n = 0;  // interceptor pays per byte of stack)
+  if (!n) {
+    const char* e = getenv("VPPB_EMU_STACK_KB");
+    n = (size_t)(e && atoi(e) >= 16 ? atoi(e) : 512) * 1024;
+  }
+  return n;
+}
 
 struct Fiber {
   ucontext_t ctx;
@@ -181,12 +188,12 @@ void run_block(unsigned nthreads, void (*entry)(void*), void* arg) {
   for (unsigned t = 0; t < nthreads; t++) {
     Fiber& f = g.fibers[t];
     if (!f.stack) {
-      f.stack = static_cast<char*>(mmap(nullptr, kStack, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_STACK, -1, 0));
+      f.stack = static_cast<char*>(mmap(nullptr, stack_bytes(), PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_STACK, -1, 0));
       if (f.stack == MAP_FAILED) { perror("emu: mmap"); abort(); }
     }
     getcontext(&f.ctx);
     f.ctx.uc_stack.ss_sp = f.stack;
-    f.ctx.uc_stack.ss_size = kStack;
+    f.ctx.uc_stack.ss_size = stack_bytes();
     f.ctx.uc_link = nullptr;
     makecontext(&f.ctx, fiber_main, 0);
     f.done = false;

@@ -30,7 +30,7 @@ def vpp(built, request):
     sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
     import build_emu
 
-    path = build_emu.build()
+    path = build_emu.build(asan=os.environ.get("VPPB_EMU_ASAN") == "1")  # the ASan variant needs libasan preloaded (tests/test_emulated_asan.py)
     for f in glob.glob(UBSAN_LOG + "*"):
         os.remove(f)
     os.environ.setdefault("UBSAN_OPTIONS", "log_path=%s" % UBSAN_LOG)  # same path as tests/test_emulated_kernels.py: the .so is loaded once per process
