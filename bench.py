@@ -189,6 +189,38 @@ def cpu_extras(budget_s=6.0):
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
+def probe_batch(device, rows, cols, nframes):
+    """Child process of the `--box-launch auto` selection: run the batched box kernel on the geometry the bench will use and
+    compare every frame with the per-frame kernel.  Exit code 0 = identical.  A kernel that faults takes only this
+    process (and its CUDA context) down, not the bench."""
+    import __graft_entry__ as g
+
+    g.build(only_if_missing=True)
+    import vpp_b200 as vpp
+    from vpp_b200 import capi
+
+    capi.check(capi.lib.vppb_init(device))
+    rng = np.random.default_rng(11)
+    uniq = [rng.integers(0, 256, (rows, cols, 3), dtype=np.uint8) for _ in range(min(nframes, 3))]
+    srcs, d1, d2 = [], [], []
+    for i in range(nframes):
+        s_ = vpp.Image2d.from_host(uniq[i % len(uniq)], "vuchar3", border=2)
+        vpp.fill_border_mirror(s_)
+        srcs.append(s_)
+        d1.append(vpp.Image2d(rows, cols, "vuchar3"))
+        d2.append(vpp.Image2d(rows, cols, "vuchar3"))
+    for s_, d_ in zip(srcs, d1):
+        vpp.box5x5(s_, d_)
+    for _ in range(3):
+        vpp.box5x5_batch(srcs, d2)
+    capi.check(capi.lib.vppb_sync(None))
+    for i in range(nframes):
+        if not np.array_equal(d1[i].download(), d2[i].download()):
+            sys.stderr.write("probe: batched box differs from the per-frame kernel on frame %d\n" % i)
+            return 4
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -201,8 +233,14 @@ def main():
     ap.add_argument("--graph", type=int, default=1, help="replay the step as a CUDA graph (single GPU)")
     ap.add_argument("--streams", type=int, default=4, help="CUDA streams the frames of a step are spread over")
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work for the cpu_baseline sample")
+    ap.add_argument("--box-launch", default="auto", choices=["auto", "per-frame", "batch"],
+                    help="one box launch per frame (spread over --streams) or one persistent launch per step (vppb_box5x5_u8c3_batch); "
+                         "auto = probe the batched kernel in a child process, time both, keep the faster")
+    ap.add_argument("--probe-batch", nargs=4, type=int, default=None, metavar=("DEVICE", "ROWS", "COLS", "FRAMES"), help=argparse.SUPPRESS)
     args = ap.parse_args()
 
+    if args.probe_batch:
+        return probe_batch(*args.probe_batch)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -300,9 +338,24 @@ def main():
     fork, fork2, comm_done = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
     base["config"]["streams"] = max(args.streams, 1)
 
+    box_mode = ["per-frame"]  # or "batch": ONE persistent launch over the tiles of all frames of the step
+    batch_descs = {}
+
     def fan_out(stream, pairs, ev):
-        """one box5x5 launch per (src, dst) pair, spread over the side streams, joined back into `stream`"""
+        """per-frame: one box5x5 launch per (src, dst) pair, spread over the side streams, joined back into `stream`;
+        batch: the whole list in one vppb_box5x5_u8c3_batch call (one launch per 32 frames) on `stream`"""
         sp = C.c_void_p(stream.cuda_stream)
+        if box_mode[0] == "batch":
+            key = id(pairs[0][0])
+            if key not in batch_descs:
+                n_ = len(pairs)
+                ins, outs = (capi.VppbImg * n_)(), (capi.VppbImg * n_)()
+                for i, (s, d) in enumerate(pairs):
+                    ins[i], outs[i] = s.desc, d.desc
+                batch_descs[key] = (ins, outs, n_)
+            ins, outs, n_ = batch_descs[key]
+            capi.check(capi.lib.vppb_box5x5_u8c3_batch(ins, outs, n_, sp))
+            return (n_ + 31) // 32
         if len(side) > 1:
             ev.record(stream)
             for s_ in side:
@@ -315,6 +368,45 @@ def main():
             for s, d in pairs:
                 capi.check(capi.lib.vppb_box5x5_u8c3(s.ptr(), d.ptr(), sp))
         return len(pairs)
+
+    def batch_kernel_usable():
+        """--box-launch auto: the batched kernel first runs in a child process on this rank's device and geometry; every rank must agree"""
+        if args.box_launch == "per-frame":
+            return False, "not requested"
+        if args.box_launch == "batch":
+            return True, "forced"
+        env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT", "LOCAL_WORLD_SIZE",
+                                                                 "GROUP_RANK", "ROLE_RANK", "TORCHELASTIC_RUN_ID")}
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--probe-batch", str(local_rank if world > 1 else 0), str(th), str(W), str(nframes)],
+                               capture_output=True, text=True, timeout=300, env=env, cwd=ROOT)
+            ok, why = r.returncode == 0, "probe rc %d %s" % (r.returncode, r.stderr.strip()[-200:])
+        except Exception as ex:  # pragma: no cover
+            ok, why = False, "probe did not run: %r" % (ex,)
+        if dist is not None:
+            flag = torch.tensor([1.0 if ok else 0.0], dtype=torch.float64, device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            ok = bool(flag.item() > 0.5)
+        return ok, why
+
+    def device_ms(fn, reps):
+        """CUDA-event time of `reps` calls of fn on the current stream, max over ranks"""
+        a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a_.record(torch.cuda.current_stream())
+        for _ in range(reps):
+            fn()
+        b_.record(torch.cuda.current_stream())
+        torch.cuda.synchronize()
+        t_ = torch.tensor([a_.elapsed_time(b_) / reps], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(t_, op=dist.ReduceOp.MAX)
+        return float(t_.item())
+
+    batch_ok, batch_why = batch_kernel_usable()
+    modes = ["per-frame", "batch"] if (batch_ok and args.box_launch == "auto") else (["batch"] if batch_ok else ["per-frame"])
+    mode_ms = {}
+    base["config"]["box_launch"] = {"requested": args.box_launch, "batch_probe": batch_why}
 
     if world > 1:
         hb = int(capi.lib.vppb_halo_bytes(src[0].ptr(), halo))
@@ -369,7 +461,16 @@ def main():
     if world > 1:
         piece("pack", pack_all)
         piece("unpack", unpack_all)
-        piece("boxes", lambda st: fan_out(st, list(zip(src, dst)), fork))
+        # the box piece once per candidate launch form; the faster one (device time, max over ranks) is kept
+        for m_ in modes:
+            box_mode[0] = m_
+            piece("boxes:" + m_, lambda st: fan_out(st, list(zip(src, dst)), fork))
+            pieces["boxes:" + m_][0]()
+            mode_ms[m_] = device_ms(pieces["boxes:" + m_][0], 20)
+        box_mode[0] = min(mode_ms, key=mode_ms.get)
+        pieces["boxes"] = pieces["boxes:" + box_mode[0]]
+        for m_ in modes:
+            del pieces["boxes:" + m_]
         unpacked = torch.cuda.Event()
         primed = [False]
 
@@ -414,19 +515,43 @@ def main():
     # The step (one launch per frame, fork/join over the side streams) is captured once into a CUDA graph
     # and replayed: same kernels, same work, without the per-launch host cost of the Python/ctypes loop.
     graph, run_step = None, step
-    if args.graph and world == 1:  # at N>1 the device pieces are graphs already; NCCL P2P inside a captured graph hung on this stack
-        try:
-            g_ = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g_):
+    if world == 1:  # at N>1 the device pieces are graphs already; NCCL P2P inside a captured graph hung on this stack
+        runners, snap = {}, {}
+        for m_ in modes:
+            box_mode[0] = m_
+            for _ in range(3):
                 step()
-            for _ in range(2):
-                g_.replay()
-            barrier()
-            graph, run_step = g_, g_.replay
-        except Exception as ex:  # e.g. NCCL P2P not capturable in this build: stay eager
-            sys.stderr.write("CUDA graph capture failed, running eagerly: %r\n" % (ex,))
             torch.cuda.synchronize()
-            graph, run_step = None, step
+            snap[m_] = (dst[0].download(), dst[-1].download())
+            g_ = None
+            if args.graph:
+                try:
+                    g_ = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g_):
+                        step()
+                    for _ in range(2):
+                        g_.replay()
+                    barrier()
+                except Exception as ex:
+                    sys.stderr.write("CUDA graph capture failed, running eagerly: %r\n" % (ex,))
+                    torch.cuda.synchronize()
+                    g_ = None
+            if g_ is not None:
+                runners[m_] = (g_, g_.replay)
+            else:
+                runners[m_] = (None, (lambda mm: (lambda: (box_mode.__setitem__(0, mm), step())))(m_))
+            mode_ms[m_] = device_ms(runners[m_][1], max(10, min(100, steps // 10)))
+        if "batch" in snap and "per-frame" in snap and not all(np.array_equal(a_, b_) for a_, b_ in zip(snap["batch"], snap["per-frame"])):
+            sys.stderr.write("batched box launch differs from the per-frame launches: not used\n")
+            mode_ms.pop("batch")
+        box_mode[0] = min(mode_ms, key=mode_ms.get)
+        graph, run_step = runners[box_mode[0]]
+        for _ in range(3):
+            run_step()
+        barrier()
+    base["config"]["box_launch"].update({"used": box_mode[0], "ms_per_step_by_mode": dict(mode_ms)})
+    if world == 1:  # graph replays do not run step(): count the launches of the chosen form
+        launches_per_step = nframes if box_mode[0] == "per-frame" else (nframes + 31) // 32
     base["config"]["cuda_graph"] = (graph is not None) or (world > 1 and all(v[1] is not None for v in pieces.values()))
     sampler = ClockSampler(local_rank if world > 1 else 0)
     if rank == 0:
@@ -488,9 +613,13 @@ def main():
             traffic = json.load(open(tp)).get(workload if n_gpus == 1 else "%s_tile%d" % (workload, n_gpus))
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": "k_box5_bytes_tma<3>", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+    batched = box_mode[0] == "batch"
+    if batched:
+        traffic = None  # the ncu capture in profiles/ is of the per-frame kernel
+    roofline = {"bound": "hbm", "kernel": "k_box5_bytes_tma_batch<3>" if batched else "k_box5_bytes_tma<3>", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "us_per_launch": launch_us_timed, "algorithmic_bytes_per_launch": alg_bytes,
-                "how": "bytes of the %d box launches per step / CUDA-event time of the timed region (launches overlap on %d streams)" % (nframes, max(args.streams, 1)),
+                "how": ("bytes of the %d frames of a step (one persistent launch per step) / CUDA-event time of the timed region; us_per_launch is per frame" % nframes) if batched else
+                       ("bytes of the %d box launches per step / CUDA-event time of the timed region (launches overlap on %d streams)" % (nframes, max(args.streams, 1))),
                 "alone": {"us_per_launch": us_per_launch, "achieved": alone, "frac": alone / peak,
                           "how": "same kernel, launches issued back to back on one stream"}}
 

@@ -105,6 +105,12 @@ int vppb_box5x5_u8c3(const vppb_img* in, const vppb_img* out, void* stream);
 int vppb_box5x5_i32(const vppb_img* in, const vppb_img* out, void* stream);
 /* same on single-channel u8 (image2d<unsigned char>) */
 int vppb_box5x5_u8(const vppb_img* in, const vppb_img* out, void* stream);
+/* The same filter over a batch of n image pairs (the frames of a video step) with as few launches as possible: equally
+ * shaped library-layout images go through ONE persistent launch per 32 images (the per-launch ramp-up and tail, which
+ * rival the run time of a whole 1080p frame, are paid once per batch); any other mix is processed image by image.
+ * ins / outs: arrays of n descriptors.  Results are identical to n calls of the single-image entry. */
+int vppb_box5x5_u8c3_batch(const vppb_img* ins, const vppb_img* outs, int32_t n, void* stream);
+int vppb_box5x5_u8_batch(const vppb_img* ins, const vppb_img* outs, int32_t n, void* stream);
 
 /* ---- frame ingest: rgb_to_graylevel (colorspace_conversions.hh:10-47), SURVEY 8(f) N1 ------------------- */
 /* out(p) = (in(p)[0] + in(p)[1] + in(p)[2]) / 3 (int, truncating) over out's domain_with_border, as

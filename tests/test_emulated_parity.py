@@ -72,6 +72,8 @@ test_box5x5_vuchar3_bit_exact = G.test_box5x5_vuchar3_bit_exact
 test_box5x5_extremes_and_u8 = G.test_box5x5_extremes_and_u8
 test_box5x5_direct_path_on_views_matches = G.test_box5x5_direct_path_on_views_matches
 test_box5x5_i32 = G.test_box5x5_i32
+test_box5x5_batch_equals_oracle = G.test_box5x5_batch_equals_oracle
+test_box5x5_batch_fallbacks_and_errors = G.test_box5x5_batch_fallbacks_and_errors
 test_box_border_too_small_is_an_error = G.test_box_border_too_small_is_an_error
 # frame ingest (rgb_to_graylevel, fused with the mirror border)
 test_rgb_to_graylevel_and_frame_ingest = G.test_rgb_to_graylevel_and_frame_ingest

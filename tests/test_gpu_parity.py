@@ -201,6 +201,55 @@ def test_box5x5_direct_path_on_views_matches(vpp):
     assert np.array_equal(D.download(), exp)
 
 
+@pytest.mark.parametrize("pix,shape,n", [("vuchar3", (64, 341), 3), ("vuchar3", (270, 480), 5), ("vuchar3", (40, 330), 33), ("u8", (57, 1000), 4),
+                                         ("vuchar3", (1080, 1920), 2), ("vuchar3", (7, 9), 2)])
+def test_box5x5_batch_equals_oracle(vpp, pix, shape, n):
+    """vppb_box5x5_*_batch: one persistent launch over the tiles of all images (two launches for 33 images), every image
+    with its own tensor map / output base; each result must equal the oracle's"""
+    o = orc.load()
+    ch = 3 if pix == "vuchar3" else 1
+    srcs, dsts, exp = [], [], []
+    for i in range(n):
+        data = rng(1000 * i + shape[0]).integers(0, 256, shape + ((ch,) if ch > 1 else ()), dtype=np.uint8)
+        S = vpp.Image2d.from_host(data, pix, border=2)
+        vpp.fill_border_mirror(S)
+        srcs.append(S)
+        dsts.append(vpp.Image2d(shape[0], shape[1], pix))
+        hs = orc.HostImage(shape[0], shape[1], pix, border=2, data=data, fill_border="mirror")
+        hd = orc.HostImage(shape[0], shape[1], pix)
+        o.vo_box5x5_u8(hs.ptr(), hd.ptr(), ch)
+        exp.append(hd.get())
+    vpp.box5x5_batch(srcs, dsts)
+    for i in range(n):
+        assert np.array_equal(dsts[i].download(), exp[i]), i
+
+
+def test_box5x5_batch_fallbacks_and_errors(vpp):
+    """mixed shapes, views and small alignments take the image-by-image route with the same results; errors as the single entry"""
+    from vpp_b200 import capi
+
+    o = orc.load()
+    shapes = [(40, 50), (64, 341), (40, 50)]
+    srcs, dsts, exp = [], [], []
+    for i, sh in enumerate(shapes):
+        data = rng(70 + i).integers(0, 256, sh + (3,), dtype=np.uint8)
+        S = vpp.Image2d.from_host(data, "vuchar3", border=2, aligned=128 if i else 4)
+        vpp.fill_border_mirror(S)
+        srcs.append(S)
+        dsts.append(vpp.Image2d(sh[0], sh[1], "vuchar3"))
+        hs, hd = orc.HostImage(sh[0], sh[1], "vuchar3", border=2, data=data, fill_border="mirror"), orc.HostImage(sh[0], sh[1], "vuchar3")
+        o.vo_box5x5_u8(hs.ptr(), hd.ptr(), 3)
+        exp.append(hd.get())
+    vpp.box5x5_batch(srcs, dsts)
+    for i in range(len(shapes)):
+        assert np.array_equal(dsts[i].download(), exp[i]), i
+    bad = vpp.Image2d(40, 50, "vuchar3", border=1)
+    with pytest.raises(capi.VppbError) as e:
+        vpp.box5x5_batch([srcs[0], bad], [dsts[0], vpp.Image2d(40, 50, "vuchar3")])
+    assert e.value.code == capi.VPPB_E_BORDER
+    assert capi.lib.vppb_box5x5_u8c3_batch(None, None, 0, None) == capi.VPPB_E_ARG
+
+
 def test_box5x5_i32(vpp):
     # benchmarks/box_5x5_filter.cc:191 style values in [0,1000) + negative values (trunc toward 0)
     for lo, hi in ((0, 1000), (-1000, 1000)):

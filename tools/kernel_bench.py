@@ -70,6 +70,10 @@ for (H, W, tag) in [(1080, 1920, "1080p"), (2160, 3840, "4k")]:
     D = [vpp.Image2d(H, W, "vuchar3") for _ in range(n)]
     report("fill_border_mirror_u8c3_b2_" + tag, timed(lambda i: capi.lib.vppb_fill_border_mirror(S[i].ptr(), sp), n), 2.0 * 3 * 2 * (2 * (W + 4) + 2 * H), "border px only")
     report("box5x5_u8c3_" + tag, timed(lambda i: capi.lib.vppb_box5x5_u8c3(S[i].ptr(), D[i].ptr(), sp), n), 6.0 * H * W)
+    nb = min(n, 32)
+    bi, bo = (capi.VppbImg * nb)(*[x.desc for x in S[:nb]]), (capi.VppbImg * nb)(*[x.desc for x in D[:nb]])
+    us_b = timed(lambda i: capi.lib.vppb_box5x5_u8c3_batch(bi, bo, nb, sp) if i == 0 else 0, nb) * 1.0  # one call per sweep of the set
+    report("box5x5_u8c3_batch%d_per_frame_" % nb + tag, us_b, 6.0 * H * W, "one persistent launch over %d frames; time per frame" % nb)
     del S, D
     # --- u8: box, scharr, pyramid step, fast9 pieces
     n = nsets(9 * H * W)

@@ -96,6 +96,8 @@ PROTOTYPES = {
     "vppb_box5x5_u8c3": (C.c_int, [_IMG, _IMG, _VP]),
     "vppb_box5x5_i32": (C.c_int, [_IMG, _IMG, _VP]),
     "vppb_box5x5_u8": (C.c_int, [_IMG, _IMG, _VP]),
+    "vppb_box5x5_u8c3_batch": (C.c_int, [_IMG, _IMG, _I32, _VP]),
+    "vppb_box5x5_u8_batch": (C.c_int, [_IMG, _IMG, _I32, _VP]),
     "vppb_rgb_to_graylevel_u8": (C.c_int, [_IMG, _IMG, _VP]),
     "vppb_rgb_to_graylevel_u8_mirror": (C.c_int, [_IMG, _IMG, _VP]),
     "vppb_scharr_u8": (C.c_int, [_IMG, _IMG, C.c_int, _VP]),

@@ -7,6 +7,7 @@
 // (cp.async.bulk.tensor.2d + mbarrier); see k_box5_bytes_tma below for the two-phase scheme.
 #include "common.cuh"
 
+#include <algorithm>
 #include <atomic>
 #include "tma.cuh"
 
@@ -108,6 +109,87 @@ __device__ __forceinline__ uint32_t box_div_pack(uint32_t se, uint32_t so) {
   return __byte_perm(lo, hi, 0x5410);
 }
 
+// ---------------- phase 1 of a tile: 5-row column sums of the raw box -> E / O planes in shared memory
+template <int BX_TH>
+__device__ __forceinline__ void box_phase1(const unsigned char* raw, uint32_t* csE, uint32_t* csO, int tid, uint32_t minus_one) {
+  constexpr int RG_ROWS = BX_TH / 2;  // output rows per phase-1 row group
+  const int cg = tid & 63, rg = tid >> 6;
+  const unsigned char* col = raw + (rg * RG_ROWS) * BX_BOXW + cg * 16;
+  uint32_t ringE[5][4], ringO[5][4], VE[4], VO[4];
+#pragma unroll
+  for (int q = 0; q < 4; q++) { VE[q] = 0; VO[q] = 0; }
+#pragma unroll
+  for (int j = 0; j < RG_ROWS + 4; j++) {
+    const uint4 v = *reinterpret_cast<const uint4*>(col + j * BX_BOXW);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    const int slot = j % 5;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const uint32_t e = w[q] & 0x00FF00FFu, o = __byte_perm(w[q], 0u, 0x4341);
+      if (j >= 5) {
+        VE[q] = fadd_u32(ringE[slot][q], minus_one, VE[q] + e);   // V += e - old  (one IADD3 + one IMAD)
+        VO[q] = fadd_u32(ringO[slot][q], minus_one, VO[q] + o);
+      } else { VE[q] += e; VO[q] += o; }
+      ringE[slot][q] = e;
+      ringO[slot][q] = o;
+    }
+    if (j >= 4) {
+      const int orow = rg * RG_ROWS + j - 4;
+      *reinterpret_cast<uint4*>(csE + orow * BX_CS_ROW_WORDS + cg * 4) = make_uint4(VE[0], VE[1], VE[2], VE[3]);
+      *reinterpret_cast<uint4*>(csO + orow * BX_CS_ROW_WORDS + cg * 4) = make_uint4(VO[0], VO[1], VO[2], VO[3]);
+    }
+  }
+}
+
+// ---------------- phase 2 of a tile: horizontal taps, divide, store (out_base / out_pitch: the image the tile belongs to)
+template <int CS, int BX_TH>
+__device__ __forceinline__ void box_phase2(const uint32_t* csE, const uint32_t* csO, unsigned char* out_base, long long out_pitch, int out_nrows,
+                                           int rowbytes, int x0, int y0, int vec_store, int tid, uint32_t one) {
+  const int rows_here = min(BX_TH, out_nrows - y0);
+  for (int u = tid; u < BX_TH * 62; u += BX_THREADS) {
+    const int row = u / 62, og = u - row * 62;
+    const int x = x0 + og * 16;
+    if (row >= rows_here || x >= rowbytes) continue;
+    // own words are box words 4og+4 .. 4og+7 (the box starts 16 bytes left of x0); window = words k-2 .. k+5
+    const uint32_t* pe = csE + row * BX_CS_ROW_WORDS + og * 4 + 2;
+    const uint32_t* po = csO + row * BX_CS_ROW_WORDS + og * 4 + 2;
+    const uint2 e0 = *reinterpret_cast<const uint2*>(pe), e2 = *reinterpret_cast<const uint2*>(pe + 6);
+    const uint4 e1 = *reinterpret_cast<const uint4*>(pe + 2);
+    const uint2 o0 = *reinterpret_cast<const uint2*>(po), o2 = *reinterpret_cast<const uint2*>(po + 6);
+    const uint4 o1 = *reinterpret_cast<const uint4*>(po + 2);
+    const uint32_t E[8] = {e0.x, e0.y, e1.x, e1.y, e1.z, e1.w, e2.x, e2.y};
+    const uint32_t O[8] = {o0.x, o0.y, o1.x, o1.y, o1.z, o1.w, o2.x, o2.y};
+    uint32_t SE[7], SO[7];
+#pragma unroll
+    for (int i = 0; i < 7; i++) {
+      SE[i] = __byte_perm(E[i], E[i + 1], 0x5432);  // lanes (byte2 of word i, byte0 of word i+1)
+      SO[i] = __byte_perm(O[i], O[i + 1], 0x5432);  // lanes (byte3 of word i, byte1 of word i+1)
+    }
+    uint32_t ow[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int i = j + 2;
+      uint32_t he, ho;
+      if (CS == 3) {
+        // lanes (x, x+2): taps x-6, x-3, x, x+3, x+6 ; lanes (x+1, x+3) likewise.  3 terms on the ALU (IADD3), 2 on the FMA pipe.
+        he = fadd_u32(SE[i + 1], one, fadd_u32(SO[i], one, SE[i - 2] + O[i - 1] + E[i]));
+        ho = fadd_u32(SO[i + 1], one, fadd_u32(E[i + 1], one, SO[i - 2] + SE[i - 1] + O[i]));
+      } else {
+        he = fadd_u32(SE[i], one, fadd_u32(O[i], one, SE[i - 1] + SO[i - 1] + E[i]));  // CS == 1: taps x-2 .. x+2
+        ho = fadd_u32(SO[i], one, fadd_u32(SE[i], one, SO[i - 1] + E[i] + O[i]));
+      }
+      ow[j] = box_div_pack(he, ho);
+    }
+    unsigned char* dst = out_base + (long long)(y0 + row) * out_pitch + x;
+    if (vec_store && x + 16 <= rowbytes) {
+      *reinterpret_cast<uint4*>(dst) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+    } else {
+      for (int k = 0; k < 16; k++)
+        if (x + k < rowbytes) dst[k] = (unsigned char)(ow[k >> 2] >> ((k & 3) * 8));
+    }
+  }
+}
+
 // Persistent: each CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...; the TMA load of the NEXT tile is
 // issued right after phase 1 (the raw box is dead once the column sums are in shared memory), so its
 // latency hides behind phase 2.
@@ -115,7 +197,6 @@ template <int CS, int BX_TH>
 __global__ void __launch_bounds__(BX_THREADS, BX_TH == 16 ? 4 : 6) k_box5_bytes_tma(const __grid_constant__ CUtensorMap tmap, Img out, int rowbytes, int strips,
                                                                  int ntiles, int vec_store, uint32_t one) {
   constexpr int BX_RAW_BYTES = BoxCfg<BX_TH>::RAW_BYTES, BX_CS_BYTES = BoxCfg<BX_TH>::CS_BYTES;
-  constexpr int RG_ROWS = BX_TH / 2;  // output rows per phase-1 row group
   extern __shared__ __align__(128) unsigned char smem[];
   unsigned char* raw = smem;
   uint32_t* csE = reinterpret_cast<uint32_t*>(smem + BX_RAW_BYTES);
@@ -140,36 +221,7 @@ __global__ void __launch_bounds__(BX_THREADS, BX_TH == 16 ? 4 : 6) k_box5_bytes_
     const int x0 = (tile % strips) * BX_OUTW, y0 = (tile / strips) * BX_TH;
     mbar_wait(bar, parity);
     parity ^= 1;
-
-    // ---------------- phase 1: 5-row column sums
-    {
-      const int cg = tid & 63, rg = tid >> 6;
-      const unsigned char* col = raw + (rg * RG_ROWS) * BX_BOXW + cg * 16;
-      uint32_t ringE[5][4], ringO[5][4], VE[4], VO[4];
-#pragma unroll
-      for (int q = 0; q < 4; q++) { VE[q] = 0; VO[q] = 0; }
-#pragma unroll
-      for (int j = 0; j < RG_ROWS + 4; j++) {
-        const uint4 v = *reinterpret_cast<const uint4*>(col + j * BX_BOXW);
-        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-        const int slot = j % 5;
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-          const uint32_t e = w[q] & 0x00FF00FFu, o = __byte_perm(w[q], 0u, 0x4341);
-          if (j >= 5) {
-            VE[q] = fadd_u32(ringE[slot][q], minus_one, VE[q] + e);   // V += e - old  (one IADD3 + one IMAD)
-            VO[q] = fadd_u32(ringO[slot][q], minus_one, VO[q] + o);
-          } else { VE[q] += e; VO[q] += o; }
-          ringE[slot][q] = e;
-          ringO[slot][q] = o;
-        }
-        if (j >= 4) {
-          const int orow = rg * RG_ROWS + j - 4;
-          *reinterpret_cast<uint4*>(csE + orow * BX_CS_ROW_WORDS + cg * 4) = make_uint4(VE[0], VE[1], VE[2], VE[3]);
-          *reinterpret_cast<uint4*>(csO + orow * BX_CS_ROW_WORDS + cg * 4) = make_uint4(VO[0], VO[1], VO[2], VO[3]);
-        }
-      }
-    }
+    box_phase1<BX_TH>(raw, csE, csO, tid, minus_one);
     __syncthreads();
     // the raw box is dead: prefetch the next tile of this CTA behind phase 2
     if (tid == 0 && tile + (int)gridDim.x < ntiles) {
@@ -177,51 +229,61 @@ __global__ void __launch_bounds__(BX_THREADS, BX_TH == 16 ? 4 : 6) k_box5_bytes_
       mbar_arrive_expect_tx(bar, BX_RAW_BYTES);
       tma_load_2d(raw, &tmap, (nt % strips) * (BX_OUTW / 8), (nt / strips) * BX_TH, bar);
     }
+    box_phase2<CS, BX_TH>(csE, csO, out.base, out.pitch, out.nrows, rowbytes, x0, y0, vec_store, tid, one);
+    __syncthreads();  // column sums consumed before the next tile's phase 1 overwrites them
+  }
+}
 
-    // ---------------- phase 2: horizontal taps, divide, store
-    const int rows_here = min(BX_TH, out.nrows - y0);
-    for (int u = tid; u < BX_TH * 62; u += BX_THREADS) {
-      const int row = u / 62, og = u - row * 62;
-      const int x = x0 + og * 16;
-      if (row >= rows_here || x >= rowbytes) continue;
-      // own words are box words 4og+4 .. 4og+7 (the box starts 16 bytes left of x0); window = words k-2 .. k+5
-      const uint32_t* pe = csE + row * BX_CS_ROW_WORDS + og * 4 + 2;
-      const uint32_t* po = csO + row * BX_CS_ROW_WORDS + og * 4 + 2;
-      const uint2 e0 = *reinterpret_cast<const uint2*>(pe), e2 = *reinterpret_cast<const uint2*>(pe + 6);
-      const uint4 e1 = *reinterpret_cast<const uint4*>(pe + 2);
-      const uint2 o0 = *reinterpret_cast<const uint2*>(po), o2 = *reinterpret_cast<const uint2*>(po + 6);
-      const uint4 o1 = *reinterpret_cast<const uint4*>(po + 2);
-      const uint32_t E[8] = {e0.x, e0.y, e1.x, e1.y, e1.z, e1.w, e2.x, e2.y};
-      const uint32_t O[8] = {o0.x, o0.y, o1.x, o1.y, o1.z, o1.w, o2.x, o2.y};
-      uint32_t SE[7], SO[7];
-#pragma unroll
-      for (int i = 0; i < 7; i++) {
-        SE[i] = __byte_perm(E[i], E[i + 1], 0x5432);  // lanes (byte2 of word i, byte0 of word i+1)
-        SO[i] = __byte_perm(O[i], O[i + 1], 0x5432);  // lanes (byte3 of word i, byte1 of word i+1)
-      }
-      uint32_t ow[4];
-#pragma unroll
-      for (int j = 0; j < 4; j++) {
-        const int i = j + 2;
-        uint32_t he, ho;
-        if (CS == 3) {
-          // lanes (x, x+2): taps x-6, x-3, x, x+3, x+6 ; lanes (x+1, x+3) likewise.  3 terms on the ALU (IADD3), 2 on the FMA pipe.
-          he = fadd_u32(SE[i + 1], one, fadd_u32(SO[i], one, SE[i - 2] + O[i - 1] + E[i]));
-          ho = fadd_u32(SO[i + 1], one, fadd_u32(E[i + 1], one, SO[i - 2] + SE[i - 1] + O[i]));
-        } else {
-          he = fadd_u32(SE[i], one, fadd_u32(O[i], one, SE[i - 1] + SO[i - 1] + E[i]));  // CS == 1: taps x-2 .. x+2
-          ho = fadd_u32(SO[i], one, fadd_u32(SE[i], one, SO[i - 1] + E[i] + O[i]));
-        }
-        ow[j] = box_div_pack(he, ho);
-      }
-      unsigned char* dst = out.base + (long long)(y0 + row) * out.pitch + x;
-      if (vec_store && x + 16 <= rowbytes) {
-        *reinterpret_cast<uint4*>(dst) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
-      } else {
-        for (int k = 0; k < 16; k++)
-          if (x + k < rowbytes) dst[k] = (unsigned char)(ow[k >> 2] >> ((k & 3) * 8));
-      }
+// The same walk over the tiles of a BATCH of equally shaped images in ONE launch (a video batch: the frames of a step):
+// global tile g = image * tiles_per_image + tile, every image has its own tensor map and output base.  The ramp-up and
+// tail of a launch (a few microseconds, comparable to a whole 1080p frame) are paid once per batch instead of once per
+// frame, and the prefetch chain never drains between frames.  The maps live in the kernel parameter space
+// (__grid_constant__): TMA reads them in place.
+constexpr int BX_MAX_BATCH = 32;
+struct BoxBatch {
+  CUtensorMap maps[BX_MAX_BATCH];
+  unsigned char* out_base[BX_MAX_BATCH];
+};
+
+template <int CS, int BX_TH>
+__global__ void __launch_bounds__(BX_THREADS, BX_TH == 16 ? 4 : 6) k_box5_bytes_tma_batch(const __grid_constant__ BoxBatch batch, int nimg, int out_pitch, int out_nrows,
+                                                                       int rowbytes, int strips, int tiles_per_image, int vec_store, uint32_t one) {
+  constexpr int BX_RAW_BYTES = BoxCfg<BX_TH>::RAW_BYTES, BX_CS_BYTES = BoxCfg<BX_TH>::CS_BYTES;
+  extern __shared__ __align__(128) unsigned char smem[];
+  unsigned char* raw = smem;
+  uint32_t* csE = reinterpret_cast<uint32_t*>(smem + BX_RAW_BYTES);
+  uint32_t* csO = csE + BX_TH * BX_CS_ROW_WORDS;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + BX_RAW_BYTES + BX_CS_BYTES);
+  const int tid = threadIdx.x;
+  const uint32_t minus_one = 0u - one;
+  const int total = nimg * tiles_per_image;
+
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    fence_barrier_init();
+    if ((int)blockIdx.x < total) {
+      const int img = blockIdx.x / tiles_per_image, tile = blockIdx.x - img * tiles_per_image;
+      mbar_arrive_expect_tx(bar, BX_RAW_BYTES);
+      tma_load_2d(raw, &batch.maps[img], (tile % strips) * (BX_OUTW / 8), (tile / strips) * BX_TH, bar);
     }
+  }
+  __syncthreads();  // barrier init visible to the waiters
+  uint32_t parity = 0;
+
+  for (int g = blockIdx.x; g < total; g += gridDim.x) {
+    const int img = g / tiles_per_image, tile = g - img * tiles_per_image;
+    const int x0 = (tile % strips) * BX_OUTW, y0 = (tile / strips) * BX_TH;
+    mbar_wait(bar, parity);
+    parity ^= 1;
+    box_phase1<BX_TH>(raw, csE, csO, tid, minus_one);
+    __syncthreads();
+    if (tid == 0 && g + (int)gridDim.x < total) {  // prefetch this CTA's next tile (possibly of the next image) behind phase 2
+      const int ng = g + gridDim.x;
+      const int nimg_ = ng / tiles_per_image, nt = ng - nimg_ * tiles_per_image;
+      mbar_arrive_expect_tx(bar, BX_RAW_BYTES);
+      tma_load_2d(raw, &batch.maps[nimg_], (nt % strips) * (BX_OUTW / 8), (nt / strips) * BX_TH, bar);
+    }
+    box_phase2<CS, BX_TH>(csE, csO, batch.out_base[img], out_pitch, out_nrows, rowbytes, x0, y0, vec_store, tid, one);
     __syncthreads();  // column sums consumed before the next tile's phase 1 overwrites them
   }
 }
@@ -303,11 +365,84 @@ static int box5_bytes(const vppb_img* in, const vppb_img* out, void* stream, con
   return VPPB_OK;
 }
 
+// A batch of equally shaped images in one launch per <= 32 images (k_box5_bytes_tma_batch).  Anything the batched
+// kernel cannot take (mixed shapes, a view or an unaligned buffer among them) falls back to one launch per image -
+// same results either way.
+template <int CS>
+static int box5_bytes_batch(const vppb_img* ins, const vppb_img* outs, int n, void* stream, const char* name) {
+  VPPB_REQUIRE(ins && outs && n >= 0, VPPB_E_ARG, "%s: NULL batch", name);
+  if (n == 0) return VPPB_OK;
+  bool uniform = true;
+  for (int i = 0; i < n; i++) {
+    const vppb_img *in = &ins[i], *out = &outs[i];
+    VPPB_REQUIRE(in->base && out->base, VPPB_E_ARG, "%s: NULL image %d", name, i);
+    VPPB_REQUIRE(in->elem_bytes == CS && out->elem_bytes == CS, VPPB_E_ARG, "%s: element size must be %d (image %d)", name, CS, i);
+    VPPB_REQUIRE(same_domain(in, out), VPPB_E_ARG, "%s: domains differ (image %d)", name, i);
+    VPPB_REQUIRE(in->border >= 2, VPPB_E_BORDER, "%s: input border %d < 2 (image %d)", name, in->border, i);
+    uniform = uniform && tma_eligible(in) && same_domain(in, &ins[0]) && out->pitch == outs[0].pitch &&
+              (((uintptr_t)out->base % 16) == 0) == (((uintptr_t)outs[0].base % 16) == 0);
+  }
+  if (!uniform || n == 1) {
+    for (int i = 0; i < n; i++) {
+      int rc = box5_bytes<CS>(&ins[i], &outs[i], stream, name);
+      if (rc) return rc;
+    }
+    return VPPB_OK;
+  }
+  cudaStream_t st = as_stream(stream);
+  const int rowbytes = ins[0].ncols * CS, nrows = ins[0].nrows;
+  const int strips = (rowbytes + BX_OUTW - 1) / BX_OUTW;
+  // 16-row tiles (25 % halo rows instead of 50 %) as soon as the whole batch fills the machine with them
+  const long long tiles16 = (long long)strips * ((nrows + 15) / 16) * std::min(n, BX_MAX_BATCH);
+  const int th = tiles16 >= 4LL * sm_count() ? 16 : 8;
+  const int row_tiles = (nrows + th - 1) / th, tpi = strips * row_tiles;
+  const int vec_store = (((uintptr_t)outs[0].base % 16) == 0 && (outs[0].pitch % 16) == 0) ? 1 : 0;
+  static std::atomic<unsigned long long> attr_done{0};
+  int dev = 0;
+  VPPB_CUDA(cudaGetDevice(&dev));
+  const unsigned long long bit = 1ULL << (dev & 63);
+  if (!(attr_done.load(std::memory_order_acquire) & bit)) {
+    VPPB_CUDA(cudaFuncSetAttribute(k_box5_bytes_tma_batch<CS, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, BoxCfg<16>::SMEM));
+    VPPB_CUDA(cudaFuncSetAttribute(k_box5_bytes_tma_batch<CS, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, BoxCfg<8>::SMEM));
+    attr_done.fetch_or(bit, std::memory_order_release);
+  }
+  const uint64_t width_el = ((uint64_t)rowbytes + 32 + 7) / 8;
+  for (int i0 = 0; i0 < n; i0 += BX_MAX_BATCH) {
+    const int m = std::min(BX_MAX_BATCH, n - i0);
+    BoxBatch batch;
+    memset(&batch, 0, sizeof(batch));
+    for (int k = 0; k < m; k++) {
+      const vppb_img* in = &ins[i0 + k];
+      unsigned char* origin = static_cast<unsigned char*>(in->base) - 2LL * in->pitch - 16;
+      int rc = encode_tensor_map_2d(&batch.maps[k], origin, CU_TENSOR_MAP_DATA_TYPE_UINT64, 8, width_el, (uint64_t)nrows + 4, (uint64_t)in->pitch,
+                                    BX_BOXW / 8, th + 4);
+      if (rc) return rc;
+      batch.out_base[k] = static_cast<unsigned char*>(outs[i0 + k].base);
+    }
+    const long long total = (long long)m * tpi;
+    const int resident = sm_count() * (th == 16 ? 4 : 6);
+    const int grid = (int)(total < resident ? total : resident);
+    if (th == 16)
+      k_box5_bytes_tma_batch<CS, 16><<<grid, BX_THREADS, BoxCfg<16>::SMEM, st>>>(batch, m, outs[0].pitch, nrows, rowbytes, strips, tpi, vec_store, 1u);
+    else
+      k_box5_bytes_tma_batch<CS, 8><<<grid, BX_THREADS, BoxCfg<8>::SMEM, st>>>(batch, m, outs[0].pitch, nrows, rowbytes, strips, tpi, vec_store, 1u);
+    VPPB_LAUNCH_CHECK(name);
+  }
+  return VPPB_OK;
+}
+
 }  // namespace vppb
 
 using namespace vppb;
 
 extern "C" {
+
+int vppb_box5x5_u8c3_batch(const vppb_img* ins, const vppb_img* outs, int32_t n, void* stream) {
+  return box5_bytes_batch<3>(ins, outs, n, stream, "vppb_box5x5_u8c3_batch");
+}
+int vppb_box5x5_u8_batch(const vppb_img* ins, const vppb_img* outs, int32_t n, void* stream) {
+  return box5_bytes_batch<1>(ins, outs, n, stream, "vppb_box5x5_u8_batch");
+}
 
 int vppb_box5x5_u8c3(const vppb_img* in, const vppb_img* out, void* stream) {
   return box5_bytes<3>(in, out, stream, "vppb_box5x5_u8c3");

@@ -24,6 +24,9 @@ struct window3x3 {
   VPP_HD vint2 operator[](int i) const { return at(i); }
 };
 
+#if defined(__CUDACC__)
+#pragma nv_exec_check_disable  // f may be a host lambda when foreach is called from host code
+#endif
 template <int N, int MASK, typename F>
 VPP_HD void foreach(window3x3<N, MASK>, F f) {
 #pragma unroll

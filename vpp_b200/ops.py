@@ -88,6 +88,18 @@ def ingest_rgb_frame(src, border, dst=None, stream=None):
 
 
 # ---- stencils -------------------------------------------------------------------------------
+def box5x5_batch(srcs, dsts, stream=None):
+    """box5x5 over a batch of (src, dst) pairs in as few launches as possible (vppb_box5x5_*_batch): one persistent launch per
+    32 equally shaped images.  Same results as calling box5x5 pair by pair."""
+    assert len(srcs) == len(dsts) and len(srcs) > 0
+    n = len(srcs)
+    ins, outs = (capi.VppbImg * n)(), (capi.VppbImg * n)()
+    for i in range(n):
+        ins[i], outs[i] = srcs[i].desc, dsts[i].desc
+    fn = {"vuchar3": lib.vppb_box5x5_u8c3_batch, "u8": lib.vppb_box5x5_u8_batch}[srcs[0].pixel]
+    check(fn(ins, outs, n, stream))
+
+
 def box5x5(src, dst, stream=None):
     """pixel_wise(dst, relative_access(src)) | sum of the 5x5 neighbourhood / 25
     (benchmarks/box_5x5_filter2.cc:71-81; vuchar3 form examples/box_filter.cc:23-32)."""
