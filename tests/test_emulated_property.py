@@ -107,7 +107,7 @@ def test_fast9(vpp, nr, nc, th, seed, mode, bs, ring, maskval, levels):
     assert np.array_equal(np.asarray(got_sc, np.int32), sc[:n])
 
 
-@settings(max_examples=int(8 * SCALE), **SET)
+@settings(max_examples=int(5 * SCALE), **SET)
 @given(seed=st.integers(0, 1000), winsize=st.sampled_from([5, 7, 9, 11, 13, 15]), nscales=st.sampled_from([1, 2, 3]), niter=st.integers(1, 25), edge=st.booleans(),
        sr=st.floats(-3, 3), sc=st.floats(-3, 3))
 def test_lucas_kanade(vpp, seed, winsize, nscales, niter, edge, sr, sc):
