@@ -379,7 +379,7 @@ def main():
                                                                  "GROUP_RANK", "ROLE_RANK", "TORCHELASTIC_RUN_ID")}
         try:
             r = subprocess.run([sys.executable, os.path.abspath(__file__), "--probe-batch", str(local_rank if world > 1 else 0), str(th), str(W), str(nframes)],
-                               capture_output=True, text=True, timeout=300, env=env, cwd=ROOT)
+                               capture_output=True, text=True, timeout=150, env=env, cwd=ROOT)
             ok, why = r.returncode == 0, "probe rc %d %s" % (r.returncode, r.stderr.strip()[-200:])
         except Exception as ex:  # pragma: no cover
             ok, why = False, "probe did not run: %r" % (ex,)
