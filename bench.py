@@ -2,14 +2,18 @@
 """bench.py — the hot path of BASELINE.json on N B200s of one node, one JSON line on stdout.
 
 Headline metric: Mpix/s of the 5x5 box filter on image2d<vuchar3> (BASELINE configs[1]).
-  --gpus 1 : a batch of 1920x1080 vuchar3 frames (batch sized > L2), one box5x5 launch per frame.
+  --gpus 1 : a batch of 1920x1080 vuchar3 frames (batch sized > L2); the frames of a step go through one box5x5 launch
+             per frame (4 streams) or ONE batched persistent launch (vppb_box5x5_u8c3_batch) - `--box-launch auto`
+             probes the batched kernel in a child process, times both forms and keeps the faster (both times are
+             reported under config.box_launch).
   --gpus N : 7680x4320 vuchar3 frames row-tiled over N ranks; each step = ONE grouped NCCL halo
              exchange (2 edge rows per neighbour per frame, all frames of the batch packed) + the
              box kernel on every tile.  Same frames for every N  ->  "scaling": "strong".
   value  : whole-job Mpix/s with inputs resident in HBM (CUDA events on the launch stream, max over ranks).
   e2e    : same metric through the C-ABI with HOST buffers (pinned): upload + mirror border fill +
            box5x5 + download inside the timed region, for every frame of the batch.
-  extras : pixel_wise add (4K int32), FAST9 (4K) and pyrLK (1080p, 3 levels, 10k kps, 7x7) numbers.
+  extras : pixel_wise add (4K int32), 4K box, RGB frame ingest (4K), FAST9 (4K) and pyrLK (1080p, 3 levels, 10k kps, 7x7)
+           numbers, each measured on its own (a failing row reports an error instead of taking the line down).
 --impl reference times the reference's CPU implementation (oracle/_ref if built, else the oracle
 port compiled with the reference's benchmark flags -O3 -march=native -fopenmp) on the host cores.
 """
@@ -512,7 +516,7 @@ def main():
     for _ in range(warmup):
         step()
     barrier()
-    # The step (one launch per frame, fork/join over the side streams) is captured once into a CUDA graph
+    # The step (per launch form: one launch per frame with fork/join over the side streams, or one batched launch) is captured once into a CUDA graph
     # and replayed: same kernels, same work, without the per-launch host cost of the Python/ctypes loop.
     graph, run_step = None, step
     if world == 1:  # at N>1 the device pieces are graphs already; NCCL P2P inside a captured graph hung on this stack
