@@ -93,3 +93,4 @@ test_pyrlk_match = G.test_pyrlk_match
 test_halo_pack_unpack_single_and_batch = G.test_halo_pack_unpack_single_and_batch
 test_semi_dense_optical_flow_bit_exact = G.test_semi_dense_optical_flow_bit_exact
 test_video_extruder_gpu_equals_oracle = G.test_video_extruder_gpu_equals_oracle
+test_video_extruder_eventful_sequence_equals_reference_tables = G.test_video_extruder_eventful_sequence_equals_reference_tables

@@ -635,3 +635,27 @@ def test_video_extruder_gpu_equals_oracle(vpp):
         assert np.array_equal(ve.state_table(g), ve.state_table(c)), "frame %d" % f
     t = ve.state_table(g)
     assert len(t) > 20 and (t[:, 2] > 1).sum() > 5
+
+
+@pytest.mark.parametrize("tag,nframes,th", [("7f_th4", 7, 4), ("9f_th5", 9, 5)])
+def test_video_extruder_eventful_sequence_equals_reference_tables(vpp, tag, nframes, th):
+    """the committed eventful sequence (an occluder appears, a patch is mirrored: keypoints die, merge and are re-detected)
+    through the CUDA path (Python orchestration) against the tables the REFERENCE's own video_extruder_update produced
+    (tests/golden/make_video_extruder_fixture.py); frame by frame against the oracle-backed orchestration too"""
+    import os
+
+    from vpp_b200 import video_extruder as ve
+    from tests.oracle_video import OracleOps
+
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    frames = np.fromfile(os.path.join(gold, "video_extruder_frames_9x121x161.u8"), np.uint8).reshape(9, 121, 161)
+    expected = np.fromfile(os.path.join(gold, "video_extruder_expected_%s.i32" % tag), np.int32).reshape(-1, 6)
+    kw = dict(detector_th=th, keypoint_spacing=10, detector_period=3, max_trajectory_length=5, nscales=3, winsize=9, propagation=2)
+    g, c = ve.video_extruder_init(121, 161), ve.video_extruder_init(121, 161)
+    gops, cops = ve.GpuOps(), OracleOps()
+    for f in range(1, nframes):
+        ve.video_extruder_update(g, frames[f - 1], frames[f], gops, **kw)
+        ve.video_extruder_update(c, frames[f - 1], frames[f], cops, **kw)
+        assert np.array_equal(ve.state_table(g), ve.state_table(c)), "frame %d" % f
+    assert np.array_equal(ve.state_table(g), expected)
+    assert (expected[:, 2] == 0).any()  # the sequence does leave dead, not yet compacted keypoints behind
