@@ -645,12 +645,24 @@ def main():
     rowb = W * 3
     h2d = (th * rowb) if world == 1 else (th + 4) * (W + 4) * 3
 
+    # Two ways to bring a whole host frame into the bordered device image (N = 1), both through the public C-ABI:
+    #   direct: vppb_upload straight into the pitched image (a 2-D copy: host rows are tight, device rows are padded for the
+    #           border), then vppb_fill_border_mirror;
+    #   staged: vppb_upload into a border-less image whose rows are as tight as the host's (one LINEAR copy), then
+    #           vppb_copy2d_mirror = copy + mirror border in one launch (HBM cost ~2 us, the PCIe copy is ~100 us).
+    # Both are timed below; the faster carries the e2e number and both times are reported.
+    e_stage = [vpp.Image2d(th, W, "vuchar3") for _ in range(NE2E)] if world == 1 else []
+    e2e_mode = ["direct"]
+
     def e2e_step():
         for i in range(nframes):
             k = i % NE2E
             st = C.c_void_p(streams[k].cuda_stream)
             hin = host_in[i % len(host_in)]
-            if world == 1:
+            if world == 1 and e2e_mode[0] == "staged":
+                capi.check(capi.lib.vppb_upload(e_stage[k].ptr(), C.c_void_p(hin.data_ptr()), rowb, 0, st))
+                capi.check(capi.lib.vppb_copy2d_mirror(e_stage[k].ptr(), e_src[k].ptr(), st))
+            elif world == 1:
                 capi.check(capi.lib.vppb_upload(e_src[k].ptr(), C.c_void_p(hin.data_ptr()), rowb, 0, st))
                 capi.check(capi.lib.vppb_fill_border_mirror(e_src[k].ptr(), st))
             else:
@@ -661,6 +673,21 @@ def main():
         for s_ in streams:
             s_.synchronize()
 
+    e2e_ms = {}
+    for m_ in (["direct", "staged"] if world == 1 else ["direct"]):
+        e2e_mode[0] = m_
+        for _ in range(2):
+            e2e_step()
+        torch.cuda.synchronize()
+        if m_ == "staged" and not np.array_equal(host_out[0].numpy(), hd.get()):  # must equal the oracle like the direct form
+            sys.stderr.write("staged upload gives a different result: not used\n")
+            continue
+        t0 = time.perf_counter()
+        for _ in range(3):
+            e2e_step()
+        torch.cuda.synchronize()
+        e2e_ms[m_] = (time.perf_counter() - t0) / 3 * 1e3
+    e2e_mode[0] = min(e2e_ms, key=e2e_ms.get)
     for _ in range(2):
         e2e_step()
     barrier()
@@ -676,7 +703,9 @@ def main():
     dt = float(te.item())
     e2e = {"value": esteps * nframes * H * W / 1e6 / dt, "unit": "Mpix/s", "h2d_bytes_per_step": nframes * h2d * world,
            "d2h_bytes_per_step": nframes * th * rowb * world, "ms_per_step": dt / esteps * 1e3,
-           "note": "pinned host frames -> vppb_upload -> (mirror fill) -> box5x5 -> vppb_download, 4 streams per rank, max over ranks"}
+           "upload": {"used": e2e_mode[0], "ms_per_step_by_form": e2e_ms},
+           "note": "pinned host frames -> vppb_upload (direct 2-D copy + mirror fill, or linear copy into a tight image + copy/mirror launch: the faster of the two) "
+                   "-> box5x5 -> vppb_download, 4 frames in flight per rank, max over ranks"}
     # the end-to-end result must equal the oracle's too
     parity_ok = parity_ok and bool(np.array_equal(host_out[0].numpy(), hd.get()))
 

@@ -45,6 +45,7 @@ def test_bench_single_gpu_control_flow(built, box_launch, probe_rc):
     assert line["gpu_launches"] == 3 * (5 if bl["used"] == "per-frame" else 1)
     assert line["roofline"]["kernel"] == ("k_box5_bytes_tma_batch<3>" if bl["used"] == "batch" else "k_box5_bytes_tma<3>")
     assert line["e2e"]["h2d_bytes_per_step"] == 5 * 48 * 400 * 3
+    assert set(line["e2e"]["upload"]["ms_per_step_by_form"]) == {"direct", "staged"} and line["e2e"]["upload"]["used"] in ("direct", "staged")
 
 
 @pytest.mark.parametrize("box_launch", ["auto", "per-frame"])

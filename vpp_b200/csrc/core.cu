@@ -157,6 +157,11 @@ static int xfer(const vppb_img* im, void* host, int64_t host_pitch, int with_bor
                (long long)width);
   unsigned char* d = static_cast<unsigned char*>(im->base) - (int64_t)b * im->pitch - (int64_t)b * im->elem_bytes;
   unsigned char* h = static_cast<unsigned char*>(host) - (int64_t)b * host_pitch - (int64_t)b * im->elem_bytes;
+  if (host_pitch == width && im->pitch == width) {  // gap-free on both sides: one linear copy instead of a pitched one
+    if (up) VPPB_CUDA(cudaMemcpyAsync(d, h, (size_t)(width * height), cudaMemcpyHostToDevice, as_stream(stream)));
+    else VPPB_CUDA(cudaMemcpyAsync(h, d, (size_t)(width * height), cudaMemcpyDeviceToHost, as_stream(stream)));
+    return VPPB_OK;
+  }
   if (up)
     VPPB_CUDA(cudaMemcpy2DAsync(d, im->pitch, h, host_pitch, width, height, cudaMemcpyHostToDevice, as_stream(stream)));
   else
