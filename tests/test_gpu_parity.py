@@ -35,6 +35,15 @@ def test_layout_alignment_and_roundtrip(vpp):
         img.upload(a, with_border=True)
         assert np.array_equal(img.download(with_border=True), a)
         assert np.array_equal(img.download(), a[b:b + nr, b:b + nc] if b else a)
+    # gap-free images (row bytes a multiple of the alignment, no border) take the single linear copy of vppb_upload / download
+    for (nr, nc, pix) in [(33, 128, "vuchar3"), (17, 64, "i32"), (9, 256, "u8")]:
+        img = vpp.Image2d(nr, nc, pix)
+        assert img.pitch == nc * img.elem_bytes
+        a = rng(3).integers(0, 255, img._host_shape(False)).astype(img.dtype)
+        img.upload(a)
+        assert np.array_equal(img.download(), a)
+        sub = img | vpp.Box2d((2, 8), (5, 40))  # a view of it is pitched again
+        assert np.array_equal(sub.download(), a[2:6, 8:41])
 
 
 def test_subimage_aliases_pixels(vpp):
