@@ -12,4 +12,7 @@ timeout -k 10 200 python dbg/exp_e2e.py > gpurun_out/exp_e2e.txt 2>&1; cat gpuru
 # launch list of the pyrLK extra (9 pyramid launches expected) and one full capture of the ingest kernel
 timeout -k 10 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_r2.csv python bench.py --steps 2 --warmup 3 --cpu-budget 1 > /dev/null 2>&1
 timeout -k 10 300 ncu --set full --clock-control none --import-source on -k regex:k_rgb_to_gray -c 2 -f -o gpurun_out/prof_ingest python bench.py --steps 2 --warmup 3 --cpu-budget 1 > /dev/null 2>&1
+# the kernels that have never run on hardware before, once under compute-sanitizer (memcheck, then racecheck on shared memory)
+timeout -k 10 400 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py -q -x -k "batch or rgb or fused_level or pyramid" > gpurun_out/sanitizer_memcheck.txt 2>&1; tail -5 gpurun_out/sanitizer_memcheck.txt
+timeout -k 10 400 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py -q -x -k "box5x5_batch_equals_oracle and 270" > gpurun_out/sanitizer_racecheck.txt 2>&1; tail -5 gpurun_out/sanitizer_racecheck.txt
 ls -la gpurun_out | tail
