@@ -17,6 +17,7 @@ import sys
 import pytest
 
 from tests import test_gpu_parity as G
+from tests import test_gpu_parity_late as L
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 UBSAN_LOG = os.path.join(ROOT, "tests", "emu", "_build", "ubsan.log")
@@ -72,16 +73,16 @@ test_box5x5_vuchar3_bit_exact = G.test_box5x5_vuchar3_bit_exact
 test_box5x5_extremes_and_u8 = G.test_box5x5_extremes_and_u8
 test_box5x5_direct_path_on_views_matches = G.test_box5x5_direct_path_on_views_matches
 test_box5x5_i32 = G.test_box5x5_i32
-test_box5x5_batch_equals_oracle = G.test_box5x5_batch_equals_oracle
-test_box5x5_batch_fallbacks_and_errors = G.test_box5x5_batch_fallbacks_and_errors
+test_box5x5_batch_equals_oracle = L.test_box5x5_batch_equals_oracle
+test_box5x5_batch_fallbacks_and_errors = L.test_box5x5_batch_fallbacks_and_errors
 test_box_border_too_small_is_an_error = G.test_box_border_too_small_is_an_error
 # frame ingest (rgb_to_graylevel, fused with the mirror border)
-test_rgb_to_graylevel_and_frame_ingest = G.test_rgb_to_graylevel_and_frame_ingest
+test_rgb_to_graylevel_and_frame_ingest = L.test_rgb_to_graylevel_and_frame_ingest
 # Scharr, pyramids (fused level launches)
 test_scharr = G.test_scharr
 test_pyramid_u8 = G.test_pyramid_u8
 test_gradient_pyramid = G.test_gradient_pyramid
-test_fused_level_equals_lowpass_then_mirror = G.test_fused_level_equals_lowpass_then_mirror
+test_fused_level_equals_lowpass_then_mirror = L.test_fused_level_equals_lowpass_then_mirror
 # FAST9 (ballots, block scans, atomics), Lucas-Kanade (4 keypoints per warp, ordered float sums), semi-dense flow
 test_fast9_keypoints_bit_exact = G.test_fast9_keypoints_bit_exact
 test_fast9_mask_semantics = G.test_fast9_mask_semantics
@@ -93,4 +94,5 @@ test_pyrlk_match = G.test_pyrlk_match
 test_halo_pack_unpack_single_and_batch = G.test_halo_pack_unpack_single_and_batch
 test_semi_dense_optical_flow_bit_exact = G.test_semi_dense_optical_flow_bit_exact
 test_video_extruder_gpu_equals_oracle = G.test_video_extruder_gpu_equals_oracle
-test_video_extruder_eventful_sequence_equals_reference_tables = G.test_video_extruder_eventful_sequence_equals_reference_tables
+test_video_extruder_eventful_sequence_equals_reference_tables = L.test_video_extruder_eventful_sequence_equals_reference_tables
+test_linear_copy_path_of_upload_download = L.test_linear_copy_path_of_upload_download

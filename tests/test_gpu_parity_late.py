@@ -1,0 +1,185 @@
+"""GPU parity tests of what was built AFTER the round's last GPU run (verified on the CPU emulator only, see
+profiles/r1_emulator_verification.md): they live in their own module, which sorts after tests/test_gpu_parity.py, so that
+`pytest -m gpu -x` reaches them only once everything that already ran on hardware has been re-checked.
+tests/test_emulated_parity.py collects them for the emulator like the others."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from tests import oracle as orc
+from tests.test_gpu_parity import rng, vpp  # noqa: F401  (the module-scoped CUDA fixture)
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_linear_copy_path_of_upload_download(vpp):
+    # gap-free images (row bytes a multiple of the alignment, no border) take the single linear copy of vppb_upload / download
+    for (nr, nc, pix) in [(33, 128, "vuchar3"), (17, 64, "i32"), (9, 256, "u8")]:
+        img = vpp.Image2d(nr, nc, pix)
+        assert img.pitch == nc * img.elem_bytes
+        a = rng(3).integers(0, 255, img._host_shape(False)).astype(img.dtype)
+        img.upload(a)
+        assert np.array_equal(img.download(), a)
+        sub = img | vpp.Box2d((2, 8), (5, 40))  # a view of it is pitched again
+        assert np.array_equal(sub.download(), a[2:6, 8:41])
+
+
+@pytest.mark.parametrize("pix,shape,n", [("vuchar3", (64, 341), 3), ("vuchar3", (270, 480), 5), ("vuchar3", (40, 330), 33), ("u8", (57, 1000), 4),
+                                         ("vuchar3", (1080, 1920), 2), ("vuchar3", (7, 9), 2)])
+def test_box5x5_batch_equals_oracle(vpp, pix, shape, n):
+    """vppb_box5x5_*_batch: one persistent launch over the tiles of all images (two launches for 33 images), every image
+    with its own tensor map / output base; each result must equal the oracle's"""
+    o = orc.load()
+    ch = 3 if pix == "vuchar3" else 1
+    srcs, dsts, exp = [], [], []
+    for i in range(n):
+        data = rng(1000 * i + shape[0]).integers(0, 256, shape + ((ch,) if ch > 1 else ()), dtype=np.uint8)
+        S = vpp.Image2d.from_host(data, pix, border=2)
+        vpp.fill_border_mirror(S)
+        srcs.append(S)
+        dsts.append(vpp.Image2d(shape[0], shape[1], pix))
+        hs = orc.HostImage(shape[0], shape[1], pix, border=2, data=data, fill_border="mirror")
+        hd = orc.HostImage(shape[0], shape[1], pix)
+        o.vo_box5x5_u8(hs.ptr(), hd.ptr(), ch)
+        exp.append(hd.get())
+    vpp.box5x5_batch(srcs, dsts)
+    for i in range(n):
+        assert np.array_equal(dsts[i].download(), exp[i]), i
+
+
+def test_box5x5_batch_fallbacks_and_errors(vpp):
+    """mixed shapes, views and small alignments take the image-by-image route with the same results; errors as the single entry"""
+    from vpp_b200 import capi
+
+    o = orc.load()
+    shapes = [(40, 50), (64, 341), (40, 50)]
+    srcs, dsts, exp = [], [], []
+    for i, sh in enumerate(shapes):
+        data = rng(70 + i).integers(0, 256, sh + (3,), dtype=np.uint8)
+        S = vpp.Image2d.from_host(data, "vuchar3", border=2, aligned=128 if i else 4)
+        vpp.fill_border_mirror(S)
+        srcs.append(S)
+        dsts.append(vpp.Image2d(sh[0], sh[1], "vuchar3"))
+        hs, hd = orc.HostImage(sh[0], sh[1], "vuchar3", border=2, data=data, fill_border="mirror"), orc.HostImage(sh[0], sh[1], "vuchar3")
+        o.vo_box5x5_u8(hs.ptr(), hd.ptr(), 3)
+        exp.append(hd.get())
+    vpp.box5x5_batch(srcs, dsts)
+    for i in range(len(shapes)):
+        assert np.array_equal(dsts[i].download(), exp[i]), i
+    bad = vpp.Image2d(40, 50, "vuchar3", border=1)
+    with pytest.raises(capi.VppbError) as e:
+        vpp.box5x5_batch([srcs[0], bad], [dsts[0], vpp.Image2d(40, 50, "vuchar3")])
+    assert e.value.code == capi.VPPB_E_BORDER
+    assert capi.lib.vppb_box5x5_u8c3_batch(None, None, 0, None) == capi.VPPB_E_ARG
+
+
+@pytest.mark.parametrize("pix,kind", [("u8", 0), ("vint2", 1), ("vfloat2", 2)])
+def test_fused_level_equals_lowpass_then_mirror(vpp, pix, kind):
+    """vppb_lowpass_sub2_mirror == vppb_lowpass_sub2 + vppb_fill_border_mirror on every geometry: even / odd parents
+    (tail work items of the u8 launch), tiny levels where one pixel mirrors into both borders, prefixes of the level,
+    unaligned parents (generic kernel), borders 0..5."""
+    from vpp_b200 import capi
+
+    dt, ch = orc.PIXEL_TYPES[pix]
+    cases = [(4, 4, 2, 128), (5, 9, 3, 128), (8, 8, 4, 128), (9, 6, 2, 128), (16, 40, 5, 128), (33, 70, 3, 128), (64, 65, 0, 128), (97, 130, 4, 128),
+             (270, 481, 3, 128), (21, 30, 3, 1), (40, 41, 2, 4), (12, 200, 5, 128), (200, 12, 5, 128)]
+    for nr, nc, b, al in cases:
+        shape = (nr, nc) + ((ch,) if ch > 1 else ())
+        data = rng(nr * 1000 + nc).integers(0, 256, shape).astype(dt)
+        parent = vpp.Image2d.from_host(data, pix, border=2, aligned=al)
+        vpp.fill_border_mirror(parent)
+        for onr, onc in ((1 + nr // 2, 1 + nc // 2), (max(nr // 2, b, 1), max(nc // 2 - 1, b, 1))):
+            if b > onr or b > onc:
+                continue
+            a = vpp.Image2d(onr, onc, pix, border=b, aligned=al)
+            f = vpp.Image2d(onr, onc, pix, border=b, aligned=al)
+            for im in (a, f):
+                vpp.fill(im, 77 if ch == 1 else [77] * ch)
+                vpp.fill_border_with_value(im, 33 if ch == 1 else [33] * ch)
+            capi.check(capi.lib.vppb_lowpass_sub2(parent.ptr(), a.ptr(), kind, None))
+            vpp.fill_border_mirror(a)
+            capi.check(capi.lib.vppb_lowpass_sub2_mirror(parent.ptr(), f.ptr(), kind, None))
+            x, y = a.download(with_border=True), f.download(with_border=True)
+            assert np.array_equal(x.view(np.uint8), y.view(np.uint8)), (nr, nc, b, al, onr, onc)
+    # a border wider than the level cannot be mirrored
+    small = vpp.Image2d(3, 3, pix, border=4)
+    big = vpp.Image2d.from_host(rng(1).integers(0, 256, (5, 5) + ((ch,) if ch > 1 else ())).astype(dt), pix, border=2)
+    assert capi.lib.vppb_lowpass_sub2_mirror(big.ptr(), small.ptr(), kind, None) == capi.VPPB_E_BORDER
+
+
+@pytest.mark.parametrize("pix", ["vuchar3", "vuchar4"])
+@pytest.mark.parametrize("shape", [(45, 67), (270, 480), (1, 1), (33, 16), (64, 1000)])
+def test_rgb_to_graylevel_and_frame_ingest(vpp, pix, shape):
+    """vppb_rgb_to_graylevel_u8 (domain_with_border form of colorspace_conversions.hh:22-47) and the fused ingest
+    clone(_border) + fill_border_mirror + rgb_to_graylevel (examples/video_extruder.cc:46-48) vs the oracle"""
+    from vpp_b200 import capi
+
+    o = orc.load()
+    ch = 3 if pix == "vuchar3" else 4
+    data = rng(shape[0] * 7 + shape[1]).integers(0, 256, shape + (ch,), dtype=np.uint8)
+    for b in (0, 2):
+        if b > min(shape):
+            continue
+        for al in (128, 16, 4):
+            hs = orc.HostImage(shape[0], shape[1], pix, border=b, aligned=al, data=data, fill_border="mirror" if b else None)
+            exp = orc.HostImage(shape[0], shape[1], "u8", border=b, aligned=al)
+            o.vo_rgb_to_graylevel(hs.ptr(), exp.ptr())
+            src = vpp.Image2d.from_host(data, pix, border=b, aligned=al)
+            if b:
+                vpp.fill_border_mirror(src)
+            got = vpp.rgb_to_graylevel(src)
+            assert (got.border, got.nrows, got.ncols) == (b, shape[0], shape[1])
+            assert np.array_equal(got.download(with_border=True), exp.get(True)), (b, al)
+    # ingest: tight source without border -> gray with a mirror border of 3 (what fast9 / the pyramids want)
+    for bb in (0, 1, 3):
+        if bb > min(shape):
+            continue
+        hs = orc.HostImage(shape[0], shape[1], pix, data=data)
+        exp = orc.HostImage(shape[0], shape[1], "u8", border=bb)
+        o.vo_rgb_to_graylevel(hs.ptr(), exp.ptr())
+        o.vo_fill_border_mirror(exp.ptr())
+        for al in (128, 1):
+            got = vpp.ingest_rgb_frame(vpp.Image2d.from_host(data, pix, aligned=al), bb)
+            assert np.array_equal(got.download(with_border=True), exp.get(True)), (bb, al)
+    # errors: output border wider than the input's (plain form), border wider than the image (ingest form)
+    a, g = vpp.Image2d(8, 8, pix), vpp.Image2d(8, 8, "u8", border=2)
+    assert capi.lib.vppb_rgb_to_graylevel_u8(a.ptr(), g.ptr(), None) == capi.VPPB_E_BORDER
+    g9 = vpp.Image2d(8, 8, "u8", border=9)
+    assert capi.lib.vppb_rgb_to_graylevel_u8_mirror(a.ptr(), g9.ptr(), None) == capi.VPPB_E_BORDER
+
+
+@pytest.mark.parametrize("tag,nframes,th", [("7f_th4", 7, 4), ("9f_th5", 9, 5)])
+def test_video_extruder_eventful_sequence_equals_reference_tables(vpp, tag, nframes, th):
+    """the committed eventful sequence (an occluder appears, a patch is mirrored: keypoints die, merge and are re-detected)
+    through the CUDA path (Python orchestration) against the tables the REFERENCE's own video_extruder_update produced
+    (tests/golden/make_video_extruder_fixture.py); frame by frame against the oracle-backed orchestration too"""
+    import os
+
+    from vpp_b200 import video_extruder as ve
+    from tests.oracle_video import OracleOps
+
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    frames = np.fromfile(os.path.join(gold, "video_extruder_frames_9x121x161.u8"), np.uint8).reshape(9, 121, 161)
+    expected = np.fromfile(os.path.join(gold, "video_extruder_expected_%s.i32" % tag), np.int32).reshape(-1, 6)
+    kw = dict(detector_th=th, keypoint_spacing=10, detector_period=3, max_trajectory_length=5, nscales=3, winsize=9, propagation=2)
+    g, c = ve.video_extruder_init(121, 161), ve.video_extruder_init(121, 161)
+    gops, cops = ve.GpuOps(), OracleOps()
+    for f in range(1, nframes):
+        ve.video_extruder_update(g, frames[f - 1], frames[f], gops, **kw)
+        ve.video_extruder_update(c, frames[f - 1], frames[f], cops, **kw)
+        assert np.array_equal(ve.state_table(g), ve.state_table(c)), "frame %d" % f
+    assert np.array_equal(ve.state_table(g), expected)
+    assert (expected[:, 2] == 0).any()  # the sequence does leave dead, not yet compacted keypoints behind
+
+
+@pytest.mark.parametrize("name", ["nbh_tests", "extruder_tests"])
+def test_new_cpp_programs(gpu, name):
+    """C++ host API added after the last GPU run: box_nbh2d / window.hh / colorspace_conversions.hh (nbh_tests) and
+    video_extruder.hh / keypoint_container.hh (extruder_tests); built by build.sh, run here on the GPU"""
+    exe = os.path.join(ROOT, "tests", "cpp", "_build", name)
+    assert os.path.exists(exe), "build.sh did not produce %s" % exe
+    r = subprocess.run([exe, os.path.join(ROOT, "tests", "golden")], capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert r.returncode == 0 and "ALL OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
