@@ -833,7 +833,45 @@ def gpu_extras(vpp, capi, torch, stream, sp):
         return {"kpts_per_s_match_only": len(pts) / (ms_lk / 1e3), "kpts_per_s_with_pyramids": len(pts) / ((ms_lk + ms_build) / 1e3),
                 "ms_match": ms_lk, "ms_pyramids_scharr": ms_build, "launches_pyramids_scharr": 9}
 
-    for row in (add_i32_4k, box5x5_vuchar3_4k, ingest_rgb_4k, fast9_4k, pyrlk_1080p_10k):
+    def sdof_1080p():  # semi-dense flow with video_extruder's settings on blockwise-FAST keypoints, pyramids prebuilt: both sweep schedules
+        H_, W_ = 1080, 1920
+        base_ = scenes.rectangles_scene(H_ + 16, W_ + 16, seed=5, noise=3)
+        f1, f2 = base_[8:8 + H_, 8:8 + W_].copy(), base_[5:5 + H_, 10:10 + W_].copy()  # motion (3, -2)
+        G = vpp.Image2d.from_host(f1, "u8", border=3)
+        vpp.fill_border_mirror(G)
+        kps = vpp.fast9(G, 10, blockwise=True, block_size=10)
+        n = len(kps)
+        from vpp_b200.ops import _DeviceBuffer
+
+        P = capi.VppbSdofParams(9, 3, 0, 2, 5)
+        p1 = vpp.Pyramid2d(vpp.Image2d.from_host(f1, "u8"), 3, 2, border=18)
+        p2 = vpp.Pyramid2d(vpp.Image2d.from_host(f2, "u8"), 3, 2, border=18)
+        wsb = _DeviceBuffer(capi.lib.vppb_sdof_workspace_bytes(H_, W_, C.byref(P)))
+        d_kp = _DeviceBuffer(kps.nbytes).from_host(kps)
+        d_pos, d_dist, d_valid = _DeviceBuffer(n * 8), _DeviceBuffer(n * 4), _DeviceBuffer(n)
+        a1, a2 = p1.desc_array(), p2.desc_array()
+
+        def run():
+            capi.check(capi.lib.vppb_sdof_u8(a1, a2, C.byref(P), d_kp.ptr, n, wsb.ptr, wsb.nbytes, d_pos.ptr, d_dist.ptr, d_valid.ptr, sp))
+
+        res, outs = {"keypoints": n}, {}
+        saved = os.environ.pop("VPPB_SDOF_SCHEDULE", None)
+        try:
+            for name_ in ("antidiagonals", "levels"):
+                if name_ == "levels":
+                    os.environ["VPPB_SDOF_SCHEDULE"] = "levels"
+                run()
+                res["ms_" + name_] = timed(run, 3)
+                outs[name_] = (d_pos.to_host(np.int32, n * 2), d_dist.to_host(np.int32, n), d_valid.to_host(np.uint8, n))
+        finally:
+            os.environ.pop("VPPB_SDOF_SCHEDULE", None)
+            if saved is not None:
+                os.environ["VPPB_SDOF_SCHEDULE"] = saved
+        res["schedules_agree"] = bool(all(np.array_equal(x, y) for x, y in zip(outs["antidiagonals"], outs["levels"])))
+        res["note"] = "default = one launch per anti-diagonal; VPPB_SDOF_SCHEDULE=levels (opt-in) = dependency levels of the marked cells, same results"
+        return res
+
+    for row in (add_i32_4k, box5x5_vuchar3_4k, ingest_rgb_4k, fast9_4k, pyrlk_1080p_10k, sdof_1080p):  # the never-run-on-hardware schedule goes last
         try:
             out[row.__name__] = row()
         except Exception as ex:  # pragma: no cover - a broken extra must not cost the headline line

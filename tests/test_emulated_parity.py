@@ -96,3 +96,4 @@ test_semi_dense_optical_flow_bit_exact = G.test_semi_dense_optical_flow_bit_exac
 test_video_extruder_gpu_equals_oracle = G.test_video_extruder_gpu_equals_oracle
 test_video_extruder_eventful_sequence_equals_reference_tables = L.test_video_extruder_eventful_sequence_equals_reference_tables
 test_linear_copy_path_of_upload_download = L.test_linear_copy_path_of_upload_download
+test_semi_dense_flow_level_schedule = L.test_semi_dense_flow_level_schedule

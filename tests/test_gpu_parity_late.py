@@ -183,3 +183,35 @@ def test_new_cpp_programs(gpu, name):
     assert os.path.exists(exe), "build.sh did not produce %s" % exe
     r = subprocess.run([exe, os.path.join(ROOT, "tests", "golden")], capture_output=True, text=True, timeout=300, cwd=ROOT)
     assert r.returncode == 0 and "ALL OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("density", ["sparse", "dense"])
+def test_semi_dense_flow_level_schedule(vpp, monkeypatch, density):
+    """VPPB_SDOF_SCHEDULE=levels (opt-in): the propagation sweeps run as dependency levels of the marked cells instead of
+    anti-diagonals - same serial semantics, so the results must equal the oracle bit for bit.  sparse: blockwise-FAST
+    keypoints (video_extruder's case: few levels); dense: a keypoint in every cell (the schedule falls back to anti-diagonals
+    wherever levels would not halve the launches)."""
+    from tests import scenes
+
+    monkeypatch.setenv("VPPB_SDOF_SCHEDULE", "levels")
+    nr, nc = 121, 161
+    f1, f2, _ = scenes.lk_pair(nr, nc, 4, seed=23, shift=(3.0, -2.0), margin=10)
+    o = orc.load()
+    if density == "sparse":
+        h = orc.HostImage(nr, nc, "u8", border=3, data=f1, fill_border="mirror")
+        k = np.zeros((f1.size, 2), np.int32)
+        n = o.vo_fast9_u8(h.ptr(), 8, None, 2, 10, 0, k.ctypes.data, None, len(k))
+        kps = np.ascontiguousarray(k[:n])
+    else:
+        rr, cc = np.meshgrid(np.arange(2, nr, 5), np.arange(2, nc, 5), indexing="ij")
+        kps = np.stack([rr.ravel(), cc.ravel()], axis=1).astype(np.int32)
+    for (ws, nscales, prop, patch) in [(9, 3, 2, 5), (7, 2, 3, 5), (9, 1, 1, 3)]:
+        pos, dist, valid = vpp.semi_dense_optical_flow(kps, vpp.Image2d.from_host(f1, "u8"), vpp.Image2d.from_host(f2, "u8"), winsize=ws, nscales=nscales,
+                                                       propagation=prop, patchsize=patch)
+        h1, h2 = orc.HostImage(nr, nc, "u8", data=f1), orc.HostImage(nr, nc, "u8", data=f2)
+        m = len(kps)
+        rpos, rdist, rvalid = np.zeros((m, 2), np.int32), np.zeros(m, np.int32), np.zeros(m, np.uint8)
+        o.vo_semi_dense_flow(h1.ptr(), h2.ptr(), kps.ctypes.data, m, ws, nscales, 0, prop, patch, rpos.ctypes.data, rdist.ctypes.data, rvalid.ctypes.data)
+        assert np.array_equal(valid, rvalid.astype(bool)) and valid.sum() > 10
+        ok = rvalid > 0
+        assert np.array_equal(pos[ok], rpos[ok]) and np.array_equal(dist[ok], rdist[ok]), (density, ws, nscales, prop, patch)

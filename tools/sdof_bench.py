@@ -34,12 +34,19 @@ for (H, W) in [(1080, 1920), (4320, 7680)]:
         capi.check(capi.lib.vppb_sdof_u8(p1.desc_array(), p2.desc_array(), C.byref(P), d_kp.ptr, n, ws.ptr, ws.nbytes, d_pos.ptr, d_dist.ptr, d_valid.ptr, None))
         capi.check(capi.lib.vppb_sync(None))
 
-    run()
-    t0 = time.perf_counter()
-    reps = 3
-    for _ in range(reps):
+    for sched in ("levels", None):  # the opt-in dependency-level schedule first, the default (anti-diagonals) last: its numbers print below
+        if sched:
+            os.environ["VPPB_SDOF_SCHEDULE"] = sched
+        else:
+            os.environ.pop("VPPB_SDOF_SCHEDULE", None)
         run()
-    dt = (time.perf_counter() - t0) / reps
+        t0 = time.perf_counter()
+        reps = 3
+        for _ in range(reps):
+            run()
+        dt = (time.perf_counter() - t0) / reps
+        if sched:
+            print("%dx%d: schedule=%s %.2f ms per frame pair" % (W, H, sched, dt * 1e3))
     pos = d_pos.to_host(np.int32, n * 2).reshape(-1, 2)
     valid = d_valid.to_host(np.uint8, n).astype(bool)
     flow = (pos - kps)[valid]

@@ -17,6 +17,9 @@
 #include "common.cuh"
 
 #include <limits.h>
+#include <string.h>
+
+#include <vector>
 
 namespace vppb {
 
@@ -103,42 +106,121 @@ __global__ void __launch_bounds__(128) k_sdof_match(SdofLevel L, SdofLevel coars
   }
 }
 
-// :149-189 for the iterations (kr, kc) of one sweep with kc + 2 kr == t; forward sweeps start at pixel 0 and step
+// :149-189, iteration (kr, kc) of a propagation sweep, executed by one warp; forward sweeps start at pixel 0 and step
 // +patch, backward sweeps start at the last pixel and step -patch (so p is not the cell corner there)
+__device__ __forceinline__ void sdof_prop_cell(const SdofLevel& L, int kr, int kc, int forward, int patch, int ws, int lane) {
+  const int inr = L.i1.nrows, inc = L.i1.ncols;
+  const int r = forward ? kr * patch : inr - 1 - kr * patch, c = forward ? kc * patch : inc - 1 - kc * patch;
+  const int fr = r / patch, fc = c / patch;
+  const int cell = fr * L.cstride + fc;
+  if (!L.mark[cell]) return;  // warp-uniform
+  int2 cur = L.flow[cell];
+  const int2 prev = cur;
+  int d1 = L.dist[cell];
+  bool changed = false;
+  for (int dr = -1; dr <= 1; dr++)
+    for (int dc = -1; dc <= 1; dc++) {
+      if (!dr && !dc) continue;
+      const int nr = fr + dr, nc = fc + dc;
+      if (nr < 0 || nr >= L.cr || nc < 0 || nc >= L.cc) continue;
+      const int ncell = nr * L.cstride + nc;
+      if (!L.mark[ncell]) continue;
+      const int2 nf = L.flow[ncell];
+      const int a0 = cur.x - nf.x, a1 = cur.y - nf.y, b0 = prev.x - nf.x, b1 = prev.y - nf.y;
+      if (a0 * a0 + a1 * a1 < 9 || b0 * b0 + b1 * b1 < 9) continue;  // integer norm() > 2
+      const int d2 = sad_warp(L.i1, L.i2, r, c, r + nf.x, c + nf.y, ws);
+      if (d2 < d1) {
+        int flr, flc, d;
+        descent_warp(L.i1, L.i2, r, c, r + nf.x, c + nf.y, ws, 5, flr, flc, d);
+        if (d < d1) { cur = make_int2(flr, flc); d1 = d; changed = true; }
+      }
+    }
+  if (changed && lane == 0) { L.flow[cell] = cur; L.dist[cell] = d1; L.mark[cell] = 1; }
+}
+
+// the iterations (kr, kc) of one sweep with kc + 2 kr == t: iteration (kr, kc) only reads what (kr, kc-1) and
+// (kr-1, kc-1..kc+1) wrote, so a whole anti-diagonal is independent
 __global__ void __launch_bounds__(128) k_sdof_prop_wave(SdofLevel L, int t, int forward, int nkr, int nkc, int patch, int ws) {
   const int lane = threadIdx.x & 31;
   const int kr_lo = max(0, (t - (nkc - 1) + 1) / 2), kr_hi = min(nkr - 1, t / 2);
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
-  const int inr = L.i1.nrows, inc = L.i1.ncols;
   for (int kr = kr_lo + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5); kr <= kr_hi; kr += nwarps) {
     const int kc = t - 2 * kr;
     if (kc < 0 || kc >= nkc) continue;
-    const int r = forward ? kr * patch : inr - 1 - kr * patch, c = forward ? kc * patch : inc - 1 - kc * patch;
-    const int fr = r / patch, fc = c / patch;
-    const int cell = fr * L.cstride + fc;
-    if (!L.mark[cell]) continue;  // warp-uniform
-    int2 cur = L.flow[cell];
-    const int2 prev = cur;
-    int d1 = L.dist[cell];
-    bool changed = false;
-    for (int dr = -1; dr <= 1; dr++)
-      for (int dc = -1; dc <= 1; dc++) {
-        if (!dr && !dc) continue;
-        const int nr = fr + dr, nc = fc + dc;
-        if (nr < 0 || nr >= L.cr || nc < 0 || nc >= L.cc) continue;
-        const int ncell = nr * L.cstride + nc;
-        if (!L.mark[ncell]) continue;
-        const int2 nf = L.flow[ncell];
-        const int a0 = cur.x - nf.x, a1 = cur.y - nf.y, b0 = prev.x - nf.x, b1 = prev.y - nf.y;
-        if (a0 * a0 + a1 * a1 < 9 || b0 * b0 + b1 * b1 < 9) continue;  // integer norm() > 2
-        const int d2 = sad_warp(L.i1, L.i2, r, c, r + nf.x, c + nf.y, ws);
-        if (d2 < d1) {
-          int flr, flc, d;
-          descent_warp(L.i1, L.i2, r, c, r + nf.x, c + nf.y, ws, 5, flr, flc, d);
-          if (d < d1) { cur = make_int2(flr, flc); d1 = d; changed = true; }
-        }
+    sdof_prop_cell(L, kr, kc, forward, patch, ws, lane);
+  }
+}
+
+// ---- dependency-level schedule of a sweep (opt-in, VPPB_SDOF_SCHEDULE=levels) ---------------------------------
+// Only marked cells do anything in a sweep, and a marked cell only interacts with its marked 8-neighbours.  Give every
+// marked cell the level 1 + max(level of the marked neighbours that PRECEDE it in the sweep) (0 if none): two
+// adjacent marked cells always get different levels, ordered as the serial sweep orders them, so running the levels
+// one after another - all cells of a level at once - reproduces the Gauss-Seidel sweep exactly, in (longest chain of
+// adjacent marked cells) launches instead of (cols + 2 rows) anti-diagonals.  With video_extruder's keypoints (one per
+// 10 x 10 block, cells of 5 px) the finest scale needs a handful of levels instead of ~800 wavefronts.
+// k_sdof_levels: ONE CTA walks the anti-diagonals (integer work only, a __syncthreads per diagonal), then buckets the
+// marked cells by level.  sched[0] = number of levels, sched[1] = number of marked cells, start = sched + 2 (cap + 1
+// entries: bucket starts, then the total), hist = start + cap + 1 (scratch: histogram, then bucket cursors).
+// cells: (kr << 16 | kc) of the marked cells, grouped by level (order inside a level is irrelevant: its cells are independent).
+__global__ void __launch_bounds__(1024) k_sdof_levels(SdofLevel L, int forward, int nkr, int nkc, int patch, int* level, int* sched, int cap, unsigned* cells) {
+  const int inr = L.i1.nrows, inc = L.i1.ncols;
+  const int waves = nkc + 2 * (nkr - 1);
+  int* start = sched + 2;
+  int* hist = start + cap + 1;
+  __shared__ int s_max, s_cnt;
+  if (threadIdx.x == 0) { s_max = -1; s_cnt = 0; }
+  for (int i = threadIdx.x; i < cap; i += blockDim.x) hist[i] = 0;
+  __syncthreads();
+  const int sgn = forward ? 1 : -1;  // a step of +1 in sweep coordinates is a step of sgn in cell coordinates
+  for (int t = 0; t < waves; t++) {
+    const int kr_lo = max(0, (t - (nkc - 1) + 1) / 2), kr_hi = min(nkr - 1, t / 2);
+    for (int kr = kr_lo + (int)threadIdx.x; kr <= kr_hi; kr += blockDim.x) {
+      const int kc = t - 2 * kr;
+      if (kc < 0 || kc >= nkc) continue;
+      const int r = forward ? kr * patch : inr - 1 - kr * patch, c = forward ? kc * patch : inc - 1 - kc * patch;
+      const int fr = r / patch, fc = c / patch;
+      const int cell = fr * L.cstride + fc;
+      if (!L.mark[cell]) continue;
+      int lv = 0;
+      // predecessors in sweep order: (kr, kc-1), (kr-1, kc-1), (kr-1, kc), (kr-1, kc+1) - counted only where sdof_prop_cell reads them
+      const int pr[4] = {fr, fr - sgn, fr - sgn, fr - sgn}, pc[4] = {fc - sgn, fc - sgn, fc, fc + sgn};
+      for (int k = 0; k < 4; k++) {
+        if (pr[k] < 0 || pr[k] >= L.cr || pc[k] < 0 || pc[k] >= L.cc) continue;
+        const int pcell = pr[k] * L.cstride + pc[k];
+        if (L.mark[pcell]) lv = max(lv, level[pcell] + 1);
       }
-    if (changed && lane == 0) { L.flow[cell] = cur; L.dist[cell] = d1; L.mark[cell] = 1; }
+      level[cell] = lv;
+      atomicMax(&s_max, lv);
+      atomicAdd(&s_cnt, 1);
+      atomicAdd(&hist[lv], 1);
+    }
+    __syncthreads();
+  }
+  const int nlevels = s_max + 1;
+  if (threadIdx.x == 0) {
+    sched[0] = nlevels;
+    sched[1] = s_cnt;
+    int run = 0;
+    for (int l = 0; l < nlevels; l++) { start[l] = run; run += hist[l]; hist[l] = start[l]; }  // hist becomes the fill cursor
+    start[nlevels] = run;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < nkr * nkc; i += blockDim.x) {
+    const int kr = i / nkc, kc = i - kr * nkc;
+    const int r = forward ? kr * patch : inr - 1 - kr * patch, c = forward ? kc * patch : inc - 1 - kc * patch;
+    const int cell = (r / patch) * L.cstride + (c / patch);
+    if (!L.mark[cell]) continue;
+    cells[atomicAdd(&hist[level[cell]], 1)] = ((unsigned)kr << 16) | (unsigned)kc;
+  }
+}
+
+// one level of the schedule: n independent iterations, one warp each
+__global__ void __launch_bounds__(128) k_sdof_prop_list(SdofLevel L, const unsigned* cells, int n, int forward, int patch, int ws) {
+  const int lane = threadIdx.x & 31;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += nwarps) {
+    const unsigned v = cells[i];
+    sdof_prop_cell(L, (int)(v >> 16), (int)(v & 0xFFFFu), forward, patch, ws, lane);
   }
 }
 
@@ -158,6 +240,17 @@ static void cell_dims(int nrows, int ncols, int patch, int level, int& cr, int& 
   cr = nrows / patch; cc = ncols / patch;
   for (int s = 0; s < level; s++) { cr = (int)(1 + cr / 2.f); cc = (int)(1 + cc / 2.f); }  // pyramid.hh:140 on pf_domain
 }
+// buffers of the dependency-level schedule (sized for the finest scale): level per cell, the cell list, sched[]
+static void sched_dims(int nrows, int ncols, int patch, long long& cells, int& cap) {
+  const int nkr = (nrows + patch - 1) / patch, nkc = (ncols + patch - 1) / patch;
+  cells = (long long)(nkr + 3) * (nkc + 3);
+  cap = nkc + 2 * nkr + 2;  // more than the number of anti-diagonals = upper bound of the number of levels
+}
+static long long sched_bytes(int nrows, int ncols, int patch) {
+  long long cells; int cap;
+  sched_dims(nrows, ncols, patch, cells, cap);
+  return ((cells * 8 + (2LL + 2LL * (cap + 1)) * 4 + 255) / 256) * 256 + 256;
+}
 static long long level_bytes(int cr, int cc) {
   const long long cells = (long long)(cr + 2) * (cc + 2);
   return ((cells * (8 + 4 + 4 + 1) + 255) / 256) * 256 + 1024;
@@ -173,7 +266,7 @@ int64_t vppb_sdof_workspace_bytes(int32_t nrows, int32_t ncols, const vppb_sdof_
   if (!p || p->patchsize <= 0 || p->nscales <= 0 || p->nscales > 8) return 0;
   long long total = 0;
   for (int s = 0; s < p->nscales; s++) { int cr, cc; cell_dims(nrows, ncols, p->patchsize, s, cr, cc); total += level_bytes(cr, cc); }
-  return total;
+  return total + sched_bytes(nrows, ncols, p->patchsize);
 }
 
 int vppb_sdof_u8(const vppb_img* pyr1, const vppb_img* pyr2, const vppb_sdof_params* p, const vppb_int2* kps, int32_t n, void* workspace,
@@ -202,6 +295,16 @@ int vppb_sdof_u8(const vppb_img* pyr1, const vppb_img* pyr2, const vppb_sdof_par
     L[s].mark = w + cells * 16;
     w += level_bytes(cr, cc);
   }
+  // opt-in: VPPB_SDOF_SCHEDULE=levels runs every sweep as dependency levels of the marked cells when that is shorter than the
+  // anti-diagonals (one blocking read-back of the schedule size per sweep); the default is one launch per anti-diagonal
+  const char* sched_env = getenv("VPPB_SDOF_SCHEDULE");
+  const bool use_levels = sched_env && strcmp(sched_env, "levels") == 0;
+  long long sched_cells; int sched_cap;
+  sched_dims(pyr1[0].nrows, pyr1[0].ncols, p->patchsize, sched_cells, sched_cap);
+  int* lvl = reinterpret_cast<int*>(w);
+  unsigned* cell_list = reinterpret_cast<unsigned*>(w + sched_cells * 4);
+  int* sched = reinterpret_cast<int*>(w + sched_cells * 8);
+  std::vector<int> h_sched;
   const int sms = sm_count();
   for (int scale = p->nscales - 1; scale >= p->min_scale; scale--) {
     const int scale_div = 1 << scale;
@@ -217,6 +320,23 @@ int vppb_sdof_u8(const vppb_img* pyr1, const vppb_img* pyr2, const vppb_sdof_par
     for (int Ki = 0; Ki < p->propagation; Ki++) {
       const int forward = Ki % 2;  // :191-200: odd iterations forward, even (incl. the first) backward
       const int waves = nkc + 2 * (nkr - 1);
+      if (use_levels) {
+        k_sdof_levels<<<1, 1024, 0, st>>>(Ls, forward, nkr, nkc, p->patchsize, lvl, sched, sched_cap, cell_list);
+        VPPB_LAUNCH_CHECK("vppb_sdof_u8 (levels)");
+        h_sched.assign((size_t)sched_cap + 3, 0);
+        VPPB_CUDA(cudaMemcpyAsync(h_sched.data(), sched, ((size_t)sched_cap + 3) * sizeof(int), cudaMemcpyDeviceToHost, st));
+        VPPB_CUDA(cudaStreamSynchronize(st));
+        const int nlevels = h_sched[0];
+        if (nlevels * 2 <= waves) {  // worth it: at most half as many launches as anti-diagonals
+          for (int l = 0; l < nlevels; l++) {
+            const int first = h_sched[2 + l], cnt = h_sched[2 + l + 1] - first;
+            if (cnt <= 0) continue;
+            const int blocks = (cnt + 3) / 4;
+            k_sdof_prop_list<<<blocks < sms * 16 ? blocks : sms * 16, 128, 0, st>>>(Ls, cell_list + first, cnt, forward, p->patchsize, p->winsize);
+          }
+          continue;
+        }
+      }
       for (int t = 0; t < waves; t++) {
         const int width = (nkr < (nkc + 1) / 2 + 1 ? nkr : (nkc + 1) / 2 + 1);
         const int blocks = (width + 3) / 4;
