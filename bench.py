@@ -194,9 +194,10 @@ def cpu_extras(budget_s=6.0):
 
 # ------------------------------------------------------------------------------------------ GPU arm
 def probe_batch(device, rows, cols, nframes):
-    """Child process of the `--box-launch auto` selection: run the batched box kernel on the geometry the bench will use and
-    compare every frame with the per-frame kernel.  Exit code 0 = identical.  A kernel that faults takes only this
-    process (and its CUDA context) down, not the bench."""
+    """Child process of the bench: the two code paths that have not run on hardware before the bench itself - the batched box
+    kernel and the fused copy + mirror launch of the staged e2e upload - run here first, on the geometry the bench will use,
+    and are compared with the per-frame kernel / the two-step upload.  A kernel that faults takes only this process (and
+    its CUDA context) down, not the bench."""
     import __graft_entry__ as g
 
     g.build(only_if_missing=True)
@@ -213,6 +214,14 @@ def probe_batch(device, rows, cols, nframes):
         srcs.append(s_)
         d1.append(vpp.Image2d(rows, cols, "vuchar3"))
         d2.append(vpp.Image2d(rows, cols, "vuchar3"))
+    rc = 0
+    # the e2e leg's staged upload: tight image -> vppb_copy2d_mirror must give the bordered image of upload + fill_border_mirror
+    tight = vpp.Image2d.from_host(uniq[0], "vuchar3")
+    staged = vpp.Image2d(rows, cols, "vuchar3", border=2)
+    capi.check(capi.lib.vppb_copy2d_mirror(tight.ptr(), staged.ptr(), None))
+    if not np.array_equal(staged.download(with_border=True), srcs[0].download(with_border=True)):
+        sys.stderr.write("probe: vppb_copy2d_mirror differs from upload + fill_border_mirror\n")
+        rc |= 1
     for s_, d_ in zip(srcs, d1):
         vpp.box5x5(s_, d_)
     for _ in range(3):
@@ -221,8 +230,9 @@ def probe_batch(device, rows, cols, nframes):
     for i in range(nframes):
         if not np.array_equal(d1[i].download(), d2[i].download()):
             sys.stderr.write("probe: batched box differs from the per-frame kernel on frame %d\n" % i)
-            return 4
-    return 0
+            rc |= 2
+            break
+    return 4 + rc if rc else 0  # 0 = both fine, 5 = staged upload bad, 6 = batched box bad, 7 = both; anything else = the probe died
 
 
 def main():
@@ -373,10 +383,10 @@ def main():
                 capi.check(capi.lib.vppb_box5x5_u8c3(s.ptr(), d.ptr(), sp))
         return len(pairs)
 
+    staged_ok = [False]  # set by the probe: may the e2e leg try the staged upload (vppb_copy2d_mirror)?
+
     def batch_kernel_usable():
         """--box-launch auto: the batched kernel first runs in a child process on this rank's device and geometry; every rank must agree"""
-        if args.box_launch == "per-frame":
-            return False, "not requested"
         if args.box_launch == "batch":
             return True, "forced"
         env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT", "LOCAL_WORLD_SIZE",
@@ -384,13 +394,17 @@ def main():
         try:
             r = subprocess.run([sys.executable, os.path.abspath(__file__), "--probe-batch", str(local_rank if world > 1 else 0), str(th), str(W), str(nframes)],
                                capture_output=True, text=True, timeout=150, env=env, cwd=ROOT)
-            ok, why = r.returncode == 0, "probe rc %d %s" % (r.returncode, r.stderr.strip()[-200:])
+            ok = r.returncode in (0, 5)           # batched box kernel fine
+            staged_ok[0] = r.returncode in (0, 6)  # fused copy + mirror launch fine
+            why = "probe rc %d %s" % (r.returncode, r.stderr.strip()[-200:])
         except Exception as ex:  # pragma: no cover
             ok, why = False, "probe did not run: %r" % (ex,)
         if dist is not None:
             flag = torch.tensor([1.0 if ok else 0.0], dtype=torch.float64, device=dev)
             dist.all_reduce(flag, op=dist.ReduceOp.MIN)
             ok = bool(flag.item() > 0.5)
+        if args.box_launch == "per-frame":
+            return False, "not requested; " + why
         return ok, why
 
     def device_ms(fn, reps):
@@ -674,7 +688,7 @@ def main():
             s_.synchronize()
 
     e2e_ms = {}
-    for m_ in (["direct", "staged"] if world == 1 else ["direct"]):
+    for m_ in (["direct", "staged"] if (world == 1 and staged_ok[0]) else ["direct"]):
         e2e_mode[0] = m_
         for _ in range(2):
             e2e_step()
@@ -703,7 +717,7 @@ def main():
     dt = float(te.item())
     e2e = {"value": esteps * nframes * H * W / 1e6 / dt, "unit": "Mpix/s", "h2d_bytes_per_step": nframes * h2d * world,
            "d2h_bytes_per_step": nframes * th * rowb * world, "ms_per_step": dt / esteps * 1e3,
-           "upload": {"used": e2e_mode[0], "ms_per_step_by_form": e2e_ms},
+           "upload": {"used": e2e_mode[0], "ms_per_step_by_form": e2e_ms, "staged_probe_ok": staged_ok[0]},
            "note": "pinned host frames -> vppb_upload (direct 2-D copy + mirror fill, or linear copy into a tight image + copy/mirror launch: the faster of the two) "
                    "-> box5x5 -> vppb_download, 4 frames in flight per rank, max over ranks"}
     # the end-to-end result must equal the oracle's too

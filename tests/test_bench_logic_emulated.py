@@ -40,12 +40,16 @@ def test_bench_single_gpu_control_flow(built, box_launch, probe_rc):
             assert bl["used"] == "per-frame" and list(bl["ms_per_step_by_mode"]) == ["per-frame"]
         else:
             assert set(bl["ms_per_step_by_mode"]) == {"per-frame", "batch"}
+    elif box_launch == "per-frame":
+        assert bl["used"] == "per-frame" and probes == ["PROBE 0 48 400 5"]  # the probe still runs: it also vouches for the staged upload
     else:
         assert bl["used"] == box_launch and not probes
     assert line["gpu_launches"] == 3 * (5 if bl["used"] == "per-frame" else 1)
     assert line["roofline"]["kernel"] == ("k_box5_bytes_tma_batch<3>" if bl["used"] == "batch" else "k_box5_bytes_tma<3>")
     assert line["e2e"]["h2d_bytes_per_step"] == 5 * 48 * 400 * 3
-    assert set(line["e2e"]["upload"]["ms_per_step_by_form"]) == {"direct", "staged"} and line["e2e"]["upload"]["used"] in ("direct", "staged")
+    # the staged upload is tried only when the probe ran and vouched for vppb_copy2d_mirror (rc 0; --box-launch batch skips the probe)
+    forms = {"direct", "staged"} if (probe_rc == 0 and box_launch != "batch") else {"direct"}
+    assert set(line["e2e"]["upload"]["ms_per_step_by_form"]) == forms and line["e2e"]["upload"]["used"] in forms
 
 
 @pytest.mark.parametrize("box_launch", ["auto", "per-frame"])
@@ -73,3 +77,11 @@ def test_bench_two_ranks_control_flow(built, box_launch):
     if box_launch == "auto":
         assert set(bl["ms_per_step_by_mode"]) == {"per-frame", "batch"}
         assert any(l.startswith("PROBE 1 32 400 4") for l in outs[1][1].splitlines())  # rank 1 probed its own device and tile
+
+
+def test_probe_child_on_the_emulator(built):
+    """the child process of the launch-form selection (bench.py --probe-batch): batched box == per-frame box, fused copy + mirror ==
+    upload + mirror fill, on the emulated library -> exit code 0"""
+    p = _run(0, 48, 400, ["--probe-batch", "0", "48", "400", "5"])
+    out, err = p.communicate(timeout=600)
+    assert p.returncode == 0, err[-3000:]
