@@ -7,6 +7,8 @@ timeout -k 10 600 python -m pytest tests -m gpu -q --timeout 180 --timeout-metho
 tail -5 gpurun_out/pytest_gpu.log
 timeout -k 10 300 python tools/kernel_bench.py > gpurun_out/kernel_bench.txt 2>&1; tail -40 gpurun_out/kernel_bench.txt
 timeout -k 10 600 python bench.py > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; tail -c 3500 gpurun_out/bench_n1.json; tail -5 gpurun_out/bench_n1.err
+# semi-dense flow: default anti-diagonal schedule vs the opt-in dependency-level schedule, 1080p and 8K
+timeout -k 10 300 python tools/sdof_bench.py > gpurun_out/sdof_bench.txt 2>&1; cat gpurun_out/sdof_bench.txt
 # PCIe legs of the e2e path: 2-D vs linear copies, duplex overlap, pipeline depth, staged upload + fused copy/mirror
 timeout -k 10 200 python dbg/exp_e2e.py > gpurun_out/exp_e2e.txt 2>&1; cat gpurun_out/exp_e2e.txt
 # launch list of the pyrLK extra (9 pyramid launches expected) and one full capture of the ingest kernel
