@@ -176,6 +176,12 @@ bool mbar_phase_done(uint64_t* bar, uint32_t parity) {
 }
 
 void run_block(unsigned nthreads, void (*entry)(void*), void* arg) {
+  static bool env_read = false;
+  if (!env_read) {  // programs that cannot call vppb_emu_set_* (the C++ test binaries) pick the schedule from the environment
+    env_read = true;
+    if (const char* e = getenv("VPPB_EMU_SHUFFLE")) shuffle_seed = (unsigned)atoi(e);
+    if (const char* e = getenv("VPPB_EMU_REVERSE")) reverse_order = atoi(e) != 0;
+  }
   if (g.fibers.size() < nthreads) g.fibers.resize(nthreads);
   g.mbars.clear();
   g.n = g.alive = nthreads;
