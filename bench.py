@@ -491,6 +491,7 @@ def main():
             del pieces["boxes:" + m_]
         unpacked = torch.cuda.Event()
         primed = [False]
+        exchange_ops = tiles.halo_ops(dist, rank, world, st_send_up, st_send_dn, st_recv_up, st_recv_dn)
 
     def issue_exchange(stream):
         """[comm stream] pack the edge rows of all frames, ONE grouped NCCL send/recv with both neighbours.
@@ -499,7 +500,7 @@ def main():
         comm_stream.wait_event(unpacked) if primed[0] else comm_stream.wait_stream(stream)
         with torch.cuda.stream(comm_stream):
             r = pieces["pack"][0]()
-            tiles.exchange_halos(dist, rank, world, st_send_up, st_send_dn, st_recv_up, st_recv_dn)
+            tiles.run_halo_ops(dist, exchange_ops)  # built once: the staging buffers never change
             comm_done.record(comm_stream)
         primed[0] = True
         return pieces["pack"][1] if pieces["pack"][1] is not None else r

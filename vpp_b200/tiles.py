@@ -15,19 +15,28 @@ def neighbours(rank, world):
     return (rank - 1 if rank > 0 else None), (rank + 1 if rank + 1 < world else None)
 
 
-def exchange_halos(dist, rank, world, send_up, send_dn, recv_up, recv_dn):
-    """One grouped exchange: my top edge rows go up, my bottom edge rows go down; the neighbours'
-    edge rows land in recv_up / recv_dn.  Tensors are flat staging buffers (all frames packed)."""
+def halo_ops(dist, rank, world, send_up, send_dn, recv_up, recv_dn):
+    """The P2P operations of one grouped exchange (build once per set of staging buffers, run every step)."""
     up, down = neighbours(rank, world)
     ops = []
     if up is not None:
         ops += [dist.P2POp(dist.isend, send_up, up), dist.P2POp(dist.irecv, recv_up, up)]
     if down is not None:
         ops += [dist.P2POp(dist.isend, send_dn, down), dist.P2POp(dist.irecv, recv_dn, down)]
+    return ops
+
+
+def run_halo_ops(dist, ops):
     if ops:
         for w in dist.batch_isend_irecv(ops):
             w.wait()
-    return up, down
+
+
+def exchange_halos(dist, rank, world, send_up, send_dn, recv_up, recv_dn):
+    """One grouped exchange: my top edge rows go up, my bottom edge rows go down; the neighbours'
+    edge rows land in recv_up / recv_dn.  Tensors are flat staging buffers (all frames packed)."""
+    run_halo_ops(dist, halo_ops(dist, rank, world, send_up, send_dn, recv_up, recv_dn))
+    return neighbours(rank, world)
 
 
 def exchange_halos_inplace(dist, rank, world, send_up, send_dn, recv_up, recv_dn):
