@@ -175,10 +175,12 @@ def test_video_extruder_eventful_sequence_equals_reference_tables(vpp, tag, nfra
     assert (expected[:, 2] == 0).any()  # the sequence does leave dead, not yet compacted keypoints behind
 
 
-@pytest.mark.parametrize("name", ["nbh_tests", "extruder_tests"])
-def test_new_cpp_programs(gpu, name):
-    """C++ host API added after the last GPU run: box_nbh2d / window.hh / colorspace_conversions.hh (nbh_tests) and
-    video_extruder.hh / keypoint_container.hh (extruder_tests); built by build.sh, run here on the GPU"""
+@pytest.mark.parametrize("name", ["core_tests", "algo_tests", "nbh_tests", "extruder_tests"])
+def test_cpp_programs(gpu, name):
+    """The C++ host API on the GPU: the reference's own tests rewritten with device kernels (core_tests, algo_tests - they ran on
+    hardware before, but now go through the reworked pyramid launches and the lvalue kernel invocation of pixel_wise.hh) and
+    the headers added after the last GPU run: box_nbh2d / window.hh / colorspace_conversions.hh (nbh_tests), video_extruder.hh /
+    keypoint_container.hh (extruder_tests); built by build.sh"""
     exe = os.path.join(ROOT, "tests", "cpp", "_build", name)
     assert os.path.exists(exe), "build.sh did not produce %s" % exe
     r = subprocess.run([exe, os.path.join(ROOT, "tests", "golden")], capture_output=True, text=True, timeout=300, cwd=ROOT)
