@@ -288,6 +288,173 @@ __global__ void __launch_bounds__(BX_THREADS, BX_TH == 16 ? 4 : 6) k_box5_bytes_
   }
 }
 
+// ------------------------------------------------------------------ streaming kernel (bytes)
+// Every WARP is an independent stream processor: it owns a strip of 32 x 4 LW output bytes (LW words per lane) and
+// walks down a chunk of R output rows.  Lane 0 keeps a ring of STAGES TMA boxes in flight (16 bytes left + strip + 16
+// right, by BS_K = 5 rows; one mbarrier per stage, owned by the warp) - no CTA-wide barrier anywhere, and the pipeline
+// keeps running from one task of the warp into its next one.  Per input row a lane
+//   loads its window from the stage (LDS.64 + LW/4 x LDS.128 + LDS.64: bytes x-8 .. x+4LW+7),
+//   splits the words into packed 16-bit lanes E = (b0,b2), O = (b1,b3) and forms the 5 horizontal taps CS bytes apart
+//     (whole or word-straddling lane pairs, one PRMT each)  ->  H = horizontal 5-sum of the raw row, 2 LW registers,
+//   slides the vertical window in registers: S += H - H(5 rows ago)  (ring of 5 rows, statically indexed because a
+//     stage is exactly 5 rows),
+//   and for every completed window divides by 25 (exact multiply-shift) and stores its bytes (contiguous per warp).
+// Horizontal-first means the only data exchanged between lanes is the raw halo, which TMA already put in shared memory:
+// no shared-memory writes, no __syncthreads; one __syncwarp per stage before its buffer is handed back to TMA.
+// The packed-lane additions are split between the ALU pipe (IADD3 / PRMT / LOP3, the busier one) and the FMA pipe
+// (IMAD with a run-time multiplier of 1, which ptxas cannot fold back into an IADD3).
+constexpr int BS_K = 5;  // rows per stage == rows of the vertical window
+template <int LW> struct BoxStreamCfg {
+  static constexpr int STRIP = 32 * 4 * LW;          // output bytes per warp row
+  static constexpr int BOXW = STRIP + 32;            // bytes per box row
+  static constexpr int STAGE_BYTES = ((BS_K * BOXW + 127) / 128) * 128;
+  static constexpr int WARPS = 4;
+  static constexpr int STAGES = LW == 4 ? 4 : 3;
+  static constexpr int CTAS_PER_SM = LW == 4 ? 4 : 3;
+  static constexpr int SMEM = WARPS * STAGES * STAGE_BYTES + WARPS * STAGES * 8;
+};
+
+struct BoxStream {
+  CUtensorMap maps[BX_MAX_BATCH];
+  unsigned char* out_base[BX_MAX_BATCH];
+  int nimg, out_pitch, nrows, rowbytes, strips, chunks, R, groups, vec_store, total;
+  uint32_t one;
+};
+
+// floor(lane / 25) of the four 16-bit lanes of (se, so) packed to bytes (q(x), q(x+1), q(x+2), q(x+3)); all four
+// multiplies are high products (lo lanes moved up by a multiply by 2^16 on the FMA pipe), quotients in byte 1.
+__device__ __forceinline__ uint32_t box_div_pack_hi(uint32_t se, uint32_t so, uint32_t shl16) {
+  const uint32_t pel = __umulhi(se * shl16, BX_DIV25), pol = __umulhi(so * shl16, BX_DIV25);
+  const uint32_t peh = __umulhi(se, BX_DIV25), poh = __umulhi(so, BX_DIV25);
+  const uint32_t lo = __byte_perm(pel, pol, 0x0051);
+  const uint32_t hi = __byte_perm(peh, poh, 0x0051);
+  return __byte_perm(lo, hi, 0x5410);
+}
+
+template <int CS, int LW>
+__global__ void __launch_bounds__(BoxStreamCfg<LW>::WARPS * 32, BoxStreamCfg<LW>::CTAS_PER_SM) k_box5_stream(const __grid_constant__ BoxStream p) {
+  typedef BoxStreamCfg<LW> Cfg;
+  constexpr int NW = LW + 4;  // words of a lane's window: 2 left + LW own + 2 right
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  unsigned char* ring = smem + warp * (Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::WARPS * Cfg::STAGES * Cfg::STAGE_BYTES) + warp * Cfg::STAGES;
+  const int gw = blockIdx.x * Cfg::WARPS + warp, nw = gridDim.x * Cfg::WARPS;
+  const int per_img = p.strips * p.chunks;
+  const uint32_t one = p.one, minus_one = 0u - p.one, shl16 = p.one << 16;
+
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < Cfg::STAGES; s++) mbar_init(&bars[s], 1);
+    fence_barrier_init();
+  }
+  __syncwarp();
+
+  // producer cursor (meaningful in lane 0 only): next (task, group of 5 rows) to fetch and the stage it goes to
+  int ptask = gw, pgrp = 0, pslot = 0;
+  auto produce = [&]() {
+    if (ptask < p.total) {
+      const int img = ptask / per_img, rem = ptask - img * per_img;
+      const int chunk = rem / p.strips, strip = rem - chunk * p.strips;
+      mbar_arrive_expect_tx(&bars[pslot], BS_K * Cfg::BOXW);
+      // tensor origin = 16 bytes left of x = 0 and 2 rows above y = 0; 8-byte elements (x coordinate * 8 is a multiple of 16)
+      tma_load_2d(ring + pslot * Cfg::STAGE_BYTES, &p.maps[img], strip * (Cfg::STRIP / 8), chunk * p.R + pgrp * BS_K, &bars[pslot]);
+      if (++pgrp == p.groups) { pgrp = 0; ptask += nw; }
+    }
+    pslot = (pslot + 1 == Cfg::STAGES) ? 0 : pslot + 1;
+  };
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < Cfg::STAGES; s++) produce();
+  }
+
+  int cslot = 0;
+  uint32_t parity = 0;
+  for (int task = gw; task < p.total; task += nw) {
+    const int img = task / per_img, rem = task - img * per_img;
+    const int chunk = rem / p.strips, strip = rem - chunk * p.strips;
+    const int x = strip * Cfg::STRIP + lane * (4 * LW);
+    const int y0 = chunk * p.R, yend = min(y0 + p.R, p.nrows);
+    unsigned char* dst = p.out_base[img] + (long long)y0 * p.out_pitch + x;
+    const int nbytes = min(4 * LW, p.rowbytes - x);  // <= 0: this lane is right of the image
+    const bool full = nbytes == 4 * LW && p.vec_store;
+
+    uint32_t rE[BS_K][LW], rO[BS_K][LW], SE[LW], SO[LW];
+#pragma unroll
+    for (int q = 0; q < LW; q++) {
+      SE[q] = 0; SO[q] = 0;
+#pragma unroll
+      for (int j = 0; j < BS_K; j++) { rE[j][q] = 0; rO[j][q] = 0; }
+    }
+
+    for (int g = 0; g < p.groups; g++) {
+      mbar_wait(&bars[cslot], parity);
+      const unsigned char* st = ring + cslot * Cfg::STAGE_BYTES + lane * (4 * LW);
+#pragma unroll
+      for (int j = 0; j < BS_K; j++) {
+        const unsigned char* rp = st + j * Cfg::BOXW;
+        uint32_t w[NW];
+        {
+          const uint2 wl = *reinterpret_cast<const uint2*>(rp + 8);
+          w[0] = wl.x; w[1] = wl.y;
+#pragma unroll
+          for (int v = 0; v < LW / 4; v++) {
+            const uint4 wm = *reinterpret_cast<const uint4*>(rp + 16 + 16 * v);
+            w[2 + 4 * v] = wm.x; w[3 + 4 * v] = wm.y; w[4 + 4 * v] = wm.z; w[5 + 4 * v] = wm.w;
+          }
+          const uint2 wr = *reinterpret_cast<const uint2*>(rp + 16 + 4 * LW);
+          w[NW - 2] = wr.x; w[NW - 1] = wr.y;
+        }
+        uint32_t E[NW], O[NW], XE[NW - 1], XO[NW - 1];
+#pragma unroll
+        for (int i = 0; i < NW; i++) { E[i] = w[i] & 0x00FF00FFu; O[i] = __byte_perm(w[i], 0u, 0x4341); }
+#pragma unroll
+        for (int i = 0; i < NW - 1; i++) { XE[i] = __byte_perm(E[i], E[i + 1], 0x5432); XO[i] = __byte_perm(O[i], O[i + 1], 0x5432); }
+#pragma unroll
+        for (int q = 0; q < LW; q++) {
+          const int i = q + 2;
+          uint32_t he, ho;
+          if (CS == 3) {  // lanes (x, x+2): taps x-6, x-3, x, x+3, x+6; lanes (x+1, x+3) likewise
+            he = XE[i + 1] + XO[i] + XE[i - 2] + O[i - 1] + E[i];
+            ho = XO[i + 1] + E[i + 1] + XO[i - 2] + XE[i - 1] + O[i];
+          } else {        // CS == 1: taps x-2 .. x+2
+            he = XE[i] + O[i] + XE[i - 1] + XO[i - 1] + E[i];
+            ho = XO[i] + XE[i] + XO[i - 1] + E[i] + O[i];
+          }
+          // S += H - H(5 rows ago), on the FMA pipe
+          const uint32_t te = fadd_u32(rE[j][q], minus_one, SE[q]), to = fadd_u32(rO[j][q], minus_one, SO[q]);
+          rE[j][q] = he;
+          rO[j][q] = ho;
+          SE[q] = fadd_u32(he, one, te);
+          SO[q] = fadd_u32(ho, one, to);
+        }
+        const int row = g * BS_K + j;  // input row of the task (0 = image row y0 - 2)
+        if (row >= 4) {
+          const int y = y0 + row - 4;
+          if (y < yend && nbytes > 0) {
+            uint32_t ow[LW];
+#pragma unroll
+            for (int q = 0; q < LW; q++) ow[q] = box_div_pack_hi(SE[q], SO[q], shl16);
+            unsigned char* d = dst + (long long)(row - 4) * p.out_pitch;
+            if (full) {
+#pragma unroll
+              for (int v = 0; v < LW / 4; v++)
+                *reinterpret_cast<uint4*>(d + 16 * v) = make_uint4(ow[4 * v], ow[4 * v + 1], ow[4 * v + 2], ow[4 * v + 3]);
+            } else {
+#pragma unroll
+              for (int k = 0; k < 4 * LW; k++)
+                if (k < nbytes) d[k] = (unsigned char)(ow[k >> 2] >> ((k & 3) * 8));
+            }
+          }
+        }
+      }
+      __syncwarp();  // every lane is done reading the stage before TMA refills it
+      if (lane == 0) produce();
+      if (++cslot == Cfg::STAGES) { cslot = 0; parity ^= 1; }
+    }
+  }
+}
+
 static int layout_pitch(const vppb_img* i) {
   if (i->align <= 0) return -1;
   long long bs = (long long)i->border * i->elem_bytes;
@@ -319,6 +486,91 @@ static int box_tile_rows(int nrows, int rowbytes) {
   return tiles16 >= 4LL * sm_count() ? 16 : 8;
 }
 
+// which byte kernel: VPPB_BOX_IMPL=tile selects the round-1 CTA tile kernels (kept for A/B timing), default = stream
+static bool box_use_stream() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("VPPB_BOX_IMPL");
+    v = (e && !strcmp(e, "tile")) ? 0 : 1;
+  }
+  return v == 1;
+}
+
+// Rows per task: R = 5 m - 4 (a task then reads exactly m stages).  Small R = more tasks (parallelism for a single
+// frame) but 4 extra input rows per task; pick the R with the smallest makespan estimate over the resident warps.
+static int box_stream_rows(long long strips_x_imgs, int nrows, int warps_per_sm, int* chunks_out) {
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("VPPB_BOX_R");
+    forced = e ? atoi(e) : 0;
+  }
+  const long long warps = (long long)sm_count() * warps_per_sm;
+  int best_r = 16;
+  double best = 1e300;
+  for (int m = 4; m <= 26; m++) {
+    const int r = 5 * m - 4;
+    if (forced > 0 && r != forced) continue;
+    const long long chunks = (nrows + r - 1) / r, tasks = chunks * strips_x_imgs;
+    const long long waves = (tasks + warps - 1) / warps;
+    // per task: m stages of 5 rows + ~2 stages of pipeline fill when the warp starts; a wave costs its slowest warp
+    const double cost = (double)waves * (5.0 * m + 2.0) + 10.0;
+    if (cost < best) { best = cost; best_r = r; }
+  }
+  *chunks_out = (nrows + best_r - 1) / best_r;
+  return best_r;
+}
+
+// n equally shaped, TMA-eligible images (n <= BX_MAX_BATCH) in one launch of the streaming kernel
+template <int CS, int LW>
+static int box5_stream_launch_lw(const vppb_img* ins, const vppb_img* outs, int n, cudaStream_t st, const char* name) {
+  typedef BoxStreamCfg<LW> Cfg;
+  const int rowbytes = ins[0].ncols * CS, nrows = ins[0].nrows;
+  static std::atomic<unsigned long long> attr_done{0};
+  int dev = 0;
+  VPPB_CUDA(cudaGetDevice(&dev));
+  const unsigned long long bit = 1ULL << (dev & 63);
+  if (!(attr_done.load(std::memory_order_acquire) & bit)) {
+    VPPB_CUDA(cudaFuncSetAttribute(k_box5_stream<CS, LW>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    attr_done.fetch_or(bit, std::memory_order_release);
+  }
+  BoxStream p;
+  memset(&p, 0, sizeof(p));
+  p.nimg = n;
+  p.out_pitch = outs[0].pitch;
+  p.nrows = nrows;
+  p.rowbytes = rowbytes;
+  p.strips = (rowbytes + Cfg::STRIP - 1) / Cfg::STRIP;
+  p.R = box_stream_rows((long long)p.strips * n, nrows, Cfg::WARPS * Cfg::CTAS_PER_SM, &p.chunks);
+  p.groups = (p.R + 4 + BS_K - 1) / BS_K;
+  p.vec_store = (((uintptr_t)outs[0].base % 16) == 0 && (outs[0].pitch % 16) == 0) ? 1 : 0;
+  p.total = n * p.strips * p.chunks;
+  p.one = 1u;
+  const uint64_t width_el = ((uint64_t)rowbytes + 32 + 7) / 8;
+  for (int k = 0; k < n; k++) {
+    const vppb_img* in = &ins[k];
+    unsigned char* origin = static_cast<unsigned char*>(in->base) - 2LL * in->pitch - 16;
+    int rc = encode_tensor_map_2d(&p.maps[k], origin, CU_TENSOR_MAP_DATA_TYPE_UINT64, 8, width_el, (uint64_t)nrows + 4, (uint64_t)in->pitch,
+                                  Cfg::BOXW / 8, BS_K);
+    if (rc) return rc;
+    p.out_base[k] = static_cast<unsigned char*>(outs[k].base);
+  }
+  const int ctas = (p.total + Cfg::WARPS - 1) / Cfg::WARPS, resident = sm_count() * Cfg::CTAS_PER_SM;
+  k_box5_stream<CS, LW><<<ctas < resident ? ctas : resident, Cfg::WARPS * 32, Cfg::SMEM, st>>>(p);
+  VPPB_LAUNCH_CHECK(name);
+  return VPPB_OK;
+}
+
+template <int CS>
+static int box5_stream_launch(const vppb_img* ins, const vppb_img* outs, int n, cudaStream_t st, const char* name) {
+  static int lw = -1;
+  if (lw < 0) {
+    const char* e = getenv("VPPB_BOX_LW");
+    lw = e ? atoi(e) : 4;
+  }
+  if (lw == 8) return box5_stream_launch_lw<CS, 8>(ins, outs, n, st, name);
+  return box5_stream_launch_lw<CS, 4>(ins, outs, n, st, name);
+}
+
 template <int CS>
 static int box5_bytes(const vppb_img* in, const vppb_img* out, void* stream, const char* name) {
   VPPB_REQUIRE(in && out && in->base && out->base, VPPB_E_ARG, "%s: NULL image", name);
@@ -327,6 +579,7 @@ static int box5_bytes(const vppb_img* in, const vppb_img* out, void* stream, con
   VPPB_REQUIRE(in->border >= 2, VPPB_E_BORDER, "%s: input border %d < 2", name, in->border);
   cudaStream_t st = as_stream(stream);
   const int rowbytes = in->ncols * CS;
+  if (tma_eligible(in) && box_use_stream()) return box5_stream_launch<CS>(in, out, 1, st, name);
   if (tma_eligible(in)) {
     CUtensorMap tmap;
     unsigned char* origin = static_cast<unsigned char*>(in->base) - 2LL * in->pitch - 16;
@@ -390,6 +643,13 @@ static int box5_bytes_batch(const vppb_img* ins, const vppb_img* outs, int n, vo
     return VPPB_OK;
   }
   cudaStream_t st = as_stream(stream);
+  if (box_use_stream()) {
+    for (int i0 = 0; i0 < n; i0 += BX_MAX_BATCH) {
+      int rc = box5_stream_launch<CS>(ins + i0, outs + i0, std::min(BX_MAX_BATCH, n - i0), st, name);
+      if (rc) return rc;
+    }
+    return VPPB_OK;
+  }
   const int rowbytes = ins[0].ncols * CS, nrows = ins[0].nrows;
   const int strips = (rowbytes + BX_OUTW - 1) / BX_OUTW;
   // 16-row tiles (25 % halo rows instead of 50 %) as soon as the whole batch fills the machine with them
