@@ -140,7 +140,8 @@ int vppb_lowpass_sub2_mirror(const vppb_img* in, const vppb_img* out, int kind, 
 /* ---- FAST9 (fast.hpp:253-508, 643-799, 889-955) ------------------------------------------- */
 enum { VPPB_FAST_REFERENCE_RING = 0, VPPB_FAST_TRUE_RING = 1 };
 enum { VPPB_FAST_ALL = 0, VPPB_FAST_LOCAL_MAXIMA = 1, VPPB_FAST_BLOCKWISE = 2 };
-/* Workspace bytes needed by vppb_fast9_u8 for an nrows x ncols image. */
+/* Workspace bytes needed by vppb_fast9_u8 for an nrows x ncols image (block_size: the blockwise cell side, or <= 0
+ * for a workspace that is large enough for every mode and block size). */
 int64_t vppb_fast9_workspace_bytes(int32_t nrows, int32_t ncols, int32_t block_size);
 /* fast9(A, th, [_local_maxima|_blockwise, _block_size=, _mask=, _scores=]).
  * mask may be NULL (== 0xFF everywhere).  kps_out (device, capacity records) receives the
@@ -152,6 +153,13 @@ int vppb_fast9_u8(const vppb_img* img, int32_t th, const vppb_img* mask, int32_t
                   int32_t ring, void* workspace, int64_t workspace_bytes,
                   vppb_int2* kps_out, int32_t* scores_out, int32_t capacity, int32_t* count_out,
                   void* stream);
+/* The same without any host synchronisation: the keypoint count is stored to count_dev (DEVICE int32), keypoints
+ * beyond `capacity` are dropped (the count still tells how many there were).  What a pipeline that keeps its keypoints
+ * on the device (video_extruder) calls; fast9() itself reads count_dev back once to size its std::vector. */
+int vppb_fast9_u8_async(const vppb_img* img, int32_t th, const vppb_img* mask, int32_t mode, int32_t block_size,
+                        int32_t ring, void* workspace, int64_t workspace_bytes,
+                        vppb_int2* kps_out, int32_t* scores_out, int32_t capacity, int32_t* count_dev,
+                        void* stream);
 /* fast9_scores (fast.hpp:643-652): score of n given points (device arrays). */
 int vppb_fast9_scores(const vppb_img* img, int32_t th, const vppb_int2* kps, int32_t n, int32_t* scores_out,
                       void* stream);

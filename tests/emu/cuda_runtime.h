@@ -16,6 +16,7 @@
 #define __device__
 #define __host__
 #define __forceinline__ inline
+#define __noinline__
 #define __launch_bounds__(...)
 #define __constant__ static
 #define __grid_constant__
@@ -44,7 +45,7 @@ inline float4 make_float4(float x, float y, float z, float w) { return float4{x,
 
 typedef void* cudaStream_t;
 typedef int cudaError_t;
-enum { cudaSuccess = 0, cudaMemcpyDeviceToHost = 2, cudaMemcpyHostToDevice = 1 };
+enum { cudaSuccess = 0, cudaMemcpyDeviceToHost = 2, cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToDevice = 3 };
 inline const char* cudaGetErrorString(cudaError_t) { return "emulated"; }
 inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 inline cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
@@ -159,6 +160,26 @@ inline int __popc(unsigned v) { return __builtin_popcount(v); }
 inline int __ffs(int v) { return __builtin_ffs(v); }
 inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
 inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((uint64_t)a * b) >> 32); }
+inline unsigned __vabsdiffu4(unsigned a, unsigned b) {  // VABSDIFF4.U8: per-byte |a - b|
+  unsigned r = 0;
+  for (int i = 0; i < 4; i++) {
+    const int x = (a >> (8 * i)) & 0xFF, y = (b >> (8 * i)) & 0xFF;
+    r |= (unsigned)(x > y ? x - y : y - x) << (8 * i);
+  }
+  return r;
+}
+inline unsigned __vsadu4(unsigned a, unsigned b) {  // sum of the four per-byte absolute differences
+  unsigned r = 0;
+  for (int i = 0; i < 4; i++) {
+    const int x = (a >> (8 * i)) & 0xFF, y = (b >> (8 * i)) & 0xFF;
+    r += (unsigned)(x > y ? x - y : y - x);
+  }
+  return r;
+}
+inline unsigned __funnelshift_l(unsigned lo, unsigned hi, unsigned shift) {  // SHF.L.W: upper word of (hi:lo) << (shift & 31)
+  shift &= 31;
+  return shift ? (hi << shift) | (lo >> (32 - shift)) : hi;
+}
 inline unsigned __byte_perm(unsigned x, unsigned y, unsigned s) {  // PRMT, default mode, selectors 0..7
   const uint64_t v = ((uint64_t)y << 32) | x;
   unsigned r = 0;

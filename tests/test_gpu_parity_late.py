@@ -217,3 +217,45 @@ def test_semi_dense_flow_level_schedule(vpp, monkeypatch, density):
         assert np.array_equal(valid, rvalid.astype(bool)) and valid.sum() > 10
         ok = rvalid > 0
         assert np.array_equal(pos[ok], rpos[ok]) and np.array_equal(dist[ok], rdist[ok]), (density, ws, nscales, prop, patch)
+
+
+# ------------------------------------------------------------------ FAST9 band kernel: several TMA boxes per band, ragged tails
+@pytest.mark.parametrize("shape", [(21, 4100), (9, 2017), (8, 2016), (17, 6050)])
+def test_fast9_wide_images_multibox(vpp, shape):
+    """The band kernel walks a row band in boxes of 2016 pixels: widths around the box size, a partial last band, a mask and
+    both rings, exact keypoint arrays and scores against the oracle."""
+    from tests import scenes
+    from tests.test_gpu_parity import _oracle_fast
+
+    img = scenes.rectangles_scene(shape[0], shape[1], seed=shape[1], nrect=shape[1] // 12)
+    G = vpp.Image2d.from_host(img, "u8", border=3)
+    vpp.fill_border_mirror(G)
+    mask = np.full(img.shape, 0xFF, dtype=np.uint8)
+    mask[:, ::3] = 0x01
+    mask[::4, :] = 0
+    M = vpp.Image2d.from_host(mask, "u8")
+    for ring in ("reference", "true"):
+        for m, hm in ((None, None), (M, mask)):
+            sc = []
+            kps = vpp.fast9(G, 12, mask=m, ring=ring, scores=sc)
+            rk, rs = _oracle_fast(img, 12, mask=hm, ring=0 if ring == "reference" else 1, want_scores=True)
+            assert len(rk) > 10
+            assert np.array_equal(kps, rk)
+            assert np.array_equal(np.asarray(sc, dtype=np.int32), rs)
+
+
+@pytest.mark.parametrize("th", [0, 127, 128, 200, 255, 300])
+def test_fast9_threshold_extremes(vpp, th):
+    """The packed prefilter switches formula at th >= 127 and nothing can pass at (th & 255) == 255; th is used modulo 256 as the
+    reference's S::repeat(th) does."""
+    from tests.test_gpu_parity import _oracle_fast
+
+    r = np.random.default_rng(th)
+    img = r.integers(0, 256, (40, 300), dtype=np.uint8)
+    img[10:30, 50:200] = 0
+    img[12:28, 60:190] = 255
+    G = vpp.Image2d.from_host(img, "u8", border=3)
+    vpp.fill_border_mirror(G)
+    kps = vpp.fast9(G, th)
+    rk, _ = _oracle_fast(img, th)
+    assert np.array_equal(kps, rk)

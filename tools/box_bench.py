@@ -15,11 +15,11 @@ VARIANTS = [
     ("tile", {"VPPB_BOX_IMPL": "tile"}),
     ("stream_lw4", {"VPPB_BOX_LW": "4"}),
     ("stream_lw8", {"VPPB_BOX_LW": "8"}),
-    ("stream_lw4_R16", {"VPPB_BOX_LW": "4", "VPPB_BOX_R": "16"}),
-    ("stream_lw4_R31", {"VPPB_BOX_LW": "4", "VPPB_BOX_R": "31"}),
-    ("stream_lw4_R61", {"VPPB_BOX_LW": "4", "VPPB_BOX_R": "61"}),
-    ("stream_lw8_R31", {"VPPB_BOX_LW": "8", "VPPB_BOX_R": "31"}),
-    ("stream_lw8_R61", {"VPPB_BOX_LW": "8", "VPPB_BOX_R": "61"}),
+    ("stream_lw4_bal", {"VPPB_BOX_LW": "4", "VPPB_BOX_BAL": "1"}),
+    ("stream_lw8_bal", {"VPPB_BOX_LW": "8", "VPPB_BOX_BAL": "1"}),
+    ("stream_lw4_R21", {"VPPB_BOX_LW": "4", "VPPB_BOX_R": "21"}),
+    ("stream_lw4_R36", {"VPPB_BOX_LW": "4", "VPPB_BOX_R": "36"}),
+    ("stream_lw8_R21", {"VPPB_BOX_LW": "8", "VPPB_BOX_R": "21"}),
 ]
 
 

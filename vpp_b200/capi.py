@@ -106,6 +106,7 @@ PROTOTYPES = {
     "vppb_lowpass_sub2_mirror": (C.c_int, [_IMG, _IMG, C.c_int, _VP]),
     "vppb_fast9_workspace_bytes": (_I64, [_I32, _I32, _I32]),
     "vppb_fast9_u8": (C.c_int, [_IMG, _I32, _IMG, _I32, _I32, _I32, _VP, _I64, _VP, _VP, _I32, _P(_I32), _VP]),
+    "vppb_fast9_u8_async": (C.c_int, [_IMG, _I32, _IMG, _I32, _I32, _I32, _VP, _I64, _VP, _VP, _I32, _VP, _VP]),
     "vppb_fast9_scores": (C.c_int, [_IMG, _I32, _VP, _I32, _VP, _VP]),
     "vppb_lk_match_u8": (C.c_int, [_IMG, _IMG, _IMG, _P(VppbLkParams), _VP, _VP, _I32, _VP, _VP, _VP]),
     "vppb_sdof_workspace_bytes": (_I64, [_I32, _I32, _P(VppbSdofParams)]),

@@ -331,7 +331,13 @@ __device__ __forceinline__ uint32_t box_div_pack_hi(uint32_t se, uint32_t so, ui
   return __byte_perm(lo, hi, 0x5410);
 }
 
-template <int CS, int LW>
+// the rare partial store of a lane that straddles the right edge of the image (kept out of the hot loop)
+template <int LW>
+__device__ __noinline__ void box_store_partial(unsigned char* d, const uint32_t* ow, int nbytes) {
+  for (int k = 0; k < nbytes; k++) d[k] = (unsigned char)(ow[k >> 2] >> ((k & 3) * 8));
+}
+
+template <int CS, int LW, int BAL>
 __global__ void __launch_bounds__(BoxStreamCfg<LW>::WARPS * 32, BoxStreamCfg<LW>::CTAS_PER_SM) k_box5_stream(const __grid_constant__ BoxStream p) {
   typedef BoxStreamCfg<LW> Cfg;
   constexpr int NW = LW + 4;  // words of a lane's window: 2 left + LW own + 2 right
@@ -421,12 +427,16 @@ __global__ void __launch_bounds__(BoxStreamCfg<LW>::WARPS * 32, BoxStreamCfg<LW>
             he = XE[i] + O[i] + XE[i - 1] + XO[i - 1] + E[i];
             ho = XO[i] + XE[i] + XO[i - 1] + E[i] + O[i];
           }
-          // S += H - H(5 rows ago), on the FMA pipe
-          const uint32_t te = fadd_u32(rE[j][q], minus_one, SE[q]), to = fadd_u32(rO[j][q], minus_one, SO[q]);
+          if (BAL) {  // S += H - H(5 rows ago) on the FMA pipe (two IMAD)
+            const uint32_t te = fadd_u32(rE[j][q], minus_one, SE[q]), to = fadd_u32(rO[j][q], minus_one, SO[q]);
+            SE[q] = fadd_u32(he, one, te);
+            SO[q] = fadd_u32(ho, one, to);
+          } else {    // one IADD3 with a negated operand
+            SE[q] = SE[q] + he - rE[j][q];
+            SO[q] = SO[q] + ho - rO[j][q];
+          }
           rE[j][q] = he;
           rO[j][q] = ho;
-          SE[q] = fadd_u32(he, one, te);
-          SO[q] = fadd_u32(ho, one, to);
         }
         const int row = g * BS_K + j;  // input row of the task (0 = image row y0 - 2)
         if (row >= 4) {
@@ -434,16 +444,14 @@ __global__ void __launch_bounds__(BoxStreamCfg<LW>::WARPS * 32, BoxStreamCfg<LW>
           if (y < yend && nbytes > 0) {
             uint32_t ow[LW];
 #pragma unroll
-            for (int q = 0; q < LW; q++) ow[q] = box_div_pack_hi(SE[q], SO[q], shl16);
+            for (int q = 0; q < LW; q++) ow[q] = BAL ? box_div_pack_hi(SE[q], SO[q], shl16) : box_div_pack(SE[q], SO[q]);
             unsigned char* d = dst + (long long)(row - 4) * p.out_pitch;
             if (full) {
 #pragma unroll
               for (int v = 0; v < LW / 4; v++)
                 *reinterpret_cast<uint4*>(d + 16 * v) = make_uint4(ow[4 * v], ow[4 * v + 1], ow[4 * v + 2], ow[4 * v + 3]);
             } else {
-#pragma unroll
-              for (int k = 0; k < 4 * LW; k++)
-                if (k < nbytes) d[k] = (unsigned char)(ow[k >> 2] >> ((k & 3) * 8));
+              box_store_partial<LW>(d, ow, nbytes);
             }
           }
         }
@@ -521,7 +529,7 @@ static int box_stream_rows(long long strips_x_imgs, int nrows, int warps_per_sm,
 }
 
 // n equally shaped, TMA-eligible images (n <= BX_MAX_BATCH) in one launch of the streaming kernel
-template <int CS, int LW>
+template <int CS, int LW, int BAL>
 static int box5_stream_launch_lw(const vppb_img* ins, const vppb_img* outs, int n, cudaStream_t st, const char* name) {
   typedef BoxStreamCfg<LW> Cfg;
   const int rowbytes = ins[0].ncols * CS, nrows = ins[0].nrows;
@@ -530,7 +538,7 @@ static int box5_stream_launch_lw(const vppb_img* ins, const vppb_img* outs, int 
   VPPB_CUDA(cudaGetDevice(&dev));
   const unsigned long long bit = 1ULL << (dev & 63);
   if (!(attr_done.load(std::memory_order_acquire) & bit)) {
-    VPPB_CUDA(cudaFuncSetAttribute(k_box5_stream<CS, LW>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    VPPB_CUDA(cudaFuncSetAttribute(k_box5_stream<CS, LW, BAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
     attr_done.fetch_or(bit, std::memory_order_release);
   }
   BoxStream p;
@@ -555,7 +563,7 @@ static int box5_stream_launch_lw(const vppb_img* ins, const vppb_img* outs, int 
     p.out_base[k] = static_cast<unsigned char*>(outs[k].base);
   }
   const int ctas = (p.total + Cfg::WARPS - 1) / Cfg::WARPS, resident = sm_count() * Cfg::CTAS_PER_SM;
-  k_box5_stream<CS, LW><<<ctas < resident ? ctas : resident, Cfg::WARPS * 32, Cfg::SMEM, st>>>(p);
+  k_box5_stream<CS, LW, BAL><<<ctas < resident ? ctas : resident, Cfg::WARPS * 32, Cfg::SMEM, st>>>(p);
   VPPB_LAUNCH_CHECK(name);
   return VPPB_OK;
 }
@@ -567,8 +575,13 @@ static int box5_stream_launch(const vppb_img* ins, const vppb_img* outs, int n, 
     const char* e = getenv("VPPB_BOX_LW");
     lw = e ? atoi(e) : 4;
   }
-  if (lw == 8) return box5_stream_launch_lw<CS, 8>(ins, outs, n, st, name);
-  return box5_stream_launch_lw<CS, 4>(ins, outs, n, st, name);
+  static int bal = -1;
+  if (bal < 0) {
+    const char* e = getenv("VPPB_BOX_BAL");
+    bal = e ? atoi(e) : 0;
+  }
+  if (lw == 8) return bal ? box5_stream_launch_lw<CS, 8, 1>(ins, outs, n, st, name) : box5_stream_launch_lw<CS, 8, 0>(ins, outs, n, st, name);
+  return bal ? box5_stream_launch_lw<CS, 4, 1>(ins, outs, n, st, name) : box5_stream_launch_lw<CS, 4, 0>(ins, outs, n, st, name);
 }
 
 template <int CS>

@@ -13,6 +13,9 @@
 // HBM-bound: 1 byte read per pixel (+1 with a mask) + 8 bytes per keypoint.
 #include "common.cuh"
 
+#include <atomic>
+#include "tma.cuh"
+
 namespace vppb {
 
 // ring slot -> (dr, dc).  Row 0: as implemented by fast9() (fast.hpp:327-461); row 1: true ring.
@@ -88,6 +91,217 @@ __global__ void __launch_bounds__(256) k_fast9_detect(Img im, Img mask, int has_
       bits[w] = word;
       if (word) atomicAdd(&rowcount[r], __popc(word));
     }
+  }
+}
+
+// ------------------------------------------------------------------ band kernel (TMA-staged detection)
+// One CTA per band of FB_ROWS image rows; the band is walked in boxes of 2016 pixels.  Thread 0 keeps two TMA boxes in
+// flight (2048 bytes = 16 halo + 2016 + 16 halo, by FB_ROWS + 6 rows), the CTA works on one while the other lands.
+//   phase 1 (prefilter, 4 pixels per thread per step, packed bytes): every 9-arc of the ring contains slot 0 (r-3, c) or
+//     slot 8 (r+3, c) (fast.hpp:326-337), and both sit in the same column as the centre, so |v - a0| > th or |v - a8| > th
+//     is evaluated on whole aligned words: VABSDIFF4 + a 3-instruction packed "greater than th".  Survivors (a few percent
+//     of a natural frame, the pixels within 3 rows of a strong horizontal contrast) are appended to a candidate list in
+//     shared memory.
+//   phase 2 (exact test, one candidate per thread, no idle lanes): the 16 ring bytes come from the staged box; bright /
+//     dark flags are shifted into two 16-bit masks (one subtraction + one funnel shift per slot and polarity), the 9-arc
+//     test is the bit trick of arc9(); corners set their bit in the band's bitmask (shared memory).
+// After the last box the band's bitmask rows and their per-row / per-band counts go to global memory; k_fast9_emit_bands
+// turns them into raster-ordered keypoints.  No atomics on global memory, nothing to zero beforehand.
+constexpr int FB_ROWS = 8;
+constexpr int FB_BOXW = 2048;
+constexpr int FB_INNER = FB_BOXW - 32;
+constexpr int FB_INH = FB_ROWS + 6;
+constexpr int FB_STAGE = FB_INH * FB_BOXW;
+constexpr int FB_THREADS = 256;
+constexpr int FB_MAXW = 16384;  // widest image of this path: the band bitmask (8 rows x ncols / 8 bytes) lives in shared memory
+
+static inline int fb_smem_bytes(int wpr) { return 2 * FB_STAGE + FB_ROWS * FB_INNER * 2 + FB_ROWS * wpr * 4 + 64; }
+
+template <int RING>
+__global__ void __launch_bounds__(FB_THREADS, 2) k_fast9_band(const __grid_constant__ CUtensorMap tmap, Img im, Img mask, int has_mask, int th, int nboxes,
+                                                              int wpr, uint32_t* bits, int* rowcount, int* bandtotal) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  unsigned char* stage0 = smem;
+  unsigned short* list = reinterpret_cast<unsigned short*>(smem + 2 * FB_STAGE);
+  uint32_t* bm = reinterpret_cast<uint32_t*>(smem + 2 * FB_STAGE + FB_ROWS * FB_INNER * 2);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * FB_STAGE + FB_ROWS * FB_INNER * 2 + FB_ROWS * wpr * 4);
+  int* ncand = reinterpret_cast<int*>(bars + 2);   // [2], alternating between boxes
+  int* rowcnt = ncand + 2;                         // [FB_ROWS]
+  const int tid = threadIdx.x;
+  const int band = blockIdx.x, r0 = band * FB_ROWS;
+  const int rows_here = min(FB_ROWS, im.nrows - r0);
+  const int thb = th & 255;  // S::repeat(th) replicates the low byte (fast.hpp:120-126)
+
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    fence_barrier_init();
+    ncand[0] = 0; ncand[1] = 0;
+    // tensor origin = 16 bytes left of column 0 and 3 rows above row 0; 8-byte elements, 252 elements per inner box
+    for (int k = 0; k < 2 && k < nboxes; k++) {
+      mbar_arrive_expect_tx(&bars[k], FB_STAGE);
+      tma_load_2d(stage0 + k * FB_STAGE, &tmap, k * (FB_INNER / 8), r0, &bars[k]);
+    }
+  }
+  for (int i = tid; i < FB_ROWS * wpr; i += FB_THREADS) bm[i] = 0;
+  __syncthreads();
+
+  // packed "byte > thb":  u = thb + 1;  x >= u  <=>  bit 7 of ((x | H) - (U & ~H)) combined with bit 7 of x
+  const uint32_t H = 0x80808080u;
+  const uint32_t K = (((uint32_t)(thb + 1) & 0x7Fu) * 0x01010101u);
+  const bool u_high = (thb + 1) >= 128;
+
+  for (int k = 0; k < nboxes && thb < 255; k++) {
+    const int s = k & 1;
+    const unsigned char* st = stage0 + s * FB_STAGE;
+    mbar_wait(&bars[s], (k >> 1) & 1);
+    const int xbase = k * FB_INNER;                        // image column of box byte 16
+    const int cols_here = min(FB_INNER, im.ncols - xbase);
+    const int words = (cols_here + 3) >> 2;
+    // ---- phase 1
+    for (int j = 0; j < rows_here; j++) {
+      const unsigned char* rowc = st + (j + 3) * FB_BOXW + 16;
+      for (int wi = tid; wi < words; wi += FB_THREADS) {
+        const uint32_t v = *reinterpret_cast<const uint32_t*>(rowc + 4 * wi);
+        const uint32_t a0 = *reinterpret_cast<const uint32_t*>(rowc - 3 * FB_BOXW + 4 * wi);
+        const uint32_t a8 = *reinterpret_cast<const uint32_t*>(rowc + 3 * FB_BOXW + 4 * wi);
+        const uint32_t d0 = __vabsdiffu4(v, a0), d8 = __vabsdiffu4(v, a8);
+        const uint32_t t0 = (d0 | H) - K, t8 = (d8 | H) - K;
+        uint32_t g = u_high ? ((t0 & d0) | (t8 & d8)) : (t0 | d0 | t8 | d8);
+        g &= H;
+        if (g) {
+          const int x = 4 * wi;  // box-inner column of byte 0
+          if (x + 4 > cols_here) g &= (1u << (8 * (cols_here - x))) - 1u;  // bytes right of the image
+          if (has_mask && g) {
+            const unsigned char* mp = mask.base + (long long)(r0 + j) * mask.pitch + xbase + x;
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+              if (((g >> (8 * q + 7)) & 1u) && __ldg(mp + q) == 0) g &= ~(0x80u << (8 * q));
+          }
+          while (g) {
+            const int q = (__ffs(g) - 1) >> 3;
+            g &= g - 1;
+            const int idx = atomicAdd(&ncand[s], 1);
+            list[idx] = (unsigned short)((j << 11) | (16 + x + q));
+          }
+        }
+      }
+    }
+    __syncthreads();
+    // ---- phase 2
+    const int n = ncand[s];
+    for (int e = tid; e < n; e += FB_THREADS) {
+      const int code = list[e];
+      const int j = code >> 11, xl = code & 2047;
+      const unsigned char* p = st + (j + 3) * FB_BOXW + xl;
+      const int v = p[0];
+      const int cb = v + thb, cd = v - thb;  // brighter: a > cb (== a > min(v+th,255)); darker: a < cd
+      uint32_t mb = 0, md = 0;
+#define VPPB_FAST_SLOT(DR, DC)                                                  \
+      {                                                                         \
+        const int a = p[(DR) * FB_BOXW + (DC)];                                 \
+        mb = __funnelshift_l((uint32_t)(cb - a), mb, 1);                        \
+        md = __funnelshift_l((uint32_t)(a - cd), md, 1);                        \
+      }
+      VPPB_FAST_SLOT(-3, 0) VPPB_FAST_SLOT(-3, 1) VPPB_FAST_SLOT(-2, 2) VPPB_FAST_SLOT(-1, 3)
+      if (RING == 0) VPPB_FAST_SLOT(-3, 3) else VPPB_FAST_SLOT(0, 3)
+      VPPB_FAST_SLOT(1, 3) VPPB_FAST_SLOT(2, 2) VPPB_FAST_SLOT(3, 1) VPPB_FAST_SLOT(3, 0) VPPB_FAST_SLOT(3, -1)
+      VPPB_FAST_SLOT(2, -2) VPPB_FAST_SLOT(1, -3)
+      if (RING == 0) VPPB_FAST_SLOT(-3, -3) else VPPB_FAST_SLOT(0, -3)
+      VPPB_FAST_SLOT(-1, -3) VPPB_FAST_SLOT(-2, -2) VPPB_FAST_SLOT(-3, -1)
+#undef VPPB_FAST_SLOT
+      const int c = xbase + xl - 16;
+      int m = 0xFF;
+      if (has_mask) m = __ldg(mask.base + (long long)(r0 + j) * mask.pitch + c);
+      const bool corner = ((m & 0x10) && arc9(mb & 0xFFFFu)) || ((m & 0x01) && arc9(md & 0xFFFFu));
+      if (corner) atomicOr(&bm[j * wpr + (c >> 5)], 1u << (c & 31));
+    }
+    __syncthreads();  // the stage and the list are free again
+    if (tid == 0) {
+      ncand[s] = 0;
+      if (k + 2 < nboxes) {
+        mbar_arrive_expect_tx(&bars[s], FB_STAGE);
+        tma_load_2d(stage0 + s * FB_STAGE, &tmap, (k + 2) * (FB_INNER / 8), r0, &bars[s]);
+      }
+    }
+  }
+  __syncthreads();
+  // ---- bitmask rows and counts to global memory
+  const int warp = tid >> 5, lane = tid & 31;
+  if (warp < FB_ROWS) {
+    int cnt = 0;
+    if (warp < rows_here)
+      for (int w = lane; w < wpr; w += 32) {
+        const uint32_t word = bm[warp * wpr + w];
+        bits[(long long)(r0 + warp) * wpr + w] = word;
+        cnt += __popc(word);
+      }
+    for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (lane == 0) {
+      rowcnt[warp] = cnt;
+      if (warp < rows_here) rowcount[r0 + warp] = cnt;
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int t = 0;
+    for (int j = 0; j < FB_ROWS; j++) t += rowcnt[j];
+    bandtotal[band] = t;
+  }
+}
+
+// Raster-ordered emission from the band kernel's output: CTA = band; its first keypoint index is the sum of the totals of
+// the bands above (a few hundred integers, summed by the CTA itself - no scan launch), one warp per row walks the
+// bitmask.  The last band also stores the total count.
+__global__ void __launch_bounds__(FB_THREADS) k_fast9_emit_bands(Img im, int th, const uint32_t* bits, int wpr, const int* rowcount, const int* bandtotal,
+                                                                int nbands, vppb_int2* kps, int* scores, int score_div, int capacity, int* count_dev) {
+  __shared__ int part[FB_THREADS / 32];
+  __shared__ int base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int band = blockIdx.x, r0 = band * FB_ROWS;
+  int acc = 0;
+  for (int i = tid; i < band; i += FB_THREADS) acc += bandtotal[i];
+  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) part[warp] = acc;
+  __syncthreads();
+  if (tid == 0) {
+    int b = 0;
+    for (int i = 0; i < FB_THREADS / 32; i++) b += part[i];
+    base_s = b;
+    if (band == nbands - 1 && count_dev) *count_dev = b + bandtotal[band];
+  }
+  __syncthreads();
+  if (warp >= FB_ROWS) return;
+  const int r = r0 + warp;
+  if (r >= im.nrows) return;
+  int off = base_s;
+  for (int j = 0; j < warp; j++) off += rowcount[r0 + j];
+  if (rowcount[r] == 0) return;
+  for (int w0 = 0; w0 < wpr; w0 += 32) {
+    const int wi = w0 + lane;
+    uint32_t word = wi < wpr ? bits[(long long)r * wpr + wi] : 0u;
+    const int cnt = __popc(word);
+    int incl = cnt;
+    for (int o = 1; o < 32; o <<= 1) {
+      int y = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += y;
+    }
+    int pos = off + incl - cnt;
+    while (word) {
+      const int b = __ffs(word) - 1;
+      word &= word - 1;
+      if (pos < capacity) {
+        const int c = wi * 32 + b;
+        kps[pos].r = r;
+        kps[pos].c = c;
+        if (scores) {
+          const int sc = fast9_score_at(im, r, c, th);
+          scores[pos] = score_div ? ((sc / 16) & 255) : sc;
+        }
+      }
+      pos++;
+    }
+    off += __shfl_sync(0xffffffffu, incl, 31);
   }
 }
 
@@ -271,6 +485,8 @@ struct FastWs {
   uint32_t* bits_b;
   int* rowcount;
   int* rowoff;
+  int* bandtotal;
+  int* count;   // device copy of the keypoint count of the last call
   int* cellkp;
   long long bytes;
 };
@@ -285,10 +501,14 @@ static FastWs fast_ws_layout(void* base, int nrows, int ncols, int block_size) {
   w.bits_b = reinterpret_cast<uint32_t*>(p + bits_bytes);
   w.rowcount = reinterpret_cast<int*>(p + 2 * bits_bytes);
   w.rowoff = reinterpret_cast<int*>(p + 2 * bits_bytes + rows_bytes);
-  w.cellkp = reinterpret_cast<int*>(p + 2 * bits_bytes + 2 * rows_bytes);
-  const int bs = block_size > 0 ? block_size : 10;
+  w.bandtotal = reinterpret_cast<int*>(p + 2 * bits_bytes + 2 * rows_bytes);   // <= nrows / FB_ROWS + 1 entries fit in rows_bytes
+  w.count = reinterpret_cast<int*>(p + 2 * bits_bytes + 3 * rows_bytes);
+  w.cellkp = reinterpret_cast<int*>(p + 2 * bits_bytes + 3 * rows_bytes + 256);
+  // the cell array only exists for the blockwise mode; block_size <= 0 sizes it for the smallest block the library
+  // accepts there (1 pixel), so that a workspace sized without knowing the mode is always large enough
+  const int bs = block_size > 0 ? block_size : 1;
   const long long cells = (long long)((nrows + bs - 1) / bs) * ((ncols + bs - 1) / bs);
-  w.bytes = 2 * bits_bytes + 2 * rows_bytes + ((cells * 4 + 255) / 256) * 256;
+  w.bytes = 2 * bits_bytes + 3 * rows_bytes + 256 + ((cells * 4 + 255) / 256) * 256;
   return w;
 }
 
@@ -296,39 +516,75 @@ static FastWs fast_ws_layout(void* base, int nrows, int ncols, int block_size) {
 
 using namespace vppb;
 
-extern "C" {
-
-int64_t vppb_fast9_workspace_bytes(int32_t nrows, int32_t ncols, int32_t block_size) {
-  if (nrows <= 0 || ncols <= 0) return 0;
-  return fast_ws_layout(nullptr, nrows, ncols, block_size).bytes;
+// TMA needs the library layout (>= 16 addressable bytes left of column 0, 16-byte aligned rows); FB_MAXW bounds the band bitmask
+static bool fast_band_eligible(const vppb_img* img) {
+  if (img->align < 16 || ((uintptr_t)img->base % 16) || (img->pitch % 16)) return false;
+  long long bs = (long long)img->border * img->elem_bytes;
+  if (bs % img->align) bs += img->align - (bs % img->align);
+  long long pch = (long long)img->ncols * img->elem_bytes + 2 * bs;
+  if (pch % img->align) pch += img->align - (pch % img->align);
+  if (pch != img->pitch || bs < 16) return false;
+  return img->ncols <= FB_MAXW;
 }
 
-int vppb_fast9_u8(const vppb_img* img, int32_t th, const vppb_img* mask, int32_t mode, int32_t block_size, int32_t ring,
-                  void* workspace, int64_t workspace_bytes, vppb_int2* kps_out, int32_t* scores_out, int32_t capacity,
-                  int32_t* count_out, void* stream) {
-  VPPB_REQUIRE(img && img->base && workspace && count_out, VPPB_E_ARG, "vppb_fast9_u8: NULL argument");
-  VPPB_REQUIRE(img->elem_bytes == 1, VPPB_E_ARG, "vppb_fast9_u8: image must be u8");
+static int fast9_core(const vppb_img* img, int32_t th, const vppb_img* mask, int32_t mode, int32_t block_size, int32_t ring, void* workspace,
+                      int64_t workspace_bytes, vppb_int2* kps_out, int32_t* scores_out, int32_t capacity, int32_t* count_dev, int** count_src, void* stream,
+                      const char* name) {
+  VPPB_REQUIRE(img && img->base && workspace, VPPB_E_ARG, "%s: NULL argument", name);
+  VPPB_REQUIRE(img->elem_bytes == 1, VPPB_E_ARG, "%s: image must be u8", name);
   // fast.hpp:937-938
   VPPB_REQUIRE(img->border >= 3, VPPB_E_BORDER, "Image need a border of 3px at least for the FAST detector");
-  VPPB_REQUIRE(mode >= 0 && mode <= 2 && (ring == 0 || ring == 1), VPPB_E_ARG, "vppb_fast9_u8: bad mode/ring");
-  VPPB_REQUIRE(mode != VPPB_FAST_BLOCKWISE || block_size > 0, VPPB_E_ARG, "vppb_fast9_u8: block_size must be > 0");
-  VPPB_REQUIRE(capacity == 0 || kps_out, VPPB_E_ARG, "vppb_fast9_u8: NULL keypoint buffer");
+  VPPB_REQUIRE(mode >= 0 && mode <= 2 && (ring == 0 || ring == 1), VPPB_E_ARG, "%s: bad mode/ring", name);
+  VPPB_REQUIRE(mode != VPPB_FAST_BLOCKWISE || block_size > 0, VPPB_E_ARG, "%s: block_size must be > 0", name);
+  VPPB_REQUIRE(capacity == 0 || kps_out, VPPB_E_ARG, "%s: NULL keypoint buffer", name);
   const bool has_mask = mask && mask->base;
   if (has_mask)
-    VPPB_REQUIRE(mask->elem_bytes == 1 && mask->nrows >= img->nrows && mask->ncols >= img->ncols, VPPB_E_ARG,
-                 "vppb_fast9_u8: mask must be u8 and cover the image");
-  VPPB_REQUIRE(img->nrows < 65536 && img->ncols < 65536, VPPB_E_ARG, "vppb_fast9_u8: image larger than 65535 in one dimension");
-  FastWs ws = fast_ws_layout(workspace, img->nrows, img->ncols, mode == VPPB_FAST_BLOCKWISE ? block_size : 10);
-  VPPB_REQUIRE(workspace_bytes >= ws.bytes, VPPB_E_ARG, "vppb_fast9_u8: workspace %lld < %lld bytes", (long long)workspace_bytes, ws.bytes);
+    VPPB_REQUIRE(mask->elem_bytes == 1 && mask->nrows >= img->nrows && mask->ncols >= img->ncols, VPPB_E_ARG, "%s: mask must be u8 and cover the image", name);
+  VPPB_REQUIRE(img->nrows < 65536 && img->ncols < 65536, VPPB_E_ARG, "%s: image larger than 65535 in one dimension", name);
+  // the reference ignores block_size outside the blockwise mode: so does the workspace rule
+  FastWs ws = fast_ws_layout(workspace, img->nrows, img->ncols, mode == VPPB_FAST_BLOCKWISE ? block_size : (1 << 30));
+  VPPB_REQUIRE(workspace_bytes >= ws.bytes, VPPB_E_ARG, "%s: workspace %lld < %lld bytes", name, (long long)workspace_bytes, ws.bytes);
   cudaStream_t st = as_stream(stream);
   const int wpr = (img->ncols + 31) / 32;
   const long long words = (long long)img->nrows * wpr;
   Img im = view(img);
   Img mk = has_mask ? view(mask) : im;
   const int sms = sm_count();
+  int* cnt = count_dev ? count_dev : ws.count;
+  *count_src = cnt;
+  const int nbands = (img->nrows + FB_ROWS - 1) / FB_ROWS;
 
-  VPPB_CUDA(cudaMemsetAsync(ws.rowcount, 0, ((size_t)img->nrows + 1) * sizeof(int), st));
-  {
+  static int force_old = -1;
+  if (force_old < 0) {
+    const char* e = getenv("VPPB_FAST_IMPL");
+    force_old = (e && !strcmp(e, "warp")) ? 1 : 0;
+  }
+  const bool band_path = fast_band_eligible(img) && !force_old;
+  if (band_path) {
+    CUtensorMap tmap;
+    unsigned char* origin = static_cast<unsigned char*>(img->base) - 3LL * img->pitch - 16;
+    const uint64_t width_el = ((uint64_t)img->ncols + 32 + 7) / 8;
+    int rc = encode_tensor_map_2d(&tmap, origin, CU_TENSOR_MAP_DATA_TYPE_UINT64, 8, width_el, (uint64_t)img->nrows + 6, (uint64_t)img->pitch, FB_BOXW / 8, FB_INH);
+    if (rc) return rc;
+    const int smem = fb_smem_bytes(wpr);
+    static std::atomic<int> attr_done{0};
+    if (attr_done.load(std::memory_order_acquire) < smem) {  // grows only: the opt-in limit is per function and device
+      VPPB_CUDA(cudaFuncSetAttribute(k_fast9_band<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, fb_smem_bytes(FB_MAXW / 32)));
+      VPPB_CUDA(cudaFuncSetAttribute(k_fast9_band<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, fb_smem_bytes(FB_MAXW / 32)));
+      attr_done.store(fb_smem_bytes(FB_MAXW / 32), std::memory_order_release);
+    }
+    const int nboxes = (img->ncols + FB_INNER - 1) / FB_INNER;
+    if (ring == 0)
+      k_fast9_band<0><<<nbands, FB_THREADS, smem, st>>>(tmap, im, mk, has_mask ? 1 : 0, th, nboxes, wpr, ws.bits_a, ws.rowcount, ws.bandtotal);
+    else
+      k_fast9_band<1><<<nbands, FB_THREADS, smem, st>>>(tmap, im, mk, has_mask ? 1 : 0, th, nboxes, wpr, ws.bits_a, ws.rowcount, ws.bandtotal);
+    if (mode == VPPB_FAST_ALL) {
+      k_fast9_emit_bands<<<nbands, FB_THREADS, 0, st>>>(im, th, ws.bits_a, wpr, ws.rowcount, ws.bandtotal, nbands, kps_out, scores_out, 0, capacity, cnt);
+      VPPB_LAUNCH_CHECK(name);
+      return VPPB_OK;
+    }
+  } else {
+    VPPB_CUDA(cudaMemsetAsync(ws.rowcount, 0, ((size_t)img->nrows + 1) * sizeof(int), st));
     long long blocks = (words + 7) / 8;  // 8 warps per CTA
     int grid = (int)(blocks < (long long)sms * 8 ? blocks : (long long)sms * 8);
     k_fast9_detect<<<grid, 256, 0, st>>>(im, mk, has_mask ? 1 : 0, th, ring, ws.bits_a, wpr, ws.rowcount);
@@ -350,12 +606,9 @@ int vppb_fast9_u8(const vppb_img* img, int32_t th, const vppb_img* mask, int32_t
       long long eb = ((long long)cells_r + 7) / 8;
       k_fast9_emit_cells<<<(int)(eb < (long long)sms * 8 ? eb : (long long)sms * 8), 256, 0, st>>>(im, th, ws.cellkp, cells_r, cells_c, ws.rowoff, kps_out, scores_out,
                                                                                                  capacity);
-      VPPB_LAUNCH_CHECK("vppb_fast9_u8");
-      int total = 0;
-      VPPB_CUDA(cudaMemcpyAsync(&total, ws.rowoff + cells_r, sizeof(int), cudaMemcpyDeviceToHost, st));
-      VPPB_CUDA(cudaStreamSynchronize(st));
-      *count_out = total;
-      VPPB_REQUIRE(total <= capacity, VPPB_E_CAPACITY, "vppb_fast9_u8: %d keypoints exceed the capacity %d", total, capacity);
+      VPPB_LAUNCH_CHECK(name);
+      *count_src = ws.rowoff + cells_r;
+      if (count_dev) VPPB_CUDA(cudaMemcpyAsync(count_dev, ws.rowoff + cells_r, sizeof(int), cudaMemcpyDeviceToDevice, st));
       return VPPB_OK;
     }
     final_bits = ws.bits_b;
@@ -366,13 +619,40 @@ int vppb_fast9_u8(const vppb_img* img, int32_t th, const vppb_img* mask, int32_t
     int grid = (int)(blocks < (long long)sms * 8 ? blocks : (long long)sms * 8);
     k_fast9_emit<<<grid, 256, 0, st>>>(im, th, final_bits, wpr, ws.rowoff, kps_out, scores_out, mode != VPPB_FAST_ALL ? 1 : 0, capacity);
   }
-  VPPB_LAUNCH_CHECK("vppb_fast9_u8");
+  VPPB_LAUNCH_CHECK(name);
+  *count_src = ws.rowoff + img->nrows;
+  if (count_dev) VPPB_CUDA(cudaMemcpyAsync(count_dev, ws.rowoff + img->nrows, sizeof(int), cudaMemcpyDeviceToDevice, st));
+  return VPPB_OK;
+}
+
+extern "C" {
+
+int64_t vppb_fast9_workspace_bytes(int32_t nrows, int32_t ncols, int32_t block_size) {
+  if (nrows <= 0 || ncols <= 0) return 0;
+  return fast_ws_layout(nullptr, nrows, ncols, block_size).bytes;
+}
+
+int vppb_fast9_u8(const vppb_img* img, int32_t th, const vppb_img* mask, int32_t mode, int32_t block_size, int32_t ring,
+                  void* workspace, int64_t workspace_bytes, vppb_int2* kps_out, int32_t* scores_out, int32_t capacity,
+                  int32_t* count_out, void* stream) {
+  VPPB_REQUIRE(count_out, VPPB_E_ARG, "vppb_fast9_u8: NULL argument");
+  int* src = nullptr;
+  int rc = fast9_core(img, th, mask, mode, block_size, ring, workspace, workspace_bytes, kps_out, scores_out, capacity, nullptr, &src, stream, "vppb_fast9_u8");
+  if (rc) return rc;
   int total = 0;
-  VPPB_CUDA(cudaMemcpyAsync(&total, ws.rowoff + img->nrows, sizeof(int), cudaMemcpyDeviceToHost, st));
-  VPPB_CUDA(cudaStreamSynchronize(st));
+  VPPB_CUDA(cudaMemcpyAsync(&total, src, sizeof(int), cudaMemcpyDeviceToHost, as_stream(stream)));
+  VPPB_CUDA(cudaStreamSynchronize(as_stream(stream)));
   *count_out = total;
   VPPB_REQUIRE(total <= capacity, VPPB_E_CAPACITY, "vppb_fast9_u8: %d keypoints exceed the capacity %d", total, capacity);
   return VPPB_OK;
+}
+
+int vppb_fast9_u8_async(const vppb_img* img, int32_t th, const vppb_img* mask, int32_t mode, int32_t block_size, int32_t ring,
+                        void* workspace, int64_t workspace_bytes, vppb_int2* kps_out, int32_t* scores_out, int32_t capacity,
+                        int32_t* count_dev, void* stream) {
+  VPPB_REQUIRE(count_dev, VPPB_E_ARG, "vppb_fast9_u8_async: NULL argument");
+  int* src = nullptr;
+  return fast9_core(img, th, mask, mode, block_size, ring, workspace, workspace_bytes, kps_out, scores_out, capacity, count_dev, &src, stream, "vppb_fast9_u8_async");
 }
 
 int vppb_fast9_scores(const vppb_img* img, int32_t th, const vppb_int2* kps, int32_t n, int32_t* scores_out, void* stream) {

@@ -173,24 +173,25 @@ class _DeviceBuffer:
     def ptr(self):
         return self.img.base
 
-    def to_host(self, dtype, count):
+    def to_host(self, dtype, count, stream=None):
+        """Copy back on `stream` - the stream the producing kernels were launched on - and wait for it."""
         out = np.empty(count, dtype=dtype)
         if count:
             view = capi.VppbImg()
             C.memmove(C.byref(view), C.byref(self.img), C.sizeof(capi.VppbImg))
             view.ncols = out.nbytes
-            check(lib.vppb_download(C.byref(view), out.ctypes.data, out.nbytes, 0, None))
-            check(lib.vppb_sync(None))
+            check(lib.vppb_download(C.byref(view), out.ctypes.data, out.nbytes, 0, stream))
+            check(lib.vppb_sync(stream))
         return out
 
-    def from_host(self, arr):
+    def from_host(self, arr, stream=None):
         arr = np.ascontiguousarray(arr)
         if arr.nbytes:
             view = capi.VppbImg()
             C.memmove(C.byref(view), C.byref(self.img), C.sizeof(capi.VppbImg))
             view.ncols = arr.nbytes
-            check(lib.vppb_upload(C.byref(view), arr.ctypes.data, arr.nbytes, 0, None))
-            check(lib.vppb_sync(None))
+            check(lib.vppb_upload(C.byref(view), arr.ctypes.data, arr.nbytes, 0, stream))
+            check(lib.vppb_sync(stream))  # the host array may be a temporary
         return self
 
     def __del__(self):
@@ -200,54 +201,72 @@ class _DeviceBuffer:
             pass
 
 
+_FAST_CACHE = {}  # (nrows, ncols, block_size) -> workspace; (capacity, with_scores) -> output buffers: allocated once, reused
+
+
+def _fast_buffers(img, block_size, cap, want_scores):
+    key = (img.nrows, img.ncols, block_size)
+    ent = _FAST_CACHE.get(key)
+    if ent is None:
+        if len(_FAST_CACHE) > 8:
+            _FAST_CACHE.clear()
+        ent = {"ws": _DeviceBuffer(lib.vppb_fast9_workspace_bytes(img.nrows, img.ncols, block_size)), "count": _DeviceBuffer(4), "cap": 0}
+        _FAST_CACHE[key] = ent
+    if ent["cap"] < cap:
+        ent["kps"], ent["sc"], ent["cap"] = _DeviceBuffer(cap * 8), _DeviceBuffer(cap * 4), cap
+    return ent
+
+
 def fast9(img, th, local_maxima=False, blockwise=False, block_size=10, mask=None, scores=None, ring="reference",
           capacity=None, stream=None):
     """std::vector<vint2> fast9(A, th, [_local_maxima | _blockwise, _block_size=, _mask=, _scores=&vec])
     (fast.hpp:931-955).  Returns an (n, 2) int32 array of (row, col) in raster order (blockwise: cell raster order, the
     reference's serial order); if `scores` is a
-    list it is replaced by the matching scores.  Raises RuntimeError if A.border() < 3 (fast.hpp:937-938)."""
+    list it is replaced by the matching scores.  Raises RuntimeError if A.border() < 3 (fast.hpp:937-938).
+    Workspace and output buffers are allocated once per image shape and reused; the device work is queued without a
+    host synchronisation (vppb_fast9_u8_async), then the 4-byte count and the keypoints are read back on `stream`."""
     mode = capi.FAST_LOCAL_MAXIMA if local_maxima else (capi.FAST_BLOCKWISE if blockwise else capi.FAST_ALL)
     ring_id = capi.FAST_REFERENCE_RING if ring == "reference" else capi.FAST_TRUE_RING
-    ws = _DeviceBuffer(lib.vppb_fast9_workspace_bytes(img.nrows, img.ncols, block_size))
     cap = capacity if capacity is not None else max(1024, (img.nrows * img.ncols) // 8)
-    count = C.c_int32()
     while True:
-        kps = _DeviceBuffer(cap * 8)
-        sc = _DeviceBuffer(cap * 4) if scores is not None else None
-        rc = lib.vppb_fast9_u8(img.ptr(), th, mask.ptr() if mask is not None else None, mode, block_size, ring_id, ws.ptr,
-                               ws.nbytes, kps.ptr, sc.ptr if sc else None, cap, C.byref(count), stream)
-        if rc == capi.VPPB_E_CAPACITY and capacity is None:
-            cap = count.value
+        ent = _fast_buffers(img, block_size, cap, scores is not None)
+        kps, sc = ent["kps"], ent["sc"] if scores is not None else None
+        check(lib.vppb_fast9_u8_async(img.ptr(), th, mask.ptr() if mask is not None else None, mode, block_size, ring_id, ent["ws"].ptr,
+                                      ent["ws"].nbytes, kps.ptr, sc.ptr if sc else None, cap, ent["count"].ptr, stream))
+        count = int(ent["count"].to_host(np.int32, 1, stream)[0])
+        if count > cap:
+            if capacity is not None:
+                raise capi.VppbError(capi.VPPB_E_CAPACITY, "fast9: %d keypoints exceed the capacity %d" % (count, cap))
+            cap = count
             continue
-        check(rc)
         break
-    out = kps.to_host(np.int32, count.value * 2).reshape(-1, 2)
+    out = kps.to_host(np.int32, count * 2, stream).reshape(-1, 2)
     if scores is not None:
-        scores[:] = list(sc.to_host(np.int32, count.value))
+        scores[:] = list(sc.to_host(np.int32, count, stream))
     return out
 
 
 def fast9_scores(img, th, keypoints, stream=None):  # fast.hpp:643-652
     kp = np.ascontiguousarray(keypoints, dtype=np.int32).reshape(-1, 2)
-    d_kp = _DeviceBuffer(kp.nbytes).from_host(kp)
+    d_kp = _DeviceBuffer(kp.nbytes).from_host(kp, stream)
     d_sc = _DeviceBuffer(len(kp) * 4)
     check(lib.vppb_fast9_scores(img.ptr(), th, d_kp.ptr, len(kp), d_sc.ptr, stream))
-    return d_sc.to_host(np.int32, len(kp))
+    return d_sc.to_host(np.int32, len(kp), stream)
 
 
 # ---- Lucas-Kanade -----------------------------------------------------------------------------
 def _lk_run(pyr_prev, pyr_next, pyr_grad, params, keypoints, prediction, stream):
     kp = np.ascontiguousarray(keypoints, dtype=np.float32).reshape(-1, 2)
     n = len(kp)
-    d_kp = _DeviceBuffer(kp.nbytes).from_host(kp)
+    d_kp = _DeviceBuffer(kp.nbytes).from_host(kp, stream)
     d_pred = None
     if prediction is not None:
-        d_pred = _DeviceBuffer(kp.nbytes).from_host(np.ascontiguousarray(prediction, dtype=np.float32).reshape(-1, 2))
+        d_pred = _DeviceBuffer(kp.nbytes).from_host(np.ascontiguousarray(prediction, dtype=np.float32).reshape(-1, 2), stream)
     d_flow = _DeviceBuffer(n * 8)
     d_err = _DeviceBuffer(n * 4)
     check(lib.vppb_lk_match_u8(pyr_prev.desc_array(), pyr_next.desc_array(), pyr_grad.desc_array(), C.byref(params), d_kp.ptr,
                                d_pred.ptr if d_pred else None, n, d_flow.ptr, d_err.ptr, stream))
-    return d_flow.to_host(np.float32, n * 2).reshape(-1, 2), d_err.to_host(np.float32, n)
+    return d_flow.to_host(np.float32, n * 2, stream).reshape(-1, 2), d_err.to_host(np.float32, n, stream)
 
 
 def lucas_kanade(i1, i2, keypoints, niterations=21, winsize=11, nscales=3, min_ev=0.0001, delta=0.1, prediction=None,
@@ -297,8 +316,9 @@ def semi_dense_optical_flow(keypoints, i1, i2, winsize=7, nscales=4, min_scale=0
     p2 = Pyramid2d(i2, nscales, 2, border=2 * winsize)
     P = capi.VppbSdofParams(winsize, nscales, min_scale, propagation, patchsize)
     ws = _DeviceBuffer(lib.vppb_sdof_workspace_bytes(i1.nrows, i1.ncols, C.byref(P)))
-    d_kp = _DeviceBuffer(kp.nbytes).from_host(kp)
+    d_kp = _DeviceBuffer(kp.nbytes).from_host(kp, stream)
     d_pos, d_dist, d_valid = _DeviceBuffer(n * 8), _DeviceBuffer(n * 4), _DeviceBuffer(n)
     check(lib.vppb_sdof_u8(p1.desc_array(), p2.desc_array(), C.byref(P), d_kp.ptr, n, ws.ptr, ws.nbytes, d_pos.ptr, d_dist.ptr,
                            d_valid.ptr, stream))
-    return d_pos.to_host(np.int32, n * 2).reshape(-1, 2), d_dist.to_host(np.int32, n), d_valid.to_host(np.uint8, n).astype(bool)
+    return (d_pos.to_host(np.int32, n * 2, stream).reshape(-1, 2), d_dist.to_host(np.int32, n, stream),
+            d_valid.to_host(np.uint8, n, stream).astype(bool))
