@@ -5,7 +5,7 @@ cd "$(dirname "$0")"
 mkdir -p vpp_b200/lib oracle/_build
 nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -fmad=false \
      -Xcompiler -fPIC -shared ${VPPB_NVCC_EXTRA} \
-     -o vpp_b200/lib/libvppb.so vpp_b200/csrc/*.cu
+     -o vpp_b200/lib/libvppb.so vpp_b200/csrc/*.cu -ldl
 gcc -O2 -ffp-contract=off -fno-fast-math -fPIC -shared -o oracle/_build/libvpp_oracle.so oracle/*.c -lm
 gcc -O3 -march=native -fopenmp -DNDEBUG -ffp-contract=off -fPIC -shared -o oracle/_build/libvpp_oracle_omp.so oracle/*.c -lm
 # C++14 host API tests (the reference's own tests rewritten with device kernels), run by tests/test_cpp_api.py on the GPU box

@@ -216,6 +216,35 @@ int vppb_halo_unpack(const vppb_img* img, int32_t halo, int which, const void* s
 int vppb_halo_pack_batch(const vppb_img* imgs, int32_t n, int32_t halo, int which, void* staging, void* stream);
 int vppb_halo_unpack_batch(const vppb_img* imgs, int32_t n, int32_t halo, int which, const void* staging, void* stream);
 
+/* ---- multi-GPU row tiles, peer memory ----------------------------------------------------- */
+/* Frames shard by contiguous row tiles, one tile per GPU (the reference's only parallelism is OpenMP over
+ * rows, vpp/core/pixel_wise.hpp:85-105).  A tile is an image2d whose border rows above / below are its halo.
+ *
+ * Fused form: the 5x5 box over n row tiles whose halo rows are NOT materialised: `ups[i]` / `downs[i]` describe the tiles
+ * above / below tile i (base == NULL, or the whole array NULL: none - the tile's own, caller-filled border rows are
+ * used, as for the outermost tiles).  A neighbour may live on a peer GPU (same process with peer access enabled, or
+ * another process through vppb_ipc_open): the kernel pulls the 2 halo rows of every strip straight from the
+ * neighbour's memory over NVLink with bulk copies inside its own load pipeline - no exchange step, no border writes.
+ * All tiles of a call share one shape and layout (vppb_layout with the same border / align); the tile above must have
+ * the same number of rows.  The caller orders the call after the neighbours' tiles are complete. */
+int vppb_box5x5_u8c3_tiles(const vppb_img* ins, const vppb_img* ups, const vppb_img* downs, const vppb_img* outs, int32_t n, void* stream);
+int vppb_box5x5_u8_tiles(const vppb_img* ins, const vppb_img* ups, const vppb_img* downs, const vppb_img* outs, int32_t n, void* stream);
+/* CUDA IPC for one-process-per-GPU jobs: export an image that owns its allocation (vppb_alloc) as a 64-byte handle + the
+ * offset of pixel (0,0); open it in another process (geometry = the exporter's descriptor; base / alloc are replaced by
+ * the local mapping, peer access is enabled on demand); close unmaps. */
+int vppb_ipc_export(const vppb_img* img, void* handle64, int64_t* offset_out);
+int vppb_ipc_open(const void* handle64, int64_t offset, const vppb_img* geometry, vppb_img* out);
+int vppb_ipc_close(vppb_img* img);
+/* Materialised form: ONE grouped NCCL send/recv with both neighbours for n tiles (the `halo` top rows of every tile go to
+ * rank - 1 and land in its bottom border rows, the bottom rows to rank + 1): what Scharr (1 row), FAST9 (3), the
+ * pyramid (2 per level), LK windows and the semi-dense flow (64) use before their single-GPU kernels run on the tile.
+ * comm: from vppb_comm_init (NCCL is loaded at run time; VPPB_E_NCCL if it is missing or fails).  The 128-byte id comes
+ * from vppb_comm_unique_id on one rank and reaches the others by any means (MPI, torch.distributed, a file). */
+int vppb_comm_unique_id(void* id128);
+int vppb_comm_init(const void* id128, int32_t rank, int32_t nranks, void** comm_out);
+int vppb_comm_destroy(void* comm);
+int vppb_halo_exchange(void* comm, int32_t rank, int32_t nranks, const vppb_img* imgs, int32_t n, int32_t halo, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

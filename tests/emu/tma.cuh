@@ -48,6 +48,11 @@ inline void tma_load_2d(void* smem_dst, const CUtensorMap* map, int x, int y, ui
     }
   emu::mbar_complete_tx(bar, (uint32_t)(t->box_w * t->box_h * t->elem_bytes));
 }
+inline void tma_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  if (((uintptr_t)smem_dst % 16) != 0 || ((uintptr_t)gsrc % 16) != 0 || (bytes % 16) != 0) emu::fail("tma_load_1d: source, destination and size must be multiples of 16 bytes");
+  memcpy(smem_dst, gsrc, bytes);
+  emu::mbar_complete_tx(bar, bytes);
+}
 inline void tma_prefetch_desc(const CUtensorMap*) {}
 
 }  // namespace vppb

@@ -102,3 +102,4 @@ test_linear_copy_path_of_upload_download = L.test_linear_copy_path_of_upload_dow
 test_semi_dense_flow_level_schedule = L.test_semi_dense_flow_level_schedule
 test_fast9_wide_images_multibox = L.test_fast9_wide_images_multibox
 test_fast9_threshold_extremes = L.test_fast9_threshold_extremes
+test_box5x5_row_tiles_read_neighbours = L.test_box5x5_row_tiles_read_neighbours

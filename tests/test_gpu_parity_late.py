@@ -2,6 +2,7 @@
 profiles/r1_emulator_verification.md): they live in their own module, which sorts after tests/test_gpu_parity.py, so that
 `pytest -m gpu -x` reaches them only once everything that already ran on hardware has been re-checked.
 tests/test_emulated_parity.py collects them for the emulator like the others."""
+import ctypes as C
 import os
 import subprocess
 
@@ -259,3 +260,59 @@ def test_fast9_threshold_extremes(vpp, th):
     kps = vpp.fast9(G, th)
     rk, _ = _oracle_fast(img, th)
     assert np.array_equal(kps, rk)
+
+
+# ------------------------------------------------------------------ row tiles: halo rows pulled from the neighbouring tiles by the box kernel itself
+@pytest.mark.parametrize("pix,ntiles,rows,cols", [("vuchar3", 3, 37, 300), ("vuchar3", 2, 2, 700), ("u8", 4, 23, 1100), ("vuchar3", 8, 16, 190)])
+def test_box5x5_row_tiles_read_neighbours(vpp, pix, ntiles, rows, cols):
+    """vppb_box5x5_*_tiles: a frame cut into equally tall row tiles held in SEPARATE allocations (on the GPUs of a node: one
+    per device, mapped with vppb_ipc_open); the tiles' top / bottom border rows are filled with garbage, the kernel must take
+    the halo rows from the neighbours' domain rows.  Every tile of the result equals the oracle's full-frame box.  """
+    from vpp_b200 import capi
+
+    ch = 3 if pix == "vuchar3" else 1
+    r = rng(900 + rows)
+    H = ntiles * rows
+    frame = r.integers(0, 256, (H, cols, ch) if ch > 1 else (H, cols), dtype=np.uint8)
+    hs = orc.HostImage(H, cols, pix, border=2, data=frame, fill_border="mirror")
+    hd = orc.HostImage(H, cols, pix)
+    orc.load().vo_box5x5_u8(hs.ptr(), hd.ptr(), ch)
+    want = hd.get()
+    full = hs.get(with_border=True)  # (H + 4, cols + 4[, ch]) with the mirror border
+    tiles, outs = [], []
+    for t in range(ntiles):
+        T = vpp.Image2d(rows, cols, pix, border=2)
+        blk = np.array(full[t * rows:t * rows + rows + 4])
+        if t > 0:
+            blk[:2] = 0xA5   # the halo rows above are NOT in the tile
+        if t < ntiles - 1:
+            blk[-2:] = 0x5A  # nor the ones below
+        T.upload(blk, with_border=True)
+        tiles.append(T)
+        outs.append(vpp.Image2d(rows, cols, pix))
+    mapped = []
+    emulated = hasattr(capi.lib, "vppb_emu_set_reverse")
+    for T in tiles:
+        h, off, m = (C.c_char * 64)(), C.c_int64(), capi.VppbImg()
+        capi.check(capi.lib.vppb_ipc_export(T.ptr(), h, C.byref(off)))
+        assert off.value == T.desc.base - T.desc.alloc
+        if emulated:  # a CUDA IPC handle cannot be opened by the process that exported it: the open leg runs in the 2-rank tools/tiles_check.py
+            capi.check(capi.lib.vppb_ipc_open(h, off.value, T.ptr(), C.byref(m)))
+        else:
+            C.memmove(C.byref(m), C.byref(T.desc), C.sizeof(capi.VppbImg))
+        mapped.append(m)
+    null = capi.VppbImg()
+    ins = (capi.VppbImg * ntiles)(*[T.desc for T in tiles])
+    ups = (capi.VppbImg * ntiles)(*[mapped[t - 1] if t > 0 else null for t in range(ntiles)])
+    dns = (capi.VppbImg * ntiles)(*[mapped[t + 1] if t < ntiles - 1 else null for t in range(ntiles)])
+    dst = (capi.VppbImg * ntiles)(*[o.desc for o in outs])
+    fn = capi.lib.vppb_box5x5_u8c3_tiles if ch == 3 else capi.lib.vppb_box5x5_u8_tiles
+    capi.check(fn(ins, ups, dns, dst, ntiles, None))
+    capi.check(capi.lib.vppb_sync(None))
+    for t in range(ntiles):
+        assert np.array_equal(outs[t].download(), want[t * rows:(t + 1) * rows]), "tile %d" % t
+    # one tile at a time, as each rank of a multi-GPU job calls it
+    for t in range(ntiles):
+        o = vpp.Image2d(rows, cols, pix)
+        capi.check(fn(C.byref(ins[t]), C.byref(ups[t]), C.byref(dns[t]), o.ptr(), 1, None))
+        assert np.array_equal(o.download(), want[t * rows:(t + 1) * rows]), "single tile %d" % t

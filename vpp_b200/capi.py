@@ -116,6 +116,15 @@ PROTOTYPES = {
     "vppb_halo_unpack": (C.c_int, [_IMG, _I32, C.c_int, _VP, _VP]),
     "vppb_halo_pack_batch": (C.c_int, [_IMG, _I32, _I32, C.c_int, _VP, _VP]),
     "vppb_halo_unpack_batch": (C.c_int, [_IMG, _I32, _I32, C.c_int, _VP, _VP]),
+    "vppb_box5x5_u8c3_tiles": (C.c_int, [_IMG, _IMG, _IMG, _IMG, _I32, _VP]),
+    "vppb_box5x5_u8_tiles": (C.c_int, [_IMG, _IMG, _IMG, _IMG, _I32, _VP]),
+    "vppb_ipc_export": (C.c_int, [_IMG, _VP, _P(_I64)]),
+    "vppb_ipc_open": (C.c_int, [_VP, _I64, _IMG, _IMG]),
+    "vppb_ipc_close": (C.c_int, [_IMG]),
+    "vppb_comm_unique_id": (C.c_int, [_VP]),
+    "vppb_comm_init": (C.c_int, [_VP, _I32, _I32, _P(_VP)]),
+    "vppb_comm_destroy": (C.c_int, [_VP]),
+    "vppb_halo_exchange": (C.c_int, [_VP, _I32, _I32, _IMG, _I32, _I32, _VP]),
 }
 
 

@@ -317,7 +317,13 @@ template <int LW> struct BoxStreamCfg {
 struct BoxStream {
   CUtensorMap maps[BX_MAX_BATCH];
   unsigned char* out_base[BX_MAX_BATCH];
+  // row tiles (multi-GPU): pixel (0,0) of the tile itself and of the tiles above / below it (NULL: none, the tile's own
+  // border rows are the halo).  The neighbours' memory may be a peer GPU's, mapped into this process.
+  const unsigned char* in_base[BX_MAX_BATCH];
+  const unsigned char* up_base[BX_MAX_BATCH];
+  const unsigned char* dn_base[BX_MAX_BATCH];
   int nimg, out_pitch, nrows, rowbytes, strips, chunks, R, groups, vec_store, total;
+  int in_pitch, row_room;   // row_room: addressable bytes of a row from pixel (0,0) to the end of its pitch
   uint32_t one;
 };
 
@@ -362,9 +368,32 @@ __global__ void __launch_bounds__(BoxStreamCfg<LW>::WARPS * 32, BoxStreamCfg<LW>
     if (ptask < p.total) {
       const int img = ptask / per_img, rem = ptask - img * per_img;
       const int chunk = rem / p.strips, strip = rem - chunk * p.strips;
-      mbar_arrive_expect_tx(&bars[pslot], BS_K * Cfg::BOXW);
-      // tensor origin = 16 bytes left of x = 0 and 2 rows above y = 0; 8-byte elements (x coordinate * 8 is a multiple of 16)
-      tma_load_2d(ring + pslot * Cfg::STAGE_BYTES, &p.maps[img], strip * (Cfg::STRIP / 8), chunk * p.R + pgrp * BS_K, &bars[pslot]);
+      const int ty = chunk * p.R + pgrp * BS_K;  // first row of the stage, counted from image row -2
+      const unsigned char* up = p.up_base[img];
+      const unsigned char* dn = p.dn_base[img];
+      if ((up && ty < 2) || (dn && ty + BS_K > p.nrows + 2)) {
+        // the stage straddles a tile boundary: row by row, each from the tile that owns it - the halo rows come straight
+        // from the neighbour's (peer GPU's) memory as 1-D bulk copies, the transfer is part of the kernel's own pipeline
+        const int xoff = strip * Cfg::STRIP - 16;
+        const int len = min(Cfg::BOXW, p.row_room - xoff);
+        int rows = 0;
+#pragma unroll
+        for (int i = 0; i < BS_K; i++) rows += (ty + i - 2 <= p.nrows + 1) ? 1 : 0;
+        mbar_arrive_expect_tx(&bars[pslot], rows * len);
+#pragma unroll
+        for (int i = 0; i < BS_K; i++) {
+          const int v = ty + i - 2;  // image row of the tile
+          if (v > p.nrows + 1) continue;
+          const unsigned char* src = (v < 0 && up) ? up + (long long)(p.nrows + v) * p.in_pitch
+                                   : (v >= p.nrows && dn) ? dn + (long long)(v - p.nrows) * p.in_pitch
+                                                          : p.in_base[img] + (long long)v * p.in_pitch;
+          tma_load_1d(ring + pslot * Cfg::STAGE_BYTES + i * Cfg::BOXW, src + xoff, len, &bars[pslot]);
+        }
+      } else {
+        mbar_arrive_expect_tx(&bars[pslot], BS_K * Cfg::BOXW);
+        // tensor origin = 16 bytes left of x = 0 and 2 rows above y = 0; 8-byte elements (x coordinate * 8 is a multiple of 16)
+        tma_load_2d(ring + pslot * Cfg::STAGE_BYTES, &p.maps[img], strip * (Cfg::STRIP / 8), ty, &bars[pslot]);
+      }
       if (++pgrp == p.groups) { pgrp = 0; ptask += nw; }
     }
     pslot = (pslot + 1 == Cfg::STAGES) ? 0 : pslot + 1;
@@ -530,7 +559,7 @@ static int box_stream_rows(long long strips_x_imgs, int nrows, int warps_per_sm,
 
 // n equally shaped, TMA-eligible images (n <= BX_MAX_BATCH) in one launch of the streaming kernel
 template <int CS, int LW, int BAL>
-static int box5_stream_launch_lw(const vppb_img* ins, const vppb_img* outs, int n, cudaStream_t st, const char* name) {
+static int box5_stream_launch_lw(const vppb_img* ins, const vppb_img* ups, const vppb_img* dns, const vppb_img* outs, int n, cudaStream_t st, const char* name) {
   typedef BoxStreamCfg<LW> Cfg;
   const int rowbytes = ins[0].ncols * CS, nrows = ins[0].nrows;
   static std::atomic<unsigned long long> attr_done{0};
@@ -561,6 +590,15 @@ static int box5_stream_launch_lw(const vppb_img* ins, const vppb_img* outs, int 
                                   Cfg::BOXW / 8, BS_K);
     if (rc) return rc;
     p.out_base[k] = static_cast<unsigned char*>(outs[k].base);
+    p.in_base[k] = static_cast<const unsigned char*>(in->base);
+    p.up_base[k] = (ups && ups[k].base) ? static_cast<const unsigned char*>(ups[k].base) : nullptr;
+    p.dn_base[k] = (dns && dns[k].base) ? static_cast<const unsigned char*>(dns[k].base) : nullptr;
+  }
+  {
+    long long bs = (long long)ins[0].border * ins[0].elem_bytes;
+    if (bs % ins[0].align) bs += ins[0].align - (bs % ins[0].align);
+    p.in_pitch = ins[0].pitch;
+    p.row_room = ins[0].pitch - (int)bs;
   }
   const int ctas = (p.total + Cfg::WARPS - 1) / Cfg::WARPS, resident = sm_count() * Cfg::CTAS_PER_SM;
   k_box5_stream<CS, LW, BAL><<<ctas < resident ? ctas : resident, Cfg::WARPS * 32, Cfg::SMEM, st>>>(p);
@@ -569,7 +607,7 @@ static int box5_stream_launch_lw(const vppb_img* ins, const vppb_img* outs, int 
 }
 
 template <int CS>
-static int box5_stream_launch(const vppb_img* ins, const vppb_img* outs, int n, cudaStream_t st, const char* name) {
+static int box5_stream_launch(const vppb_img* ins, const vppb_img* ups, const vppb_img* dns, const vppb_img* outs, int n, cudaStream_t st, const char* name) {
   static int lw = -1;
   if (lw < 0) {
     const char* e = getenv("VPPB_BOX_LW");
@@ -580,8 +618,8 @@ static int box5_stream_launch(const vppb_img* ins, const vppb_img* outs, int n, 
     const char* e = getenv("VPPB_BOX_BAL");
     bal = e ? atoi(e) : 0;
   }
-  if (lw == 8) return bal ? box5_stream_launch_lw<CS, 8, 1>(ins, outs, n, st, name) : box5_stream_launch_lw<CS, 8, 0>(ins, outs, n, st, name);
-  return bal ? box5_stream_launch_lw<CS, 4, 1>(ins, outs, n, st, name) : box5_stream_launch_lw<CS, 4, 0>(ins, outs, n, st, name);
+  if (lw == 8) return bal ? box5_stream_launch_lw<CS, 8, 1>(ins, ups, dns, outs, n, st, name) : box5_stream_launch_lw<CS, 8, 0>(ins, ups, dns, outs, n, st, name);
+  return bal ? box5_stream_launch_lw<CS, 4, 1>(ins, ups, dns, outs, n, st, name) : box5_stream_launch_lw<CS, 4, 0>(ins, ups, dns, outs, n, st, name);
 }
 
 template <int CS>
@@ -592,7 +630,7 @@ static int box5_bytes(const vppb_img* in, const vppb_img* out, void* stream, con
   VPPB_REQUIRE(in->border >= 2, VPPB_E_BORDER, "%s: input border %d < 2", name, in->border);
   cudaStream_t st = as_stream(stream);
   const int rowbytes = in->ncols * CS;
-  if (tma_eligible(in) && box_use_stream()) return box5_stream_launch<CS>(in, out, 1, st, name);
+  if (tma_eligible(in) && box_use_stream()) return box5_stream_launch<CS>(in, nullptr, nullptr, out, 1, st, name);
   if (tma_eligible(in)) {
     CUtensorMap tmap;
     unsigned char* origin = static_cast<unsigned char*>(in->base) - 2LL * in->pitch - 16;
@@ -658,7 +696,7 @@ static int box5_bytes_batch(const vppb_img* ins, const vppb_img* outs, int n, vo
   cudaStream_t st = as_stream(stream);
   if (box_use_stream()) {
     for (int i0 = 0; i0 < n; i0 += BX_MAX_BATCH) {
-      int rc = box5_stream_launch<CS>(ins + i0, outs + i0, std::min(BX_MAX_BATCH, n - i0), st, name);
+      int rc = box5_stream_launch<CS>(ins + i0, nullptr, nullptr, outs + i0, std::min(BX_MAX_BATCH, n - i0), st, name);
       if (rc) return rc;
     }
     return VPPB_OK;
@@ -704,6 +742,36 @@ static int box5_bytes_batch(const vppb_img* ins, const vppb_img* outs, int n, vo
   return VPPB_OK;
 }
 
+// Row tiles: equally shaped TMA-eligible tiles; neighbours given per tile (base == NULL: none)
+template <int CS>
+static int box5_bytes_tiles(const vppb_img* ins, const vppb_img* ups, const vppb_img* dns, const vppb_img* outs, int n, void* stream, const char* name) {
+  VPPB_REQUIRE(ins && outs && n >= 0, VPPB_E_ARG, "%s: NULL batch", name);
+  for (int i = 0; i < n; i++) {
+    const vppb_img *in = &ins[i], *out = &outs[i];
+    VPPB_REQUIRE(in->base && out->base, VPPB_E_ARG, "%s: NULL image %d", name, i);
+    VPPB_REQUIRE(in->elem_bytes == CS && out->elem_bytes == CS, VPPB_E_ARG, "%s: element size must be %d (image %d)", name, CS, i);
+    VPPB_REQUIRE(same_domain(in, out) && same_domain(in, &ins[0]), VPPB_E_ARG, "%s: domains differ (image %d)", name, i);
+    VPPB_REQUIRE(in->border >= 2 && in->nrows >= 2, VPPB_E_BORDER, "%s: tile %d needs border >= 2 and at least 2 rows", name, i);
+    VPPB_REQUIRE(tma_eligible(in) && in->pitch == ins[0].pitch && in->border == ins[0].border && in->align == ins[0].align, VPPB_E_ARG,
+                 "%s: tiles must share the library layout (image %d)", name, i);
+    VPPB_REQUIRE(out->pitch == outs[0].pitch && (((uintptr_t)out->base % 16) == 0) == (((uintptr_t)outs[0].base % 16) == 0), VPPB_E_ARG,
+                 "%s: outputs must share pitch and alignment (image %d)", name, i);
+    for (const vppb_img* nb : {ups ? &ups[i] : nullptr, dns ? &dns[i] : nullptr})
+      if (nb && nb->base)
+        VPPB_REQUIRE(nb->pitch == in->pitch && nb->ncols == in->ncols && nb->nrows >= 2 && nb->elem_bytes == CS && nb->border == in->border &&
+                         nb->align == in->align && ((uintptr_t)nb->base % 16) == 0,
+                     VPPB_E_ARG, "%s: neighbour of tile %d must have the tile's layout", name, i);
+    // the tile above contributes its LAST rows: they are addressed from its pixel (0,0) with ITS row count
+    VPPB_REQUIRE(!(ups && ups[i].base) || ups[i].nrows == in->nrows, VPPB_E_ARG, "%s: the tile above tile %d must have as many rows (pass a sub-image of its last rows otherwise)", name, i);
+  }
+  cudaStream_t st = as_stream(stream);
+  for (int i0 = 0; i0 < n; i0 += BX_MAX_BATCH) {
+    int rc = box5_stream_launch<CS>(ins + i0, ups ? ups + i0 : nullptr, dns ? dns + i0 : nullptr, outs + i0, std::min(BX_MAX_BATCH, n - i0), st, name);
+    if (rc) return rc;
+  }
+  return VPPB_OK;
+}
+
 }  // namespace vppb
 
 using namespace vppb;
@@ -715,6 +783,13 @@ int vppb_box5x5_u8c3_batch(const vppb_img* ins, const vppb_img* outs, int32_t n,
 }
 int vppb_box5x5_u8_batch(const vppb_img* ins, const vppb_img* outs, int32_t n, void* stream) {
   return box5_bytes_batch<1>(ins, outs, n, stream, "vppb_box5x5_u8_batch");
+}
+
+int vppb_box5x5_u8c3_tiles(const vppb_img* ins, const vppb_img* ups, const vppb_img* downs, const vppb_img* outs, int32_t n, void* stream) {
+  return box5_bytes_tiles<3>(ins, ups, downs, outs, n, stream, "vppb_box5x5_u8c3_tiles");
+}
+int vppb_box5x5_u8_tiles(const vppb_img* ins, const vppb_img* ups, const vppb_img* downs, const vppb_img* outs, int32_t n, void* stream) {
+  return box5_bytes_tiles<1>(ins, ups, downs, outs, n, stream, "vppb_box5x5_u8_tiles");
 }
 
 int vppb_box5x5_u8c3(const vppb_img* in, const vppb_img* out, void* stream) {

@@ -113,21 +113,23 @@ constexpr int FB_INNER = FB_BOXW - 32;
 constexpr int FB_INH = FB_ROWS + 6;
 constexpr int FB_STAGE = FB_INH * FB_BOXW;
 constexpr int FB_THREADS = 256;
+constexpr int FB_WARPS = FB_THREADS / 32;
+constexpr int FB_WCOLS = FB_INNER / FB_WARPS;  // 252 pixels = 63 words of a box row per warp
 constexpr int FB_MAXW = 16384;  // widest image of this path: the band bitmask (8 rows x ncols / 8 bytes) lives in shared memory
 
-static inline int fb_smem_bytes(int wpr) { return 2 * FB_STAGE + FB_ROWS * FB_INNER * 2 + FB_ROWS * wpr * 4 + 64; }
+static inline int fb_smem_bytes(int wpr) { return 2 * FB_STAGE + FB_ROWS * FB_INNER * 2 + FB_ROWS * wpr * 4 + 16 + (FB_WARPS + FB_ROWS) * 4 + 32; }
 
 template <int RING>
 __global__ void __launch_bounds__(FB_THREADS, 2) k_fast9_band(const __grid_constant__ CUtensorMap tmap, Img im, Img mask, int has_mask, int th, int nboxes,
                                                               int wpr, uint32_t* bits, int* rowcount, int* bandtotal) {
   extern __shared__ __align__(128) unsigned char smem[];
   unsigned char* stage0 = smem;
-  unsigned short* list = reinterpret_cast<unsigned short*>(smem + 2 * FB_STAGE);
+  unsigned short* lists = reinterpret_cast<unsigned short*>(smem + 2 * FB_STAGE);
   uint32_t* bm = reinterpret_cast<uint32_t*>(smem + 2 * FB_STAGE + FB_ROWS * FB_INNER * 2);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * FB_STAGE + FB_ROWS * FB_INNER * 2 + FB_ROWS * wpr * 4);
-  int* ncand = reinterpret_cast<int*>(bars + 2);   // [2], alternating between boxes
-  int* rowcnt = ncand + 2;                         // [FB_ROWS]
-  const int tid = threadIdx.x;
+  int* ncand = reinterpret_cast<int*>(bars + 2);   // [FB_WARPS], one counter per warp
+  int* rowcnt = ncand + FB_WARPS;                  // [FB_ROWS]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int band = blockIdx.x, r0 = band * FB_ROWS;
   const int rows_here = min(FB_ROWS, im.nrows - r0);
   const int thb = th & 255;  // S::repeat(th) replicates the low byte (fast.hpp:120-126)
@@ -136,13 +138,13 @@ __global__ void __launch_bounds__(FB_THREADS, 2) k_fast9_band(const __grid_const
     mbar_init(&bars[0], 1);
     mbar_init(&bars[1], 1);
     fence_barrier_init();
-    ncand[0] = 0; ncand[1] = 0;
     // tensor origin = 16 bytes left of column 0 and 3 rows above row 0; 8-byte elements, 252 elements per inner box
     for (int k = 0; k < 2 && k < nboxes; k++) {
       mbar_arrive_expect_tx(&bars[k], FB_STAGE);
       tma_load_2d(stage0 + k * FB_STAGE, &tmap, k * (FB_INNER / 8), r0, &bars[k]);
     }
   }
+  if (tid < FB_WARPS) ncand[tid] = 0;
   for (int i = tid; i < FB_ROWS * wpr; i += FB_THREADS) bm[i] = 0;
   __syncthreads();
 
@@ -150,6 +152,9 @@ __global__ void __launch_bounds__(FB_THREADS, 2) k_fast9_band(const __grid_const
   const uint32_t H = 0x80808080u;
   const uint32_t K = (((uint32_t)(thb + 1) & 0x7Fu) * 0x01010101u);
   const bool u_high = (thb + 1) >= 128;
+  // every warp owns a column strip of the box (FB_WCOLS pixels = 2 words per lane) and works on it alone: its own
+  // candidate list, __syncwarp between its two phases; the CTA only meets to recycle a stage and at the very end
+  unsigned short* list = lists + warp * (FB_ROWS * FB_WCOLS);
 
   for (int k = 0; k < nboxes && thb < 255; k++) {
     const int s = k & 1;
@@ -157,40 +162,47 @@ __global__ void __launch_bounds__(FB_THREADS, 2) k_fast9_band(const __grid_const
     mbar_wait(&bars[s], (k >> 1) & 1);
     const int xbase = k * FB_INNER;                        // image column of box byte 16
     const int cols_here = min(FB_INNER, im.ncols - xbase);
-    const int words = (cols_here + 3) >> 2;
-    // ---- phase 1
-    for (int j = 0; j < rows_here; j++) {
-      const unsigned char* rowc = st + (j + 3) * FB_BOXW + 16;
-      for (int wi = tid; wi < words; wi += FB_THREADS) {
-        const uint32_t v = *reinterpret_cast<const uint32_t*>(rowc + 4 * wi);
-        const uint32_t a0 = *reinterpret_cast<const uint32_t*>(rowc - 3 * FB_BOXW + 4 * wi);
-        const uint32_t a8 = *reinterpret_cast<const uint32_t*>(rowc + 3 * FB_BOXW + 4 * wi);
-        const uint32_t d0 = __vabsdiffu4(v, a0), d8 = __vabsdiffu4(v, a8);
-        const uint32_t t0 = (d0 | H) - K, t8 = (d8 | H) - K;
-        uint32_t g = u_high ? ((t0 & d0) | (t8 & d8)) : (t0 | d0 | t8 | d8);
-        g &= H;
-        if (g) {
-          const int x = 4 * wi;  // box-inner column of byte 0
-          if (x + 4 > cols_here) g &= (1u << (8 * (cols_here - x))) - 1u;  // bytes right of the image
-          if (has_mask && g) {
-            const unsigned char* mp = mask.base + (long long)(r0 + j) * mask.pitch + xbase + x;
+    // ---- phase 1: lane = word column; the 14 rows of the column are loaded once, every row serves as slot 0 of the row 3
+    //      below it, as centre, and as slot 8 of the row 3 above it
 #pragma unroll
-            for (int q = 0; q < 4; q++)
-              if (((g >> (8 * q + 7)) & 1u) && __ldg(mp + q) == 0) g &= ~(0x80u << (8 * q));
-          }
-          while (g) {
-            const int q = (__ffs(g) - 1) >> 3;
-            g &= g - 1;
-            const int idx = atomicAdd(&ncand[s], 1);
-            list[idx] = (unsigned short)((j << 11) | (16 + x + q));
+    for (int half = 0; half < 2; half++) {
+      const int wi = warp * (FB_WCOLS / 4) + half * 32 + lane;   // word of the box-inner row
+      const int x = 4 * wi;
+      if (half * 32 + lane < FB_WCOLS / 4 && x < cols_here) {
+        const unsigned char* colp = st + 16 + x;
+        uint32_t w[FB_INH];
+#pragma unroll
+        for (int j = 0; j < FB_INH; j++) w[j] = *reinterpret_cast<const uint32_t*>(colp + j * FB_BOXW);
+        uint32_t edge = 0xFFFFFFFFu;
+        if (x + 4 > cols_here) edge = (1u << (8 * (cols_here - x))) - 1u;  // bytes right of the image
+#pragma unroll
+        for (int j = 0; j < FB_ROWS; j++) {
+          const uint32_t v = w[j + 3];
+          const uint32_t d0 = __vabsdiffu4(v, w[j]), d8 = __vabsdiffu4(v, w[j + 6]);
+          const uint32_t t0 = (d0 | H) - K, t8 = (d8 | H) - K;
+          uint32_t g = u_high ? ((t0 & d0) | (t8 & d8)) : (t0 | d0 | t8 | d8);
+          g &= H & edge;
+          if (g && j < rows_here) {
+            if (has_mask) {
+              const unsigned char* mp = mask.base + (long long)(r0 + j) * mask.pitch + xbase + x;
+#pragma unroll
+              for (int q = 0; q < 4; q++)
+                if (((g >> (8 * q + 7)) & 1u) && __ldg(mp + q) == 0) g &= ~(0x80u << (8 * q));
+            }
+            while (g) {
+              const int q = (__ffs(g) - 1) >> 3;
+              g &= g - 1;
+              const int idx = atomicAdd(&ncand[warp], 1);
+              list[idx] = (unsigned short)((j << 11) | (16 + x + q));
+            }
           }
         }
       }
     }
-    __syncthreads();
-    // ---- phase 2
-    const int n = ncand[s];
-    for (int e = tid; e < n; e += FB_THREADS) {
+    __syncwarp();
+    // ---- phase 2: exact test, one candidate per lane
+    const int n = ncand[warp];
+    for (int e = lane; e < n; e += 32) {
       const int code = list[e];
       const int j = code >> 11, xl = code & 2047;
       const unsigned char* p = st + (j + 3) * FB_BOXW + xl;
@@ -216,10 +228,12 @@ __global__ void __launch_bounds__(FB_THREADS, 2) k_fast9_band(const __grid_const
       const bool corner = ((m & 0x10) && arc9(mb & 0xFFFFu)) || ((m & 0x01) && arc9(md & 0xFFFFu));
       if (corner) atomicOr(&bm[j * wpr + (c >> 5)], 1u << (c & 31));
     }
-    __syncthreads();  // the stage and the list are free again
-    if (tid == 0) {
-      ncand[s] = 0;
-      if (k + 2 < nboxes) {
+    __syncwarp();
+    if (lane == 0) ncand[warp] = 0;
+    __syncwarp();  // the counter is reset before any lane appends candidates of the next box
+    if (k + 2 < nboxes) {  // recycle the stage for the box after next: every warp must be done with it
+      __syncthreads();
+      if (tid == 0) {
         mbar_arrive_expect_tx(&bars[s], FB_STAGE);
         tma_load_2d(stage0 + s * FB_STAGE, &tmap, (k + 2) * (FB_INNER / 8), r0, &bars[s]);
       }
@@ -227,7 +241,6 @@ __global__ void __launch_bounds__(FB_THREADS, 2) k_fast9_band(const __grid_const
   }
   __syncthreads();
   // ---- bitmask rows and counts to global memory
-  const int warp = tid >> 5, lane = tid & 31;
   if (warp < FB_ROWS) {
     int cnt = 0;
     if (warp < rows_here)
@@ -274,9 +287,14 @@ __global__ void __launch_bounds__(FB_THREADS) k_fast9_emit_bands(Img im, int th,
   if (warp >= FB_ROWS) return;
   const int r = r0 + warp;
   if (r >= im.nrows) return;
+  // first keypoint of this row: band base + the counts of the band's rows above (one load per lane, then a shuffle sum)
+  const int rc = (lane < FB_ROWS && r0 + lane < im.nrows) ? rowcount[r0 + lane] : 0;
   int off = base_s;
-  for (int j = 0; j < warp; j++) off += rowcount[r0 + j];
-  if (rowcount[r] == 0) return;
+  for (int j = 0; j < FB_ROWS; j++) {
+    const int cj = __shfl_sync(0xffffffffu, rc, j);
+    if (j < warp) off += cj;
+  }
+  if (__shfl_sync(0xffffffffu, rc, warp) == 0) return;
   for (int w0 = 0; w0 < wpr; w0 += 32) {
     const int wi = w0 + lane;
     uint32_t word = wi < wpr ? bits[(long long)r * wpr + wi] : 0u;
