@@ -53,3 +53,58 @@ def exchange_halos_inplace(dist, rank, world, send_up, send_dn, recv_up, recv_dn
         for w in dist.batch_isend_irecv(ops):
             w.wait()
     return up, down
+
+
+# ---- peer-memory form: every rank maps its neighbours' tiles and the kernels read the halo rows from there -----------
+def open_neighbour_tiles(dist, rank, world, images):
+    """Exchange CUDA IPC handles of `images` (Image2d that own their allocation, same count and geometry on every rank) and
+    map the tiles of rank - 1 and rank + 1.  Returns (ups, downs): ctypes arrays of vppb_img (base == NULL where there is
+    no neighbour) to pass to vppb_box5x5_*_tiles, plus the list of opened descriptors to close with close_neighbour_tiles."""
+    import ctypes as C
+
+    from . import capi
+
+    mine = []
+    for im in images:
+        h, off = (C.c_char * 64)(), C.c_int64()
+        capi.check(capi.lib.vppb_ipc_export(im.ptr(), h, C.byref(off)))
+        mine.append((bytes(h.raw), int(off.value)))
+    everyone = [None] * world
+    dist.all_gather_object(everyone, mine)
+    up, down = neighbours(rank, world)
+    n = len(images)
+    ups, downs, opened = (capi.VppbImg * n)(), (capi.VppbImg * n)(), []
+    for who, arr in ((up, ups), (down, downs)):
+        if who is None:
+            continue
+        for i, (hb, off) in enumerate(everyone[who]):
+            buf = (C.c_char * 64).from_buffer_copy(hb)
+            capi.check(capi.lib.vppb_ipc_open(buf, off, images[i].ptr(), C.byref(arr[i])))
+            opened.append(arr[i])
+    return ups, downs, opened
+
+
+def close_neighbour_tiles(opened):
+    import ctypes as C
+
+    from . import capi
+
+    for d in opened:
+        capi.lib.vppb_ipc_close(C.byref(d))
+
+
+def nccl_comm(dist, rank, world):
+    """A vppb (NCCL) communicator for vppb_halo_exchange: rank 0 draws the unique id, torch.distributed carries it."""
+    import ctypes as C
+
+    from . import capi
+
+    idb = (C.c_char * 128)()
+    if rank == 0:
+        capi.check(capi.lib.vppb_comm_unique_id(idb))
+    box = [bytes(idb.raw)]
+    dist.broadcast_object_list(box, src=0)
+    idb = (C.c_char * 128).from_buffer_copy(box[0])
+    comm = C.c_void_p()
+    capi.check(capi.lib.vppb_comm_init(idb, rank, world, C.byref(comm)))
+    return comm
