@@ -3,15 +3,15 @@
 set -e
 cd "$(dirname "$0")"
 mkdir -p vpp_b200/lib oracle/_build
-nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -fmad=false \
+nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++14 -fmad=false \
      -Xcompiler -fPIC -shared ${VPPB_NVCC_EXTRA} \
      -o vpp_b200/lib/libvppb.so vpp_b200/csrc/*.cu -ldl
 gcc -O2 -ffp-contract=off -fno-fast-math -fPIC -shared -o oracle/_build/libvpp_oracle.so oracle/*.c -lm
 gcc -O3 -march=native -fopenmp -DNDEBUG -ffp-contract=off -fPIC -shared -o oracle/_build/libvpp_oracle_omp.so oracle/*.c -lm
 # C++14 host API tests (the reference's own tests rewritten with device kernels), run by tests/test_cpp_api.py on the GPU box
 mkdir -p tests/cpp/_build
-for t in core_tests algo_tests nbh_tests extruder_tests; do
-  nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -std=c++17 --extended-lambda -O1 -fmad=false -I vpp_b200/include \
+for t in core_tests algo_tests nbh_tests extruder_tests pw_bench; do
+  nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -std=c++14 --extended-lambda -O2 -fmad=false -I vpp_b200/include \
        -o tests/cpp/_build/$t tests/cpp/$t.cu -L vpp_b200/lib -lvppb -Xlinker -rpath -Xlinker '$ORIGIN/../../../vpp_b200/lib'
 done
 # the headers must also parse as plain C++14 host code (no nvcc): containers, options, algorithms

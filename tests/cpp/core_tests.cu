@@ -135,6 +135,87 @@ static void test_pixel_wise() {  // tests/pixel_wise.cc
     }
 }
 
+struct add_k { VPP_KERNEL void operator()(int& a, const int& b, const int& c) const { a = b + c; } };
+
+// The vectorised lowering of the default traversal (16 bytes per thread and image, written back only when changed) against
+// plain host loops: ragged widths, mixed element sizes, a box range, a sub-image (rows not 16-byte aligned: scalar path), the
+// same image twice (must stay one memory), read-only inputs keep their host mirror.
+static void test_pixel_wise_vectorised() {
+  const int sizes[][2] = {{1, 1}, {3, 5}, {17, 33}, {64, 96}, {50, 131}, {9, 260}};
+  for (auto& sz : sizes) {
+    const int nr = sz[0], nc = sz[1];
+    image2d<int> A(nr, nc), B(nr, nc), C(nr, nc);
+    for (auto p : B.domain()) { B(p) = p[0] * 1000 + p[1]; C(p) = 7 * p[1] - p[0]; A(p) = -1; }
+    pixel_wise(A, B, C) | [=] VPP_KERNEL(int& a, int& b, int& c) { a = b + c; };
+    for (auto p : A.domain()) { assert(A(p) == B(p) + C(p)); assert(B(p) == p[0] * 1000 + p[1]); }
+    // u8 -> int with the coordinates (16 pixels per thread: 16 B of u8, 64 B of int)
+    image2d<unsigned char> U(nr, nc);
+    image2d<int> W(nr, nc, _border = 2);
+    for (auto p : U.domain()) U(p) = (unsigned char)(p[0] * 7 + p[1] * 3);
+    fill_with_border(W, 5);
+    pixel_wise(W, U, W.domain()) | [=] VPP_KERNEL(int& w, unsigned char& u, vint2 p) { w = 2 * u + p[0] * 100000 + p[1]; };
+    for (auto p : W.domain_with_border())
+      assert(W(p) == (W.has(p) ? 2 * (int)U(p) + p[0] * 100000 + p[1] : 5));
+    // in place through two ranges naming the same pixels
+    pixel_wise(A, A) | [=] VPP_KERNEL(int& x, int& y) { x = x + 1; y = y * 2; };
+    for (auto p : A.domain()) assert(A(p) == (B(p) + C(p) + 1) * 2);
+    // vint2 (8 bytes) and a value-returning kernel
+    image2d<vint2> V2(nr, nc);
+    pixel_wise(V2, V2.domain()) | [=] VPP_KERNEL(vint2& v, vint2 p) { v = vint2(p[1], -p[0]); };
+    auto S = pixel_wise(V2, B) | [=] VPP_KERNEL(vint2& v, int& b) { return v[0] - v[1] + b; };
+    for (auto p : S.domain()) assert(S(p) == p[1] + p[0] + B(p));
+    if (nr > 4 && nc > 9) {  // sub-image: unaligned rows
+      auto sub = A | box2d(vint2(1, 3), vint2(nr - 2, nc - 4));
+      auto subB = B | box2d(vint2(1, 3), vint2(nr - 2, nc - 4));
+      pixel_wise(sub, subB) | [=] VPP_KERNEL(int& a, int& b) { a = -b; };
+      for (auto p : A.domain()) {
+        const bool in = p[0] >= 1 && p[0] <= nr - 2 && p[1] >= 3 && p[1] <= nc - 4;
+        assert(A(p) == (in ? -B(p) : (B(p) + C(p) + 1) * 2));
+      }
+    }
+  }
+  // a kernel that takes its inputs by const reference does not invalidate their host mirror (no download on the next host read)
+  image2d<int> A(8, 40), B(8, 40), C(8, 40);
+  for (auto p : B.domain()) { B(p) = p[1]; C(p) = p[0]; }
+  pixel_wise(A, B, C) | add_k();
+  for (auto p : A.domain()) assert(A(p) == p[0] + p[1]);
+}
+
+// block_wise with a device callback: one launch for all blocks (block_view<V>), same tiling as the host form
+static void test_block_wise_device() {
+  image2d<int> im(10, 23, _border = 1), idx(10, 23);
+  fill_border_with_value(im, 2);
+  fill(im, 0);
+  block_wise(vint2(3, 4), im, idx, im.domain()) | [=] VPP_KERNEL(block_view<int> b, block_view<int> id, box2d d) {
+    for (int r = 0; r < b.nrows(); r++)
+      for (int c = 0; c < b.ncols(); c++) { b(r, c) = 1 + b.nrows() * 10 + b.ncols(); id(r, c) = d.p1()[0] * 100 + d.p1()[1]; }
+  };
+  for (auto p : im.domain_with_border()) {
+    if (!im.has(p)) { assert(im(p) == 2); continue; }
+    const int br = p[0] / 3, bc = p[1] / 4;
+    const int h = std::min(3, 10 - br * 3), w = std::min(4, 23 - bc * 4);
+    assert(im(p) == 1 + h * 10 + w);
+    assert(idx(p) == br * 3 * 100 + bc * 4);
+  }
+  // ordered traversal: a running counter across the blocks, raster order and its reverse
+  image2d<int> cnt(1, 1), img(4, 6);
+  for (int rev = 0; rev < 2; rev++) {
+    fill(cnt, 0);
+    const block_view<int> counter{(unsigned char*)cnt.device_write()->base, cnt.device_write()->pitch, 1, 1, vint2(0, 0)};
+    auto body = [=] VPP_KERNEL(block_view<int> b) {
+      const int k = counter(0, 0)++;
+      for (int r = 0; r < b.nrows(); r++)
+        for (int c = 0; c < b.ncols(); c++) b(r, c) = k;
+    };
+    if (rev) block_wise(vint2(2, 2), img)(_bottom_to_top, _right_to_left) | body;
+    else block_wise(vint2(2, 2), img)(_no_threads) | body;
+    for (auto p : img.domain()) {
+      const int k = (p[0] / 2) * 3 + p[1] / 2;
+      assert(img(p) == (rev ? 5 - k : k));
+    }
+  }
+}
+
 static void test_block_wise() {  // tests/block_wise.cc
   image2d<int> img(4, 4);
   vint2 b(2, 2);
@@ -206,7 +287,9 @@ int main() {
   vppb_check(vppb_init(0));
   test_imageNd(); std::puts("imageNd ok");
   test_pixel_wise(); std::puts("pixel_wise ok");
+  test_pixel_wise_vectorised(); std::puts("pixel_wise vectorised ok");
   test_block_wise(); std::puts("block_wise ok");
+  test_block_wise_device(); std::puts("block_wise device ok");
   test_fill_border_sum(); std::puts("fill/border/sum ok");
   std::puts("ALL OK");
   return 0;

@@ -26,7 +26,7 @@
 using std::max;
 using std::min;
 
-struct dim3 { unsigned x, y, z; };
+struct dim3 { unsigned x, y, z; dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {} };
 extern thread_local dim3 threadIdx, blockIdx, blockDim, gridDim;
 
 // CUDA vector types with the alignment the hardware demands of 64- / 128-bit accesses
@@ -101,6 +101,18 @@ inline void launch(long long grid, long long block, F body, size_t smem_bytes = 
     run_block((unsigned)block, [](void* f) { (*static_cast<F*>(f))(); }, &body);
   }
 }
+template <typename F>
+inline void launch(dim3 grid, dim3 block, F body, size_t smem_bytes = 0) {  // 2-D launches (the header template kernels): blocks one after another
+  set_dyn_smem(smem_bytes);
+  gridDim = grid;
+  blockDim = block;
+  const long long nb = (long long)grid.x * grid.y;
+  for (long long b = 0; b < nb; b++) {
+    const long long bb = reverse_order ? nb - 1 - b : b;
+    blockIdx = dim3{(unsigned)(bb % grid.x), (unsigned)(bb / grid.x), 0};
+    run_block(block.x * block.y, [](void* f) { (*static_cast<F*>(f))(); }, &body);
+  }
+}
 template <typename T> inline uint64_t to_bits(T v) { static_assert(sizeof(T) <= 8, "warp collectives move <= 64 bits"); uint64_t b = 0; memcpy(&b, &v, sizeof(T)); return b; }
 template <typename T> inline T from_bits(uint64_t b) { T v; memcpy(&v, &b, sizeof(T)); return v; }
 template <typename T> inline T shfl_from(unsigned mask, T v, int src_lane) {
@@ -157,6 +169,8 @@ template <typename T> inline T atomicCAS(T* p, T cmp, T v) { T o = *p; if (o == 
 
 // device intrinsics (the emu objects are built with -ffp-contract=off and without fast-math: IEEE single ops)
 template <typename T> inline T __ldg(const T* p) { return *p; }
+template <typename T> inline T __ldcs(const T* p) { return *p; }
+template <typename T> inline void __stcs(T* p, T v) { *p = v; }
 inline float __fdiv_rn(float a, float b) { return a / b; }
 inline float __fadd_rn(float a, float b) { return a + b; }
 inline float __fsub_rn(float a, float b) { return a - b; }

@@ -218,7 +218,7 @@ void run_block(unsigned nthreads, void (*entry)(void*), void* arg) {
       const unsigned t = shuffle_seed ? g.order[k] : (reverse_order ? nthreads - 1 - k : k);
       if (g.fibers[t].done) continue;
       g.current = t;
-      threadIdx = dim3{t, 0, 0};
+      threadIdx = dim3{t % blockDim.x, t / blockDim.x, 0};  // 2-D blocks: x fastest
       swapcontext(&g.sched, &g.fibers[t].ctx);
     }
     if (g.progress == before && g.alive > 0) {
