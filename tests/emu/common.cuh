@@ -47,4 +47,11 @@ inline T* row_ptr(const Img& im, int r) { return reinterpret_cast<T*>(im.base + 
 inline int4 ld_stream(const int4* p) { return *p; }
 inline void st_stream(int4* p, const int4& v) { *p = v; }
 
+inline int ld_acquire(const int* p) { return *p; }
+inline void st_release(int* p, int v) { *p = v; }
+}  // namespace vppb
+namespace emu { void yield(); }
+namespace vppb {
+inline void spin_pause() { emu::yield(); }  // a spinning fiber hands the CPU to the other threads of the block
+
 }  // namespace vppb

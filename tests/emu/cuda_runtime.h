@@ -170,6 +170,9 @@ template <typename T> inline T atomicCAS(T* p, T cmp, T v) { T o = *p; if (o == 
 // device intrinsics (the emu objects are built with -ffp-contract=off and without fast-math: IEEE single ops)
 template <typename T> inline T __ldg(const T* p) { return *p; }
 template <typename T> inline T __ldcs(const T* p) { return *p; }
+template <typename T> inline T __ldcg(const T* p) { return *p; }
+inline void __threadfence() {}
+inline void __nanosleep(unsigned) {}
 template <typename T> inline void __stcs(T* p, T v) { *p = v; }
 inline float __fdiv_rn(float a, float b) { return a / b; }
 inline float __fadd_rn(float a, float b) { return a + b; }

@@ -71,4 +71,13 @@ __device__ __forceinline__ void st_stream(int4* p, const int4& v) {
                :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
+// flags other CTAs write (dataflow sweeps): acquire load / release store at GPU scope, and the pause of a spin loop
+__device__ __forceinline__ int ld_acquire(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release(int* p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ void spin_pause() { __nanosleep(40); }
+
 }  // namespace vppb

@@ -115,37 +115,37 @@ constexpr int FB_STAGE = FB_INH * FB_BOXW;
 constexpr int FB_THREADS = 256;
 constexpr int FB_WARPS = FB_THREADS / 32;
 constexpr int FB_WCOLS = FB_INNER / FB_WARPS;  // 252 pixels = 63 words of a box row per warp
-constexpr int FB_MAXW = 16384;  // widest image of this path: the band bitmask (8 rows x ncols / 8 bytes) lives in shared memory
+constexpr int FB_MAXW = 65535;
 
-static inline int fb_smem_bytes(int wpr) { return 2 * FB_STAGE + FB_ROWS * FB_INNER * 2 + FB_ROWS * wpr * 4 + 16 + (FB_WARPS + FB_ROWS) * 4 + 32; }
+constexpr int FB_BOXWORDS = FB_INNER / 32;  // 63 bitmask words per box row
+constexpr int FB_SMEM = FB_STAGE + FB_ROWS * FB_INNER * 2 + FB_ROWS * FB_BOXWORDS * 4 + 8 + (FB_WARPS + FB_ROWS) * 4 + 32;
 
 template <int RING>
-__global__ void __launch_bounds__(FB_THREADS, 2) k_fast9_band(const __grid_constant__ CUtensorMap tmap, Img im, Img mask, int has_mask, int th, int nboxes,
+__global__ void __launch_bounds__(FB_THREADS, 3) k_fast9_band(const __grid_constant__ CUtensorMap tmap, Img im, Img mask, int has_mask, int th, int nboxes,
                                                               int wpr, uint32_t* bits, int* rowcount, int* bandtotal) {
   extern __shared__ __align__(128) unsigned char smem[];
-  unsigned char* stage0 = smem;
-  unsigned short* lists = reinterpret_cast<unsigned short*>(smem + 2 * FB_STAGE);
-  uint32_t* bm = reinterpret_cast<uint32_t*>(smem + 2 * FB_STAGE + FB_ROWS * FB_INNER * 2);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * FB_STAGE + FB_ROWS * FB_INNER * 2 + FB_ROWS * wpr * 4);
-  int* ncand = reinterpret_cast<int*>(bars + 2);   // [FB_WARPS], one counter per warp
+  unsigned char* st = smem;
+  unsigned short* lists = reinterpret_cast<unsigned short*>(smem + FB_STAGE);
+  uint32_t* bm = reinterpret_cast<uint32_t*>(smem + FB_STAGE + FB_ROWS * FB_INNER * 2);   // [FB_ROWS][FB_BOXWORDS]: this box's columns only
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + FB_STAGE + FB_ROWS * FB_INNER * 2 + FB_ROWS * FB_BOXWORDS * 4);
+  int* ncand = reinterpret_cast<int*>(bar + 1);    // [FB_WARPS], one counter per warp
   int* rowcnt = ncand + FB_WARPS;                  // [FB_ROWS]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int band = blockIdx.x, r0 = band * FB_ROWS;
+  const int band = blockIdx.x / nboxes, k = blockIdx.x - band * nboxes, r0 = band * FB_ROWS;
   const int rows_here = min(FB_ROWS, im.nrows - r0);
   const int thb = th & 255;  // S::repeat(th) replicates the low byte (fast.hpp:120-126)
+  const int xbase = k * FB_INNER;                        // image column of box byte 16
+  const int cols_here = min(FB_INNER, im.ncols - xbase);
 
   if (tid == 0) {
-    mbar_init(&bars[0], 1);
-    mbar_init(&bars[1], 1);
+    mbar_init(bar, 1);
     fence_barrier_init();
     // tensor origin = 16 bytes left of column 0 and 3 rows above row 0; 8-byte elements, 252 elements per inner box
-    for (int k = 0; k < 2 && k < nboxes; k++) {
-      mbar_arrive_expect_tx(&bars[k], FB_STAGE);
-      tma_load_2d(stage0 + k * FB_STAGE, &tmap, k * (FB_INNER / 8), r0, &bars[k]);
-    }
+    mbar_arrive_expect_tx(bar, FB_STAGE);
+    tma_load_2d(st, &tmap, k * (FB_INNER / 8), r0, bar);
   }
   if (tid < FB_WARPS) ncand[tid] = 0;
-  for (int i = tid; i < FB_ROWS * wpr; i += FB_THREADS) bm[i] = 0;
+  for (int i = tid; i < FB_ROWS * FB_BOXWORDS; i += FB_THREADS) bm[i] = 0;
   __syncthreads();
 
   // packed "byte > thb":  u = thb + 1;  x >= u  <=>  bit 7 of ((x | H) - (U & ~H)) combined with bit 7 of x
@@ -153,15 +153,11 @@ __global__ void __launch_bounds__(FB_THREADS, 2) k_fast9_band(const __grid_const
   const uint32_t K = (((uint32_t)(thb + 1) & 0x7Fu) * 0x01010101u);
   const bool u_high = (thb + 1) >= 128;
   // every warp owns a column strip of the box (FB_WCOLS pixels = 2 words per lane) and works on it alone: its own
-  // candidate list, __syncwarp between its two phases; the CTA only meets to recycle a stage and at the very end
+  // candidate list, __syncwarp between its two phases; the CTA only meets at the very end
   unsigned short* list = lists + warp * (FB_ROWS * FB_WCOLS);
 
-  for (int k = 0; k < nboxes && thb < 255; k++) {
-    const int s = k & 1;
-    const unsigned char* st = stage0 + s * FB_STAGE;
-    mbar_wait(&bars[s], (k >> 1) & 1);
-    const int xbase = k * FB_INNER;                        // image column of box byte 16
-    const int cols_here = min(FB_INNER, im.ncols - xbase);
+  if (thb < 255) {
+    mbar_wait(bar, 0);
     // ---- phase 1: lane = word column; the 14 rows of the column are loaded once, every row serves as slot 0 of the row 3
     //      below it, as centre, and as slot 8 of the row 3 above it
 #pragma unroll
@@ -226,54 +222,61 @@ __global__ void __launch_bounds__(FB_THREADS, 2) k_fast9_band(const __grid_const
       int m = 0xFF;
       if (has_mask) m = __ldg(mask.base + (long long)(r0 + j) * mask.pitch + c);
       const bool corner = ((m & 0x10) && arc9(mb & 0xFFFFu)) || ((m & 0x01) && arc9(md & 0xFFFFu));
-      if (corner) atomicOr(&bm[j * wpr + (c >> 5)], 1u << (c & 31));
-    }
-    __syncwarp();
-    if (lane == 0) ncand[warp] = 0;
-    __syncwarp();  // the counter is reset before any lane appends candidates of the next box
-    if (k + 2 < nboxes) {  // recycle the stage for the box after next: every warp must be done with it
-      __syncthreads();
-      if (tid == 0) {
-        mbar_arrive_expect_tx(&bars[s], FB_STAGE);
-        tma_load_2d(stage0 + s * FB_STAGE, &tmap, (k + 2) * (FB_INNER / 8), r0, &bars[s]);
-      }
+      if (corner) atomicOr(&bm[j * FB_BOXWORDS + ((xl - 16) >> 5)], 1u << ((xl - 16) & 31));
     }
   }
   __syncthreads();
-  // ---- bitmask rows and counts to global memory
+  // ---- this box's bitmask columns and per-row counts to global memory (2016 = 63 words: boxes start on word boundaries)
   if (warp < FB_ROWS) {
     int cnt = 0;
-    if (warp < rows_here)
-      for (int w = lane; w < wpr; w += 32) {
-        const uint32_t word = bm[warp * wpr + w];
-        bits[(long long)(r0 + warp) * wpr + w] = word;
+    if (warp < rows_here) {
+      const int w0 = xbase >> 5, nw = (cols_here + 31) >> 5;
+      for (int w = lane; w < nw; w += 32) {
+        const uint32_t word = bm[warp * FB_BOXWORDS + w];
+        bits[(long long)(r0 + warp) * wpr + w0 + w] = word;
         cnt += __popc(word);
       }
+    }
     for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
     if (lane == 0) {
       rowcnt[warp] = cnt;
-      if (warp < rows_here) rowcount[r0 + warp] = cnt;
+      if (warp < rows_here) rowcount[(long long)(r0 + warp) * nboxes + k] = cnt;
     }
   }
   __syncthreads();
   if (tid == 0) {
     int t = 0;
     for (int j = 0; j < FB_ROWS; j++) t += rowcnt[j];
-    bandtotal[band] = t;
+    bandtotal[band * nboxes + k] = t;
   }
 }
 
 // Raster-ordered emission from the band kernel's output: CTA = band; its first keypoint index is the sum of the totals of
-// the bands above (a few hundred integers, summed by the CTA itself - no scan launch), one warp per row walks the
-// bitmask.  The last band also stores the total count.
+// the (band, box) tiles above (summed by the CTA itself - no scan launch), one warp per row walks the bitmask, whose
+// words it has all loaded up front (independent loads: one memory latency per row, not one per 32 words).
+// The last band also stores the total count.
+constexpr int FE_MAXW = 16;  // bitmask words per lane held in registers: rows up to 16 * 32 * 32 = 16384 pixels in one pass
 __global__ void __launch_bounds__(FB_THREADS) k_fast9_emit_bands(Img im, int th, const uint32_t* bits, int wpr, const int* rowcount, const int* bandtotal,
-                                                                int nbands, vppb_int2* kps, int* scores, int score_div, int capacity, int* count_dev) {
+                                                                int nbands, int nboxes, vppb_int2* kps, int* scores, int score_div, int capacity, int* count_dev) {
   __shared__ int part[FB_THREADS / 32];
   __shared__ int base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int band = blockIdx.x, r0 = band * FB_ROWS;
+  const int r = r0 + warp;
+  const bool row_ok = warp < FB_ROWS && r < im.nrows;
+  // issue every load of this warp first
+  uint32_t words[FE_MAXW];
+#pragma unroll
+  for (int q = 0; q < FE_MAXW; q++) {
+    const int wi = q * 32 + lane;
+    words[q] = (row_ok && wi < wpr) ? __ldg(&bits[(long long)r * wpr + wi]) : 0u;
+  }
+  int rc = 0;  // lane j < FB_ROWS: keypoints of row r0 + j (all boxes)
+  if (lane < FB_ROWS && r0 + lane < im.nrows)
+    for (int k = 0; k < nboxes; k++) rc += __ldg(&rowcount[(long long)(r0 + lane) * nboxes + k]);
   int acc = 0;
-  for (int i = tid; i < band; i += FB_THREADS) acc += bandtotal[i];
+  const int before = band * nboxes;
+  for (int i = tid; i < before; i += FB_THREADS) acc += __ldg(&bandtotal[i]);
   for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
   if (lane == 0) part[warp] = acc;
   __syncthreads();
@@ -281,45 +284,50 @@ __global__ void __launch_bounds__(FB_THREADS) k_fast9_emit_bands(Img im, int th,
     int b = 0;
     for (int i = 0; i < FB_THREADS / 32; i++) b += part[i];
     base_s = b;
-    if (band == nbands - 1 && count_dev) *count_dev = b + bandtotal[band];
+    if (band == nbands - 1 && count_dev) {
+      int t = b;
+      for (int k = 0; k < nboxes; k++) t += bandtotal[before + k];
+      *count_dev = t;
+    }
   }
   __syncthreads();
-  if (warp >= FB_ROWS) return;
-  const int r = r0 + warp;
-  if (r >= im.nrows) return;
-  // first keypoint of this row: band base + the counts of the band's rows above (one load per lane, then a shuffle sum)
-  const int rc = (lane < FB_ROWS && r0 + lane < im.nrows) ? rowcount[r0 + lane] : 0;
-  int off = base_s;
+  if (!row_ok) return;
+  int off = base_s, mine = 0;
   for (int j = 0; j < FB_ROWS; j++) {
     const int cj = __shfl_sync(0xffffffffu, rc, j);
     if (j < warp) off += cj;
+    if (j == warp) mine = cj;
   }
-  if (__shfl_sync(0xffffffffu, rc, warp) == 0) return;
-  for (int w0 = 0; w0 < wpr; w0 += 32) {
-    const int wi = w0 + lane;
-    uint32_t word = wi < wpr ? bits[(long long)r * wpr + wi] : 0u;
-    const int cnt = __popc(word);
-    int incl = cnt;
-    for (int o = 1; o < 32; o <<= 1) {
-      int y = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += y;
-    }
-    int pos = off + incl - cnt;
-    while (word) {
-      const int b = __ffs(word) - 1;
-      word &= word - 1;
-      if (pos < capacity) {
-        const int c = wi * 32 + b;
-        kps[pos].r = r;
-        kps[pos].c = c;
-        if (scores) {
-          const int sc = fast9_score_at(im, r, c, th);
-          scores[pos] = score_div ? ((sc / 16) & 255) : sc;
-        }
+  if (mine == 0) return;
+  for (int w0 = 0; w0 < wpr; w0 += 32 * FE_MAXW) {
+#pragma unroll
+    for (int q = 0; q < FE_MAXW; q++) {
+      const int wi = w0 + q * 32 + lane;
+      uint32_t word = words[q];
+      if (w0 > 0) word = wi < wpr ? bits[(long long)r * wpr + wi] : 0u;  // rows wider than 16384 pixels: later passes load as they go
+      if (w0 + q * 32 >= wpr) break;
+      const int cnt = __popc(word);
+      int incl = cnt;
+      for (int o = 1; o < 32; o <<= 1) {
+        int y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += y;
       }
-      pos++;
+      int pos = off + incl - cnt;
+      while (word) {
+        const int b = __ffs(word) - 1;
+        word &= word - 1;
+        if (pos < capacity) {
+          const int c = wi * 32 + b;
+          kps[pos] = vppb_int2{r, c};
+          if (scores) {
+            const int sc = fast9_score_at(im, r, c, th);
+            scores[pos] = score_div ? ((sc / 16) & 255) : sc;
+          }
+        }
+        pos++;
+      }
+      off += __shfl_sync(0xffffffffu, incl, 31);
     }
-    off += __shfl_sync(0xffffffffu, incl, 31);
   }
 }
 
@@ -513,7 +521,8 @@ static FastWs fast_ws_layout(void* base, int nrows, int ncols, int block_size) {
   FastWs w;
   const long long wpr = (ncols + 31) / 32;
   const long long bits_bytes = ((long long)nrows * wpr * 4 + 255) / 256 * 256;
-  const long long rows_bytes = (((long long)nrows + 1) * 4 + 255) / 256 * 256;
+  const long long nboxes = (ncols + FB_INNER - 1) / FB_INNER;
+  const long long rows_bytes = (((long long)nrows + 8) * nboxes * 4 + 255) / 256 * 256;  // per (row, box) counts of the band kernel; the other paths use the first nrows + 1
   unsigned char* p = static_cast<unsigned char*>(base);
   w.bits_a = reinterpret_cast<uint32_t*>(p);
   w.bits_b = reinterpret_cast<uint32_t*>(p + bits_bytes);
@@ -584,20 +593,19 @@ static int fast9_core(const vppb_img* img, int32_t th, const vppb_img* mask, int
     const uint64_t width_el = ((uint64_t)img->ncols + 32 + 7) / 8;
     int rc = encode_tensor_map_2d(&tmap, origin, CU_TENSOR_MAP_DATA_TYPE_UINT64, 8, width_el, (uint64_t)img->nrows + 6, (uint64_t)img->pitch, FB_BOXW / 8, FB_INH);
     if (rc) return rc;
-    const int smem = fb_smem_bytes(wpr);
     static std::atomic<int> attr_done{0};
-    if (attr_done.load(std::memory_order_acquire) < smem) {  // grows only: the opt-in limit is per function and device
-      VPPB_CUDA(cudaFuncSetAttribute(k_fast9_band<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, fb_smem_bytes(FB_MAXW / 32)));
-      VPPB_CUDA(cudaFuncSetAttribute(k_fast9_band<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, fb_smem_bytes(FB_MAXW / 32)));
-      attr_done.store(fb_smem_bytes(FB_MAXW / 32), std::memory_order_release);
+    if (!attr_done.load(std::memory_order_acquire)) {
+      VPPB_CUDA(cudaFuncSetAttribute(k_fast9_band<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM));
+      VPPB_CUDA(cudaFuncSetAttribute(k_fast9_band<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM));
+      attr_done.store(1, std::memory_order_release);
     }
     const int nboxes = (img->ncols + FB_INNER - 1) / FB_INNER;
     if (ring == 0)
-      k_fast9_band<0><<<nbands, FB_THREADS, smem, st>>>(tmap, im, mk, has_mask ? 1 : 0, th, nboxes, wpr, ws.bits_a, ws.rowcount, ws.bandtotal);
+      k_fast9_band<0><<<nbands * nboxes, FB_THREADS, FB_SMEM, st>>>(tmap, im, mk, has_mask ? 1 : 0, th, nboxes, wpr, ws.bits_a, ws.rowcount, ws.bandtotal);
     else
-      k_fast9_band<1><<<nbands, FB_THREADS, smem, st>>>(tmap, im, mk, has_mask ? 1 : 0, th, nboxes, wpr, ws.bits_a, ws.rowcount, ws.bandtotal);
+      k_fast9_band<1><<<nbands * nboxes, FB_THREADS, FB_SMEM, st>>>(tmap, im, mk, has_mask ? 1 : 0, th, nboxes, wpr, ws.bits_a, ws.rowcount, ws.bandtotal);
     if (mode == VPPB_FAST_ALL) {
-      k_fast9_emit_bands<<<nbands, FB_THREADS, 0, st>>>(im, th, ws.bits_a, wpr, ws.rowcount, ws.bandtotal, nbands, kps_out, scores_out, 0, capacity, cnt);
+      k_fast9_emit_bands<<<nbands, FB_THREADS, 0, st>>>(im, th, ws.bits_a, wpr, ws.rowcount, ws.bandtotal, nbands, nboxes, kps_out, scores_out, 0, capacity, cnt);
       VPPB_LAUNCH_CHECK(name);
       return VPPB_OK;
     }

@@ -31,6 +31,7 @@ struct SdofLevel {
   unsigned char* mark;
   int* dist;
   int* owner;
+  int* done;             // per cell: the last sweep (1-based) of this scale that has finished with the cell
   int cr, cc, cstride;   // cell-map domain (pf_domain pyramid level) and row stride
 };
 
@@ -76,7 +77,7 @@ __device__ __forceinline__ void descent_warp(const Img& a, const Img& b, int pr,
 
 __global__ void k_sdof_clear(SdofLevel L) {
   const int total = (L.cr + 2) * L.cstride;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) { L.mark[i] = 0; L.owner[i] = INT_MAX; }
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) { L.mark[i] = 0; L.owner[i] = INT_MAX; L.done[i] = 0; }
 }
 
 __global__ void k_sdof_claim(SdofLevel L, const vppb_int2* kps, int n, int scale_div, int patch) {
@@ -114,9 +115,9 @@ __device__ __forceinline__ void sdof_prop_cell(const SdofLevel& L, int kr, int k
   const int fr = r / patch, fc = c / patch;
   const int cell = fr * L.cstride + fc;
   if (!L.mark[cell]) return;  // warp-uniform
-  int2 cur = L.flow[cell];
+  int2 cur = __ldcg(&L.flow[cell]);
   const int2 prev = cur;
-  int d1 = L.dist[cell];
+  int d1 = __ldcg(&L.dist[cell]);
   bool changed = false;
   for (int dr = -1; dr <= 1; dr++)
     for (int dc = -1; dc <= 1; dc++) {
@@ -125,7 +126,7 @@ __device__ __forceinline__ void sdof_prop_cell(const SdofLevel& L, int kr, int k
       if (nr < 0 || nr >= L.cr || nc < 0 || nc >= L.cc) continue;
       const int ncell = nr * L.cstride + nc;
       if (!L.mark[ncell]) continue;
-      const int2 nf = L.flow[ncell];
+      const int2 nf = __ldcg(&L.flow[ncell]);  // written by other SMs during a dataflow sweep: read it where they wrote it (L2)
       const int a0 = cur.x - nf.x, a1 = cur.y - nf.y, b0 = prev.x - nf.x, b1 = prev.y - nf.y;
       if (a0 * a0 + a1 * a1 < 9 || b0 * b0 + b1 * b1 < 9) continue;  // integer norm() > 2
       const int d2 = sad_warp(L.i1, L.i2, r, c, r + nf.x, c + nf.y, ws);
@@ -148,6 +149,63 @@ __global__ void __launch_bounds__(128) k_sdof_prop_wave(SdofLevel L, int t, int 
     const int kc = t - 2 * kr;
     if (kc < 0 || kc >= nkc) continue;
     sdof_prop_cell(L, kr, kc, forward, patch, ws, lane);
+  }
+}
+
+// ---- dataflow schedule of a sweep (default): ONE persistent launch per sweep ----------------------------------------
+// Only marked cells do anything in a sweep and a marked cell only reads its marked 8-neighbours, so the Gauss-Seidel order
+// is a partial order on the marked cells: (kr, kc) must come after its marked predecessors (kr, kc-1), (kr-1, kc-1..kc+1)
+// and before its marked successors.  Warps draw chunks of 32 consecutive iterations of the sweep's raster order from a
+// ticket counter, walk the marked ones in order, and for each one wait until the `done` flag of its marked predecessors
+// carries this sweep's number (acquire loads at GPU scope), do the iteration, and publish their own flag (release store).
+// Every predecessor lives in the same chunk (done earlier by this very warp) or in a chunk with a smaller ticket, which a
+// running warp already holds: no deadlock.  The critical path is the longest chain of adjacent marked cells times one
+// flag hop, instead of (columns + 2 rows) kernel launches.
+__global__ void __launch_bounds__(128) k_sdof_sweep(SdofLevel L, int forward, int nkr, int nkc, int patch, int ws, int epoch, int* ticket) {
+  const int lane = threadIdx.x & 31;
+  const int inr = L.i1.nrows, inc = L.i1.ncols;
+  const int total = nkr * nkc, nchunks = (total + 31) / 32;
+  const int sgn = forward ? 1 : -1;  // a step of +1 in sweep coordinates is a step of sgn in cell coordinates
+  for (;;) {
+    int t = 0;
+    if (lane == 0) t = atomicAdd(ticket, 1);
+    t = __shfl_sync(FULLM, t, 0);
+    if (t >= nchunks) break;
+    const int i = t * 32 + lane;
+    int kr = 0, kc = 0, cell = -1;
+    bool marked = false;
+    if (i < total) {
+      kr = i / nkc; kc = i - kr * nkc;
+      const int r = forward ? kr * patch : inr - 1 - kr * patch, c = forward ? kc * patch : inc - 1 - kc * patch;
+      cell = (r / patch) * L.cstride + (c / patch);
+      marked = L.mark[cell] != 0;  // marks only go from 2 to 1 during the sweeps: "marked" never changes
+    }
+    unsigned todo = __ballot_sync(FULLM, marked);
+    while (todo) {
+      const int src = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const int ckr = __shfl_sync(FULLM, kr, src), ckc = __shfl_sync(FULLM, kc, src), ccell = __shfl_sync(FULLM, cell, src);
+      // lanes 0..3 watch one predecessor each
+      if (lane < 4) {
+        const int r = forward ? ckr * patch : inr - 1 - ckr * patch, c = forward ? ckc * patch : inc - 1 - ckc * patch;
+        const int fr = r / patch, fc = c / patch;
+        const int pr = lane == 0 ? fr : fr - sgn, pc = lane == 0 ? fc - sgn : fc + (lane - 2) * sgn;
+        // the predecessor must be an iteration of the sweep (inside the cell map AND inside the sweep's kr/kc range)
+        const int pkr = lane == 0 ? ckr : ckr - 1, pkc = lane == 0 ? ckc - 1 : ckc + (lane - 2);
+        if (pkr >= 0 && pkc >= 0 && pkc < nkc && pr >= 0 && pr < L.cr && pc >= 0 && pc < L.cc) {
+          const int pcell = pr * L.cstride + pc;
+          if (L.mark[pcell])
+            while (ld_acquire(&L.done[pcell]) < epoch) spin_pause();
+        }
+      }
+      __syncwarp();
+      sdof_prop_cell(L, ckr, ckc, forward, patch, ws, lane);
+      __syncwarp();
+      if (lane == 0) {
+        __threadfence();
+        st_release(&L.done[ccell], epoch);
+      }
+    }
   }
 }
 
@@ -249,11 +307,11 @@ static void sched_dims(int nrows, int ncols, int patch, long long& cells, int& c
 static long long sched_bytes(int nrows, int ncols, int patch) {
   long long cells; int cap;
   sched_dims(nrows, ncols, patch, cells, cap);
-  return ((cells * 8 + (2LL + 2LL * (cap + 1)) * 4 + 255) / 256) * 256 + 256;
+  return ((cells * 8 + (2LL + 2LL * (cap + 1)) * 4 + 255) / 256) * 256 + 256 + 1024;  // + the ticket counters of the dataflow sweeps
 }
 static long long level_bytes(int cr, int cc) {
   const long long cells = (long long)(cr + 2) * (cc + 2);
-  return ((cells * (8 + 4 + 4 + 1) + 255) / 256) * 256 + 1024;
+  return ((cells * (8 + 4 + 4 + 4 + 1) + 255) / 256) * 256 + 1024;
 }
 
 }  // namespace vppb
@@ -292,18 +350,24 @@ int vppb_sdof_u8(const vppb_img* pyr1, const vppb_img* pyr2, const vppb_sdof_par
     L[s].flow = reinterpret_cast<int2*>(w);
     L[s].dist = reinterpret_cast<int*>(w + cells * 8);
     L[s].owner = reinterpret_cast<int*>(w + cells * 12);
-    L[s].mark = w + cells * 16;
+    L[s].done = reinterpret_cast<int*>(w + cells * 16);
+    L[s].mark = w + cells * 20;
     w += level_bytes(cr, cc);
   }
   // opt-in: VPPB_SDOF_SCHEDULE=levels runs every sweep as dependency levels of the marked cells when that is shorter than the
   // anti-diagonals (one blocking read-back of the schedule size per sweep); the default is one launch per anti-diagonal
   const char* sched_env = getenv("VPPB_SDOF_SCHEDULE");
   const bool use_levels = sched_env && strcmp(sched_env, "levels") == 0;
+  const bool use_waves = sched_env && strcmp(sched_env, "antidiagonals") == 0;
+  const bool use_dataflow = !use_levels && !use_waves;  // default: one persistent launch per sweep
   long long sched_cells; int sched_cap;
   sched_dims(pyr1[0].nrows, pyr1[0].ncols, p->patchsize, sched_cells, sched_cap);
   int* lvl = reinterpret_cast<int*>(w);
   unsigned* cell_list = reinterpret_cast<unsigned*>(w + sched_cells * 4);
   int* sched = reinterpret_cast<int*>(w + sched_cells * 8);
+  int* tickets = reinterpret_cast<int*>(w + sched_bytes(pyr1[0].nrows, pyr1[0].ncols, p->patchsize) - 1024);  // 256 counters, one per (scale, sweep)
+  VPPB_REQUIRE(!use_dataflow || p->nscales * p->propagation <= 256, VPPB_E_ARG, "vppb_sdof_u8: more than 256 sweeps");
+  if (use_dataflow) VPPB_CUDA(cudaMemsetAsync(tickets, 0, 1024, st));
   std::vector<int> h_sched;
   const int sms = sm_count();
   for (int scale = p->nscales - 1; scale >= p->min_scale; scale--) {
@@ -320,6 +384,11 @@ int vppb_sdof_u8(const vppb_img* pyr1, const vppb_img* pyr2, const vppb_sdof_par
     for (int Ki = 0; Ki < p->propagation; Ki++) {
       const int forward = Ki % 2;  // :191-200: odd iterations forward, even (incl. the first) backward
       const int waves = nkc + 2 * (nkr - 1);
+      if (use_dataflow) {
+        const int chunks = (nkr * nkc + 31) / 32, blocks = (chunks + 3) / 4;
+        k_sdof_sweep<<<blocks < sms * 8 ? blocks : sms * 8, 128, 0, st>>>(Ls, forward, nkr, nkc, p->patchsize, p->winsize, Ki + 1, tickets + scale * p->propagation + Ki);
+        continue;
+      }
       if (use_levels) {
         k_sdof_levels<<<1, 1024, 0, st>>>(Ls, forward, nkr, nkc, p->patchsize, lvl, sched, sched_cap, cell_list);
         VPPB_LAUNCH_CHECK("vppb_sdof_u8 (levels)");
