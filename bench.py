@@ -1,21 +1,22 @@
 #!/usr/bin/env python
-"""bench.py — the hot path of BASELINE.json on N B200s of one node, one JSON line on stdout.
+"""bench.py - the hot path of BASELINE.json on N B200s of one node, one JSON line on stdout.
 
 Headline metric: Mpix/s of the 5x5 box filter on image2d<vuchar3> (BASELINE configs[1]).
-  --gpus 1 : a batch of 1920x1080 vuchar3 frames (batch sized > L2); the frames of a step go through one box5x5 launch
-             per frame (4 streams) or ONE batched persistent launch (vppb_box5x5_u8c3_batch) - `--box-launch auto`
-             probes the batched kernel in a child process, times both forms and keeps the faster (both times are
-             reported under config.box_launch).
-  --gpus N : 7680x4320 vuchar3 frames row-tiled over N ranks; each step = ONE grouped NCCL halo
-             exchange (2 edge rows per neighbour per frame, all frames of the batch packed) + the
-             box kernel on every tile.  Same frames for every N  ->  "scaling": "strong".
+  --gpus 1 : 1920x1080 vuchar3 frames.  32 frame pairs are resident (398 MB > the 126 MB L2); a STEP filters
+             PASSES x 32 = 2048 frames (>= 5 ms of GPU work): one vppb_box5x5_u8c3_batch call per 32 frames = one launch of
+             the per-warp streaming kernel (TMA ring per warp), the whole step replayed as a CUDA graph.
+  --gpus N : 7680x4320 vuchar3 frames row-tiled over N ranks (one tile per GPU and frame).  A step filters PASSES x 32 frames
+             with vppb_box5x5_u8c3_tiles: the kernel pulls the 2 halo rows above / below each tile straight from the
+             neighbour GPU's memory (CUDA IPC mapping, bulk copies inside its own TMA pipeline) - compute and halo transfer
+             are ONE kernel, there is no exchange step.  Same frames for every N > 1 ("strong"); the single-GPU figure of the
+             same 8K workload is measured in the N = 1 run (extras.box5x5_vuchar3_8k_x32 = scaling_anchor_n1).
   value  : whole-job Mpix/s with inputs resident in HBM (CUDA events on the launch stream, max over ranks).
-  e2e    : same metric through the C-ABI with HOST buffers (pinned): upload + mirror border fill +
-           box5x5 + download inside the timed region, for every frame of the batch.
-  extras : pixel_wise add (4K int32), 4K box, RGB frame ingest (4K), FAST9 (4K) and pyrLK (1080p, 3 levels, 10k kps, 7x7)
-           numbers, each measured on its own (a failing row reports an error instead of taking the line down).
---impl reference times the reference's CPU implementation (oracle/_ref if built, else the oracle
-port compiled with the reference's benchmark flags -O3 -march=native -fopenmp) on the host cores.
+  e2e    : same metric through the C-ABI with HOST buffers (pinned): upload + mirror border fill + box5x5 + download inside
+           the timed region, for every frame of the step.
+  extras : (N = 1) pixel_wise add 4K, single-launch 4K box, 8K batch, frame ingest, FAST9 4K, pyrLK 1080p/10k, semi-dense flow -
+           each with `parity` (checked against the oracle in this run) and a reference-kind CPU figure beside it.
+--impl reference times the reference's own CPU implementation (oracle/_ref = the reference headers compiled with its
+benchmark flags -O3 -march=native -fopenmp; the oracle port only if that library is missing) on the host cores.
 """
 import argparse
 import ctypes as C
@@ -32,7 +33,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {"1080p": (1080, 1920), "4k": (2160, 3840), "8k": (4320, 7680)}
-BOX_BYTES_PER_PX = 6.0  # algorithmic: 3 B read + 3 B written per vuchar3 pixel (SURVEY §8d)
+BOX_BYTES_PER_PX = 6.0  # algorithmic: 3 B read + 3 B written per vuchar3 pixel (SURVEY 8d)
+BATCH = 32              # resident frame pairs = frames per launch
 
 
 def peaks():
@@ -89,31 +91,13 @@ def host_threads():
         n = min(n, len(os.sched_getaffinity(0)))
     except Exception:
         pass
-    for path in ("/sys/fs/cgroup/cpu.max",):
-        try:
-            q, per = open(path).read().split()[:2]
-            if q != "max":
-                n = max(1, min(n, int(float(q) / float(per))))
-        except Exception:
-            pass
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if q != "max":
+            n = max(1, min(n, int(float(q) / float(per))))
+    except Exception:
+        pass
     return n
-
-
-def pick_threads(lib, fn):
-    """All the host threads the reference can use: try the full count and half of it (SMT), keep the faster."""
-    best, best_t = None, None
-    full = host_threads()
-    for n in sorted({full, max(1, full // 2)}, reverse=True):
-        lib.vo_set_num_threads(n)
-        fn()
-        t0 = time.perf_counter()
-        for _ in range(3):
-            fn()
-        dt = time.perf_counter() - t0
-        if best_t is None or dt < best_t:
-            best, best_t = n, dt
-    lib.vo_set_num_threads(best)
-    return best
 
 
 def make_frames(h, w, nframes, seed=42):
@@ -122,26 +106,77 @@ def make_frames(h, w, nframes, seed=42):
 
 
 # ------------------------------------------------------------------------------------------ CPU arm
-def cpu_box_bench(h, w, steps, warmup, budget_s, want_ref=True):
-    """Reference CPU path for the headline workload: image2d<vuchar3> 5x5 box, OpenMP over rows."""
-    from tests import oracle as orc
+class CpuRef:
+    """The reference's own code on the host cores: oracle/_ref/libvppref_omp.so (kind "reference": the reference headers compiled
+    verbatim with its benchmark flags); the C port of the oracle (kind "port") only where that library is missing."""
 
-    kind, lib, fn = "port", orc.load(omp=True), None
-    ref_path = os.path.join(ROOT, "oracle", "_ref", "libvppref_omp.so")
-    if want_ref and os.path.exists(ref_path):
-        try:  # the reference's own headers (oracle/ref_shim/build_ref.sh), benchmark flags, OpenMP
-            r = C.CDLL(ref_path)
-            r.vppref_box5x5_u8c3.argtypes = [C.POINTER(orc.VoImg), C.POINTER(orc.VoImg)]
-            r.vo_set_num_threads = r.vppref_set_num_threads
-            fn, kind, lib = r.vppref_box5x5_u8c3, "reference", r
-        except Exception:
-            fn = None
-    if fn is None:
-        fn = lambda a, b: lib.vo_box5x5_u8(a, b, 3)
+    def __init__(self):
+        from tests import oracle as orc
+
+        self.orc = orc
+        self.port = orc.load(omp=True)
+        self.ref = None
+        path = os.path.join(ROOT, "oracle", "_ref", "libvppref_omp.so")
+        if os.path.exists(path):
+            try:
+                r = C.CDLL(path)
+                I, P = C.POINTER(orc.VoImg), C.c_void_p
+                r.vppref_box5x5_u8c3.argtypes = [I, I]
+                r.vppref_pw_add_i32.argtypes = [I, I, I]
+                r.vppref_fast9_u8.argtypes = [I, C.c_int, I, C.c_int, C.c_int, P, P, C.c_int]
+                r.vppref_pyrlk_levels.argtypes = [I, I, I, C.c_int, C.c_int, C.c_int, P, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, P, P]
+                r.vppref_semi_dense_flow.argtypes = [I, I, P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, P, P, P]
+                r.vppref_num_threads.restype = C.c_int
+                self.ref = r
+            except Exception:
+                self.ref = None
+        self.threads = host_threads()
+        self.set_threads(self.threads)
+
+    def set_threads(self, n):
+        self.port.vo_set_num_threads(n)
+        if self.ref is not None:
+            self.ref.vppref_set_num_threads(n)
+        self.threads = n
+
+    def pick_threads(self, fn):
+        """All the host threads the reference can use: the full count and half of it (SMT), the faster is kept."""
+        best, best_t, full = None, None, host_threads()
+        for n in sorted({full, max(1, full // 2)}, reverse=True):
+            self.set_threads(n)
+            fn()
+            t0 = time.perf_counter()
+            for _ in range(3):
+                fn()
+            dt = time.perf_counter() - t0
+            if best_t is None or dt < best_t:
+                best, best_t = n, dt
+        self.set_threads(best)
+        return best
+
+    @property
+    def kind(self):
+        return "reference" if self.ref is not None else "port"
+
+
+def timed_cpu(fn, budget_s, max_reps=1000):
+    fn()
+    t0, reps = time.perf_counter(), 0
+    while reps < 1 or (time.perf_counter() - t0 < budget_s and reps < max_reps):
+        fn()
+        reps += 1
+    return (time.perf_counter() - t0) / reps
+
+
+def cpu_box_bench(h, w, steps, warmup, budget_s):
+    """Reference CPU path for the headline workload: image2d<vuchar3> 5x5 box (examples/box_filter.cc form), OpenMP over rows."""
+    cpu = CpuRef()
+    orc = cpu.orc
+    fn = cpu.ref.vppref_box5x5_u8c3 if cpu.ref is not None else (lambda a, b: cpu.port.vo_box5x5_u8(a, b, 3))
     src = make_frames(h, w, 1)[0]
     hs = orc.HostImage(h, w, "vuchar3", border=2, aligned=32, data=src, fill_border="mirror")
     hd = orc.HostImage(h, w, "vuchar3", aligned=32)
-    cores = pick_threads(lib, lambda: fn(hs.ptr(), hd.ptr()))
+    cores = cpu.pick_threads(lambda: fn(hs.ptr(), hd.ptr()))
     fn(hs.ptr(), hd.ptr())
     t0 = time.perf_counter()
     fn(hs.ptr(), hd.ptr())
@@ -156,120 +191,147 @@ def cpu_box_bench(h, w, steps, warmup, budget_s, want_ref=True):
             fn(hs.ptr(), hd.ptr())
     dt = time.perf_counter() - t0
     mpix = steps * per_step * h * w / 1e6 / dt
-    return {"value": mpix, "unit": "Mpix/s", "cores": int(cores), "kind": kind,
+    return {"value": mpix, "unit": "Mpix/s", "cores": int(cores), "kind": cpu.kind,
             "sample": "%d frames of %dx%d vuchar3 per step x %d steps (%.1f s)" % (per_step, w, h, steps, dt)}, dt / steps * 1e3
 
 
-def cpu_extras(budget_s=6.0):
-    """pyrLK (pyrlk-style OpenMP over keypoints) and 4K add on the host cores, bounded samples."""
-    from tests import oracle as orc, scenes
-    from tests.oracle_ops import oracle_grad_pyramid, oracle_lk, oracle_pyramid
+def cpu_extras(budget_s=10.0):
+    """The reference's own code (kind "reference") for the other rows of the path, bounded samples, all host threads."""
+    from tests import scenes
+    from tests.oracle_ops import oracle_grad_pyramid, oracle_pyramid
 
-    o = orc.load(omp=True)
-    o.vo_set_num_threads(host_threads())
-    out = {}
-    f1, f2, pts = scenes.lk_pair(1080, 1920, 10000, seed=5)
-    prev, nxt = oracle_pyramid(f1, 3, "u8", 3, o), oracle_pyramid(f2, 3, "u8", 3, o)
-    grad = oracle_grad_pyramid(prev, "vint2", 3, o)
-    P = orc.VoLkParams(nlevels=3, min_scale=0, winsize=7, max_iter=21, grad_is_float=0, err_mode=0, gate_on_max_err=0, min_ev=0.0,
-                       delta=0.0, max_err=0.0, factor=2.0, pred_div=8.0)
-    oracle_lk(prev, nxt, grad, P, pts, lib=o)
-    t0, reps = time.perf_counter(), 0
-    while time.perf_counter() - t0 < budget_s / 2 and reps < 50:
-        oracle_lk(prev, nxt, grad, P, pts, lib=o)
-        reps += 1
-    out["pyrlk_kpts_per_s"] = reps * len(pts) / (time.perf_counter() - t0)
+    cpu = CpuRef()
+    orc, o, r = cpu.orc, cpu.port, cpu.ref
+    out = {"cores": cpu.threads, "kind": cpu.kind}
+    share = budget_s / 4.0
+    # pixel_wise add, 4K int32 (benchmarks/image_add.cc)
     b = np.random.default_rng(1).integers(0, 2 ** 30, (2, 2160, 3840), dtype=np.int32)
-    ha, hb, hc = orc.HostImage(2160, 3840, "i32", aligned=32), orc.HostImage(2160, 3840, "i32", aligned=32, data=b[0]), \
-        orc.HostImage(2160, 3840, "i32", aligned=32, data=b[1])
-    o.vo_pw_add_i32(ha.ptr(), hb.ptr(), hc.ptr())
-    t0, reps = time.perf_counter(), 0
-    while time.perf_counter() - t0 < budget_s / 4 and reps < 200:
-        o.vo_pw_add_i32(ha.ptr(), hb.ptr(), hc.ptr())
-        reps += 1
-    out["add_i32_4k_mpix_per_s"] = reps * 2160 * 3840 / 1e6 / (time.perf_counter() - t0)
-    out["cores"] = o.vo_num_threads()
+    ha, hb, hc = (orc.HostImage(2160, 3840, "i32", aligned=32), orc.HostImage(2160, 3840, "i32", aligned=32, data=b[0]),
+                  orc.HostImage(2160, 3840, "i32", aligned=32, data=b[1]))
+    add = (lambda: r.vppref_pw_add_i32(ha.ptr(), hb.ptr(), hc.ptr())) if r is not None else (lambda: o.vo_pw_add_i32(ha.ptr(), hb.ptr(), hc.ptr()))
+    s = timed_cpu(add, share)
+    out["add_i32_4k"] = {"mpix_per_s": 2160 * 3840 / 1e6 / s, "kind": cpu.kind, "cores": cpu.threads}
+    # FAST9 4K (fast.hpp:253-508, AVX2 pruning tree in the reference build)
+    img = scenes.rectangles_scene(2160, 3840, seed=42)
+    hg = orc.HostImage(2160, 3840, "u8", border=3, aligned=32, data=img, fill_border="mirror")
+    cap = img.size // 4
+    kps = np.zeros((cap, 2), dtype=np.int32)
+    fast = (lambda: r.vppref_fast9_u8(hg.ptr(), 20, None, 0, 10, kps.ctypes.data, None, cap)) if r is not None else \
+        (lambda: o.vo_fast9_u8(hg.ptr(), 20, None, 0, 10, 0, kps.ctypes.data, None, cap))
+    s = timed_cpu(fast, share)
+    out["fast9_4k"] = {"mpix_per_s": 2160 * 3840 / 1e6 / s, "ms": s * 1e3, "kind": cpu.kind, "cores": cpu.threads}
+    # pyrLK 1080p, 3 levels, 10k keypoints, 7x7: the pyrlk_match loop (OpenMP over keypoints, pyrlk_match.hh:24) around lk_match_point_square_win<7>
+    f1, f2, pts = scenes.lk_pair(1080, 1920, 10000, seed=5)
+    prev, nxt = oracle_pyramid(f1, 3, "u8", 4, o), oracle_pyramid(f2, 3, "u8", 4, o)
+    grad = oracle_grad_pyramid(prev, "vfloat2", 4, o)
+    n = len(pts)
+    flow, dist = np.zeros((n, 2), np.float32), np.zeros(n, np.float32)
+    kp = np.ascontiguousarray(pts, dtype=np.float32)
+    if r is not None:
+        lk = lambda: r.vppref_pyrlk_levels(orc.desc_array(prev), orc.desc_array(nxt), orc.desc_array(grad), 3, 0, 7, kp.ctypes.data, n, 0.01, 0.6, 21.0, 0.01,
+                                           flow.ctypes.data, dist.ctypes.data)
+    else:
+        P = orc.VoLkParams(nlevels=3, min_scale=0, winsize=7, max_iter=21, grad_is_float=1, err_mode=1, gate_on_max_err=1, min_ev=0.01, delta=0.01,
+                           max_err=0.6, factor=2.0, pred_div=1.0)
+        lk = lambda: o.vo_lk_match_u8(orc.desc_array(prev), orc.desc_array(nxt), orc.desc_array(grad), C.byref(P), kp.ctypes.data, None, n, flow.ctypes.data, dist.ctypes.data)
+    s = timed_cpu(lk, share)
+    out["pyrlk_1080p_10k"] = {"kpts_per_s": n / s, "kind": cpu.kind, "cores": cpu.threads,
+                              "note": "matching only (pyramids prebuilt), pyrlk_match loop with lk_match_point_square_win<7>, vfloat2 gradient"}
+    # semi-dense flow 1080p with video_extruder's settings (semi_dense_optical_flow.hpp:46-214: serial by construction, 1 thread)
+    g1, g2, _ = scenes.lk_pair(1080, 1920, 4, seed=55, shift=(3.0, -2.0), margin=10)
+    h1 = orc.HostImage(1080, 1920, "u8", border=3, aligned=32, data=g1, fill_border="mirror")
+    kk = np.zeros((g1.size // 4, 2), dtype=np.int32)
+    nk = o.vo_fast9_u8(h1.ptr(), 10, None, 2, 10, 0, kk.ctypes.data, None, len(kk))
+    kk = np.ascontiguousarray(kk[:nk])
+    i1, i2 = orc.HostImage(1080, 1920, "u8", aligned=32, data=g1), orc.HostImage(1080, 1920, "u8", aligned=32, data=g2)
+    rp, rd, rv = np.zeros((nk, 2), np.int32), np.zeros(nk, np.int32), np.zeros(nk, np.uint8)
+    sd = (lambda: r.vppref_semi_dense_flow(i1.ptr(), i2.ptr(), kk.ctypes.data, nk, 9, 3, 0, 2, 5, rp.ctypes.data, rd.ctypes.data, rv.ctypes.data)) if r is not None else \
+        (lambda: o.vo_semi_dense_flow(i1.ptr(), i2.ptr(), kk.ctypes.data, nk, 9, 3, 0, 2, 5, rp.ctypes.data, rd.ctypes.data, rv.ctypes.data))
+    s = timed_cpu(sd, share, max_reps=20)
+    out["sdof_1080p"] = {"ms": s * 1e3, "keypoints": int(nk), "kind": cpu.kind, "cores": cpu.threads if r is not None else 1,
+                         "note": "pyramids included (the reference builds them inside the call)"}
     return out
 
 
-# ------------------------------------------------------------------------------------------ GPU arm
-def probe_batch(device, rows, cols, nframes):
-    """Child process of the bench: the two code paths that have not run on hardware before the bench itself - the batched box
-    kernel and the fused copy + mirror launch of the staged e2e upload - run here first, on the geometry the bench will use,
-    and are compared with the per-frame kernel / the two-step upload.  A kernel that faults takes only this process (and
-    its CUDA context) down, not the bench."""
-    import __graft_entry__ as g
+# ------------------------------------------------------------------------------------------ GPU arm: shared pieces
+def device_ms(torch, dist, dev, fn, reps):
+    """CUDA-event time of `reps` calls of fn on the current stream, max over ranks"""
+    a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    a_.record(torch.cuda.current_stream())
+    for _ in range(reps):
+        fn()
+    b_.record(torch.cuda.current_stream())
+    torch.cuda.synchronize()
+    t_ = torch.tensor([a_.elapsed_time(b_) / reps], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t_, op=dist.ReduceOp.MAX)
+    return float(t_.item())
 
-    g.build(only_if_missing=True)
-    import vpp_b200 as vpp
-    from vpp_b200 import capi
 
-    capi.check(capi.lib.vppb_init(device))
-    rng = np.random.default_rng(11)
-    uniq = [rng.integers(0, 256, (rows, cols, 3), dtype=np.uint8) for _ in range(min(nframes, 3))]
-    srcs, d1, d2 = [], [], []
-    for i in range(nframes):
-        s_ = vpp.Image2d.from_host(uniq[i % len(uniq)], "vuchar3", border=2)
-        vpp.fill_border_mirror(s_)
-        srcs.append(s_)
-        d1.append(vpp.Image2d(rows, cols, "vuchar3"))
-        d2.append(vpp.Image2d(rows, cols, "vuchar3"))
-    rc = 0
-    # the e2e leg's staged upload: tight image -> vppb_copy2d_mirror must give the bordered image of upload + fill_border_mirror
-    tight = vpp.Image2d.from_host(uniq[0], "vuchar3")
-    staged = vpp.Image2d(rows, cols, "vuchar3", border=2)
-    capi.check(capi.lib.vppb_copy2d_mirror(tight.ptr(), staged.ptr(), None))
-    if not np.array_equal(staged.download(with_border=True), srcs[0].download(with_border=True)):
-        sys.stderr.write("probe: vppb_copy2d_mirror differs from upload + fill_border_mirror\n")
-        rc |= 1
-    for s_, d_ in zip(srcs, d1):
-        vpp.box5x5(s_, d_)
-    for _ in range(3):
-        vpp.box5x5_batch(srcs, d2)
-    capi.check(capi.lib.vppb_sync(None))
-    for i in range(nframes):
-        if not np.array_equal(d1[i].download(), d2[i].download()):
-            sys.stderr.write("probe: batched box differs from the per-frame kernel on frame %d\n" % i)
-            rc |= 2
-            break
-    return 4 + rc if rc else 0  # 0 = both fine, 5 = staged upload bad, 6 = batched box bad, 7 = both; anything else = the probe died
+def graph_of(torch, fn):
+    """fn replayed as a CUDA graph (same kernels, without the per-launch host cost of the ctypes calls); eager if capture fails"""
+    try:
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        g_ = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g_):
+            fn()
+        g_.replay()
+        torch.cuda.synchronize()
+        return g_.replay, True
+    except Exception as ex:  # pragma: no cover
+        sys.stderr.write("CUDA graph capture failed, running eagerly: %r\n" % (ex,))
+        torch.cuda.synchronize()
+        return fn, False
+
+
+def box_traffic(key):
+    """DRAM bytes per launch of the streaming kernel from the committed ncu capture of this bench regime (profiles/box_traffic.json)"""
+    tp = os.path.join(ROOT, "profiles", "box_traffic.json")
+    if os.path.exists(tp):
+        try:
+            return json.load(open(tp)).get(key)
+        except Exception:
+            return None
+    return None
+
+
+def passes_for(ms_per_batch, target_ms=5.5):
+    return int(max(1, min(512, np.ceil(target_ms / max(ms_per_batch, 1e-3)))))
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=2000)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=None, choices=[None] + list(WORKLOADS))
-    ap.add_argument("--frames", type=int, default=None, help="frames per step (batch)")
+    ap.add_argument("--passes", type=int, default=0, help="launches of the 32-frame batch per step (0 = enough for >= 5 ms of GPU work)")
     ap.add_argument("--no-extras", action="store_true")
-    ap.add_argument("--graph", type=int, default=1, help="replay the step as a CUDA graph (single GPU)")
-    ap.add_argument("--streams", type=int, default=4, help="CUDA streams the frames of a step are spread over")
+    ap.add_argument("--graph", type=int, default=1)
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work for the cpu_baseline sample")
-    ap.add_argument("--box-launch", default="auto", choices=["auto", "per-frame", "batch"],
-                    help="one box launch per frame (spread over --streams) or one persistent launch per step (vppb_box5x5_u8c3_batch); "
-                         "auto = probe the batched kernel in a child process, time both, keep the faster")
-    ap.add_argument("--probe-batch", nargs=4, type=int, default=None, metavar=("DEVICE", "ROWS", "COLS", "FRAMES"), help=argparse.SUPPRESS)
     args = ap.parse_args()
 
-    if args.probe_batch:
-        return probe_batch(*args.probe_batch)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     n_gpus = max(args.gpus, 1)
     workload = args.workload or ("1080p" if n_gpus == 1 else "8k")
     H, W = WORKLOADS[workload]
-    nframes = args.frames or {"1080p": 32, "4k": 16, "8k": 32}[workload]
-    steps, warmup = args.steps, max(args.warmup, 3)
+    steps, warmup = max(args.steps, 1), max(args.warmup, 3)
 
     base = {"metric": "box5x5_vuchar3_throughput", "unit": "Mpix/s", "n_gpus": n_gpus, "steps": steps, "warmup": warmup,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "5x5 box_filter on %dx%d image2d<vuchar3>, batch of %d frames/step%s" % (
-                W, H, nframes, "" if n_gpus == 1 else ", row-tiled over %d GPUs, one grouped NCCL halo exchange per step" % n_gpus),
-                "frame": [H, W], "frames_per_step": nframes, "border": 2, "row_align": 128,
-                "l2": "batch in+out %.0f MB > 126 MB L2, frames cycled" % (2 * nframes * H * W * 3 / 1e6)}}
+            "config": {"workload": "5x5 box_filter on %dx%d image2d<vuchar3>%s" % (
+                W, H, "" if n_gpus == 1 else ", row-tiled over %d GPUs, halo rows read from the neighbour GPU inside the box kernel (NVLink peer memory)" % n_gpus),
+                "frame": [H, W], "resident_frames": BATCH, "border": 2, "row_align": 128,
+                "l2": "resident in+out %.0f MB > 126 MB L2, frames cycled" % (2 * BATCH * H * W * 3 / 1e6)}}
+    if n_gpus == 1:
+        base["config"]["scaling_note"] = ("N=1 is BASELINE configs[1] (1080p); the N>1 lines are strong scaling of the 8K row-tiled workload, whose "
+                                          "single-GPU figure is extras.box5x5_vuchar3_8k_x32 (scaling_anchor_n1) of this run")
 
     if args.impl == "reference":
         if rank != 0:
@@ -278,6 +340,7 @@ def main():
         line = dict(base)
         line.update({"impl": "reference", "value": cb["value"], "ms_per_step": ms, "cpu_baseline": cb, "gpu_launches": 0,
                      "e2e": {"value": cb["value"], "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+        line["config"]["frames_per_step"] = int(cb["sample"].split()[0])
         print(json.dumps(line))
         return 0
 
@@ -286,7 +349,8 @@ def main():
 
     g.build(only_if_missing=True)
     import vpp_b200 as vpp
-    from vpp_b200 import capi
+    from vpp_b200 import capi, tiles
+    from tests import oracle as orc  # the checker of what was timed (never the thing measured)
 
     dist = None
     if world > 1:
@@ -295,284 +359,63 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     else:
         torch.cuda.set_device(0)
-    capi.check(capi.lib.vppb_init(local_rank if world > 1 else 0))
-    dev = torch.device("cuda", local_rank if world > 1 else 0)
+    dev_index = local_rank if world > 1 else 0
+    capi.check(capi.lib.vppb_init(dev_index))
+    dev = torch.device("cuda", dev_index)
     stream = torch.cuda.current_stream()
     sp = C.c_void_p(stream.cuda_stream)
-
-    # ---- row tile of this rank (whole frame at N=1)
-    from vpp_b200 import tiles
-
-    r0, r1 = tiles.tile_rows(H, rank, world)
-    th = r1 - r0
-    uniq = make_frames(H, W, min(nframes, 4))  # distinct host frames (device frames cycle through them)
-    frames = [uniq[i % len(uniq)] for i in range(nframes)]
-    upad = [np.pad(f, ((2, 2), (2, 2), (0, 0)), mode="symmetric") for f in uniq]
-    padded = [upad[i % len(uniq)] for i in range(nframes)]
-    src, dst, bufs = [], [], []
-    halo = 2
-
-    def torch_tile(border):
-        """image2d<vuchar3> tile inside a torch allocation (so NCCL can address its rows), described with vppb_wrap"""
-        pitch, total, _ = vpp.layout(th, W, 3, border, 128)
-        buf = torch.empty(total, dtype=torch.uint8, device=dev)
-        desc = capi.VppbImg()
-        capi.check(capi.lib.vppb_wrap(C.byref(desc), C.c_void_p(buf.data_ptr()), th, W, 3, border, 128))
-        return vpp.Image2d(0, 0, "vuchar3", _desc=desc, _owner=buf), buf, pitch
-
-    for f in padded:
-        s, buf, pitch = torch_tile(2)
-        s.upload(f[r0:r1 + 4], with_border=True)  # rows r0-2 .. r1+1 (true halos: overwritten below at N>1, restored by the exchange)
-        src.append(s)
-        bufs.append(buf)
-        dst.append(torch_tile(0)[0])
-    up, down = rank - 1, rank + 1
-    if world > 1:
-        # halo rows as views of the tile buffers: row r of the buffer starts at (border + r) * pitch
-        send_up = [b[2 * pitch:4 * pitch] for b in bufs]
-        send_dn = [b[th * pitch:(th + 2) * pitch] for b in bufs]
-        recv_up = [b[0:2 * pitch] for b in bufs]
-        recv_dn = [b[(th + 2) * pitch:(th + 4) * pitch] for b in bufs]
-        # scramble the interior tiles' halo rows so that a broken exchange cannot go unnoticed
-        for i in range(nframes):
-            if up >= 0:
-                recv_up[i].fill_(7)
-            if down < world:
-                recv_dn[i].fill_(9)
-        comm_stream = torch.cuda.Stream(device=dev)
-        inner = vpp.Box2d((2, 0), (th - 3, W - 1))
-        top, bot = vpp.Box2d((0, 0), (1, W - 1)), vpp.Box2d((th - 2, 0), (th - 1, W - 1))
-        src_in, dst_in = [s | inner for s in src], [d | inner for d in dst]
-        src_e = [s | top for s in src] + [s | bot for s in src]
-        dst_e = [d | top for d in dst] + [d | bot for d in dst]
-
-    launches_per_step = 0
-    side = [torch.cuda.Stream(device=dev) for _ in range(max(args.streams, 1))] if args.streams > 1 else []
-    side_p = [C.c_void_p(s_.cuda_stream) for s_ in side]
-    fork, fork2, comm_done = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
-    base["config"]["streams"] = max(args.streams, 1)
-
-    box_mode = ["per-frame"]  # or "batch": ONE persistent launch over the tiles of all frames of the step
-    batch_descs = {}
-
-    def fan_out(stream, pairs, ev):
-        """per-frame: one box5x5 launch per (src, dst) pair, spread over the side streams, joined back into `stream`;
-        batch: the whole list in one vppb_box5x5_u8c3_batch call (one launch per 32 frames) on `stream`"""
-        sp = C.c_void_p(stream.cuda_stream)
-        if box_mode[0] == "batch":
-            key = id(pairs[0][0])
-            if key not in batch_descs:
-                n_ = len(pairs)
-                ins, outs = (capi.VppbImg * n_)(), (capi.VppbImg * n_)()
-                for i, (s, d) in enumerate(pairs):
-                    ins[i], outs[i] = s.desc, d.desc
-                batch_descs[key] = (ins, outs, n_)
-            ins, outs, n_ = batch_descs[key]
-            capi.check(capi.lib.vppb_box5x5_u8c3_batch(ins, outs, n_, sp))
-            return (n_ + 31) // 32
-        if len(side) > 1:
-            ev.record(stream)
-            for s_ in side:
-                s_.wait_event(ev)
-            for i, (s, d) in enumerate(pairs):
-                capi.check(capi.lib.vppb_box5x5_u8c3(s.ptr(), d.ptr(), side_p[i % len(side)]))
-            for s_ in side:
-                stream.wait_stream(s_)
-        else:
-            for s, d in pairs:
-                capi.check(capi.lib.vppb_box5x5_u8c3(s.ptr(), d.ptr(), sp))
-        return len(pairs)
-
-    staged_ok = [False]  # set by the probe: may the e2e leg try the staged upload (vppb_copy2d_mirror)?
-
-    def batch_kernel_usable():
-        """--box-launch auto: the batched kernel first runs in a child process on this rank's device and geometry; every rank must agree"""
-        if args.box_launch == "batch":
-            return True, "forced"
-        env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT", "LOCAL_WORLD_SIZE",
-                                                                 "GROUP_RANK", "ROLE_RANK", "TORCHELASTIC_RUN_ID")}
-        try:
-            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--probe-batch", str(local_rank if world > 1 else 0), str(th), str(W), str(nframes)],
-                               capture_output=True, text=True, timeout=150, env=env, cwd=ROOT)
-            ok = r.returncode in (0, 5)           # batched box kernel fine
-            staged_ok[0] = r.returncode in (0, 6)  # fused copy + mirror launch fine
-            why = "probe rc %d %s" % (r.returncode, r.stderr.strip()[-200:])
-        except Exception as ex:  # pragma: no cover
-            ok, why = False, "probe did not run: %r" % (ex,)
-        if dist is not None:
-            flag = torch.tensor([1.0 if ok else 0.0], dtype=torch.float64, device=dev)
-            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-            ok = bool(flag.item() > 0.5)
-        if args.box_launch == "per-frame":
-            return False, "not requested; " + why
-        return ok, why
-
-    def device_ms(fn, reps):
-        """CUDA-event time of `reps` calls of fn on the current stream, max over ranks"""
-        a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize()
-        a_.record(torch.cuda.current_stream())
-        for _ in range(reps):
-            fn()
-        b_.record(torch.cuda.current_stream())
-        torch.cuda.synchronize()
-        t_ = torch.tensor([a_.elapsed_time(b_) / reps], dtype=torch.float64, device=dev)
-        if dist is not None:
-            dist.all_reduce(t_, op=dist.ReduceOp.MAX)
-        return float(t_.item())
-
-    batch_ok, batch_why = batch_kernel_usable()
-    modes = ["per-frame", "batch"] if (batch_ok and args.box_launch == "auto") else (["batch"] if batch_ok else ["per-frame"])
-    mode_ms = {}
-    base["config"]["box_launch"] = {"requested": args.box_launch, "batch_probe": batch_why}
-
-    if world > 1:
-        hb = int(capi.lib.vppb_halo_bytes(src[0].ptr(), halo))
-        st_send_up = torch.empty(nframes * hb, dtype=torch.uint8, device=dev)
-        st_send_dn, st_recv_up, st_recv_dn = torch.empty_like(st_send_up), torch.empty_like(st_send_up), torch.empty_like(st_send_up)
-        packed = torch.cuda.Event()
-
-    if world > 1:
-        src_descs = (capi.VppbImg * nframes)(*[s.desc for s in src])
-
-    def pack_all(stream):
-        sp = C.c_void_p(stream.cuda_stream)
-        n = 0
-        if up >= 0:
-            capi.check(capi.lib.vppb_halo_pack_batch(src_descs, nframes, halo, 0, C.c_void_p(st_send_up.data_ptr()), sp)); n += 1
-        if down < world:
-            capi.check(capi.lib.vppb_halo_pack_batch(src_descs, nframes, halo, 1, C.c_void_p(st_send_dn.data_ptr()), sp)); n += 1
-        return n
-
-    def unpack_all(stream):
-        sp = C.c_void_p(stream.cuda_stream)
-        n = 0
-        if up >= 0:
-            capi.check(capi.lib.vppb_halo_unpack_batch(src_descs, nframes, halo, 0, C.c_void_p(st_recv_up.data_ptr()), sp)); n += 1
-        if down < world:
-            capi.check(capi.lib.vppb_halo_unpack_batch(src_descs, nframes, halo, 1, C.c_void_p(st_recv_dn.data_ptr()), sp)); n += 1
-        return n
-
-    # N>1: two device-side pieces per step - [pack the edge rows of all frames] and [unpack + one box launch per
-    # tile] - each replayed as a CUDA graph; the ONE grouped NCCL send/recv of the step runs between them.
-    pieces = {}
-
-    def piece(name, fn):
-        def run():
-            stream = torch.cuda.current_stream()
-            return fn(stream)
-        if args.graph and world > 1:
-            try:
-                for _ in range(2):
-                    run()
-                torch.cuda.synchronize()
-                g_ = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g_):
-                    cnt = run()
-                pieces[name] = (g_.replay, cnt)
-                return
-            except Exception as ex:  # pragma: no cover
-                sys.stderr.write("graph capture of %s failed: %r\n" % (name, ex))
-                torch.cuda.synchronize()
-        pieces[name] = (run, None)
-
-    if world > 1:
-        piece("pack", pack_all)
-        piece("unpack", unpack_all)
-        # the box piece once per candidate launch form; the faster one (device time, max over ranks) is kept
-        for m_ in modes:
-            box_mode[0] = m_
-            piece("boxes:" + m_, lambda st: fan_out(st, list(zip(src, dst)), fork))
-            pieces["boxes:" + m_][0]()
-            mode_ms[m_] = device_ms(pieces["boxes:" + m_][0], 20)
-        box_mode[0] = min(mode_ms, key=mode_ms.get)
-        pieces["boxes"] = pieces["boxes:" + box_mode[0]]
-        for m_ in modes:
-            del pieces["boxes:" + m_]
-        unpacked = torch.cuda.Event()
-        primed = [False]
-        exchange_ops = tiles.halo_ops(dist, rank, world, st_send_up, st_send_dn, st_recv_up, st_recv_dn)
-
-    def issue_exchange(stream):
-        """[comm stream] pack the edge rows of all frames, ONE grouped NCCL send/recv with both neighbours.
-        Issued one step ahead: the exchange of step k+1 overlaps the box launches of step k (the staging buffers
-        are free once step k's unpack has run; pack only reads domain rows, unpack only writes border rows)."""
-        comm_stream.wait_event(unpacked) if primed[0] else comm_stream.wait_stream(stream)
-        with torch.cuda.stream(comm_stream):
-            r = pieces["pack"][0]()
-            tiles.run_halo_ops(dist, exchange_ops)  # built once: the staging buffers never change
-            comm_done.record(comm_stream)
-        primed[0] = True
-        return pieces["pack"][1] if pieces["pack"][1] is not None else r
-
-    def step():
-        nonlocal launches_per_step
-        n = 0
-        stream = torch.cuda.current_stream()
-        if world > 1:
-            if not primed[0]:
-                n += issue_exchange(stream)  # very first step only: nothing to overlap with yet
-            stream.wait_event(comm_done)
-            r = pieces["unpack"][0]()
-            n += pieces["unpack"][1] if pieces["unpack"][1] is not None else r
-            unpacked.record(stream)
-            n += issue_exchange(stream)  # next step's halos travel while this step's tiles are filtered
-            r = pieces["boxes"][0]()
-            n += pieces["boxes"][1] if pieces["boxes"][1] is not None else r
-        else:
-            n += fan_out(stream, list(zip(src, dst)), fork)
-        launches_per_step = n
+    peak, peak_src = peaks()
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(warmup):
-        step()
-    barrier()
-    # The step (per launch form: one launch per frame with fork/join over the side streams, or one batched launch) is captured once into a CUDA graph
-    # and replayed: same kernels, same work, without the per-launch host cost of the Python/ctypes loop.
-    graph, run_step = None, step
-    if world == 1:  # at N>1 the device pieces are graphs already; NCCL P2P inside a captured graph hung on this stack
-        runners, snap = {}, {}
-        for m_ in modes:
-            box_mode[0] = m_
-            for _ in range(3):
-                step()
-            torch.cuda.synchronize()
-            snap[m_] = (dst[0].download(), dst[-1].download())
-            g_ = None
-            if args.graph:
-                try:
-                    g_ = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(g_):
-                        step()
-                    for _ in range(2):
-                        g_.replay()
-                    barrier()
-                except Exception as ex:
-                    sys.stderr.write("CUDA graph capture failed, running eagerly: %r\n" % (ex,))
-                    torch.cuda.synchronize()
-                    g_ = None
-            if g_ is not None:
-                runners[m_] = (g_, g_.replay)
-            else:
-                runners[m_] = (None, (lambda mm: (lambda: (box_mode.__setitem__(0, mm), step())))(m_))
-            mode_ms[m_] = device_ms(runners[m_][1], max(10, min(100, steps // 10)))
-        if "batch" in snap and "per-frame" in snap and not all(np.array_equal(a_, b_) for a_, b_ in zip(snap["batch"], snap["per-frame"])):
-            sys.stderr.write("batched box launch differs from the per-frame launches: not used\n")
-            mode_ms.pop("batch")
-        box_mode[0] = min(mode_ms, key=mode_ms.get)
-        graph, run_step = runners[box_mode[0]]
-        for _ in range(3):
-            run_step()
+    # ---- this rank's row tile of every resident frame (the whole frame at N = 1)
+    r0, r1 = tiles.tile_rows(H, rank, world)
+    th = r1 - r0
+    uniq = make_frames(H, W, 4)
+    upad = [np.pad(f, ((2, 2), (2, 2), (0, 0)), mode="symmetric") for f in uniq]
+    src, dst = [], []
+    for i in range(BATCH):
+        s = vpp.Image2d(th, W, "vuchar3", border=2)
+        blk = np.array(upad[i % 4][r0:r1 + 4])
+        if rank > 0:
+            blk[:2] = 0xA5   # interior tiles do not hold their halo rows: a broken peer read cannot go unnoticed
+        if rank < world - 1:
+            blk[-2:] = 0x5A
+        s.upload(blk, with_border=True)
+        src.append(s)
+        dst.append(vpp.Image2d(th, W, "vuchar3"))
+    ins = (capi.VppbImg * BATCH)(*[s.desc for s in src])
+    outs = (capi.VppbImg * BATCH)(*[d.desc for d in dst])
+    opened = []
+    if world > 1:
         barrier()
-    base["config"]["box_launch"].update({"used": box_mode[0], "ms_per_step_by_mode": dict(mode_ms)})
-    if world == 1:  # graph replays do not run step(): count the launches of the chosen form
-        launches_per_step = nframes if box_mode[0] == "per-frame" else (nframes + 31) // 32
-    base["config"]["cuda_graph"] = (graph is not None) or (world > 1 and all(v[1] is not None for v in pieces.values()))
-    sampler = ClockSampler(local_rank if world > 1 else 0)
+        ups, downs, opened = tiles.open_neighbour_tiles(dist, rank, world, src)
+        one_batch = lambda: capi.check(capi.lib.vppb_box5x5_u8c3_tiles(ins, ups, downs, outs, BATCH, sp))
+        kernel_name = "k_box5_stream<3,4,0> (tiles: halo rows by bulk copy from peer memory)"
+    else:
+        one_batch = lambda: capi.check(capi.lib.vppb_box5x5_u8c3_batch(ins, outs, BATCH, sp))
+        kernel_name = "k_box5_stream<3,4,0>"
+    one_batch()
+    barrier()
+    ms_batch = device_ms(torch, dist, dev, one_batch, 10)
+    passes = args.passes or passes_for(ms_batch)
+    frames_per_step = passes * BATCH
+    base["config"].update({"frames_per_step": frames_per_step, "launches_per_step": passes,
+                           "step": "%d launches x %d frames (>= 5 ms of GPU work per step)" % (passes, BATCH)})
+
+    def step_eager():
+        for _ in range(passes):
+            one_batch()
+
+    run_step, graphed = graph_of(torch, step_eager) if args.graph else (step_eager, False)
+    base["config"]["cuda_graph"] = graphed
+    for _ in range(warmup):
+        run_step()
+    barrier()
+    sampler = ClockSampler(dev_index)
     if rank == 0:
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -583,101 +426,62 @@ def main():
     e1.record(stream)
     barrier()
     ms = e0.elapsed_time(e1)
-    if rank == 0 and ms < 400.0:
-        # the timed region was too short for nvidia-smi's 100 ms sampling: keep the same load running (untimed) long enough
-        t_end = time.perf_counter() + 0.45
-        while time.perf_counter() < t_end and world == 1:
-            for _ in range(50):
+    if rank == 0 and ms < 400.0 and world == 1:
+        t_end = time.perf_counter() + 0.45  # nvidia-smi samples every 100 ms: keep the same load running (untimed) long enough
+        while time.perf_counter() < t_end:
+            for _ in range(5):
                 run_step()
             torch.cuda.synchronize()
     clocks = sampler.stop() if rank == 0 else None
     if clocks is not None:
-        clocks["note"] = "sampled every 100 ms over the timed region" + (" + an untimed continuation of the same step loop" if ms < 400.0 else "")
+        clocks["note"] = "sampled every 100 ms over the timed region" + (" + an untimed continuation of the same step loop" if ms < 400.0 and world == 1 else "")
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = float(t.item())
-    value = steps * nframes * H * W / 1e6 / (ms_total / 1e3)
+    value = steps * frames_per_step * H * W / 1e6 / (ms_total / 1e3)
 
-    # ---- parity spot check of what was just timed (frame 0, this rank's tile) against the oracle
-    from tests import oracle as orc
-    hs = orc.HostImage(th, W, "vuchar3", border=2, aligned=32)
-    hs.set(padded[0][r0:r1 + 4], with_border=True)
-    hd = orc.HostImage(th, W, "vuchar3", aligned=32)
-    orc.load(omp=True).vo_box5x5_u8(hs.ptr(), hd.ptr(), 3)
-    parity_ok = bool(np.array_equal(dst[0].download(), hd.get()))
+    # ---- parity of what was just timed (frames 0 and BATCH-1, this rank's tile) against the oracle
+    hd = []
+    for k in (0, (BATCH - 1) % 4):
+        hs = orc.HostImage(th, W, "vuchar3", border=2, aligned=32)
+        hs.set(upad[k][r0:r1 + 4], with_border=True)
+        h_ = orc.HostImage(th, W, "vuchar3", aligned=32)
+        orc.load(omp=True).vo_box5x5_u8(hs.ptr(), h_.ptr(), 3)
+        hd.append(h_.get())
+    parity_ok = bool(np.array_equal(dst[0].download(), hd[0]) and np.array_equal(dst[BATCH - 1].download(), hd[1]))
 
-    # ---- kernel-only timing for the roofline: the box kernel alone, per launch, same stream
-    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    reps = 5
-    k0.record(stream)
-    for _ in range(reps):
-        for s, d in zip(src, dst):
-            capi.check(capi.lib.vppb_box5x5_u8c3(s.ptr(), d.ptr(), sp))
-    k1.record(stream)
-    torch.cuda.synchronize()
-    us_per_launch = k0.elapsed_time(k1) * 1e3 / (reps * nframes)
-    peak, peak_src = peaks()
-    alg_bytes = BOX_BYTES_PER_PX * th * W
-    alone = alg_bytes / (us_per_launch * 1e-6) / 1e9
-    # achieved = algorithmic bytes of this rank's launches in the timed region / duration of the timed region (CUDA events):
-    # the launches of a step overlap on several streams, so this is the sustained figure; "alone" is one launch after another.
-    launch_us_timed = ms_total * 1e3 / (steps * nframes)
-    achieved = alg_bytes / (launch_us_timed * 1e-6) / 1e9
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "box_traffic.json")
-    if os.path.exists(tp):
-        try:
-            traffic = json.load(open(tp)).get(workload if n_gpus == 1 else "%s_tile%d" % (workload, n_gpus))
-        except Exception:
-            traffic = None
-    batched = box_mode[0] == "batch"
-    if batched:
-        traffic = None  # the ncu capture in profiles/ is of the per-frame kernel
-    roofline = {"bound": "hbm", "kernel": "k_box5_bytes_tma_batch<3>" if batched else "k_box5_bytes_tma<3>", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src, "us_per_launch": launch_us_timed, "algorithmic_bytes_per_launch": alg_bytes,
-                "how": ("bytes of the %d frames of a step (one persistent launch per step) / CUDA-event time of the timed region; us_per_launch is per frame" % nframes) if batched else
-                       ("bytes of the %d box launches per step / CUDA-event time of the timed region (launches overlap on %d streams)" % (nframes, max(args.streams, 1))),
-                "alone": {"us_per_launch": us_per_launch, "achieved": alone, "frac": alone / peak,
-                          "how": "same kernel, launches issued back to back on one stream"}}
+    alg_bytes = BOX_BYTES_PER_PX * th * W * BATCH  # per launch, this rank
+    us_per_launch = ms_total * 1e3 / (steps * passes)
+    achieved = alg_bytes / (us_per_launch * 1e-6) / 1e9
+    tkey = "stream_%s_x%d" % (workload, BATCH) if world == 1 else "stream_%s_tile%d_x%d" % (workload, world, BATCH)
+    roofline = {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": box_traffic(tkey), "peak_source": peak_src, "us_per_launch": us_per_launch, "algorithmic_bytes_per_launch": alg_bytes,
+                "how": "6 B/px x %d frames of a launch / (CUDA-event time of the timed region / launches); traffic = dram read + write bytes per launch of the same "
+                       "command under ncu (--cache-control none, steady state), profiles/box_traffic.json" % BATCH}
 
-    # ---- e2e: HOST buffers through the C-ABI (pinned), copies inside the timed region.
-    # N=1: whole frames, mirror border made on the device.  N>1: every rank streams its own row tile; the host
-    # frames are whole, so the 2 halo rows above/below simply ride along with the tile's upload.
-    esets = min(nframes, 8)
+    # ---- e2e: HOST buffers through the C-ABI (pinned), copies inside the timed region, 4 frames in flight per rank.
+    # N > 1: the host holds whole frames, so the 2 halo rows above / below a tile ride along with the tile's upload.
+    esets = 8
     if world == 1:
-        host_in = [torch.from_numpy(np.ascontiguousarray(frames[i])).pin_memory() for i in range(min(len(uniq), esets))]
+        host_in = [torch.from_numpy(np.ascontiguousarray(uniq[i % 4])).pin_memory() for i in range(4)]
     else:
-        host_in = [torch.from_numpy(np.ascontiguousarray(upad[i][r0:r1 + 4])).pin_memory() for i in range(min(len(uniq), esets))]
+        host_in = [torch.from_numpy(np.ascontiguousarray(upad[i % 4][r0:r1 + 4])).pin_memory() for i in range(4)]
     host_out = [torch.empty((th, W, 3), dtype=torch.uint8).pin_memory() for _ in range(esets)]
-    # 4 frames in flight: on a stream the next upload waits for the previous download (stream order), so with only two
-    # streams each copy engine idles while the other stream's frame is still going down; 4 keep both directions fed
     NE2E = 4
     e_src = [vpp.Image2d(th, W, "vuchar3", border=2) for _ in range(NE2E)]
     e_dst = [vpp.Image2d(th, W, "vuchar3") for _ in range(NE2E)]
     streams = [torch.cuda.Stream(device=dev) for _ in range(NE2E)]
     rowb = W * 3
     h2d = (th * rowb) if world == 1 else (th + 4) * (W + 4) * 3
-
-    # Two ways to bring a whole host frame into the bordered device image (N = 1), both through the public C-ABI:
-    #   direct: vppb_upload straight into the pitched image (a 2-D copy: host rows are tight, device rows are padded for the
-    #           border), then vppb_fill_border_mirror;
-    #   staged: vppb_upload into a border-less image whose rows are as tight as the host's (one LINEAR copy), then
-    #           vppb_copy2d_mirror = copy + mirror border in one launch (HBM cost ~2 us, the PCIe copy is ~100 us).
-    # Both are timed below; the faster carries the e2e number and both times are reported.
-    e_stage = [vpp.Image2d(th, W, "vuchar3") for _ in range(NE2E)] if world == 1 else []
-    e2e_mode = ["direct"]
+    e_frames = min(frames_per_step, 256)  # frames per e2e step (a bounded sample of the step: PCIe time dominates)
 
     def e2e_step():
-        for i in range(nframes):
+        for i in range(e_frames):
             k = i % NE2E
             st = C.c_void_p(streams[k].cuda_stream)
             hin = host_in[i % len(host_in)]
-            if world == 1 and e2e_mode[0] == "staged":
-                capi.check(capi.lib.vppb_upload(e_stage[k].ptr(), C.c_void_p(hin.data_ptr()), rowb, 0, st))
-                capi.check(capi.lib.vppb_copy2d_mirror(e_stage[k].ptr(), e_src[k].ptr(), st))
-            elif world == 1:
+            if world == 1:
                 capi.check(capi.lib.vppb_upload(e_src[k].ptr(), C.c_void_p(hin.data_ptr()), rowb, 0, st))
                 capi.check(capi.lib.vppb_fill_border_mirror(e_src[k].ptr(), st))
             else:
@@ -688,77 +492,82 @@ def main():
         for s_ in streams:
             s_.synchronize()
 
-    e2e_ms = {}
-    for m_ in (["direct", "staged"] if (world == 1 and staged_ok[0]) else ["direct"]):
-        e2e_mode[0] = m_
-        for _ in range(2):
-            e2e_step()
-        torch.cuda.synchronize()
-        if m_ == "staged" and not np.array_equal(host_out[0].numpy(), hd.get()):  # must equal the oracle like the direct form
-            sys.stderr.write("staged upload gives a different result: not used\n")
-            continue
-        t0 = time.perf_counter()
-        for _ in range(3):
-            e2e_step()
-        torch.cuda.synchronize()
-        e2e_ms[m_] = (time.perf_counter() - t0) / 3 * 1e3
-    e2e_mode[0] = min(e2e_ms, key=e2e_ms.get)
     for _ in range(2):
         e2e_step()
     barrier()
-    esteps = max(3, min(10, steps // 4))
+    esteps = 4
     t0 = time.perf_counter()
     for _ in range(esteps):
         e2e_step()
     torch.cuda.synchronize()
-    dt_loc = time.perf_counter() - t0
-    te = torch.tensor([dt_loc], dtype=torch.float64, device=dev)
+    te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     dt = float(te.item())
-    e2e = {"value": esteps * nframes * H * W / 1e6 / dt, "unit": "Mpix/s", "h2d_bytes_per_step": nframes * h2d * world,
-           "d2h_bytes_per_step": nframes * th * rowb * world, "ms_per_step": dt / esteps * 1e3,
-           "upload": {"used": e2e_mode[0], "ms_per_step_by_form": e2e_ms, "staged_probe_ok": staged_ok[0]},
-           "note": "pinned host frames -> vppb_upload (direct 2-D copy + mirror fill, or linear copy into a tight image + copy/mirror launch: the faster of the two) "
-                   "-> box5x5 -> vppb_download, 4 frames in flight per rank, max over ranks"}
-    # the end-to-end result must equal the oracle's too
-    parity_ok = parity_ok and bool(np.array_equal(host_out[0].numpy(), hd.get()))
-
+    e2e = {"value": esteps * e_frames * H * W / 1e6 / dt, "unit": "Mpix/s", "h2d_bytes_per_step": e_frames * h2d * world,
+           "d2h_bytes_per_step": e_frames * th * rowb * world, "ms_per_step": dt / esteps * 1e3, "frames_per_e2e_step": e_frames,
+           "note": "pinned host frames -> vppb_upload + vppb_fill_border_mirror -> vppb_box5x5_u8c3 -> vppb_download, 4 frames in flight per rank, max over ranks"}
+    parity_ok = parity_ok and bool(np.array_equal(host_out[0].numpy(), hd[0]))
     if dist is not None:  # every rank checked its own tile
         pk = torch.tensor([1.0 if parity_ok else 0.0], dtype=torch.float64, device=dev)
         dist.all_reduce(pk, op=dist.ReduceOp.MIN)
         parity_ok = bool(pk.item() > 0.5)
+
     line = dict(base)
     line.update({"value": value, "ms_per_step": ms_total / steps, "clocks": clocks, "roofline": roofline, "e2e": e2e,
-                 "gpu_launches": launches_per_step * steps, "parity_checked": parity_ok})
+                 "gpu_launches": passes * steps, "parity_checked": parity_ok})
+    if world > 1:
+        # the materialised alternative through the C-ABI, for the record: one grouped NCCL send/recv (vppb_halo_exchange) + plain batch kernel
+        try:
+            comm = tiles.nccl_comm(dist, rank, world)
+            ex = lambda: capi.check(capi.lib.vppb_halo_exchange(comm, rank, world, ins, BATCH, 2, sp))
+            plain = lambda: capi.check(capi.lib.vppb_box5x5_u8c3_batch(ins, outs, BATCH, sp))
+            ex(); plain()
+            torch.cuda.synchronize()
+            ok2 = bool(np.array_equal(dst[0].download(), hd[0]))
+            line["config"]["nccl_exchange"] = {"exchange_ms_per_launch": device_ms(torch, dist, dev, ex, 10), "exchange_plus_box_ms_per_launch": device_ms(torch, dist, dev, lambda: (ex(), plain()), 10),
+                                               "fused_ms_per_launch": ms_batch, "parity": ok2,
+                                               "note": "vppb_halo_exchange = ONE grouped NCCL send/recv of the edge rows of all 32 tiles, then the batch kernel; the timed step uses the fused kernel instead"}
+            capi.lib.vppb_comm_destroy(comm)
+        except Exception as ex_:  # pragma: no cover
+            line["config"]["nccl_exchange"] = {"error": repr(ex_)[:200]}
 
     if rank == 0 and n_gpus == 1:
-        cb, _ = cpu_box_bench(H, W, 3, 1, args.cpu_budget, want_ref=True)
+        cb, _ = cpu_box_bench(H, W, 3, 1, args.cpu_budget)
         line["cpu_baseline"] = cb
         if not args.no_extras:
             try:
-                line["extras"] = gpu_extras(vpp, capi, torch, stream, sp)
+                line["extras"] = gpu_extras(vpp, capi, torch, stream, sp, dev)
             except Exception as ex:  # pragma: no cover
                 line["extras"] = {"error": repr(ex)[:300]}
             try:
                 line["extras"]["cpu"] = cpu_extras()
             except Exception as ex:  # pragma: no cover
-                line["extras"]["cpu"] = {"error": repr(ex)}
+                line["extras"]["cpu"] = {"error": repr(ex)[:300]}
+            a8 = line["extras"].get("box5x5_vuchar3_8k_x32", {})
+            if "mpix_per_s" in a8:
+                line["scaling_anchor_n1"] = {"value": a8["mpix_per_s"], "unit": "Mpix/s", "workload": "8K vuchar3, 32 frames per launch, one GPU, no tiling",
+                                             "hbm_frac": a8.get("hbm_frac")}
     if rank == 0:
         print(json.dumps(line))
+    if opened:
+        tiles.close_neighbour_tiles(opened)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
     return 0 if parity_ok else 3
 
 
-def gpu_extras(vpp, capi, torch, stream, sp):
-    """Other rows of the hot path, device-resident inputs, CUDA-event timing.  Every row is measured on its own: one
-    that fails reports {"error": ...} and cannot take the headline line down with it."""
-    from tests import scenes
+def gpu_extras(vpp, capi, torch, stream, sp, dev):
+    """Other rows of the hot path, device-resident inputs, CUDA-event timing, each checked against the oracle (`parity`).  Every
+    row is measured on its own: one that fails reports {"error": ...} and cannot take the headline line down with it."""
+    from tests import oracle as orc, scenes
+    from tests.oracle_ops import oracle_grad_pyramid, oracle_lk, oracle_pyramid
+    from vpp_b200.ops import _DeviceBuffer
 
     peak, _ = peaks()
     out = {}
+    omp = orc.load(omp=True)
 
     def timed(fn, reps):
         fn()
@@ -776,29 +585,48 @@ def gpu_extras(vpp, capi, torch, stream, sp):
         trip = []
         for _ in range(4):
             b, c = rng.integers(0, 2 ** 30, (2, 2160, 3840), dtype=np.int32)
-            trip.append((vpp.Image2d(2160, 3840, "i32"), vpp.Image2d.from_host(b, "i32"), vpp.Image2d.from_host(c, "i32")))
+            trip.append((vpp.Image2d(2160, 3840, "i32"), vpp.Image2d.from_host(b, "i32"), vpp.Image2d.from_host(c, "i32"), b, c))
 
         def add_all():
-            for a_, b_, c_ in trip:
+            for a_, b_, c_, _, _ in trip:
                 capi.check(capi.lib.vppb_pw_add_i32(a_.ptr(), b_.ptr(), c_.ptr(), sp))
 
         ms = timed(add_all, 20) / len(trip)
-        return {"mpix_per_s": 2160 * 3840 / 1e6 / (ms / 1e3), "us_per_launch": ms * 1e3, "hbm_frac": 12.0 * 2160 * 3840 / (ms / 1e3) / 1e9 / peak}
+        ok = bool(np.array_equal(trip[3][0].download(), trip[3][3] + trip[3][4]))
+        return {"mpix_per_s": 2160 * 3840 / 1e6 / (ms / 1e3), "us_per_launch": ms * 1e3, "hbm_frac": 12.0 * 2160 * 3840 / (ms / 1e3) / 1e9 / peak, "parity": ok}
 
-    def box5x5_vuchar3_4k():
-        f = np.random.default_rng(2).integers(0, 256, (2160, 3840, 3), dtype=np.uint8)
+    def box_rows(h, w, nsets, batch):
+        f = np.random.default_rng(2).integers(0, 256, (h, w, 3), dtype=np.uint8)
         pairs = []
-        for _ in range(6):
+        for _ in range(nsets):
             s_ = vpp.Image2d.from_host(f, "vuchar3", border=2)
             vpp.fill_border_mirror(s_)
-            pairs.append((s_, vpp.Image2d(2160, 3840, "vuchar3")))
+            pairs.append((s_, vpp.Image2d(h, w, "vuchar3")))
+        hs = orc.HostImage(h, w, "vuchar3", border=2, aligned=32, data=f, fill_border="mirror")
+        hd_ = orc.HostImage(h, w, "vuchar3", aligned=32)
+        omp.vo_box5x5_u8(hs.ptr(), hd_.ptr(), 3)
+        want = hd_.get()
+        if batch:
+            n_ = len(pairs)
+            bi, bo = (capi.VppbImg * n_)(*[p_[0].desc for p_ in pairs]), (capi.VppbImg * n_)(*[p_[1].desc for p_ in pairs])
+            ms = timed(lambda: capi.check(capi.lib.vppb_box5x5_u8c3_batch(bi, bo, n_, sp)), 10) / n_
+        else:
+            def box_all():
+                for s_, d_ in pairs:
+                    capi.check(capi.lib.vppb_box5x5_u8c3(s_.ptr(), d_.ptr(), sp))
+            ms = timed(box_all, 10) / len(pairs)
+        ok = bool(np.array_equal(pairs[-1][1].download(), want) and np.array_equal(pairs[0][1].download(), want))
+        return {"mpix_per_s": h * w / 1e6 / (ms / 1e3), "us_per_frame": ms * 1e3, "hbm_frac": 6.0 * h * w / (ms / 1e3) / 1e9 / peak, "parity": ok,
+                "launch": "one launch per %d frames" % len(pairs) if batch else "one launch per frame, back to back on one stream"}
 
-        def box_all():
-            for s_, d_ in pairs:
-                capi.check(capi.lib.vppb_box5x5_u8c3(s_.ptr(), d_.ptr(), sp))
+    def box5x5_vuchar3_4k():
+        return box_rows(2160, 3840, 6, False)
 
-        ms = timed(box_all, 10) / len(pairs)
-        return {"mpix_per_s": 2160 * 3840 / 1e6 / (ms / 1e3), "us_per_launch": ms * 1e3, "hbm_frac": 6.0 * 2160 * 3840 / (ms / 1e3) / 1e9 / peak}
+    def box5x5_vuchar3_4k_x6():
+        return box_rows(2160, 3840, 6, True)
+
+    def box5x5_vuchar3_8k_x32():  # the N = 1 anchor of the strong-scaling curve: the N > 1 workload on one GPU, no tiling
+        return box_rows(4320, 7680, 32, True)
 
     def ingest_rgb_4k():  # rgb -> gray + mirror border of 3 in one launch, 4 B/px algorithmic
         f = np.random.default_rng(3).integers(0, 256, (2160, 3840, 3), dtype=np.uint8)
@@ -809,30 +637,41 @@ def gpu_extras(vpp, capi, torch, stream, sp):
                 capi.check(capi.lib.vppb_rgb_to_graylevel_u8_mirror(s_.ptr(), d_.ptr(), sp))
 
         ms = timed(ingest_all, 10) / len(pairs)
-        exp = (f.astype(np.int32).sum(axis=2) // 3).astype(np.uint8)
-        ok = bool(np.array_equal(pairs[0][1].download(), exp))
-        return {"mpix_per_s": 2160 * 3840 / 1e6 / (ms / 1e3), "us_per_launch": ms * 1e3, "hbm_frac": 4.0 * 2160 * 3840 / (ms / 1e3) / 1e9 / peak,
-                "domain_equals_numpy": ok}
+        exp = np.pad((f.astype(np.int32).sum(axis=2) // 3).astype(np.uint8), 3, mode="symmetric")
+        ok = bool(np.array_equal(pairs[0][1].download(with_border=True), exp))
+        return {"mpix_per_s": 2160 * 3840 / 1e6 / (ms / 1e3), "us_per_launch": ms * 1e3, "hbm_frac": 4.0 * 2160 * 3840 / (ms / 1e3) / 1e9 / peak, "parity": ok}
 
-    def fast9_4k():  # includes the count read-back the API performs
+    def fast9_4k():
         img = scenes.rectangles_scene(2160, 3840, seed=42)
         G = vpp.Image2d.from_host(img, "u8", border=3)
         vpp.fill_border_mirror(G)
-        nk = len(vpp.fast9(G, 20))
-        ms = timed(lambda: vpp.fast9(G, 20, capacity=max(nk, 1)), 5)
-        return {"mpix_per_s": 2160 * 3840 / 1e6 / (ms / 1e3), "ms": ms, "keypoints": nk, "note": "python wrapper incl. workspace alloc + keypoint download"}
+        kps = vpp.fast9(G, 20, stream=sp)
+        nk = len(kps)
+        hg = orc.HostImage(2160, 3840, "u8", border=3, data=img, fill_border="mirror")
+        ref = np.zeros((img.size // 4, 2), dtype=np.int32)
+        n_ref = orc.load().vo_fast9_u8(hg.ptr(), 20, None, 0, 10, 0, ref.ctypes.data, None, len(ref))
+        ok = bool(n_ref == nk and np.array_equal(kps, ref[:n_ref]))
+        from vpp_b200 import ops
+        ent = ops._fast_buffers(G, 10, 2160 * 3840 // 8, False)
+        run = lambda: capi.check(capi.lib.vppb_fast9_u8_async(G.ptr(), 20, None, 0, 10, 0, ent["ws"].ptr, ent["ws"].nbytes, ent["kps"].ptr, None, ent["cap"], ent["count"].ptr, sp))
+        ms_dev = timed(run, 20)
+        t0 = time.perf_counter()
+        for _ in range(10):
+            vpp.fast9(G, 20, stream=sp)
+        ms_py = (time.perf_counter() - t0) / 10 * 1e3
+        return {"mpix_per_s": 2160 * 3840 / 1e6 / (ms_dev / 1e3), "us_device": ms_dev * 1e3, "hbm_frac": (2160 * 3840 + 8.0 * nk) / (ms_dev / 1e3) / 1e9 / peak,
+                "ms_python_call": ms_py, "keypoints": nk, "parity": ok,
+                "note": "us_device: detect + raster emit queued by vppb_fast9_u8_async (2 launches, no host sync); ms_python_call adds the count read-back and the keypoint download"}
 
-    def pyrlk_1080p_10k():  # pyramid build (copy+mirror, one fused launch per level, Scharr+mirror) + LK of 10k keypoints
+    def pyrlk_1080p_10k():  # pyramids (copy+mirror, one fused launch per level, Scharr+mirror) + pyrlk_match of 10k keypoints, vfloat2 gradient
         f1, f2, pts = scenes.lk_pair(1080, 1920, 10000, seed=5)
         I1, I2 = vpp.Image2d.from_host(f1, "u8"), vpp.Image2d.from_host(f2, "u8")
-        prev, nxt = vpp.Pyramid2d(I1, 3, 2, border=3), vpp.Pyramid2d(I2, 3, 2, border=3)
-        grad = vpp.Pyramid2d((1080, 1920), 3, 2, pixel="vint2", border=3)
-        from vpp_b200.ops import _DeviceBuffer
-
+        prev, nxt = vpp.Pyramid2d(I1, 3, 2, border=4), vpp.Pyramid2d(I2, 3, 2, border=4)
+        grad = vpp.Pyramid2d((1080, 1920), 3, 2, pixel="vfloat2", border=4)
         d_kp = _DeviceBuffer(pts.nbytes).from_host(pts)
         d_flow, d_err = _DeviceBuffer(len(pts) * 8), _DeviceBuffer(len(pts) * 4)
-        P = capi.VppbLkParams(nlevels=3, min_scale=0, winsize=7, max_iter=21, grad_is_float=0, err_mode=0, gate_on_max_err=0, min_ev=0.0,
-                              delta=0.0, max_err=0.0, factor=2.0, pred_div=8.0)
+        P = capi.VppbLkParams(nlevels=3, min_scale=0, winsize=7, max_iter=21, grad_is_float=1, err_mode=capi.LK_ERR_SAD_OVER_MAD, gate_on_max_err=1, min_ev=0.01,
+                              delta=0.01, max_err=0.6, factor=2.0, pred_div=1.0)
         pa, na, ga = prev.desc_array(), nxt.desc_array(), grad.desc_array()
 
         def build():
@@ -842,25 +681,33 @@ def gpu_extras(vpp, capi, torch, stream, sp):
         def lk():
             capi.check(capi.lib.vppb_lk_match_u8(pa, na, ga, C.byref(P), d_kp.ptr, None, len(pts), d_flow.ptr, d_err.ptr, sp))
 
-        build()
+        build(); lk()
+        flow, err = d_flow.to_host(np.float32, len(pts) * 2, sp).reshape(-1, 2), d_err.to_host(np.float32, len(pts), sp)
+        rprev, rnxt = oracle_pyramid(f1, 3, "u8", 4, omp), oracle_pyramid(f2, 3, "u8", 4, omp)
+        rgrad = oracle_grad_pyramid(rprev, "vfloat2", 4, omp)
+        RP = orc.VoLkParams(nlevels=3, min_scale=0, winsize=7, max_iter=21, grad_is_float=1, err_mode=1, gate_on_max_err=1, min_ev=0.01, delta=0.01, max_err=0.6,
+                            factor=2.0, pred_div=1.0)
+        rflow, rerr = oracle_lk(rprev, rnxt, rgrad, RP, pts, lib=omp)
+        rel = np.abs(flow - rflow) / np.maximum(np.abs(rflow), 1.0)
+        ok = bool(np.array_equal(err >= 3e38, rerr >= 3e38) and (rel <= 1e-4).all())
         ms_build = timed(build, 10)
         ms_lk = timed(lk, 10)
-        return {"kpts_per_s_match_only": len(pts) / (ms_lk / 1e3), "kpts_per_s_with_pyramids": len(pts) / ((ms_lk + ms_build) / 1e3),
-                "ms_match": ms_lk, "ms_pyramids_scharr": ms_build, "launches_pyramids_scharr": 9}
+        return {"kpts_per_s": len(pts) / ((ms_lk + ms_build) / 1e3), "kpts_per_s_match_only": len(pts) / (ms_lk / 1e3),
+                "ms_match": ms_lk, "ms_pyramids_scharr": ms_build, "parity": ok, "max_rel_err": float(rel.max()),
+                "note": "kpts_per_s includes both u8 pyramids and the Scharr gradient pyramid; parity = failure flags identical and displacement rel. err <= 1e-4 against the oracle "
+                        "(whose 3-level definition clamps the reads the reference makes outside its border, tests/test_oracle_vs_ref.py)"}
 
-    def sdof_1080p():  # semi-dense flow with video_extruder's settings on blockwise-FAST keypoints, pyramids prebuilt: both sweep schedules
-        H_, W_ = 1080, 1920
-        base_ = scenes.rectangles_scene(H_ + 16, W_ + 16, seed=5, noise=3)
-        f1, f2 = base_[8:8 + H_, 8:8 + W_].copy(), base_[5:5 + H_, 10:10 + W_].copy()  # motion (3, -2)
-        G = vpp.Image2d.from_host(f1, "u8", border=3)
+    def sdof(H_, W_):
+        g1, g2, _ = scenes.lk_pair(1080, 1920, 4, seed=55, shift=(3.0, -2.0), margin=10)
+        if (H_, W_) != (1080, 1920):  # larger frames: the 1080p pair tiled (the generator's filters take minutes at 8K); same motion everywhere
+            g1, g2 = np.ascontiguousarray(np.tile(g1, (H_ // 1080, W_ // 1920))), np.ascontiguousarray(np.tile(g2, (H_ // 1080, W_ // 1920)))
+        G = vpp.Image2d.from_host(g1, "u8", border=3)
         vpp.fill_border_mirror(G)
-        kps = vpp.fast9(G, 10, blockwise=True, block_size=10)
+        kps = vpp.fast9(G, 10, blockwise=True, block_size=10, stream=sp)  # video_extruder.hpp:111
         n = len(kps)
-        from vpp_b200.ops import _DeviceBuffer
-
         P = capi.VppbSdofParams(9, 3, 0, 2, 5)
-        p1 = vpp.Pyramid2d(vpp.Image2d.from_host(f1, "u8"), 3, 2, border=18)
-        p2 = vpp.Pyramid2d(vpp.Image2d.from_host(f2, "u8"), 3, 2, border=18)
+        I1, I2 = vpp.Image2d.from_host(g1, "u8"), vpp.Image2d.from_host(g2, "u8")
+        p1, p2 = vpp.Pyramid2d(I1, 3, 2, border=18), vpp.Pyramid2d(I2, 3, 2, border=18)
         wsb = _DeviceBuffer(capi.lib.vppb_sdof_workspace_bytes(H_, W_, C.byref(P)))
         d_kp = _DeviceBuffer(kps.nbytes).from_host(kps)
         d_pos, d_dist, d_valid = _DeviceBuffer(n * 8), _DeviceBuffer(n * 4), _DeviceBuffer(n)
@@ -869,24 +716,28 @@ def gpu_extras(vpp, capi, torch, stream, sp):
         def run():
             capi.check(capi.lib.vppb_sdof_u8(a1, a2, C.byref(P), d_kp.ptr, n, wsb.ptr, wsb.nbytes, d_pos.ptr, d_dist.ptr, d_valid.ptr, sp))
 
-        res, outs = {"keypoints": n}, {}
-        saved = os.environ.pop("VPPB_SDOF_SCHEDULE", None)
-        try:
-            for name_ in ("antidiagonals", "levels"):
-                if name_ == "levels":
-                    os.environ["VPPB_SDOF_SCHEDULE"] = "levels"
-                run()
-                res["ms_" + name_] = timed(run, 3)
-                outs[name_] = (d_pos.to_host(np.int32, n * 2), d_dist.to_host(np.int32, n), d_valid.to_host(np.uint8, n))
-        finally:
-            os.environ.pop("VPPB_SDOF_SCHEDULE", None)
-            if saved is not None:
-                os.environ["VPPB_SDOF_SCHEDULE"] = saved
-        res["schedules_agree"] = bool(all(np.array_equal(x, y) for x, y in zip(outs["antidiagonals"], outs["levels"])))
-        res["note"] = "default = one launch per anti-diagonal; VPPB_SDOF_SCHEDULE=levels (opt-in) = dependency levels of the marked cells, same results"
-        return res
+        def pyr():
+            p1.update(I1, sp); p2.update(I2, sp)
 
-    for row in (add_i32_4k, box5x5_vuchar3_4k, ingest_rgb_4k, fast9_4k, pyrlk_1080p_10k, sdof_1080p):  # the never-run-on-hardware schedule goes last
+        run()
+        got = (d_pos.to_host(np.int32, n * 2, sp).reshape(-1, 2), d_dist.to_host(np.int32, n, sp), d_valid.to_host(np.uint8, n, sp))
+        h1, h2 = orc.HostImage(H_, W_, "u8", data=g1), orc.HostImage(H_, W_, "u8", data=g2)
+        rp, rd, rv = np.zeros((n, 2), np.int32), np.zeros(n, np.int32), np.zeros(n, np.uint8)
+        k = np.ascontiguousarray(kps)
+        orc.load().vo_semi_dense_flow(h1.ptr(), h2.ptr(), k.ctypes.data, n, 9, 3, 0, 2, 5, rp.ctypes.data, rd.ctypes.data, rv.ctypes.data)
+        ok = bool(np.array_equal(got[0], rp) and np.array_equal(got[1], rd) and np.array_equal(got[2], rv))
+        ms = timed(run, 5)
+        ms_pyr = timed(pyr, 5)
+        return {"ms": ms + ms_pyr, "ms_flow": ms, "ms_pyramids": ms_pyr, "keypoints": n, "parity": ok,
+                "note": "video_extruder's settings (winsize 9, 3 scales, patch 5, 2 sweeps); one persistent dataflow launch per sweep"}
+
+    def sdof_1080p():
+        return sdof(1080, 1920)
+
+    def sdof_8k():  # config 5's kernel on a single GPU: a 7680 x 4320 frame pair
+        return sdof(4320, 7680)
+
+    for row in (add_i32_4k, box5x5_vuchar3_4k, box5x5_vuchar3_4k_x6, box5x5_vuchar3_8k_x32, ingest_rgb_4k, fast9_4k, pyrlk_1080p_10k, sdof_1080p, sdof_8k):
         try:
             out[row.__name__] = row()
         except Exception as ex:  # pragma: no cover - a broken extra must not cost the headline line
