@@ -393,10 +393,10 @@ def main():
     if world > 1:
         barrier()
         ups, downs, opened = tiles.open_neighbour_tiles(dist, rank, world, src)
-        one_batch = lambda: capi.check(capi.lib.vppb_box5x5_u8c3_tiles(ins, ups, downs, outs, BATCH, sp))
+        one_batch = lambda: capi.check(capi.lib.vppb_box5x5_u8c3_tiles(ins, ups, downs, outs, BATCH, C.c_void_p(torch.cuda.current_stream().cuda_stream)))
         kernel_name = "k_box5_stream<3,4,0> (tiles: halo rows by bulk copy from peer memory)"
     else:
-        one_batch = lambda: capi.check(capi.lib.vppb_box5x5_u8c3_batch(ins, outs, BATCH, sp))
+        one_batch = lambda: capi.check(capi.lib.vppb_box5x5_u8c3_batch(ins, outs, BATCH, C.c_void_p(torch.cuda.current_stream().cuda_stream)))  # the stream current at call time: graph capture runs on a side stream
         kernel_name = "k_box5_stream<3,4,0>"
     one_batch()
     barrier()
@@ -439,6 +439,8 @@ def main():
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = float(t.item())
+    if ms_total / steps < 0.5 * passes * ms_batch:  # a graph that captured nothing would "run" in microseconds
+        raise RuntimeError("timed step %.4f ms is far below %d launches x %.4f ms: the step did not execute" % (ms_total / steps, passes, ms_batch))
     value = steps * frames_per_step * H * W / 1e6 / (ms_total / 1e3)
 
     # ---- parity of what was just timed (frames 0 and BATCH-1, this rank's tile) against the oracle
@@ -666,7 +668,7 @@ def gpu_extras(vpp, capi, torch, stream, sp, dev):
     def pyrlk_1080p_10k():  # pyramids (copy+mirror, one fused launch per level, Scharr+mirror) + pyrlk_match of 10k keypoints, vfloat2 gradient
         f1, f2, pts = scenes.lk_pair(1080, 1920, 10000, seed=5)
         I1, I2 = vpp.Image2d.from_host(f1, "u8"), vpp.Image2d.from_host(f2, "u8")
-        prev, nxt = vpp.Pyramid2d(I1, 3, 2, border=4), vpp.Pyramid2d(I2, 3, 2, border=4)
+        prev, nxt = vpp.Pyramid2d((1080, 1920), 3, 2, pixel="u8", border=4), vpp.Pyramid2d((1080, 1920), 3, 2, pixel="u8", border=4)
         grad = vpp.Pyramid2d((1080, 1920), 3, 2, pixel="vfloat2", border=4)
         d_kp = _DeviceBuffer(pts.nbytes).from_host(pts)
         d_flow, d_err = _DeviceBuffer(len(pts) * 8), _DeviceBuffer(len(pts) * 4)
@@ -675,8 +677,7 @@ def gpu_extras(vpp, capi, torch, stream, sp, dev):
         pa, na, ga = prev.desc_array(), nxt.desc_array(), grad.desc_array()
 
         def build():
-            prev.update(I1, sp); nxt.update(I2, sp)
-            grad.update_from_scharr(prev[0], sp)
+            vpp.pyrlk_prepare(I1, I2, prev, nxt, grad, sp)
 
         def lk():
             capi.check(capi.lib.vppb_lk_match_u8(pa, na, ga, C.byref(P), d_kp.ptr, None, len(pts), d_flow.ptr, d_err.ptr, sp))
@@ -694,7 +695,7 @@ def gpu_extras(vpp, capi, torch, stream, sp, dev):
         ms_lk = timed(lk, 10)
         return {"kpts_per_s": len(pts) / ((ms_lk + ms_build) / 1e3), "kpts_per_s_match_only": len(pts) / (ms_lk / 1e3),
                 "ms_match": ms_lk, "ms_pyramids_scharr": ms_build, "parity": ok, "max_rel_err": float(rel.max()),
-                "note": "kpts_per_s includes both u8 pyramids and the Scharr gradient pyramid; parity = failure flags identical and displacement rel. err <= 1e-4 against the oracle "
+                "note": "kpts_per_s includes both u8 pyramids and the Scharr gradient pyramid (vppb_pyrlk_prepare: 9 launches on 3 streams); parity = failure flags identical and displacement rel. err <= 1e-4 against the oracle "
                         "(whose 3-level definition clamps the reads the reference makes outside its border, tests/test_oracle_vs_ref.py)"}
 
     def sdof(H_, W_):

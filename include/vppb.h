@@ -137,6 +137,13 @@ int vppb_lowpass_sub2(const vppb_img* in, const vppb_img* out, int kind, void* s
  * that mirror it.  Needs out->border <= min(out->nrows, out->ncols) (VPPB_E_BORDER otherwise). */
 int vppb_lowpass_sub2_mirror(const vppb_img* in, const vppb_img* out, int kind, void* stream);
 
+/* Everything lucas_kanade() / a pyrlk_match caller builds before matching, in one call: pyramid2d<uchar>::update(i1) -> prev[],
+ * ::update(i2) -> next[], scharr(prev[0], grad[0]) + propagate_level0 -> grad[] (lucas_kanade.hpp:150-157).  prev / next /
+ * grad: nlevels descriptors each (allocated by the caller, borders >= 2 / >= 1).  The three chains run on three streams
+ * forked from and joined back into `stream`. */
+int vppb_pyrlk_prepare(const vppb_img* i1, const vppb_img* i2, const vppb_img* prev, const vppb_img* next, const vppb_img* grad,
+                       int32_t nlevels, int32_t grad_is_float, void* stream);
+
 /* ---- FAST9 (fast.hpp:253-508, 643-799, 889-955) ------------------------------------------- */
 enum { VPPB_FAST_REFERENCE_RING = 0, VPPB_FAST_TRUE_RING = 1 };
 enum { VPPB_FAST_ALL = 0, VPPB_FAST_LOCAL_MAXIMA = 1, VPPB_FAST_BLOCKWISE = 2 };

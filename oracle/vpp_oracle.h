@@ -82,6 +82,8 @@ void vo_lk_match_u8(const vo_img* prev, const vo_img* next, const vo_img* grad, 
                     const vo_float2* kps, const vo_float2* prediction, int n, vo_float2* flow_out, float* err_out);
 
 /* semi_dense_optical_flow.hpp:46-214 + gradient_descent.hh:10-89, serial semantics (oracle/vpp_oracle_sdof.c) */
+/* kitti::flow_error_stats, evaluation/utils/kitti.hh:75-134 */
+int vo_flow_error_stats(const vo_img* flow, const vo_img* ref, float* out, const vo_img* errors_map);
 void vo_semi_dense_flow(const vo_img* i1, const vo_img* i2, const vo_int2* kps, int n, int winsize, int nscales, int min_scale,
                         int propagation, int patchsize, vo_int2* out_pos, int32_t* out_dist, unsigned char* out_valid);
 

@@ -296,3 +296,39 @@ void vo_lk_match_u8(const vo_img* prev, const vo_img* next, const vo_img* grad, 
     err_out[k] = dist;
   }
 }
+
+/* kitti::flow_error_stats (evaluation/utils/kitti.hh:75-134): flow / ref are (nrows x ncols) vfloat3 images (12-byte pixels, channel 2 > 0 =
+ * defined).  out[0..5] = n1, n3, n5, n10 (percent), avg end-point error, density (percent); returns the number of compared vectors.
+ * errors_map (u8, may be NULL) = min(err * 20, 255). */
+int vo_flow_error_stats(const vo_img* flow, const vo_img* ref, float* out, const vo_img* errors_map) {
+  int n = 0, cpt = 0, n1 = 0, n3 = 0, n5 = 0, n10 = 0;
+  float error_sum = 0.f;
+  for (int r = 0; r < flow->nrows; r++)
+    for (int c = 0; c < flow->ncols; c++) {
+      const float* f = (const float*)((const unsigned char*)flow->base + (long long)r * flow->pitch + (long long)c * 12);
+      const float* g = (const float*)((const unsigned char*)ref->base + (long long)r * ref->pitch + (long long)c * 12);
+      if (errors_map) ((unsigned char*)errors_map->base)[(long long)r * errors_map->pitch + c] = 0;
+      if (f[2] > 0.f) cpt++;
+      if (f[2] > 0.f && g[2] > 0.f) {
+        n++;
+        const float d0 = f[0] - g[0], d1 = f[1] - g[1];
+        const float err = sqrtf(d0 * d0 + d1 * d1);
+        error_sum += err;
+        if (err > 1.f) n1++;
+        if (err > 3.f) n3++;
+        if (err > 5.f) n5++;
+        if (err > 10.f) n10++;
+        if (errors_map) {
+          const float m = err * 20.f < 255.f ? err * 20.f : 255.f;
+          ((unsigned char*)errors_map->base)[(long long)r * errors_map->pitch + c] = (unsigned char)m;
+        }
+      }
+    }
+  out[0] = n1 ? 100 * (float)n1 / n : 0;
+  out[1] = n3 ? 100 * (float)n3 / n : 0;
+  out[2] = n5 ? 100 * (float)n5 / n : 0;
+  out[3] = n10 ? 100 * (float)n10 / n : 0;
+  out[4] = error_sum / (n ? n : 1);
+  out[5] = 100.f * (float)cpt / (flow->nrows * flow->ncols);
+  return n;
+}

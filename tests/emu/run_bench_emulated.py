@@ -30,20 +30,21 @@ class Stream:
         pass
 
 
-class Event:
+class Event:  # the emulated kernels run synchronously on the CPU: wall time between two records is their time
     def __init__(self, enable_timing=False):
-        pass
+        self.t = 0.0
 
     def record(self, stream=None):
-        pass
+        import time
+        self.t = time.perf_counter()
 
     def elapsed_time(self, other):
-        return 1.0
+        return (other.t - self.t) * 1e3
 
 
-class Graph:
+class Graph:  # "capture" remembers nothing: install() makes bench.graph_of fall back to the eager step
     def replay(self):
-        pass
+        raise RuntimeError("the stand-in graph cannot replay work")
 
 
 def install(probe_rc, rows, cols):
@@ -63,7 +64,10 @@ def install(probe_rc, rows, cols):
     torch.cuda.current_stream = lambda device=None: cur
     torch.cuda.synchronize = lambda device=None: None
     torch.cuda.Stream, torch.cuda.Event, torch.cuda.CUDAGraph = Stream, Event, Graph
-    torch.cuda.graph = lambda g, **kw: contextlib.nullcontext()
+    def no_capture(g, **kw):
+        raise RuntimeError("no graph capture on the emulator")
+
+    torch.cuda.graph = no_capture
     torch.cuda.stream = lambda s: contextlib.nullcontext()
     real_empty, real_tensor = torch.empty, torch.tensor
 

@@ -50,13 +50,14 @@ def load(omp=False):
         lib.vo_interp_u8.argtypes = [I, C.c_float, C.c_float]
         lib.vo_lk_match_u8.argtypes = [I, I, I, P(VoLkParams), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         lib.vo_semi_dense_flow.argtypes = [I, I, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.vo_flow_error_stats.argtypes = [I, I, C.c_void_p, I]
         lib.vo_num_threads.restype = C.c_int
         _LIBS[key] = lib
     return _LIBS[key]
 
 
 PIXEL_TYPES = {"u8": (np.uint8, 1), "i8": (np.int8, 1), "vuchar3": (np.uint8, 3), "vuchar4": (np.uint8, 4), "i32": (np.int32, 1),
-               "f32": (np.float32, 1), "vint2": (np.int32, 2), "vfloat2": (np.float32, 2)}
+               "f32": (np.float32, 1), "vint2": (np.int32, 2), "vfloat2": (np.float32, 2), "vfloat3": (np.float32, 3)}
 
 
 class HostImage:

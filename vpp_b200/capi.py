@@ -104,6 +104,7 @@ PROTOTYPES = {
     "vppb_scharr_u8_mirror": (C.c_int, [_IMG, _IMG, C.c_int, _VP]),
     "vppb_lowpass_sub2": (C.c_int, [_IMG, _IMG, C.c_int, _VP]),
     "vppb_lowpass_sub2_mirror": (C.c_int, [_IMG, _IMG, C.c_int, _VP]),
+    "vppb_pyrlk_prepare": (C.c_int, [_IMG, _IMG, _IMG, _IMG, _IMG, _I32, _I32, _VP]),
     "vppb_fast9_workspace_bytes": (_I64, [_I32, _I32, _I32]),
     "vppb_fast9_u8": (C.c_int, [_IMG, _I32, _IMG, _I32, _I32, _I32, _VP, _I64, _VP, _VP, _I32, _P(_I32), _VP]),
     "vppb_fast9_u8_async": (C.c_int, [_IMG, _I32, _IMG, _I32, _I32, _I32, _VP, _I64, _VP, _VP, _I32, _VP, _VP]),

@@ -314,14 +314,15 @@ template <int LW> struct BoxStreamCfg {
   static constexpr int SMEM = WARPS * STAGES * STAGE_BYTES + WARPS * STAGES * 8;
 };
 
+template <int NB>
 struct BoxStream {
-  CUtensorMap maps[BX_MAX_BATCH];
-  unsigned char* out_base[BX_MAX_BATCH];
+  CUtensorMap maps[NB];
+  unsigned char* out_base[NB];
   // row tiles (multi-GPU): pixel (0,0) of the tile itself and of the tiles above / below it (NULL: none, the tile's own
   // border rows are the halo).  The neighbours' memory may be a peer GPU's, mapped into this process.
-  const unsigned char* in_base[BX_MAX_BATCH];
-  const unsigned char* up_base[BX_MAX_BATCH];
-  const unsigned char* dn_base[BX_MAX_BATCH];
+  const unsigned char* in_base[NB];
+  const unsigned char* up_base[NB];
+  const unsigned char* dn_base[NB];
   int nimg, out_pitch, nrows, rowbytes, strips, chunks, R, groups, vec_store, total;
   int in_pitch, row_room;   // row_room: addressable bytes of a row from pixel (0,0) to the end of its pitch
   uint32_t one;
@@ -343,8 +344,8 @@ __device__ __noinline__ void box_store_partial(unsigned char* d, const uint32_t*
   for (int k = 0; k < nbytes; k++) d[k] = (unsigned char)(ow[k >> 2] >> ((k & 3) * 8));
 }
 
-template <int CS, int LW, int BAL>
-__global__ void __launch_bounds__(BoxStreamCfg<LW>::WARPS * 32, BoxStreamCfg<LW>::CTAS_PER_SM) k_box5_stream(const __grid_constant__ BoxStream p) {
+template <int CS, int LW, int BAL, int NB>
+__global__ void __launch_bounds__(BoxStreamCfg<LW>::WARPS * 32, BoxStreamCfg<LW>::CTAS_PER_SM) k_box5_stream(const __grid_constant__ BoxStream<NB> p) {
   typedef BoxStreamCfg<LW> Cfg;
   constexpr int NW = LW + 4;  // words of a lane's window: 2 left + LW own + 2 right
   extern __shared__ __align__(128) unsigned char smem[];
@@ -362,12 +363,21 @@ __global__ void __launch_bounds__(BoxStreamCfg<LW>::WARPS * 32, BoxStreamCfg<LW>
   }
   __syncwarp();
 
-  // producer cursor (meaningful in lane 0 only): next (task, group of 5 rows) to fetch and the stage it goes to
-  int ptask = gw, pgrp = 0, pslot = 0;
+  // producer cursor (meaningful in lane 0 only): next (task, group of 5 rows) to fetch and the stage it goes to; the task's
+  // coordinates are decoded once per task, not per stage
+  int ptask = gw, pgrp = 0, pslot = 0, pimg = 0, pchunk = 0, pstrip = 0;
+  auto decode = [&]() {
+    if (ptask < p.total) {
+      pimg = ptask / per_img;
+      const int rem = ptask - pimg * per_img;
+      pchunk = rem / p.strips;
+      pstrip = rem - pchunk * p.strips;
+    }
+  };
+  decode();
   auto produce = [&]() {
     if (ptask < p.total) {
-      const int img = ptask / per_img, rem = ptask - img * per_img;
-      const int chunk = rem / p.strips, strip = rem - chunk * p.strips;
+      const int img = pimg, chunk = pchunk, strip = pstrip;
       const int ty = chunk * p.R + pgrp * BS_K;  // first row of the stage, counted from image row -2
       const unsigned char* up = p.up_base[img];
       const unsigned char* dn = p.dn_base[img];
@@ -394,7 +404,7 @@ __global__ void __launch_bounds__(BoxStreamCfg<LW>::WARPS * 32, BoxStreamCfg<LW>
         // tensor origin = 16 bytes left of x = 0 and 2 rows above y = 0; 8-byte elements (x coordinate * 8 is a multiple of 16)
         tma_load_2d(ring + pslot * Cfg::STAGE_BYTES, &p.maps[img], strip * (Cfg::STRIP / 8), ty, &bars[pslot]);
       }
-      if (++pgrp == p.groups) { pgrp = 0; ptask += nw; }
+      if (++pgrp == p.groups) { pgrp = 0; ptask += nw; decode(); }
     }
     pslot = (pslot + 1 == Cfg::STAGES) ? 0 : pslot + 1;
   };
@@ -422,6 +432,7 @@ __global__ void __launch_bounds__(BoxStreamCfg<LW>::WARPS * 32, BoxStreamCfg<LW>
       for (int j = 0; j < BS_K; j++) { rE[j][q] = 0; rO[j][q] = 0; }
     }
 
+    unsigned char* drow = dst - 4LL * p.out_pitch;  // where the row completed by input row 0 would go; advanced once per input row
     for (int g = 0; g < p.groups; g++) {
       mbar_wait(&bars[cslot], parity);
       const unsigned char* st = ring + cslot * Cfg::STAGE_BYTES + lane * (4 * LW);
@@ -468,13 +479,14 @@ __global__ void __launch_bounds__(BoxStreamCfg<LW>::WARPS * 32, BoxStreamCfg<LW>
           rO[j][q] = ho;
         }
         const int row = g * BS_K + j;  // input row of the task (0 = image row y0 - 2)
+        if (j > 0 || g > 0) drow += p.out_pitch;
         if (row >= 4) {
           const int y = y0 + row - 4;
           if (y < yend && nbytes > 0) {
             uint32_t ow[LW];
 #pragma unroll
             for (int q = 0; q < LW; q++) ow[q] = BAL ? box_div_pack_hi(SE[q], SO[q], shl16) : box_div_pack(SE[q], SO[q]);
-            unsigned char* d = dst + (long long)(row - 4) * p.out_pitch;
+            unsigned char* d = drow;
             if (full) {
 #pragma unroll
               for (int v = 0; v < LW / 4; v++)
@@ -558,8 +570,8 @@ static int box_stream_rows(long long strips_x_imgs, int nrows, int warps_per_sm,
 }
 
 // n equally shaped, TMA-eligible images (n <= BX_MAX_BATCH) in one launch of the streaming kernel
-template <int CS, int LW, int BAL>
-static int box5_stream_launch_lw(const vppb_img* ins, const vppb_img* ups, const vppb_img* dns, const vppb_img* outs, int n, cudaStream_t st, const char* name) {
+template <int CS, int LW, int BAL, int NB>
+static int box5_stream_launch_nb(const vppb_img* ins, const vppb_img* ups, const vppb_img* dns, const vppb_img* outs, int n, cudaStream_t st, const char* name) {
   typedef BoxStreamCfg<LW> Cfg;
   const int rowbytes = ins[0].ncols * CS, nrows = ins[0].nrows;
   static std::atomic<unsigned long long> attr_done{0};
@@ -567,10 +579,10 @@ static int box5_stream_launch_lw(const vppb_img* ins, const vppb_img* ups, const
   VPPB_CUDA(cudaGetDevice(&dev));
   const unsigned long long bit = 1ULL << (dev & 63);
   if (!(attr_done.load(std::memory_order_acquire) & bit)) {
-    VPPB_CUDA(cudaFuncSetAttribute(k_box5_stream<CS, LW, BAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    VPPB_CUDA(cudaFuncSetAttribute(k_box5_stream<CS, LW, BAL, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
     attr_done.fetch_or(bit, std::memory_order_release);
   }
-  BoxStream p;
+  BoxStream<NB> p;
   memset(&p, 0, sizeof(p));
   p.nimg = n;
   p.out_pitch = outs[0].pitch;
@@ -601,9 +613,18 @@ static int box5_stream_launch_lw(const vppb_img* ins, const vppb_img* ups, const
     p.row_room = ins[0].pitch - (int)bs;
   }
   const int ctas = (p.total + Cfg::WARPS - 1) / Cfg::WARPS, resident = sm_count() * Cfg::CTAS_PER_SM;
-  k_box5_stream<CS, LW, BAL><<<ctas < resident ? ctas : resident, Cfg::WARPS * 32, Cfg::SMEM, st>>>(p);
+  k_box5_stream<CS, LW, BAL, NB><<<ctas < resident ? ctas : resident, Cfg::WARPS * 32, Cfg::SMEM, st>>>(p);
   VPPB_LAUNCH_CHECK(name);
   return VPPB_OK;
+}
+
+// the kernel parameters carry one tensor map per image: a single image travels with a 1-entry block (launching a kernel
+// with kilobytes of parameters costs microseconds), batches with 32
+template <int CS, int LW, int BAL>
+static int box5_stream_launch_lw(const vppb_img* ins, const vppb_img* ups, const vppb_img* dns, const vppb_img* outs, int n, cudaStream_t st, const char* name) {
+  if (n == 1) return box5_stream_launch_nb<CS, LW, BAL, 1>(ins, ups, dns, outs, n, st, name);
+  if (n <= 4) return box5_stream_launch_nb<CS, LW, BAL, 4>(ins, ups, dns, outs, n, st, name);
+  return box5_stream_launch_nb<CS, LW, BAL, BX_MAX_BATCH>(ins, ups, dns, outs, n, st, name);
 }
 
 template <int CS>

@@ -78,6 +78,6 @@ __device__ __forceinline__ int ld_acquire(const int* p) {
   return v;
 }
 __device__ __forceinline__ void st_release(int* p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
-__device__ __forceinline__ void spin_pause() { __nanosleep(40); }
+__device__ __forceinline__ void spin_pause() { __nanosleep(20); }
 
 }  // namespace vppb

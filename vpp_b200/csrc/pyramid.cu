@@ -375,4 +375,49 @@ static int lowpass_sub2(const vppb_img* in, const vppb_img* out, int kind, int m
 int vppb_lowpass_sub2(const vppb_img* in, const vppb_img* out, int kind, void* stream) { return lowpass_sub2(in, out, kind, 0, stream); }
 int vppb_lowpass_sub2_mirror(const vppb_img* in, const vppb_img* out, int kind, void* stream) { return lowpass_sub2(in, out, kind, 1, stream); }
 
+
+// pyramid2d<uchar> of two frames + the Scharr gradient pyramid of the first (what lucas_kanade.hpp:150-157 and every
+// pyrlk_match caller build before matching: pyramid2d::update(i1), ::update(i2), scharr(prev[0], grad[0]),
+// grad.propagate_level0()).  Nine small launches; the three chains (prev levels, next levels, gradient levels) are
+// independent after the copy of frame 1, so they are queued on three streams (fork / join with events on `stream`, also
+// valid inside a stream capture): the critical path is 4 launches instead of 9.
+int vppb_pyrlk_prepare(const vppb_img* i1, const vppb_img* i2, const vppb_img* prev, const vppb_img* next, const vppb_img* grad, int32_t nlevels,
+                       int32_t grad_is_float, void* stream) {
+  VPPB_REQUIRE(i1 && i2 && prev && next && grad && nlevels >= 1 && nlevels <= 16, VPPB_E_ARG, "vppb_pyrlk_prepare: bad argument");
+  static thread_local cudaStream_t side[2] = {nullptr, nullptr};
+  static thread_local cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  static thread_local int side_dev = -1;
+  int dev = 0;
+  VPPB_CUDA(cudaGetDevice(&dev));
+  if (side_dev != dev) {
+    for (int k = 0; k < 2; k++) VPPB_CUDA(cudaStreamCreateWithFlags(&side[k], cudaStreamNonBlocking));
+    for (int k = 0; k < 4; k++) VPPB_CUDA(cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming));
+    side_dev = dev;
+  }
+  cudaStream_t st = as_stream(stream);
+  const int gk = grad_is_float ? 2 : 1;
+  int rc;
+  // fork: frame 2's pyramid on side[1]
+  VPPB_CUDA(cudaEventRecord(ev[0], st));
+  VPPB_CUDA(cudaStreamWaitEvent(side[1], ev[0], 0));
+  if ((rc = vppb_copy2d_mirror(i2, &next[0], side[1]))) return rc;
+  for (int l = 1; l < nlevels; l++)
+    if ((rc = vppb_lowpass_sub2_mirror(&next[l - 1], &next[l], 0, side[1]))) return rc;
+  VPPB_CUDA(cudaEventRecord(ev[1], side[1]));
+  // frame 1: level 0, then the gradient chain forks on side[0]
+  if ((rc = vppb_copy2d_mirror(i1, &prev[0], st))) return rc;
+  VPPB_CUDA(cudaEventRecord(ev[2], st));
+  VPPB_CUDA(cudaStreamWaitEvent(side[0], ev[2], 0));
+  if ((rc = vppb_scharr_u8_mirror(&prev[0], &grad[0], grad_is_float, side[0]))) return rc;
+  for (int l = 1; l < nlevels; l++)
+    if ((rc = vppb_lowpass_sub2_mirror(&grad[l - 1], &grad[l], gk, side[0]))) return rc;
+  VPPB_CUDA(cudaEventRecord(ev[3], side[0]));
+  for (int l = 1; l < nlevels; l++)
+    if ((rc = vppb_lowpass_sub2_mirror(&prev[l - 1], &prev[l], 0, st))) return rc;
+  // join
+  VPPB_CUDA(cudaStreamWaitEvent(st, ev[1], 0));
+  VPPB_CUDA(cudaStreamWaitEvent(st, ev[3], 0));
+  return VPPB_OK;
+}
+
 }  // extern "C"

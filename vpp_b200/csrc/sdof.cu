@@ -155,56 +155,55 @@ __global__ void __launch_bounds__(128) k_sdof_prop_wave(SdofLevel L, int t, int 
 // ---- dataflow schedule of a sweep (default): ONE persistent launch per sweep ----------------------------------------
 // Only marked cells do anything in a sweep and a marked cell only reads its marked 8-neighbours, so the Gauss-Seidel order
 // is a partial order on the marked cells: (kr, kc) must come after its marked predecessors (kr, kc-1), (kr-1, kc-1..kc+1)
-// and before its marked successors.  Warps draw chunks of 32 consecutive iterations of the sweep's raster order from a
-// ticket counter, walk the marked ones in order, and for each one wait until the `done` flag of its marked predecessors
-// carries this sweep's number (acquire loads at GPU scope), do the iteration, and publish their own flag (release store).
-// Every predecessor lives in the same chunk (done earlier by this very warp) or in a chunk with a smaller ticket, which a
-// running warp already holds: no deadlock.  The critical path is the longest chain of adjacent marked cells times one
-// flag hop, instead of (columns + 2 rows) kernel launches.
+// and before its marked successors.  Warps draw iterations from a ticket counter in WAVEFRONT order (anti-diagonal
+// t = kc + 2 kr, then kr): consecutive tickets are independent iterations, so as many warps as a diagonal has marked cells
+// work at once.  Before its iteration a warp waits until the `done` flag of every marked predecessor carries this sweep's
+// number (acquire loads at GPU scope), afterwards it publishes its own flag (release store).  Every predecessor sits on an
+// earlier diagonal, i.e. holds a smaller ticket, which a running warp already owns: no deadlock.  The critical path is
+// the longest chain of adjacent marked cells times one flag hop, instead of (columns + 2 rows) kernel launches.
 __global__ void __launch_bounds__(128) k_sdof_sweep(SdofLevel L, int forward, int nkr, int nkc, int patch, int ws, int epoch, int* ticket) {
   const int lane = threadIdx.x & 31;
   const int inr = L.i1.nrows, inc = L.i1.ncols;
-  const int total = nkr * nkc, nchunks = (total + 31) / 32;
+  const int total = nkr * nkc;
   const int sgn = forward ? 1 : -1;  // a step of +1 in sweep coordinates is a step of sgn in cell coordinates
+  // wavefront order: diagonal t holds the iterations kr in [lo(t), hi(t)], lo = max(0, ceil((t - nkc + 1) / 2)), hi = min(nkr - 1, t / 2).
+  // first(t) = number of iterations on the diagonals before t, in closed form for the three regimes of the band
+  // (growing, full width, shrinking) would need case analysis: a warp instead walks the diagonals incrementally - its
+  // tickets only grow.
+  int t = 0, first = 0;  // current diagonal and the ticket of its first iteration
+  auto diag_len = [&](int tt) {
+    const int lo = max(0, (tt - (nkc - 1) + 1) / 2), hi = min(nkr - 1, tt / 2);
+    return hi >= lo ? hi - lo + 1 : 0;
+  };
   for (;;) {
-    int t = 0;
-    if (lane == 0) t = atomicAdd(ticket, 1);
-    t = __shfl_sync(FULLM, t, 0);
-    if (t >= nchunks) break;
-    const int i = t * 32 + lane;
-    int kr = 0, kc = 0, cell = -1;
-    bool marked = false;
-    if (i < total) {
-      kr = i / nkc; kc = i - kr * nkc;
-      const int r = forward ? kr * patch : inr - 1 - kr * patch, c = forward ? kc * patch : inc - 1 - kc * patch;
-      cell = (r / patch) * L.cstride + (c / patch);
-      marked = L.mark[cell] != 0;  // marks only go from 2 to 1 during the sweeps: "marked" never changes
+    int i = 0;
+    if (lane == 0) i = atomicAdd(ticket, 1);
+    i = __shfl_sync(FULLM, i, 0);
+    if (i >= total) break;
+    int len = diag_len(t);
+    while (i >= first + len) { first += len; t++; len = diag_len(t); }  // warp-uniform
+    const int kr = max(0, (t - (nkc - 1) + 1) / 2) + (i - first), kc = t - 2 * kr;
+    const int r = forward ? kr * patch : inr - 1 - kr * patch, c = forward ? kc * patch : inc - 1 - kc * patch;
+    const int fr = r / patch, fc = c / patch;
+    const int cell = fr * L.cstride + fc;
+    if (!L.mark[cell]) continue;  // marks only go from 2 to 1 during the sweeps: "marked" never changes
+    // lanes 0..3 watch one predecessor each
+    if (lane < 4) {
+      const int pr = lane == 0 ? fr : fr - sgn, pc = lane == 0 ? fc - sgn : fc + (lane - 2) * sgn;
+      // the predecessor must be an iteration of the sweep (inside the cell map AND inside the sweep's kr / kc range)
+      const int pkr = lane == 0 ? kr : kr - 1, pkc = lane == 0 ? kc - 1 : kc + (lane - 2);
+      if (pkr >= 0 && pkc >= 0 && pkc < nkc && pr >= 0 && pr < L.cr && pc >= 0 && pc < L.cc) {
+        const int pcell = pr * L.cstride + pc;
+        if (L.mark[pcell])
+          while (ld_acquire(&L.done[pcell]) < epoch) spin_pause();
+      }
     }
-    unsigned todo = __ballot_sync(FULLM, marked);
-    while (todo) {
-      const int src = __ffs(todo) - 1;
-      todo &= todo - 1;
-      const int ckr = __shfl_sync(FULLM, kr, src), ckc = __shfl_sync(FULLM, kc, src), ccell = __shfl_sync(FULLM, cell, src);
-      // lanes 0..3 watch one predecessor each
-      if (lane < 4) {
-        const int r = forward ? ckr * patch : inr - 1 - ckr * patch, c = forward ? ckc * patch : inc - 1 - ckc * patch;
-        const int fr = r / patch, fc = c / patch;
-        const int pr = lane == 0 ? fr : fr - sgn, pc = lane == 0 ? fc - sgn : fc + (lane - 2) * sgn;
-        // the predecessor must be an iteration of the sweep (inside the cell map AND inside the sweep's kr/kc range)
-        const int pkr = lane == 0 ? ckr : ckr - 1, pkc = lane == 0 ? ckc - 1 : ckc + (lane - 2);
-        if (pkr >= 0 && pkc >= 0 && pkc < nkc && pr >= 0 && pr < L.cr && pc >= 0 && pc < L.cc) {
-          const int pcell = pr * L.cstride + pc;
-          if (L.mark[pcell])
-            while (ld_acquire(&L.done[pcell]) < epoch) spin_pause();
-        }
-      }
-      __syncwarp();
-      sdof_prop_cell(L, ckr, ckc, forward, patch, ws, lane);
-      __syncwarp();
-      if (lane == 0) {
-        __threadfence();
-        st_release(&L.done[ccell], epoch);
-      }
+    __syncwarp();
+    sdof_prop_cell(L, kr, kc, forward, patch, ws, lane);
+    __syncwarp();
+    if (lane == 0) {
+      __threadfence();
+      st_release(&L.done[cell], epoch);
     }
   }
 }
@@ -385,7 +384,7 @@ int vppb_sdof_u8(const vppb_img* pyr1, const vppb_img* pyr2, const vppb_sdof_par
       const int forward = Ki % 2;  // :191-200: odd iterations forward, even (incl. the first) backward
       const int waves = nkc + 2 * (nkr - 1);
       if (use_dataflow) {
-        const int chunks = (nkr * nkc + 31) / 32, blocks = (chunks + 3) / 4;
+        const int blocks = (nkr * nkc + 3) / 4;
         k_sdof_sweep<<<blocks < sms * 8 ? blocks : sms * 8, 128, 0, st>>>(Ls, forward, nkr, nkc, p->patchsize, p->winsize, Ki + 1, tickets + scale * p->propagation + Ki);
         continue;
       }

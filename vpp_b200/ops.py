@@ -278,14 +278,21 @@ def lucas_kanade(i1, i2, keypoints, niterations=21, winsize=11, nscales=3, min_e
     winsize < 5 gives the pyramids a border < 2, which the reference's 5-tap low-pass reads past (undefined values
     there); here that raises VppbError(VPPB_E_BORDER) instead."""
     border = winsize // 2
-    prev = Pyramid2d(i1, nscales, 2, border=border)
-    nxt = Pyramid2d(i2, nscales, 2, border=border)
+    prev = Pyramid2d((i1.nrows, i1.ncols), nscales, 2, pixel="u8", border=border)
+    nxt = Pyramid2d((i1.nrows, i1.ncols), nscales, 2, pixel="u8", border=border)
     grad = Pyramid2d((i1.nrows, i1.ncols), nscales, 2, pixel="vint2", border=border)
-    grad.update_from_scharr(prev[0], stream)
+    pyrlk_prepare(i1, i2, prev, nxt, grad, stream)
     P = capi.VppbLkParams(nlevels=nscales, min_scale=0, winsize=winsize, max_iter=niterations, grad_is_float=0,
                           err_mode=capi.LK_ERR_SAD, gate_on_max_err=0, min_ev=float(int(min_ev)), delta=float(int(delta)),
                           max_err=0.0, factor=2.0, pred_div=float(2 ** nscales))
     return _lk_run(prev, nxt, grad, P, keypoints, prediction, stream)
+
+
+def pyrlk_prepare(i1, i2, prev, nxt, grad, stream=None):
+    """The two u8 pyramids and the Scharr gradient pyramid of frame 1 (lucas_kanade.hpp:150-157) in one call: three
+    independent chains of launches on three streams (vppb_pyrlk_prepare)."""
+    check(lib.vppb_pyrlk_prepare(i1.ptr(), i2.ptr(), prev.desc_array(), nxt.desc_array(), grad.desc_array(), len(prev),
+                                 1 if grad.pixel == "vfloat2" else 0, stream))
 
 
 def pyrlk_match(pyr_prev, pyr_prev_grad, pyr_next, keypoints, winsize, min_ev, max_err, max_iteration, convergence_delta,
