@@ -223,6 +223,29 @@ int vppb_halo_unpack(const vppb_img* img, int32_t halo, int which, const void* s
 int vppb_halo_pack_batch(const vppb_img* imgs, int32_t n, int32_t halo, int which, void* staging, void* stream);
 int vppb_halo_unpack_batch(const vppb_img* imgs, int32_t n, int32_t halo, int which, const void* staging, void* stream);
 
+/* ---- device-resident keypoint_container + trajectories (keypoint_container.hpp:22-200, keypoint_trajectory.hh:11-73) ---- */
+/* The container of video_extruder_update (video_extruder.hpp:45-133) kept in HBM: every step of the update loop is a kernel
+ * with the reference's serial semantics (see vpp_b200/csrc/kpc.cu); the host only keeps the entry count. */
+int vppb_kpc_create(int32_t capacity, int32_t max_trajectory_length, void** handle);
+int vppb_kpc_destroy(void* handle);
+int32_t vppb_kpc_size(void* handle);                       /* entries, dead ones included (host copy) */
+const vppb_int2* vppb_kpc_positions(void* handle);         /* DEVICE array of the entries' positions: the keypoints handed to vppb_sdof_u8 */
+/* flow callback of :45-56: entry i moves to new_pos[i] (velocity, age + 1) if valid[i] and inside the frame, is removed if outside */
+int vppb_kpc_flow_update(void* handle, const vppb_int2* new_pos, const unsigned char* valid, int32_t nrows, int32_t ncols, void* stream);
+/* :59-84 merge on the keypoint_spacing grid, the older entry of a cell survives */
+int vppb_kpc_merge(void* handle, int32_t nrows, int32_t ncols, int32_t spacing, void* stream);
+/* :87-91 remove entries whose fast9_score(img, th, position) < min_score (3 in the reference); img: u8, border >= 3 */
+int vppb_kpc_score_filter(void* handle, const vppb_img* img, int32_t th, int32_t min_score, void* stream);
+/* :97-109 detector mask: 1 everywhere (border included), 0 in [-spacing, spacing)^2 around every entry; mask: u8, border >= spacing */
+int vppb_kpc_paint_mask(void* handle, const vppb_img* mask, int32_t spacing, void* stream);
+/* :111-118 add(detections) + compact() + sync_attributes(trajectories, keypoint_trajectory(frame_id)); detections / count as
+ * vppb_fast9_u8_async leaves them on the device.  Reads the new entry count back (the one host synchronisation of a frame). */
+int vppb_kpc_add_and_compact(void* handle, const vppb_int2* detections, const int32_t* det_count_dev, int32_t max_detections, int32_t frame_id, void* stream);
+/* :122-133 alive entries push their position (oldest dropped beyond max_trajectory_length), dead entries' trajectories die */
+int vppb_kpc_trajectories_update(void* handle, void* stream);
+/* 6 ints per entry into a DEVICE buffer: row, col, age, trajectory start frame, trajectory length, trajectory alive */
+int vppb_kpc_state_table(void* handle, int32_t* table_dev, void* stream);
+
 /* ---- multi-GPU row tiles, peer memory ----------------------------------------------------- */
 /* Frames shard by contiguous row tiles, one tile per GPU (the reference's only parallelism is OpenMP over
  * rows, vpp/core/pixel_wise.hpp:85-105).  A tile is an image2d whose border rows above / below are its halo.

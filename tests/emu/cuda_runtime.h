@@ -54,6 +54,7 @@ inline cudaError_t cudaMalloc(void** p, size_t n) { return posix_memalign(p, 256
 template <typename T> inline cudaError_t cudaMalloc(T** p, size_t n) { void* q = nullptr; cudaError_t e = cudaMalloc(&q, n); *p = static_cast<T*>(q); return e; }
 inline cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }  // cudaFree(0) == free(NULL)
 inline cudaError_t cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) { memset(p, v, n); return cudaSuccess; }
+inline cudaError_t cudaMemset(void* p, int v, size_t n) { memset(p, v, n); return cudaSuccess; }
 inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, int, cudaStream_t) { memcpy(d, s, n); return cudaSuccess; }
 inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
 typedef void* cudaEvent_t;

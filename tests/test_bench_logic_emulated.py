@@ -30,9 +30,11 @@ def test_bench_single_gpu_control_flow(built):
     for key in KEYS + ("cpu_baseline",):
         assert key in line, key
     assert line["parity_checked"] is True
-    assert line["config"]["frames_per_step"] == 64 and line["gpu_launches"] == 3 * 2
-    assert line["roofline"]["algorithmic_bytes_per_launch"] == 6.0 * 48 * 400 * 32
-    assert line["e2e"]["h2d_bytes_per_step"] == 64 * 48 * 400 * 3 and line["e2e"]["d2h_bytes_per_step"] == 64 * 48 * 400 * 3
+    nb = line["config"]["resident_frames"]
+    assert nb == 128 and line["config"]["frames_per_step"] == 2 * nb and line["gpu_launches"] == 3 * 2
+    assert line["roofline"]["algorithmic_bytes_per_launch"] == 6.0 * 48 * 400 * nb
+    ef = line["e2e"]["frames_per_e2e_step"]
+    assert line["e2e"]["h2d_bytes_per_step"] == ef * 48 * 400 * 3 and line["e2e"]["d2h_bytes_per_step"] == ef * 48 * 400 * 3
     assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
 
 

@@ -103,3 +103,5 @@ test_semi_dense_flow_level_schedule = L.test_semi_dense_flow_level_schedule
 test_fast9_wide_images_multibox = L.test_fast9_wide_images_multibox
 test_fast9_threshold_extremes = L.test_fast9_threshold_extremes
 test_box5x5_row_tiles_read_neighbours = L.test_box5x5_row_tiles_read_neighbours
+test_video_extruder_device_container_equals_reference_tables = L.test_video_extruder_device_container_equals_reference_tables
+test_video_extruder_device_container_merge_cases = L.test_video_extruder_device_container_merge_cases

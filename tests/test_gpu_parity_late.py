@@ -316,3 +316,71 @@ def test_box5x5_row_tiles_read_neighbours(vpp, pix, ntiles, rows, cols):
         o = vpp.Image2d(rows, cols, pix)
         capi.check(fn(C.byref(ins[t]), C.byref(ups[t]), C.byref(dns[t]), o.ptr(), 1, None))
         assert np.array_equal(o.download(), want[t * rows:(t + 1) * rows]), "single tile %d" % t
+
+
+# ------------------------------------------------------------------ video_extruder with the keypoint container in HBM (N3)
+@pytest.mark.parametrize("tag,nframes,th", [("7f_th4", 7, 4), ("9f_th5", 9, 5)])
+def test_video_extruder_device_container_equals_reference_tables(vpp, tag, nframes, th):
+    """video_extruder_update_device: container, merge grid, score filter, detector mask, add / compact and trajectories are kernels
+    (vppb_kpc_*).  Frame by frame its table equals the host orchestration's (which equals the oracle's), and the final table equals
+    the one the REFERENCE's own video_extruder_update produced on the committed eventful sequence."""
+    from vpp_b200 import video_extruder as ve
+
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    frames = np.fromfile(os.path.join(gold, "video_extruder_frames_9x121x161.u8"), np.uint8).reshape(9, 121, 161)
+    expected = np.fromfile(os.path.join(gold, "video_extruder_expected_%s.i32" % tag), np.int32).reshape(-1, 6)
+    kw = dict(detector_th=th, keypoint_spacing=10, detector_period=3, nscales=3, winsize=9, propagation=2)
+    d, g = ve.DeviceVideoExtruderCtx(121, 161, max_trajectory_length=5), ve.video_extruder_init(121, 161)
+    gops = ve.GpuOps()
+    for f in range(1, nframes):
+        ve.video_extruder_update_device(d, frames[f - 1], frames[f], **kw)
+        ve.video_extruder_update(g, frames[f - 1], frames[f], gops, max_trajectory_length=5, **kw)
+        assert np.array_equal(ve.device_state_table(d), ve.state_table(g)), "frame %d" % f
+    assert np.array_equal(ve.device_state_table(d), expected)
+
+
+def test_video_extruder_device_container_merge_cases(vpp):
+    """The merge rule on hand-made containers (ages and cell sharing chosen to hit every branch: older arrives later, younger
+    arrives later, ties, dead entries in the cell) against a direct transcription of video_extruder.hpp:59-84."""
+    import ctypes as C
+
+    from vpp_b200 import capi, video_extruder as ve
+    from vpp_b200.ops import _DeviceBuffer
+
+    r = rng(4242)
+    for trial in range(20):
+        n = int(r.integers(1, 60))
+        pos = np.stack([r.integers(0, 40, n), r.integers(0, 50, n)], 1).astype(np.int32)
+        age = r.integers(0, 4, n).astype(np.int32)
+        ctx = ve.DeviceVideoExtruderCtx(40, 50, capacity=128, max_trajectory_length=3)
+        det, cnt = _DeviceBuffer(pos.nbytes).from_host(pos), _DeviceBuffer(4).from_host(np.array([n], np.int32))
+        capi.check(capi.lib.vppb_kpc_add_and_compact(ctx.handle, det.ptr, cnt.ptr, n, 0, None))  # all enter with age 1 ...
+        assert capi.lib.vppb_kpc_size(ctx.handle) == n
+        # ... then the ages are set through the flow step: entry i "moves in place" age[i] - 1 times, or is removed (target age 0)
+        far = np.full((n, 2), -5, np.int32)
+        for k in range(1, 4):
+            newpos = np.where((age == 0)[:, None], far, pos).astype(np.int32)
+            v = ((age == 0) | (age > k)).astype(np.uint8) if k == 1 else (age > k).astype(np.uint8)
+            a, b = _DeviceBuffer(newpos.nbytes).from_host(newpos), _DeviceBuffer(n).from_host(v)
+            capi.check(capi.lib.vppb_kpc_flow_update(ctx.handle, a.ptr, b.ptr, 40, 50, None))
+        cur = age.copy()
+        tab = _DeviceBuffer(n * 24)
+        capi.check(capi.lib.vppb_kpc_state_table(ctx.handle, tab.ptr, None))
+        got_age = tab.to_host(np.int32, n * 6).reshape(-1, 6)[:, 2]
+        assert np.array_equal(got_age, cur), (got_age, cur)
+        # reference merge, transcribed
+        want, idx = cur.copy(), {}
+        for i in range(n):
+            cell = (pos[i, 0] // 10, pos[i, 1] // 10)
+            j = idx.get(cell, -1)
+            if j >= 0:
+                other = want[j]
+                if other < want[i]:
+                    want[j] = 0; idx[cell] = i
+                if other > want[i]:
+                    want[i] = 0
+            else:
+                idx[cell] = i
+        capi.check(capi.lib.vppb_kpc_merge(ctx.handle, 40, 50, 10, None))
+        capi.check(capi.lib.vppb_kpc_state_table(ctx.handle, tab.ptr, None))
+        assert np.array_equal(tab.to_host(np.int32, n * 6).reshape(-1, 6)[:, 2], want), trial

@@ -117,6 +117,17 @@ PROTOTYPES = {
     "vppb_halo_unpack": (C.c_int, [_IMG, _I32, C.c_int, _VP, _VP]),
     "vppb_halo_pack_batch": (C.c_int, [_IMG, _I32, _I32, C.c_int, _VP, _VP]),
     "vppb_halo_unpack_batch": (C.c_int, [_IMG, _I32, _I32, C.c_int, _VP, _VP]),
+    "vppb_kpc_create": (C.c_int, [_I32, _I32, _P(_VP)]),
+    "vppb_kpc_destroy": (C.c_int, [_VP]),
+    "vppb_kpc_size": (_I32, [_VP]),
+    "vppb_kpc_positions": (_VP, [_VP]),
+    "vppb_kpc_flow_update": (C.c_int, [_VP, _VP, _VP, _I32, _I32, _VP]),
+    "vppb_kpc_merge": (C.c_int, [_VP, _I32, _I32, _I32, _VP]),
+    "vppb_kpc_score_filter": (C.c_int, [_VP, _IMG, _I32, _I32, _VP]),
+    "vppb_kpc_paint_mask": (C.c_int, [_VP, _IMG, _I32, _VP]),
+    "vppb_kpc_add_and_compact": (C.c_int, [_VP, _VP, _VP, _I32, _I32, _VP]),
+    "vppb_kpc_trajectories_update": (C.c_int, [_VP, _VP]),
+    "vppb_kpc_state_table": (C.c_int, [_VP, _VP, _VP]),
     "vppb_box5x5_u8c3_tiles": (C.c_int, [_IMG, _IMG, _IMG, _IMG, _I32, _VP]),
     "vppb_box5x5_u8_tiles": (C.c_int, [_IMG, _IMG, _IMG, _IMG, _I32, _VP]),
     "vppb_ipc_export": (C.c_int, [_IMG, _VP, _P(_I64)]),

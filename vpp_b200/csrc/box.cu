@@ -304,6 +304,7 @@ __global__ void __launch_bounds__(BX_THREADS, BX_TH == 16 ? 4 : 6) k_box5_bytes_
 // The packed-lane additions are split between the ALU pipe (IADD3 / PRMT / LOP3, the busier one) and the FMA pipe
 // (IMAD with a run-time multiplier of 1, which ptxas cannot fold back into an IADD3).
 constexpr int BS_K = 5;  // rows per stage == rows of the vertical window
+constexpr int BS_MAX_BATCH = 128;  // images per launch of the streaming kernel (their tensor maps travel in the 32 KB kernel parameter space)
 template <int LW> struct BoxStreamCfg {
   static constexpr int STRIP = 32 * 4 * LW;          // output bytes per warp row
   static constexpr int BOXW = STRIP + 32;            // bytes per box row
@@ -624,7 +625,8 @@ template <int CS, int LW, int BAL>
 static int box5_stream_launch_lw(const vppb_img* ins, const vppb_img* ups, const vppb_img* dns, const vppb_img* outs, int n, cudaStream_t st, const char* name) {
   if (n == 1) return box5_stream_launch_nb<CS, LW, BAL, 1>(ins, ups, dns, outs, n, st, name);
   if (n <= 4) return box5_stream_launch_nb<CS, LW, BAL, 4>(ins, ups, dns, outs, n, st, name);
-  return box5_stream_launch_nb<CS, LW, BAL, BX_MAX_BATCH>(ins, ups, dns, outs, n, st, name);
+  if (n <= 32) return box5_stream_launch_nb<CS, LW, BAL, 32>(ins, ups, dns, outs, n, st, name);
+  return box5_stream_launch_nb<CS, LW, BAL, BS_MAX_BATCH>(ins, ups, dns, outs, n, st, name);
 }
 
 template <int CS>
@@ -651,7 +653,15 @@ static int box5_bytes(const vppb_img* in, const vppb_img* out, void* stream, con
   VPPB_REQUIRE(in->border >= 2, VPPB_E_BORDER, "%s: input border %d < 2", name, in->border);
   cudaStream_t st = as_stream(stream);
   const int rowbytes = in->ncols * CS;
-  if (tma_eligible(in) && box_use_stream()) return box5_stream_launch<CS>(in, nullptr, nullptr, out, 1, st, name);
+  // one frame per launch: below ~8 tasks per resident warp the launch is dominated by fixed costs, where the CTA tile kernel
+  // (one TMA box per CTA) is ~2 us cheaper; the per-warp streaming kernel wins as soon as the launch has real work (batches, 8K)
+  static int single_policy = -1;
+  if (single_policy < 0) {
+    const char* e = getenv("VPPB_BOX_SINGLE");
+    single_policy = (e && !strcmp(e, "stream")) ? 1 : 0;
+  }
+  const bool small = (long long)rowbytes * in->nrows < 96LL * 1024 * 1024;
+  if (tma_eligible(in) && box_use_stream() && (single_policy == 1 || !small)) return box5_stream_launch<CS>(in, nullptr, nullptr, out, 1, st, name);
   if (tma_eligible(in)) {
     CUtensorMap tmap;
     unsigned char* origin = static_cast<unsigned char*>(in->base) - 2LL * in->pitch - 16;
@@ -716,8 +726,8 @@ static int box5_bytes_batch(const vppb_img* ins, const vppb_img* outs, int n, vo
   }
   cudaStream_t st = as_stream(stream);
   if (box_use_stream()) {
-    for (int i0 = 0; i0 < n; i0 += BX_MAX_BATCH) {
-      int rc = box5_stream_launch<CS>(ins + i0, nullptr, nullptr, outs + i0, std::min(BX_MAX_BATCH, n - i0), st, name);
+    for (int i0 = 0; i0 < n; i0 += BS_MAX_BATCH) {
+      int rc = box5_stream_launch<CS>(ins + i0, nullptr, nullptr, outs + i0, std::min(BS_MAX_BATCH, n - i0), st, name);
       if (rc) return rc;
     }
     return VPPB_OK;
@@ -786,8 +796,8 @@ static int box5_bytes_tiles(const vppb_img* ins, const vppb_img* ups, const vppb
     VPPB_REQUIRE(!(ups && ups[i].base) || ups[i].nrows == in->nrows, VPPB_E_ARG, "%s: the tile above tile %d must have as many rows (pass a sub-image of its last rows otherwise)", name, i);
   }
   cudaStream_t st = as_stream(stream);
-  for (int i0 = 0; i0 < n; i0 += BX_MAX_BATCH) {
-    int rc = box5_stream_launch<CS>(ins + i0, ups ? ups + i0 : nullptr, dns ? dns + i0 : nullptr, outs + i0, std::min(BX_MAX_BATCH, n - i0), st, name);
+  for (int i0 = 0; i0 < n; i0 += BS_MAX_BATCH) {
+    int rc = box5_stream_launch<CS>(ins + i0, ups ? ups + i0 : nullptr, dns ? dns + i0 : nullptr, outs + i0, std::min(BS_MAX_BATCH, n - i0), st, name);
     if (rc) return rc;
   }
   return VPPB_OK;

@@ -120,8 +120,8 @@ constexpr int FB_MAXW = 65535;
 constexpr int FB_BOXWORDS = FB_INNER / 32;  // 63 bitmask words per box row
 constexpr int FB_SMEM = FB_STAGE + FB_ROWS * FB_INNER * 2 + FB_ROWS * FB_BOXWORDS * 4 + 8 + (FB_WARPS + FB_ROWS) * 4 + 32;
 
-template <int RING>
-__global__ void __launch_bounds__(FB_THREADS, 3) k_fast9_band(const __grid_constant__ CUtensorMap tmap, Img im, Img mask, int has_mask, int th, int nboxes,
+template <int RING, bool has_mask>
+__global__ void __launch_bounds__(FB_THREADS, 3) k_fast9_band(const __grid_constant__ CUtensorMap tmap, Img im, Img mask, int th, int nboxes,
                                                               int wpr, uint32_t* bits, int* rowcount, int* bandtotal) {
   extern __shared__ __align__(128) unsigned char smem[];
   unsigned char* st = smem;
@@ -195,11 +195,18 @@ __global__ void __launch_bounds__(FB_THREADS, 3) k_fast9_band(const __grid_const
         }
       }
     }
-    __syncwarp();
-    // ---- phase 2: exact test, one candidate per lane
-    const int n = ncand[warp];
-    for (int e = lane; e < n; e += 32) {
-      const int code = list[e];
+    __syncthreads();
+    // ---- phase 2: exact test, one candidate per thread; the candidates of all strips are shared out evenly over the CTA
+    //      (strips that cross a strong edge hold most of them)
+    int start[FB_WARPS + 1];
+    start[0] = 0;
+#pragma unroll
+    for (int w = 0; w < FB_WARPS; w++) start[w + 1] = start[w] + ncand[w];
+    for (int e = tid; e < start[FB_WARPS]; e += FB_THREADS) {
+      int w = 0;
+#pragma unroll
+      for (int q = 1; q < FB_WARPS; q++) w += (e >= start[q]) ? 1 : 0;
+      const int code = lists[w * (FB_ROWS * FB_WCOLS) + (e - start[w])];
       const int j = code >> 11, xl = code & 2047;
       const unsigned char* p = st + (j + 3) * FB_BOXW + xl;
       const int v = p[0];
@@ -595,15 +602,18 @@ static int fast9_core(const vppb_img* img, int32_t th, const vppb_img* mask, int
     if (rc) return rc;
     static std::atomic<int> attr_done{0};
     if (!attr_done.load(std::memory_order_acquire)) {
-      VPPB_CUDA(cudaFuncSetAttribute(k_fast9_band<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM));
-      VPPB_CUDA(cudaFuncSetAttribute(k_fast9_band<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM));
+      VPPB_CUDA(cudaFuncSetAttribute(k_fast9_band<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM));
+      VPPB_CUDA(cudaFuncSetAttribute(k_fast9_band<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM));
+      VPPB_CUDA(cudaFuncSetAttribute(k_fast9_band<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM));
+      VPPB_CUDA(cudaFuncSetAttribute(k_fast9_band<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM));
       attr_done.store(1, std::memory_order_release);
     }
     const int nboxes = (img->ncols + FB_INNER - 1) / FB_INNER;
-    if (ring == 0)
-      k_fast9_band<0><<<nbands * nboxes, FB_THREADS, FB_SMEM, st>>>(tmap, im, mk, has_mask ? 1 : 0, th, nboxes, wpr, ws.bits_a, ws.rowcount, ws.bandtotal);
-    else
-      k_fast9_band<1><<<nbands * nboxes, FB_THREADS, FB_SMEM, st>>>(tmap, im, mk, has_mask ? 1 : 0, th, nboxes, wpr, ws.bits_a, ws.rowcount, ws.bandtotal);
+    const int grid = nbands * nboxes;
+    if (ring == 0 && !has_mask) k_fast9_band<0, false><<<grid, FB_THREADS, FB_SMEM, st>>>(tmap, im, mk, th, nboxes, wpr, ws.bits_a, ws.rowcount, ws.bandtotal);
+    else if (ring == 0) k_fast9_band<0, true><<<grid, FB_THREADS, FB_SMEM, st>>>(tmap, im, mk, th, nboxes, wpr, ws.bits_a, ws.rowcount, ws.bandtotal);
+    else if (!has_mask) k_fast9_band<1, false><<<grid, FB_THREADS, FB_SMEM, st>>>(tmap, im, mk, th, nboxes, wpr, ws.bits_a, ws.rowcount, ws.bandtotal);
+    else k_fast9_band<1, true><<<grid, FB_THREADS, FB_SMEM, st>>>(tmap, im, mk, th, nboxes, wpr, ws.bits_a, ws.rowcount, ws.bandtotal);
     if (mode == VPPB_FAST_ALL) {
       k_fast9_emit_bands<<<nbands, FB_THREADS, 0, st>>>(im, th, ws.bits_a, wpr, ws.rowcount, ws.bandtotal, nbands, nboxes, kps_out, scores_out, 0, capacity, cnt);
       VPPB_LAUNCH_CHECK(name);

@@ -129,3 +129,79 @@ class GpuOps:
 
     def fast_blockwise(self, frame, th, block_size, mask):
         return self.o.fast9(self._img(frame, 3), th, blockwise=True, block_size=block_size, mask=self.Image2d.from_host(mask, "u8"))
+
+
+# ---- the same loop with the container in HBM -------------------------------------------------------------------
+class DeviceVideoExtruderCtx:
+    """video_extruder_ctx whose keypoint_container and trajectories live on the GPU (vppb_kpc_*): a frame costs no host round
+    trip of keypoints, flows, scores or masks; only the 4-byte entry count is read back on detection frames."""
+
+    def __init__(self, nrows, ncols, capacity=None, max_trajectory_length=15):
+        import ctypes as C
+
+        from . import capi
+
+        self.nrows, self.ncols, self.frame_id = nrows, ncols, -1
+        self.capacity = capacity or max(1024, (nrows * ncols) // 16)
+        self.max_traj = max_trajectory_length
+        self.handle = C.c_void_p()
+        capi.check(capi.lib.vppb_kpc_create(self.capacity, max_trajectory_length, C.byref(self.handle)))
+        self._bufs = None
+
+    def __del__(self):
+        try:
+            from . import capi
+            capi.lib.vppb_kpc_destroy(self.handle)
+        except Exception:
+            pass
+
+
+def video_extruder_update_device(ctx, frame1, frame2, detector_th=10, keypoint_spacing=10, detector_period=5, nscales=3, winsize=9, propagation=2,
+                                 stream=None):
+    """video_extruder_update (video_extruder.hpp:24-135) on a DeviceVideoExtruderCtx.  frame1 / frame2: (nrows, ncols) uint8 arrays
+    or u8 Image2d (any border); max_trajectory_length is the one the context was created with."""
+    import ctypes as C
+
+    from . import capi, ops
+    from .image import Image2d
+
+    lib, check = capi.lib, capi.check
+    ctx.frame_id += 1
+    nr, nc, s = ctx.nrows, ctx.ncols, keypoint_spacing
+    f1 = frame1 if isinstance(frame1, Image2d) else Image2d.from_host(frame1, "u8")
+    f2 = frame2 if isinstance(frame2, Image2d) else Image2d.from_host(frame2, "u8")
+    if ctx._bufs is None:
+        P = capi.VppbSdofParams(winsize, nscales, 0, propagation, 5)
+        ctx._bufs = {"P": P, "ws": ops._DeviceBuffer(lib.vppb_sdof_workspace_bytes(nr, nc, C.byref(P))), "pos": ops._DeviceBuffer(ctx.capacity * 8),
+                     "dist": ops._DeviceBuffer(ctx.capacity * 4), "valid": ops._DeviceBuffer(ctx.capacity),
+                     "p1": ops.Pyramid2d((nr, nc), nscales, 2, pixel="u8", border=2 * winsize), "p2": ops.Pyramid2d((nr, nc), nscales, 2, pixel="u8", border=2 * winsize),
+                     "g2": Image2d(nr, nc, "u8", border=3), "mask": Image2d(nr, nc, "u8", border=s), "det": ops._DeviceBuffer(ctx.capacity * 8),
+                     "cnt": ops._DeviceBuffer(4), "fws": ops._DeviceBuffer(lib.vppb_fast9_workspace_bytes(nr, nc, s)), "table": ops._DeviceBuffer(ctx.capacity * 24)}
+    b = ctx._bufs
+    n = lib.vppb_kpc_size(ctx.handle)
+    if n:  # optical flow of every entry, dead or alive (:45-56)
+        b["p1"].update(f1, stream); b["p2"].update(f2, stream)
+        check(lib.vppb_sdof_u8(b["p1"].desc_array(), b["p2"].desc_array(), C.byref(b["P"]), lib.vppb_kpc_positions(ctx.handle), n, b["ws"].ptr, b["ws"].nbytes,
+                               b["pos"].ptr, b["dist"].ptr, b["valid"].ptr, stream))
+        check(lib.vppb_kpc_flow_update(ctx.handle, b["pos"].ptr, b["valid"].ptr, nr, nc, stream))
+    check(lib.vppb_kpc_merge(ctx.handle, nr, nc, s, stream))
+    check(lib.vppb_copy2d_mirror(f2.ptr(), b["g2"].ptr(), stream))  # frame2 with a mirror border of 3 for the ring reads
+    check(lib.vppb_kpc_score_filter(ctx.handle, b["g2"].ptr(), detector_th, 3, stream))
+    if ctx.frame_id % detector_period == 0:
+        check(lib.vppb_kpc_paint_mask(ctx.handle, b["mask"].ptr(), s, stream))
+        check(lib.vppb_fast9_u8_async(b["g2"].ptr(), detector_th, b["mask"].ptr(), capi.FAST_BLOCKWISE, s, capi.FAST_REFERENCE_RING, b["fws"].ptr, b["fws"].nbytes,
+                                      b["det"].ptr, None, ctx.capacity, b["cnt"].ptr, stream))
+        check(lib.vppb_kpc_add_and_compact(ctx.handle, b["det"].ptr, b["cnt"].ptr, ctx.capacity, ctx.frame_id, stream))
+    check(lib.vppb_kpc_trajectories_update(ctx.handle, stream))
+    return ctx
+
+
+def device_state_table(ctx, stream=None):
+    """(n, 6) int array like state_table(): row, col, age, trajectory start frame, trajectory length, trajectory alive."""
+    from . import capi
+
+    n = capi.lib.vppb_kpc_size(ctx.handle)
+    if n == 0 or ctx._bufs is None:
+        return np.zeros((0, 6), dtype=np.int32)
+    capi.check(capi.lib.vppb_kpc_state_table(ctx.handle, ctx._bufs["table"].ptr, stream))
+    return ctx._bufs["table"].to_host(np.int32, n * 6, stream).reshape(-1, 6)
