@@ -535,6 +535,12 @@ def main():
         except Exception as ex_:  # pragma: no cover
             line["config"]["nccl_exchange"] = {"error": repr(ex_)[:200]}
 
+    if world > 1 and not args.no_extras:
+        try:
+            line.setdefault("extras", {})["sdof_8k_tiled"] = sdof_tiled(vpp, capi, torch, dist, tiles, orc, rank, world, dev, sp)
+        except Exception as ex_:  # pragma: no cover
+            line.setdefault("extras", {})["sdof_8k_tiled"] = {"error": repr(ex_)[:300]}
+
     if rank == 0 and n_gpus == 1:
         cb, _ = cpu_box_bench(H, W, 3, 1, args.cpu_budget)
         line["cpu_baseline"] = cb
@@ -559,6 +565,75 @@ def main():
         dist.barrier()
         dist.destroy_process_group()
     return 0 if parity_ok else 3
+
+
+def sdof_tiled(vpp, capi, torch, dist, tiles, orc, rank, world, dev, sp, H=4320, W=7680, halo=80):
+    """BASELINE configs[4]: video_extruder's semi-dense flow on a 7680x4320 frame pair, row-tiled over the ranks.  Every rank owns
+    H / world rows of both frames; ONE grouped NCCL halo exchange per frame pair (vppb_halo_exchange, 80 rows each way: SAD window +
+    search reach + the 3-level pyramid's footprint, a multiple of patch x 2^(nscales-1) = 20 so that cell grids and pyramid sampling
+    line up with the full frame's) extends the tile, then the tile runs the single-GPU path (FAST9 blockwise keypoints of its own rows,
+    pyramids, matching, dataflow sweeps).  Semantics are TILE-LOCAL: the propagation sweeps stop at the tile seams, so keypoints near
+    a seam may differ from a full-frame run; each rank's result is bit-exact against the oracle on the same extended tile."""
+    from tests import scenes
+    from vpp_b200.ops import _DeviceBuffer
+
+    g1, g2, _ = scenes.lk_pair(1080, 1920, 4, seed=55, shift=(3.0, -2.0), margin=10)
+    g1, g2 = np.tile(g1, (H // 1080, W // 1920)), np.tile(g2, (H // 1080, W // 1920))
+    r0, r1 = tiles.tile_rows(H, rank, world)
+    th = r1 - r0
+    assert th % 20 == 0 and halo % 20 == 0 and halo <= th
+    T = [vpp.Image2d(th, W, "u8", border=halo) for _ in range(2)]
+    for t_, g in zip(T, (g1, g2)):
+        t_.upload(np.ascontiguousarray(g[r0:r1]))
+        vpp.fill_border_mirror(t_)          # column borders (and, for the outermost tiles, the frame's own top / bottom)
+    comm = tiles.nccl_comm(dist, rank, world)
+    descs = (capi.VppbImg * 2)(T[0].desc, T[1].desc)
+    top, bot = (halo if rank > 0 else 0), (halo if rank < world - 1 else 0)
+
+    def extended(t_):  # the tile with its halo rows as ordinary domain rows (a view: no copy)
+        d = capi.VppbImg()
+        C.memmove(C.byref(d), C.byref(t_.desc), C.sizeof(capi.VppbImg))
+        d.base = t_.desc.base - top * t_.desc.pitch
+        d.alloc = None
+        d.nrows = th + top + bot
+        d.border = min(3, halo)
+        return vpp.Image2d(0, 0, "u8", _desc=d, _owner=t_)
+
+    P = capi.VppbSdofParams(9, 3, 0, 2, 5)
+    E = [extended(t_) for t_ in T]
+    eh = th + top + bot
+    p1, p2 = vpp.Pyramid2d((eh, W), 3, 2, pixel="u8", border=18), vpp.Pyramid2d((eh, W), 3, 2, pixel="u8", border=18)
+    wsb = _DeviceBuffer(capi.lib.vppb_sdof_workspace_bytes(eh, W, C.byref(P)))
+    capi.check(capi.lib.vppb_halo_exchange(comm, rank, world, descs, 2, halo, sp))
+    G = vpp.Image2d(eh, W, "u8", border=3)
+    capi.check(capi.lib.vppb_copy2d_mirror(E[0].ptr(), G.ptr(), sp))
+    kps = vpp.fast9(G, 10, blockwise=True, block_size=10, stream=sp)
+    kps = np.ascontiguousarray(kps[(kps[:, 0] >= top) & (kps[:, 0] < top + th)])  # this rank's own rows
+    n = len(kps)
+    d_kp = _DeviceBuffer(kps.nbytes).from_host(kps, sp)
+    d_pos, d_dist, d_valid = _DeviceBuffer(n * 8), _DeviceBuffer(n * 4), _DeviceBuffer(n)
+    a1, a2 = p1.desc_array(), p2.desc_array()
+
+    def frame_pair():
+        capi.check(capi.lib.vppb_halo_exchange(comm, rank, world, descs, 2, halo, sp))
+        p1.update(E[0], sp); p2.update(E[1], sp)
+        capi.check(capi.lib.vppb_sdof_u8(a1, a2, C.byref(P), d_kp.ptr, n, wsb.ptr, wsb.nbytes, d_pos.ptr, d_dist.ptr, d_valid.ptr, sp))
+
+    frame_pair()
+    got = (d_pos.to_host(np.int32, n * 2, sp).reshape(-1, 2), d_dist.to_host(np.int32, n, sp), d_valid.to_host(np.uint8, n, sp))
+    lo, hi = r0 - top, r1 + bot
+    h1, h2 = orc.HostImage(eh, W, "u8", data=g1[lo:hi]), orc.HostImage(eh, W, "u8", data=g2[lo:hi])
+    rp, rd, rv = np.zeros((n, 2), np.int32), np.zeros(n, np.int32), np.zeros(n, np.uint8)
+    orc.load().vo_semi_dense_flow(h1.ptr(), h2.ptr(), kps.ctypes.data, n, 9, 3, 0, 2, 5, rp.ctypes.data, rd.ctypes.data, rv.ctypes.data)
+    ok = bool(np.array_equal(got[0], rp) and np.array_equal(got[1], rd) and np.array_equal(got[2], rv))
+    ms = device_ms(torch, dist, dev, frame_pair, 5)
+    tot = torch.tensor([float(n), 1.0 if ok else 0.0], dtype=torch.float64, device=dev)
+    dist.all_reduce(tot[:1], op=dist.ReduceOp.SUM)
+    dist.all_reduce(tot[1:], op=dist.ReduceOp.MIN)
+    capi.lib.vppb_comm_destroy(comm)
+    return {"ms_per_frame_pair": ms, "keypoints": int(tot[0].item()), "parity": bool(tot[1].item() > 0.5), "halo_rows": halo,
+            "note": "NCCL halo exchange (80 rows each way, both frames) + pyramids + matching + sweeps per tile, max over ranks; tile-local semantics, each tile bit-exact "
+                    "against the oracle on the same extended tile; single-GPU anchor: extras.sdof_8k of the N = 1 run"}
 
 
 def gpu_extras(vpp, capi, torch, stream, sp, dev):

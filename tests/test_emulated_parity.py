@@ -105,3 +105,4 @@ test_fast9_threshold_extremes = L.test_fast9_threshold_extremes
 test_box5x5_row_tiles_read_neighbours = L.test_box5x5_row_tiles_read_neighbours
 test_video_extruder_device_container_equals_reference_tables = L.test_video_extruder_device_container_equals_reference_tables
 test_video_extruder_device_container_merge_cases = L.test_video_extruder_device_container_merge_cases
+test_out_of_frame_keypoints_are_skipped = L.test_out_of_frame_keypoints_are_skipped

@@ -384,3 +384,24 @@ def test_video_extruder_device_container_merge_cases(vpp):
         capi.check(capi.lib.vppb_kpc_merge(ctx.handle, 40, 50, 10, None))
         capi.check(capi.lib.vppb_kpc_state_table(ctx.handle, tab.ptr, None))
         assert np.array_equal(tab.to_host(np.int32, n * 6).reshape(-1, 6)[:, 2], want), trial
+
+
+def test_out_of_frame_keypoints_are_skipped(vpp):
+    """A keypoint outside the frame is an input error the reference answers with undefined behaviour; the C-ABI skips it: the
+    semi-dense flow reports it invalid and leaves every other result untouched, fast9_scores gives it a score of 0."""
+    from tests import scenes
+
+    f1, f2, _ = scenes.lk_pair(121, 161, 4, seed=21, shift=(3.0, -2.0), margin=10)
+    G = vpp.Image2d.from_host(f1, "u8", border=3)
+    vpp.fill_border_mirror(G)
+    kps = vpp.fast9(G, 8, blockwise=True, block_size=6)
+    bad = np.array([[-1, 5], [5, -3], [121, 10], [10, 161], [4000, 4000], [-7, -7]], dtype=np.int32)
+    both = np.concatenate([kps, bad])
+    I1, I2 = vpp.Image2d.from_host(f1, "u8"), vpp.Image2d.from_host(f2, "u8")
+    p0, d0, v0 = vpp.semi_dense_optical_flow(kps, I1, I2, winsize=9, nscales=3)
+    p1, d1, v1 = vpp.semi_dense_optical_flow(both, I1, I2, winsize=9, nscales=3)
+    n = len(kps)
+    assert np.array_equal(p1[:n], p0) and np.array_equal(d1[:n], d0) and np.array_equal(v1[:n], v0) and v0.sum() > 50
+    assert not v1[n:].any()
+    sc = vpp.fast9_scores(G, 8, both)
+    assert np.array_equal(sc[:n], vpp.fast9_scores(G, 8, kps)) and not sc[n:].any()

@@ -13,13 +13,11 @@ sys.path.insert(0, ROOT)
 
 VARIANTS = [
     ("tile", {"VPPB_BOX_IMPL": "tile"}),
-    ("stream_lw4", {"VPPB_BOX_LW": "4"}),
-    ("stream_lw8", {"VPPB_BOX_LW": "8"}),
-    ("stream_lw4_bal", {"VPPB_BOX_LW": "4", "VPPB_BOX_BAL": "1"}),
-    ("stream_lw8_bal", {"VPPB_BOX_LW": "8", "VPPB_BOX_BAL": "1"}),
-    ("stream_lw4_R21", {"VPPB_BOX_LW": "4", "VPPB_BOX_R": "21"}),
-    ("stream_lw4_R36", {"VPPB_BOX_LW": "4", "VPPB_BOX_R": "36"}),
-    ("stream_lw8_R21", {"VPPB_BOX_LW": "8", "VPPB_BOX_R": "21"}),
+    ("stream_lw4", {"VPPB_BOX_LW": "4", "VPPB_BOX_SINGLE": "stream"}),
+    ("stream_lw4_occ", {"VPPB_BOX_LW": "4", "VPPB_BOX_OCC": "1", "VPPB_BOX_SINGLE": "stream"}),
+    ("stream_lw8", {"VPPB_BOX_LW": "8", "VPPB_BOX_SINGLE": "stream"}),
+    ("stream_lw8_occ", {"VPPB_BOX_LW": "8", "VPPB_BOX_OCC": "1", "VPPB_BOX_SINGLE": "stream"}),
+    ("stream_lw4_bal", {"VPPB_BOX_LW": "4", "VPPB_BOX_BAL": "1", "VPPB_BOX_SINGLE": "stream"}),
 ]
 
 
@@ -54,8 +52,8 @@ def child():
     for (H, W, tag, pix, cs) in [(1080, 1920, "1080p", "vuchar3", 3), (2160, 3840, "4k", "vuchar3", 3), (4320, 7680, "8k", "vuchar3", 3),
                                  (2160, 3840, "4k_u8", "u8", 1)]:
         alg = 2.0 * cs * H * W
-        n = max(2, int(np.ceil(160e6 / alg)))
-        n = min(n, 32)
+        n = max(2, int(np.ceil(1600e6 / alg)))
+        n = min(n, 128)
         f = rng.integers(0, 256, (H, W, cs) if cs > 1 else (H, W), dtype=np.uint8)
         S = [vpp.Image2d.from_host(f, pix, border=2) for _ in range(n)]
         D = [vpp.Image2d(H, W, pix) for _ in range(n)]

@@ -305,13 +305,13 @@ __global__ void __launch_bounds__(BX_THREADS, BX_TH == 16 ? 4 : 6) k_box5_bytes_
 // (IMAD with a run-time multiplier of 1, which ptxas cannot fold back into an IADD3).
 constexpr int BS_K = 5;  // rows per stage == rows of the vertical window
 constexpr int BS_MAX_BATCH = 128;  // images per launch of the streaming kernel (their tensor maps travel in the 32 KB kernel parameter space)
-template <int LW> struct BoxStreamCfg {
+template <int LW, int OCC = 0> struct BoxStreamCfg {  // OCC = 1: one more CTA per SM (fewer registers, one stage less)
   static constexpr int STRIP = 32 * 4 * LW;          // output bytes per warp row
   static constexpr int BOXW = STRIP + 32;            // bytes per box row
   static constexpr int STAGE_BYTES = ((BS_K * BOXW + 127) / 128) * 128;
   static constexpr int WARPS = 4;
-  static constexpr int STAGES = LW == 4 ? 4 : 3;
-  static constexpr int CTAS_PER_SM = LW == 4 ? 4 : 3;
+  static constexpr int STAGES = (LW == 4 ? 4 : 3) - OCC;
+  static constexpr int CTAS_PER_SM = (LW == 4 ? 4 : 3) + OCC;
   static constexpr int SMEM = WARPS * STAGES * STAGE_BYTES + WARPS * STAGES * 8;
 };
 
@@ -345,9 +345,31 @@ __device__ __noinline__ void box_store_partial(unsigned char* d, const uint32_t*
   for (int k = 0; k < nbytes; k++) d[k] = (unsigned char)(ow[k >> 2] >> ((k & 3) * 8));
 }
 
-template <int CS, int LW, int BAL, int NB>
-__global__ void __launch_bounds__(BoxStreamCfg<LW>::WARPS * 32, BoxStreamCfg<LW>::CTAS_PER_SM) k_box5_stream(const __grid_constant__ BoxStream<NB> p) {
+// A stage that straddles a row-tile seam: row by row, each from the tile that owns it - the halo rows come straight from
+// the neighbour's (peer GPU's) memory as 1-D bulk copies, so the transfer is part of the kernel's own load pipeline.
+template <int LW, int NB>
+__device__ __noinline__ void box_stage_from_tiles(const BoxStream<NB>& p, unsigned char* stage, uint64_t* bar, int img, int strip, int ty) {
   typedef BoxStreamCfg<LW> Cfg;
+  const unsigned char* up = p.up_base[img];
+  const unsigned char* dn = p.dn_base[img];
+  const int xoff = strip * Cfg::STRIP - 16;
+  const int len = min(Cfg::BOXW, p.row_room - xoff);
+  int rows = 0;
+  for (int i = 0; i < BS_K; i++) rows += (ty + i - 2 <= p.nrows + 1) ? 1 : 0;
+  mbar_arrive_expect_tx(bar, rows * len);
+  for (int i = 0; i < BS_K; i++) {
+    const int v = ty + i - 2;  // image row of the tile
+    if (v > p.nrows + 1) continue;
+    const unsigned char* src = (v < 0 && up) ? up + (long long)(p.nrows + v) * p.in_pitch
+                             : (v >= p.nrows && dn) ? dn + (long long)(v - p.nrows) * p.in_pitch
+                                                    : p.in_base[img] + (long long)v * p.in_pitch;
+    tma_load_1d(stage + i * Cfg::BOXW, src + xoff, len, bar);
+  }
+}
+
+template <int CS, int LW, int BAL, int NB, int OCC>
+__global__ void __launch_bounds__(BoxStreamCfg<LW, OCC>::WARPS * 32, BoxStreamCfg<LW, OCC>::CTAS_PER_SM) k_box5_stream(const __grid_constant__ BoxStream<NB> p) {
+  typedef BoxStreamCfg<LW, OCC> Cfg;
   constexpr int NW = LW + 4;  // words of a lane's window: 2 left + LW own + 2 right
   extern __shared__ __align__(128) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -364,53 +386,39 @@ __global__ void __launch_bounds__(BoxStreamCfg<LW>::WARPS * 32, BoxStreamCfg<LW>
   }
   __syncwarp();
 
-  // producer cursor (meaningful in lane 0 only): next (task, group of 5 rows) to fetch and the stage it goes to; the task's
-  // coordinates are decoded once per task, not per stage
-  int ptask = gw, pgrp = 0, pslot = 0, pimg = 0, pchunk = 0, pstrip = 0;
-  auto decode = [&]() {
-    if (ptask < p.total) {
-      pimg = ptask / per_img;
-      const int rem = ptask - pimg * per_img;
-      pchunk = rem / p.strips;
-      pstrip = rem - pchunk * p.strips;
-    }
-  };
-  decode();
+  // producer cursor (meaningful in lane 0 only): the next stage to fetch is rows [py, py + 5) of tensor map pmap at element
+  // column px; pleft stages remain in the current task.  A task is decoded once (two divisions), a stage costs a handful of
+  // instructions; only stages that straddle a row-tile seam take the (out-of-line) row-by-row path.
+  int ptask = gw - nw, pslot = 0, pimg = 0, pstrip = 0, py = 0, pleft = 0;
+  bool pseam = false;
   auto produce = [&]() {
-    if (ptask < p.total) {
-      const int img = pimg, chunk = pchunk, strip = pstrip;
-      const int ty = chunk * p.R + pgrp * BS_K;  // first row of the stage, counted from image row -2
-      const unsigned char* up = p.up_base[img];
-      const unsigned char* dn = p.dn_base[img];
-      if ((up && ty < 2) || (dn && ty + BS_K > p.nrows + 2)) {
-        // the stage straddles a tile boundary: row by row, each from the tile that owns it - the halo rows come straight
-        // from the neighbour's (peer GPU's) memory as 1-D bulk copies, the transfer is part of the kernel's own pipeline
-        const int xoff = strip * Cfg::STRIP - 16;
-        const int len = min(Cfg::BOXW, p.row_room - xoff);
-        int rows = 0;
-#pragma unroll
-        for (int i = 0; i < BS_K; i++) rows += (ty + i - 2 <= p.nrows + 1) ? 1 : 0;
-        mbar_arrive_expect_tx(&bars[pslot], rows * len);
-#pragma unroll
-        for (int i = 0; i < BS_K; i++) {
-          const int v = ty + i - 2;  // image row of the tile
-          if (v > p.nrows + 1) continue;
-          const unsigned char* src = (v < 0 && up) ? up + (long long)(p.nrows + v) * p.in_pitch
-                                   : (v >= p.nrows && dn) ? dn + (long long)(v - p.nrows) * p.in_pitch
-                                                          : p.in_base[img] + (long long)v * p.in_pitch;
-          tma_load_1d(ring + pslot * Cfg::STAGE_BYTES + i * Cfg::BOXW, src + xoff, len, &bars[pslot]);
-        }
-      } else {
+    if (pleft == 0) {
+      ptask += nw;
+      if (ptask < p.total) {
+        pimg = ptask / per_img;
+        const int rem = ptask - pimg * per_img;
+        const int chunk = rem / p.strips;
+        pstrip = rem - chunk * p.strips;
+        py = chunk * p.R;
+        pleft = p.groups;
+        pseam = (p.up_base[pimg] && py < 2) || (p.dn_base[pimg] && py + p.groups * BS_K > p.nrows + 2);
+      }
+    }
+    if (pleft > 0) {
+      if (pseam && ((p.up_base[pimg] && py < 2) || (p.dn_base[pimg] && py + BS_K > p.nrows + 2)))
+        box_stage_from_tiles<LW, NB>(p, ring + pslot * Cfg::STAGE_BYTES, &bars[pslot], pimg, pstrip, py);
+      else {
         mbar_arrive_expect_tx(&bars[pslot], BS_K * Cfg::BOXW);
         // tensor origin = 16 bytes left of x = 0 and 2 rows above y = 0; 8-byte elements (x coordinate * 8 is a multiple of 16)
-        tma_load_2d(ring + pslot * Cfg::STAGE_BYTES, &p.maps[img], strip * (Cfg::STRIP / 8), ty, &bars[pslot]);
+        tma_load_2d(ring + pslot * Cfg::STAGE_BYTES, &p.maps[pimg], pstrip * (Cfg::STRIP / 8), py, &bars[pslot]);
       }
-      if (++pgrp == p.groups) { pgrp = 0; ptask += nw; decode(); }
+      py += BS_K;
+      pleft--;
     }
     pslot = (pslot + 1 == Cfg::STAGES) ? 0 : pslot + 1;
   };
   if (lane == 0) {
-#pragma unroll
+#pragma unroll 1
     for (int s = 0; s < Cfg::STAGES; s++) produce();
   }
 
@@ -571,16 +579,16 @@ static int box_stream_rows(long long strips_x_imgs, int nrows, int warps_per_sm,
 }
 
 // n equally shaped, TMA-eligible images (n <= BX_MAX_BATCH) in one launch of the streaming kernel
-template <int CS, int LW, int BAL, int NB>
-static int box5_stream_launch_nb(const vppb_img* ins, const vppb_img* ups, const vppb_img* dns, const vppb_img* outs, int n, cudaStream_t st, const char* name) {
-  typedef BoxStreamCfg<LW> Cfg;
+template <int CS, int LW, int BAL, int NB, int OCC>
+static int box5_stream_launch_occ(const vppb_img* ins, const vppb_img* ups, const vppb_img* dns, const vppb_img* outs, int n, cudaStream_t st, const char* name) {
+  typedef BoxStreamCfg<LW, OCC> Cfg;
   const int rowbytes = ins[0].ncols * CS, nrows = ins[0].nrows;
   static std::atomic<unsigned long long> attr_done{0};
   int dev = 0;
   VPPB_CUDA(cudaGetDevice(&dev));
   const unsigned long long bit = 1ULL << (dev & 63);
   if (!(attr_done.load(std::memory_order_acquire) & bit)) {
-    VPPB_CUDA(cudaFuncSetAttribute(k_box5_stream<CS, LW, BAL, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    VPPB_CUDA(cudaFuncSetAttribute(k_box5_stream<CS, LW, BAL, NB, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
     attr_done.fetch_or(bit, std::memory_order_release);
   }
   BoxStream<NB> p;
@@ -614,9 +622,20 @@ static int box5_stream_launch_nb(const vppb_img* ins, const vppb_img* ups, const
     p.row_room = ins[0].pitch - (int)bs;
   }
   const int ctas = (p.total + Cfg::WARPS - 1) / Cfg::WARPS, resident = sm_count() * Cfg::CTAS_PER_SM;
-  k_box5_stream<CS, LW, BAL, NB><<<ctas < resident ? ctas : resident, Cfg::WARPS * 32, Cfg::SMEM, st>>>(p);
+  k_box5_stream<CS, LW, BAL, NB, OCC><<<ctas < resident ? ctas : resident, Cfg::WARPS * 32, Cfg::SMEM, st>>>(p);
   VPPB_LAUNCH_CHECK(name);
   return VPPB_OK;
+}
+
+template <int CS, int LW, int BAL, int NB>
+static int box5_stream_launch_nb(const vppb_img* ins, const vppb_img* ups, const vppb_img* dns, const vppb_img* outs, int n, cudaStream_t st, const char* name) {
+  static int occ = -1;
+  if (occ < 0) {
+    const char* e = getenv("VPPB_BOX_OCC");
+    occ = e ? atoi(e) : 0;
+  }
+  if (occ == 1) return box5_stream_launch_occ<CS, LW, BAL, NB, 1>(ins, ups, dns, outs, n, st, name);
+  return box5_stream_launch_occ<CS, LW, BAL, NB, 0>(ins, ups, dns, outs, n, st, name);
 }
 
 // the kernel parameters carry one tensor map per image: a single image travels with a 1-entry block (launching a kernel

@@ -107,7 +107,8 @@ __global__ void __launch_bounds__(256) k_fast9_detect(Img im, Img mask, int has_
 //     test is the bit trick of arc9(); corners set their bit in the band's bitmask (shared memory).
 // After the last box the band's bitmask rows and their per-row / per-band counts go to global memory; k_fast9_emit_bands
 // turns them into raster-ordered keypoints.  No atomics on global memory, nothing to zero beforehand.
-constexpr int FB_ROWS = 8;
+constexpr int FB_ROWS = 4;   // rows per tile: small tiles = many CTAs per SM and fine-grained balance (a 4K frame is 1080 tiles over 888 resident CTAs)
+constexpr int FE_ROWS = 8;   // rows per CTA of the emit kernel (one warp each)
 constexpr int FB_BOXW = 2048;
 constexpr int FB_INNER = FB_BOXW - 32;
 constexpr int FB_INH = FB_ROWS + 6;
@@ -121,7 +122,7 @@ constexpr int FB_BOXWORDS = FB_INNER / 32;  // 63 bitmask words per box row
 constexpr int FB_SMEM = FB_STAGE + FB_ROWS * FB_INNER * 2 + FB_ROWS * FB_BOXWORDS * 4 + 8 + (FB_WARPS + FB_ROWS) * 4 + 32;
 
 template <int RING, bool has_mask>
-__global__ void __launch_bounds__(FB_THREADS, 3) k_fast9_band(const __grid_constant__ CUtensorMap tmap, Img im, Img mask, int th, int nboxes,
+__global__ void __launch_bounds__(FB_THREADS, 5) k_fast9_band(const __grid_constant__ CUtensorMap tmap, Img im, Img mask, int th, int nboxes,
                                                               int wpr, uint32_t* bits, int* rowcount, int* bandtotal) {
   extern __shared__ __align__(128) unsigned char smem[];
   unsigned char* st = smem;
@@ -268,9 +269,9 @@ __global__ void __launch_bounds__(FB_THREADS) k_fast9_emit_bands(Img im, int th,
   __shared__ int part[FB_THREADS / 32];
   __shared__ int base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int band = blockIdx.x, r0 = band * FB_ROWS;
+  const int r0 = blockIdx.x * FE_ROWS, band = r0 / FB_ROWS;   // FE_ROWS is a multiple of FB_ROWS: the CTA starts on a band boundary
   const int r = r0 + warp;
-  const bool row_ok = warp < FB_ROWS && r < im.nrows;
+  const bool row_ok = warp < FE_ROWS && r < im.nrows;
   // issue every load of this warp first
   uint32_t words[FE_MAXW];
 #pragma unroll
@@ -278,8 +279,8 @@ __global__ void __launch_bounds__(FB_THREADS) k_fast9_emit_bands(Img im, int th,
     const int wi = q * 32 + lane;
     words[q] = (row_ok && wi < wpr) ? __ldg(&bits[(long long)r * wpr + wi]) : 0u;
   }
-  int rc = 0;  // lane j < FB_ROWS: keypoints of row r0 + j (all boxes)
-  if (lane < FB_ROWS && r0 + lane < im.nrows)
+  int rc = 0;  // lane j < FE_ROWS: keypoints of row r0 + j (all boxes)
+  if (lane < FE_ROWS && r0 + lane < im.nrows)
     for (int k = 0; k < nboxes; k++) rc += __ldg(&rowcount[(long long)(r0 + lane) * nboxes + k]);
   int acc = 0;
   const int before = band * nboxes;
@@ -291,16 +292,16 @@ __global__ void __launch_bounds__(FB_THREADS) k_fast9_emit_bands(Img im, int th,
     int b = 0;
     for (int i = 0; i < FB_THREADS / 32; i++) b += part[i];
     base_s = b;
-    if (band == nbands - 1 && count_dev) {
+    if (blockIdx.x == gridDim.x - 1 && count_dev) {
       int t = b;
-      for (int k = 0; k < nboxes; k++) t += bandtotal[before + k];
+      for (int i = before; i < nbands * nboxes; i++) t += bandtotal[i];
       *count_dev = t;
     }
   }
   __syncthreads();
   if (!row_ok) return;
   int off = base_s, mine = 0;
-  for (int j = 0; j < FB_ROWS; j++) {
+  for (int j = 0; j < FE_ROWS; j++) {
     const int cj = __shfl_sync(0xffffffffu, rc, j);
     if (j < warp) off += cj;
     if (j == warp) mine = cj;
@@ -509,8 +510,10 @@ __global__ void __launch_bounds__(256) k_fast9_emit_cells(Img im, int th, const 
 }
 
 __global__ void k_fast9_scores(Img im, int th, const vppb_int2* kps, int n, int* scores) {
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-    scores[i] = fast9_score_at(im, kps[i].r, kps[i].c, th);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const bool inside = kps[i].r >= 0 && kps[i].r < im.nrows && kps[i].c >= 0 && kps[i].c < im.ncols;  // the ring of an in-frame point stays inside the 3-px border
+    scores[i] = inside ? fast9_score_at(im, kps[i].r, kps[i].c, th) : 0;
+  }
 }
 
 struct FastWs {
@@ -615,7 +618,7 @@ static int fast9_core(const vppb_img* img, int32_t th, const vppb_img* mask, int
     else if (!has_mask) k_fast9_band<1, false><<<grid, FB_THREADS, FB_SMEM, st>>>(tmap, im, mk, th, nboxes, wpr, ws.bits_a, ws.rowcount, ws.bandtotal);
     else k_fast9_band<1, true><<<grid, FB_THREADS, FB_SMEM, st>>>(tmap, im, mk, th, nboxes, wpr, ws.bits_a, ws.rowcount, ws.bandtotal);
     if (mode == VPPB_FAST_ALL) {
-      k_fast9_emit_bands<<<nbands, FB_THREADS, 0, st>>>(im, th, ws.bits_a, wpr, ws.rowcount, ws.bandtotal, nbands, nboxes, kps_out, scores_out, 0, capacity, cnt);
+      k_fast9_emit_bands<<<(img->nrows + FE_ROWS - 1) / FE_ROWS, FB_THREADS, 0, st>>>(im, th, ws.bits_a, wpr, ws.rowcount, ws.bandtotal, nbands, nboxes, kps_out, scores_out, 0, capacity, cnt);
       VPPB_LAUNCH_CHECK(name);
       return VPPB_OK;
     }

@@ -82,7 +82,9 @@ __global__ void k_sdof_clear(SdofLevel L) {
 
 __global__ void k_sdof_claim(SdofLevel L, const vppb_int2* kps, int n, int scale_div, int patch) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    if (kps[i].r < 0 || kps[i].c < 0) continue;  // a keypoint outside the frame claims nothing (and is reported invalid)
     const int fr = (kps[i].r / scale_div) / patch, fc = (kps[i].c / scale_div) / patch;
+    if (fr >= L.cr || fc >= L.cc || kps[i].r / scale_div >= L.i1.nrows || kps[i].c / scale_div >= L.i1.ncols) continue;
     atomicMin(&L.owner[fr * L.cstride + fc], i);
   }
 }
@@ -93,7 +95,9 @@ __global__ void __launch_bounds__(128) k_sdof_match(SdofLevel L, SdofLevel coars
   const int lane = threadIdx.x & 31;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
   for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += nwarps) {
+    if (kps[i].r < 0 || kps[i].c < 0) continue;  // warp-uniform
     const int pr = kps[i].r / scale_div, pc = kps[i].c / scale_div;
+    if (pr >= L.i1.nrows || pc >= L.i1.ncols || pr / patch >= L.cr || pc / patch >= L.cc) continue;
     const int cell = (pr / patch) * L.cstride + (pc / patch);
     if (L.owner[cell] != i) continue;  // warp-uniform
     int predr = pr, predc = pc;
@@ -285,7 +289,7 @@ __global__ void k_sdof_emit(SdofLevel L, const vppb_int2* kps, int n, int div, i
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const int fr = kps[i].r / div, fc = kps[i].c / div;
     int v = 0, pr = 0, pc = 0, d = 0;
-    if (fr >= 0 && fr < L.cr && fc >= 0 && fc < L.cc && L.mark[fr * L.cstride + fc]) {
+    if (kps[i].r >= 0 && kps[i].c >= 0 && fr < L.cr && fc < L.cc && L.mark[fr * L.cstride + fc]) {
       const int cell = fr * L.cstride + fc;
       v = 1; pr = kps[i].r + L.flow[cell].x * mul; pc = kps[i].c + L.flow[cell].y * mul; d = L.dist[cell];
     }
