@@ -259,25 +259,30 @@ __global__ void __launch_bounds__(FB_THREADS, 5) k_fast9_band(const __grid_const
   }
 }
 
+// out of line: the emit loop is unrolled over the words a lane holds, the 16 ring loads of a score must not be copied 16 times
+__device__ __noinline__ int fast9_score_out(const Img& im, int r, int c, int th, int score_div) {
+  const int sc = fast9_score_at(im, r, c, th);
+  return score_div ? ((sc / 16) & 255) : sc;
+}
+
 // Raster-ordered emission from the band kernel's output: CTA = band; its first keypoint index is the sum of the totals of
 // the (band, box) tiles above (summed by the CTA itself - no scan launch), one warp per row walks the bitmask, whose
 // words it has all loaded up front (independent loads: one memory latency per row, not one per 32 words).
 // The last band also stores the total count.
-constexpr int FE_MAXW = 16;  // bitmask words per lane held in registers: rows up to 16 * 32 * 32 = 16384 pixels in one pass
+constexpr int FE_MAXW = 16;  // bitmask words per lane staged per pass: rows up to 16 * 32 * 32 = 16384 pixels in one pass
 __global__ void __launch_bounds__(FB_THREADS) k_fast9_emit_bands(Img im, int th, const uint32_t* bits, int wpr, const int* rowcount, const int* bandtotal,
                                                                 int nbands, int nboxes, vppb_int2* kps, int* scores, int score_div, int capacity, int* count_dev) {
   __shared__ int part[FB_THREADS / 32];
   __shared__ int base_s;
+  __shared__ uint32_t rowbits[FB_THREADS / 32][FE_MAXW * 32];  // a row's words, loaded up front (independent loads), consumed by a rolled loop
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int r0 = blockIdx.x * FE_ROWS, band = r0 / FB_ROWS;   // FE_ROWS is a multiple of FB_ROWS: the CTA starts on a band boundary
   const int r = r0 + warp;
   const bool row_ok = warp < FE_ROWS && r < im.nrows;
-  // issue every load of this warp first
-  uint32_t words[FE_MAXW];
 #pragma unroll
   for (int q = 0; q < FE_MAXW; q++) {
     const int wi = q * 32 + lane;
-    words[q] = (row_ok && wi < wpr) ? __ldg(&bits[(long long)r * wpr + wi]) : 0u;
+    rowbits[warp][wi] = (row_ok && wi < wpr) ? __ldg(&bits[(long long)r * wpr + wi]) : 0u;
   }
   int rc = 0;  // lane j < FE_ROWS: keypoints of row r0 + j (all boxes)
   if (lane < FE_ROWS && r0 + lane < im.nrows)
@@ -307,35 +312,28 @@ __global__ void __launch_bounds__(FB_THREADS) k_fast9_emit_bands(Img im, int th,
     if (j == warp) mine = cj;
   }
   if (mine == 0) return;
-  for (int w0 = 0; w0 < wpr; w0 += 32 * FE_MAXW) {
-#pragma unroll
-    for (int q = 0; q < FE_MAXW; q++) {
-      const int wi = w0 + q * 32 + lane;
-      uint32_t word = words[q];
-      if (w0 > 0) word = wi < wpr ? bits[(long long)r * wpr + wi] : 0u;  // rows wider than 16384 pixels: later passes load as they go
-      if (w0 + q * 32 >= wpr) break;
-      const int cnt = __popc(word);
-      int incl = cnt;
-      for (int o = 1; o < 32; o <<= 1) {
-        int y = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += y;
-      }
-      int pos = off + incl - cnt;
-      while (word) {
-        const int b = __ffs(word) - 1;
-        word &= word - 1;
-        if (pos < capacity) {
-          const int c = wi * 32 + b;
-          kps[pos] = vppb_int2{r, c};
-          if (scores) {
-            const int sc = fast9_score_at(im, r, c, th);
-            scores[pos] = score_div ? ((sc / 16) & 255) : sc;
-          }
-        }
-        pos++;
-      }
-      off += __shfl_sync(0xffffffffu, incl, 31);
+#pragma unroll 1
+  for (int w0 = 0; w0 < wpr; w0 += 32) {
+    const int wi = w0 + lane;
+    uint32_t word = w0 < FE_MAXW * 32 ? rowbits[warp][wi] : (wi < wpr ? bits[(long long)r * wpr + wi] : 0u);  // rows wider than 16384 pixels: the rest loads as it goes
+    const int cnt = __popc(word);
+    int incl = cnt;
+    for (int o = 1; o < 32; o <<= 1) {
+      int y = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += y;
     }
+    int pos = off + incl - cnt;
+    while (word) {
+      const int b = __ffs(word) - 1;
+      word &= word - 1;
+      if (pos < capacity) {
+        const int c = wi * 32 + b;
+        kps[pos] = vppb_int2{r, c};
+        if (scores) scores[pos] = fast9_score_out(im, r, c, th, score_div);
+      }
+      pos++;
+    }
+    off += __shfl_sync(0xffffffffu, incl, 31);
   }
 }
 
