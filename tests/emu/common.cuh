@@ -29,6 +29,11 @@ int cuda_fail(cudaError_t e, const char* what);
   } while (0)
 
 inline cudaStream_t as_stream(void* s) { return s; }
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_dependent(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t, Args... args) {
+  ::emu::launch((long long)grid, (long long)block, [&]() { kernel(static_cast<KArgs>(args)...); }, smem);  // kernels run to completion one after another here
+  return cudaSuccess;
+}
 int sm_count();  // core.cu: cudaDeviceGetAttribute -> 2 here, so every thread runs several trips of its grid-stride loop
 
 struct Img {
@@ -52,6 +57,8 @@ inline void st_release(int* p, int v) { *p = v; }
 }  // namespace vppb
 namespace emu { void yield(); }
 namespace vppb {
-inline void spin_pause() { emu::yield(); }  // a spinning fiber hands the CPU to the other threads of the block
+inline void spin_pause() { emu::yield(); }
+inline void grid_dependency_wait() {}
+inline void grid_launch_dependents() {}  // a spinning fiber hands the CPU to the other threads of the block
 
 }  // namespace vppb

@@ -34,6 +34,23 @@ int cuda_fail(cudaError_t e, const char* what);
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// launch `kernel` so that it may begin before the previous kernel of the stream has finished (it must call grid_dependency_wait())
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_dependent(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)grid, 1, 1);
+  cfg.blockDim = dim3((unsigned)block, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // Number of SMs of the current device (148 on B200); cached per process.
 int sm_count();
 
@@ -79,5 +96,10 @@ __device__ __forceinline__ int ld_acquire(const int* p) {
 }
 __device__ __forceinline__ void st_release(int* p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 __device__ __forceinline__ void spin_pause() { __nanosleep(20); }
+// programmatic dependent launch: a kernel launched with launch_dependent() may start (barrier init, descriptor prefetch, loads
+// of data the previous kernel does not write) while the previous kernel of the stream drains; grid_dependency_wait() returns
+// when that kernel has completed and its writes are visible.
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 }  // namespace vppb

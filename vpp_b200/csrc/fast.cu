@@ -132,6 +132,7 @@ __global__ void __launch_bounds__(FB_THREADS, 5) k_fast9_band(const __grid_const
   int* ncand = reinterpret_cast<int*>(bar + 1);    // [FB_WARPS], one counter per warp
   int* rowcnt = ncand + FB_WARPS;                  // [FB_ROWS]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  grid_launch_dependents();  // the emit kernel may be scheduled as SMs free up; it waits for this grid before it reads anything
   const int band = blockIdx.x / nboxes, k = blockIdx.x - band * nboxes, r0 = band * FB_ROWS;
   const int rows_here = min(FB_ROWS, im.nrows - r0);
   const int thb = th & 255;  // S::repeat(th) replicates the low byte (fast.hpp:120-126)
@@ -279,6 +280,7 @@ __global__ void __launch_bounds__(FB_THREADS) k_fast9_emit_bands(Img im, int th,
   const int r0 = blockIdx.x * FE_ROWS, band = r0 / FB_ROWS;   // FE_ROWS is a multiple of FB_ROWS: the CTA starts on a band boundary
   const int r = r0 + warp;
   const bool row_ok = warp < FE_ROWS && r < im.nrows;
+  grid_dependency_wait();  // launched programmatically behind the tile kernel: its bitmask and counts are complete from here on
 #pragma unroll
   for (int q = 0; q < FE_MAXW; q++) {
     const int wi = q * 32 + lane;
@@ -616,7 +618,8 @@ static int fast9_core(const vppb_img* img, int32_t th, const vppb_img* mask, int
     else if (!has_mask) k_fast9_band<1, false><<<grid, FB_THREADS, FB_SMEM, st>>>(tmap, im, mk, th, nboxes, wpr, ws.bits_a, ws.rowcount, ws.bandtotal);
     else k_fast9_band<1, true><<<grid, FB_THREADS, FB_SMEM, st>>>(tmap, im, mk, th, nboxes, wpr, ws.bits_a, ws.rowcount, ws.bandtotal);
     if (mode == VPPB_FAST_ALL) {
-      k_fast9_emit_bands<<<(img->nrows + FE_ROWS - 1) / FE_ROWS, FB_THREADS, 0, st>>>(im, th, ws.bits_a, wpr, ws.rowcount, ws.bandtotal, nbands, nboxes, kps_out, scores_out, 0, capacity, cnt);
+      VPPB_CUDA(launch_dependent(k_fast9_emit_bands, (img->nrows + FE_ROWS - 1) / FE_ROWS, FB_THREADS, 0, st, im, th, (const uint32_t*)ws.bits_a, wpr, (const int*)ws.rowcount,
+                                 (const int*)ws.bandtotal, nbands, nboxes, kps_out, (int*)scores_out, 0, (int)capacity, cnt));
       VPPB_LAUNCH_CHECK(name);
       return VPPB_OK;
     }

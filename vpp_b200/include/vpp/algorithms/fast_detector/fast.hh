@@ -3,6 +3,8 @@
 // raster order; `_ring = 1` (extension) selects the true Bresenham ring instead of the ring fast9()
 // actually samples (fast.hpp:367-368).
 #pragma once
+#include <algorithm>
+#include <memory>
 #include <vector>
 #include <vpp/core/image2d.hh>
 
@@ -38,19 +40,29 @@ std::vector<vint2> fast9(const image2d<unsigned char>& A, int th, OPTS... opts_)
   const int block_size = opts.get(s::_block_size, 10);
   const int mode = opts.has(s::_local_maxima) ? VPPB_FAST_LOCAL_MAXIMA : (opts.has(s::_blockwise) ? VPPB_FAST_BLOCKWISE : VPPB_FAST_ALL);
   const int ring = opts.get(s::_ring, 0);
-  internals::device_array ws((size_t)vppb_fast9_workspace_bytes(A.nrows(), A.ncols(), block_size));
-  int capacity = std::max(1024, A.nrows() * A.ncols() / 16), count = 0;
+  // workspace and output buffers are kept between calls (one set per thread, regrown when an image or a result needs more):
+  // a detector that runs every frame allocates nothing; the device work is queued without a host synchronisation
+  // (vppb_fast9_u8_async), then the 4-byte count and the keypoints are read back once.
+  struct cache_t { std::unique_ptr<internals::device_array> ws, kps, sc, cnt; size_t ws_bytes = 0; int capacity = 0; };
+  static thread_local cache_t cache;
+  const size_t ws_bytes = (size_t)vppb_fast9_workspace_bytes(A.nrows(), A.ncols(), block_size);
+  if (cache.ws_bytes < ws_bytes) { cache.ws.reset(new internals::device_array(ws_bytes)); cache.ws_bytes = ws_bytes; }
+  if (!cache.cnt) cache.cnt.reset(new internals::device_array(4));
+  int capacity = std::max(std::max(1024, A.nrows() * A.ncols() / 16), cache.capacity), count = 0;
   std::vector<vint2> kps;
   for (;;) {
-    internals::device_array dk((size_t)capacity * sizeof(vppb_int2)), ds(scores ? (size_t)capacity * 4 : 0);
-    int rc = vppb_fast9_u8(A.device_read(), th, mask.has_data() ? mask.device_read() : nullptr, mode, block_size, ring, ws.ptr(),
-                           vppb_fast9_workspace_bytes(A.nrows(), A.ncols(), block_size), (vppb_int2*)dk.ptr(),
-                           scores ? (int32_t*)ds.ptr() : nullptr, capacity, &count, nullptr);
-    if (rc == VPPB_E_CAPACITY) { capacity = count; continue; }
-    vppb_check(rc);
+    if (cache.capacity < capacity) {
+      cache.kps.reset(new internals::device_array((size_t)capacity * sizeof(vppb_int2)));
+      cache.sc.reset(new internals::device_array((size_t)capacity * 4));
+      cache.capacity = capacity;
+    }
+    vppb_check(vppb_fast9_u8_async(A.device_read(), th, mask.has_data() ? mask.device_read() : nullptr, mode, block_size, ring, cache.ws->ptr(), (int64_t)cache.ws_bytes,
+                                   (vppb_int2*)cache.kps->ptr(), scores ? (int32_t*)cache.sc->ptr() : nullptr, cache.capacity, (int32_t*)cache.cnt->ptr(), nullptr));
+    cache.cnt->to_host(&count, 4);
+    if (count > cache.capacity) { capacity = count; continue; }  // keypoints beyond the capacity were dropped: run again with room for all
     kps.resize(count);
-    dk.to_host(kps.data(), (size_t)count * sizeof(vint2));
-    if (scores) { scores->resize(count); ds.to_host(scores->data(), (size_t)count * 4); }
+    cache.kps->to_host(kps.data(), (size_t)count * sizeof(vint2));
+    if (scores) { scores->resize(count); cache.sc->to_host(scores->data(), (size_t)count * 4); }
     return kps;
   }
 }
