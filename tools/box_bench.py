@@ -12,12 +12,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 VARIANTS = [
+    ("default", {}),
     ("tile", {"VPPB_BOX_IMPL": "tile"}),
     ("stream_lw4", {"VPPB_BOX_LW": "4", "VPPB_BOX_SINGLE": "stream"}),
     ("stream_lw4_occ", {"VPPB_BOX_LW": "4", "VPPB_BOX_OCC": "1", "VPPB_BOX_SINGLE": "stream"}),
-    ("stream_lw8", {"VPPB_BOX_LW": "8", "VPPB_BOX_SINGLE": "stream"}),
-    ("stream_lw8_occ", {"VPPB_BOX_LW": "8", "VPPB_BOX_OCC": "1", "VPPB_BOX_SINGLE": "stream"}),
-    ("stream_lw4_bal", {"VPPB_BOX_LW": "4", "VPPB_BOX_BAL": "1", "VPPB_BOX_SINGLE": "stream"}),
 ]
 
 

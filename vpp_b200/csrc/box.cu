@@ -204,9 +204,11 @@ __global__ void __launch_bounds__(BX_THREADS, BX_TH == 16 ? 4 : 6) k_box5_bytes_
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + BX_RAW_BYTES + BX_CS_BYTES);
   const int tid = threadIdx.x;
   const uint32_t minus_one = 0u - one;
+  grid_launch_dependents();
+  if (tid == 0) mbar_init(bar, 1);
+  grid_dependency_wait();  // launched programmatically behind the previous kernel of the stream
 
   if (tid == 0) {
-    mbar_init(bar, 1);
     fence_barrier_init();
     mbar_arrive_expect_tx(bar, BX_RAW_BYTES);
     // tensor origin = 16 bytes left of x = 0, 2 rows above y = 0; elements are 8 bytes; the box starts at
@@ -379,12 +381,14 @@ __global__ void __launch_bounds__(BoxStreamCfg<LW, OCC>::WARPS * 32, BoxStreamCf
   const int per_img = p.strips * p.chunks;
   const uint32_t one = p.one, minus_one = 0u - p.one, shl16 = p.one << 16;
 
+  grid_launch_dependents();  // the next kernel of the stream may be scheduled while this one drains (it waits before it reads)
   if (lane == 0) {
 #pragma unroll
     for (int s = 0; s < Cfg::STAGES; s++) mbar_init(&bars[s], 1);
     fence_barrier_init();
   }
   __syncwarp();
+  grid_dependency_wait();    // launched programmatically: everything above overlapped the previous kernel's tail; its writes are visible now
 
   // producer cursor (meaningful in lane 0 only): the next stage to fetch is rows [py, py + 5) of tensor map pmap at element
   // column px; pleft stages remain in the current task.  A task is decoded once (two divisions), a stage costs a handful of
@@ -622,7 +626,7 @@ static int box5_stream_launch_occ(const vppb_img* ins, const vppb_img* ups, cons
     p.row_room = ins[0].pitch - (int)bs;
   }
   const int ctas = (p.total + Cfg::WARPS - 1) / Cfg::WARPS, resident = sm_count() * Cfg::CTAS_PER_SM;
-  k_box5_stream<CS, LW, BAL, NB, OCC><<<ctas < resident ? ctas : resident, Cfg::WARPS * 32, Cfg::SMEM, st>>>(p);
+  VPPB_CUDA(launch_dependent(k_box5_stream<CS, LW, BAL, NB, OCC>, ctas < resident ? ctas : resident, Cfg::WARPS * 32, Cfg::SMEM, st, p));
   VPPB_LAUNCH_CHECK(name);
   return VPPB_OK;
 }
@@ -706,9 +710,9 @@ static int box5_bytes(const vppb_img* in, const vppb_img* out, void* stream, con
     const int resident = sm_count() * (th == 16 ? 4 : 6);
     const int grid = ntiles < resident ? ntiles : resident;
     if (th == 16)
-      k_box5_bytes_tma<CS, 16><<<grid, BX_THREADS, BoxCfg<16>::SMEM, st>>>(tmap, view(out), rowbytes, strips, ntiles, vec_store, 1u);
+      VPPB_CUDA(launch_dependent(k_box5_bytes_tma<CS, 16>, grid, BX_THREADS, BoxCfg<16>::SMEM, st, tmap, view(out), rowbytes, strips, ntiles, vec_store, 1u));
     else
-      k_box5_bytes_tma<CS, 8><<<grid, BX_THREADS, BoxCfg<8>::SMEM, st>>>(tmap, view(out), rowbytes, strips, ntiles, vec_store, 1u);
+      VPPB_CUDA(launch_dependent(k_box5_bytes_tma<CS, 8>, grid, BX_THREADS, BoxCfg<8>::SMEM, st, tmap, view(out), rowbytes, strips, ntiles, vec_store, 1u));
   } else {
     long long total = (long long)in->nrows * rowbytes;
     long long blocks = (total + 255) / 256;
