@@ -53,6 +53,8 @@ inline int4 ld_stream(const int4* p) { return *p; }
 inline void st_stream(int4* p, const int4& v) { *p = v; }
 
 inline int ld_acquire(const int* p) { return *p; }
+inline unsigned long long ld_acquire64(const unsigned long long* p) { return *p; }
+inline void st_release64(unsigned long long* p, unsigned long long v) { *p = v; }
 inline void st_release(int* p, int v) { *p = v; }
 }  // namespace vppb
 namespace emu { void yield(); }

@@ -27,13 +27,24 @@ constexpr unsigned FULLM = 0xffffffffu;
 
 struct SdofLevel {
   Img i1, i2;
-  int2* flow;            // cells: (cr + 2) x (cc + 2) entries, row stride = cstride
+  // one 64-bit record per cell: flow.x (16 bits, signed) | flow.y (16) | distance (24, 0xFFFFFF = INT_MAX) | sweep (8: the last
+  // sweep, 1-based, of this scale that has finished with the cell).  A single word so that the dataflow sweeps get a
+  // neighbour's flow together with its "done" stamp in ONE acquire load, and publish both with one release store.
+  unsigned long long* rec;  // cells: (cr + 2) x (cc + 2) entries, row stride = cstride
   unsigned char* mark;
-  int* dist;
   int* owner;
-  int* done;             // per cell: the last sweep (1-based) of this scale that has finished with the cell
   int cr, cc, cstride;   // cell-map domain (pf_domain pyramid level) and row stride
 };
+
+__device__ __forceinline__ unsigned long long rec_pack(int fx, int fy, int dist, int sweep) {
+  const unsigned d = dist == INT_MAX ? 0xFFFFFFu : (unsigned)dist;
+  return (unsigned long long)((unsigned)fx & 0xFFFFu) | ((unsigned long long)((unsigned)fy & 0xFFFFu) << 16) | ((unsigned long long)(d & 0xFFFFFFu) << 32) |
+         ((unsigned long long)((unsigned)sweep & 0xFFu) << 56);
+}
+__device__ __forceinline__ int rec_fx(unsigned long long r) { return (int)(short)(r & 0xFFFFu); }
+__device__ __forceinline__ int rec_fy(unsigned long long r) { return (int)(short)((r >> 16) & 0xFFFFu); }
+__device__ __forceinline__ int rec_dist(unsigned long long r) { const unsigned d = (unsigned)((r >> 32) & 0xFFFFFFu); return d == 0xFFFFFFu ? INT_MAX : (int)d; }
+__device__ __forceinline__ int rec_sweep(unsigned long long r) { return (int)(r >> 56); }
 
 __device__ __forceinline__ int sad_warp(const Img& a, const Img& b, int ar, int ac, int br, int bc, int ws) {
   if (ar < 0 || ar >= a.nrows || ac < 0 || ac >= a.ncols || br < 0 || br >= b.nrows || bc < 0 || bc >= b.ncols) return INT_MAX;  // :102-108
@@ -77,7 +88,7 @@ __device__ __forceinline__ void descent_warp(const Img& a, const Img& b, int pr,
 
 __global__ void k_sdof_clear(SdofLevel L) {
   const int total = (L.cr + 2) * L.cstride;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) { L.mark[i] = 0; L.owner[i] = INT_MAX; L.done[i] = 0; }
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) { L.mark[i] = 0; L.owner[i] = INT_MAX; L.rec[i] = 0ull; }
 }
 
 __global__ void k_sdof_claim(SdofLevel L, const vppb_int2* kps, int n, int scale_div, int patch) {
@@ -103,44 +114,76 @@ __global__ void __launch_bounds__(128) k_sdof_match(SdofLevel L, SdofLevel coars
     int predr = pr, predc = pc;
     if (has_coarser) {
       const int m = (pr / (2 * patch)) * coarser.cstride + (pc / (2 * patch));
-      if (coarser.mark[m]) { predr = pr + coarser.flow[m].x * 2; predc = pc + coarser.flow[m].y * 2; }
+      if (coarser.mark[m]) { const unsigned long long cr_ = coarser.rec[m]; predr = pr + rec_fx(cr_) * 2; predc = pc + rec_fy(cr_) * 2; }
     }
     int flr, flc, d;
     descent_warp(L.i1, L.i2, pr, pc, predr, predc, ws, 5, flr, flc, d);
-    if (lane == 0) { L.flow[cell] = make_int2(flr, flc); L.dist[cell] = d; L.mark[cell] = 2; }
+    if (lane == 0) { L.rec[cell] = rec_pack(flr, flc, d, 0); L.mark[cell] = 2; }
   }
 }
 
 // :149-189, iteration (kr, kc) of a propagation sweep, executed by one warp; forward sweeps start at pixel 0 and step
 // +patch, backward sweeps start at the last pixel and step -patch (so p is not the cell corner there)
-__device__ __forceinline__ void sdof_prop_cell(const SdofLevel& L, int kr, int kc, int forward, int patch, int ws, int lane) {
+// `epoch` > 0 (dataflow sweeps): the lanes that hold a PREDECESSOR of the sweep order wait until its record carries this sweep's number;
+// the cell's own record is published with it.  epoch == 0 (launch-ordered schedules): plain loads, the stamp stays 0.
+__device__ __forceinline__ void sdof_prop_cell(const SdofLevel& L, int kr, int kc, int forward, int patch, int ws, int lane, int epoch = 0, int nkc = 0) {
   const int inr = L.i1.nrows, inc = L.i1.ncols;
   const int r = forward ? kr * patch : inr - 1 - kr * patch, c = forward ? kc * patch : inc - 1 - kc * patch;
   const int fr = r / patch, fc = c / patch;
   const int cell = fr * L.cstride + fc;
   if (!L.mark[cell]) return;  // warp-uniform
-  int2 cur = __ldcg(&L.flow[cell]);
-  const int2 prev = cur;
-  int d1 = __ldcg(&L.dist[cell]);
-  bool changed = false;
-  for (int dr = -1; dr <= 1; dr++)
-    for (int dc = -1; dc <= 1; dc++) {
-      if (!dr && !dc) continue;
-      const int nr = fr + dr, nc = fc + dc;
-      if (nr < 0 || nr >= L.cr || nc < 0 || nc >= L.cc) continue;
+  // the cell's own record and its 8 neighbours' are fetched at once, one per lane (lane k = (dr + 1) * 3 + (dc + 1); lane 4 = the
+  // cell itself): the neighbours do not change while this iteration runs - predecessors of the sweep are done, successors wait
+  // for it - so one memory round trip replaces eight.
+  int nmark = 0;
+  unsigned long long nrec = 0;
+  if (lane < 9) {
+    const int dr = lane / 3 - 1, dc = lane % 3 - 1;
+    const int nr = fr + dr, nc = fc + dc;
+    if (nr >= 0 && nr < L.cr && nc >= 0 && nc < L.cc) {
       const int ncell = nr * L.cstride + nc;
-      if (!L.mark[ncell]) continue;
-      const int2 nf = __ldcg(&L.flow[ncell]);  // written by other SMs during a dataflow sweep: read it where they wrote it (L2)
-      const int a0 = cur.x - nf.x, a1 = cur.y - nf.y, b0 = prev.x - nf.x, b1 = prev.y - nf.y;
-      if (a0 * a0 + a1 * a1 < 9 || b0 * b0 + b1 * b1 < 9) continue;  // integer norm() > 2
-      const int d2 = sad_warp(L.i1, L.i2, r, c, r + nf.x, c + nf.y, ws);
-      if (d2 < d1) {
-        int flr, flc, d;
-        descent_warp(L.i1, L.i2, r, c, r + nf.x, c + nf.y, ws, 5, flr, flc, d);
-        if (d < d1) { cur = make_int2(flr, flc); d1 = d; changed = true; }
+      nmark = L.mark[ncell];
+      if (nmark) {
+        if (epoch > 0) {
+          // predecessors in sweep coordinates: (kr, kc-1), (kr-1, kc-1), (kr-1, kc), (kr-1, kc+1); a step of +1 in sweep coordinates is a
+          // step of sgn in cell coordinates
+          const int sgn = forward ? 1 : -1;
+          const int skr = dr * sgn, skc = dc * sgn;  // the neighbour's offset in sweep coordinates
+          const bool pred = (skr == -1 || (skr == 0 && skc == -1)) && kr + skr >= 0 && kc + skc >= 0 && kc + skc < nkc;
+          nrec = ld_acquire64(&L.rec[ncell]);
+          if (pred)
+            while (rec_sweep(nrec) < epoch) { spin_pause(); nrec = ld_acquire64(&L.rec[ncell]); }
+        } else {
+          nrec = __ldcg(&L.rec[ncell]);
+        }
       }
     }
-  if (changed && lane == 0) { L.flow[cell] = cur; L.dist[cell] = d1; L.mark[cell] = 1; }
+  }
+  const unsigned long long own = __shfl_sync(FULLM, nrec, 4);
+  int2 cur = make_int2(rec_fx(own), rec_fy(own));
+  const int2 prev = cur;
+  int d1 = rec_dist(own);
+#pragma unroll 1
+  for (int k = 0; k < 9; k++) {
+    if (k == 4) continue;
+    if (!__shfl_sync(FULLM, nmark, k)) continue;  // outside the cell map or unmarked
+    const unsigned long long nr_ = __shfl_sync(FULLM, nrec, k);
+    const int2 nf = make_int2(rec_fx(nr_), rec_fy(nr_));
+    const int a0 = cur.x - nf.x, a1 = cur.y - nf.y, b0 = prev.x - nf.x, b1 = prev.y - nf.y;
+    if (a0 * a0 + a1 * a1 < 9 || b0 * b0 + b1 * b1 < 9) continue;  // integer norm() > 2
+    const int d2 = sad_warp(L.i1, L.i2, r, c, r + nf.x, c + nf.y, ws);
+    if (d2 < d1) {
+      int flr, flc, d;
+      descent_warp(L.i1, L.i2, r, c, r + nf.x, c + nf.y, ws, 5, flr, flc, d);
+      if (d < d1) { cur = make_int2(flr, flc); d1 = d; }
+    }
+  }
+  const bool changed = cur.x != prev.x || cur.y != prev.y || d1 != rec_dist(own);
+  if (lane == 0) {
+    if (changed) L.mark[cell] = 1;
+    if (epoch > 0) st_release64(&L.rec[cell], rec_pack(cur.x, cur.y, d1, epoch));  // flow, distance and the "done" stamp in one store
+    else if (changed) L.rec[cell] = rec_pack(cur.x, cur.y, d1, 0);
+  }
 }
 
 // the iterations (kr, kc) of one sweep with kc + 2 kr == t: iteration (kr, kc) only reads what (kr, kc-1) and
@@ -169,7 +212,6 @@ __global__ void __launch_bounds__(128) k_sdof_sweep(SdofLevel L, int forward, in
   const int lane = threadIdx.x & 31;
   const int inr = L.i1.nrows, inc = L.i1.ncols;
   const int total = nkr * nkc;
-  const int sgn = forward ? 1 : -1;  // a step of +1 in sweep coordinates is a step of sgn in cell coordinates
   // wavefront order: diagonal t holds the iterations kr in [lo(t), hi(t)], lo = max(0, ceil((t - nkc + 1) / 2)), hi = min(nkr - 1, t / 2).
   // first(t) = number of iterations on the diagonals before t, in closed form for the three regimes of the band
   // (growing, full width, shrinking) would need case analysis: a warp instead walks the diagonals incrementally - its
@@ -191,24 +233,7 @@ __global__ void __launch_bounds__(128) k_sdof_sweep(SdofLevel L, int forward, in
     const int fr = r / patch, fc = c / patch;
     const int cell = fr * L.cstride + fc;
     if (!L.mark[cell]) continue;  // marks only go from 2 to 1 during the sweeps: "marked" never changes
-    // lanes 0..3 watch one predecessor each
-    if (lane < 4) {
-      const int pr = lane == 0 ? fr : fr - sgn, pc = lane == 0 ? fc - sgn : fc + (lane - 2) * sgn;
-      // the predecessor must be an iteration of the sweep (inside the cell map AND inside the sweep's kr / kc range)
-      const int pkr = lane == 0 ? kr : kr - 1, pkc = lane == 0 ? kc - 1 : kc + (lane - 2);
-      if (pkr >= 0 && pkc >= 0 && pkc < nkc && pr >= 0 && pr < L.cr && pc >= 0 && pc < L.cc) {
-        const int pcell = pr * L.cstride + pc;
-        if (L.mark[pcell])
-          while (ld_acquire(&L.done[pcell]) < epoch) spin_pause();
-      }
-    }
-    __syncwarp();
-    sdof_prop_cell(L, kr, kc, forward, patch, ws, lane);
-    __syncwarp();
-    if (lane == 0) {
-      __threadfence();
-      st_release(&L.done[cell], epoch);
-    }
+    sdof_prop_cell(L, kr, kc, forward, patch, ws, lane, epoch, nkc);
   }
 }
 
@@ -291,7 +316,8 @@ __global__ void k_sdof_emit(SdofLevel L, const vppb_int2* kps, int n, int div, i
     int v = 0, pr = 0, pc = 0, d = 0;
     if (kps[i].r >= 0 && kps[i].c >= 0 && fr < L.cr && fc < L.cc && L.mark[fr * L.cstride + fc]) {
       const int cell = fr * L.cstride + fc;
-      v = 1; pr = kps[i].r + L.flow[cell].x * mul; pc = kps[i].c + L.flow[cell].y * mul; d = L.dist[cell];
+      const unsigned long long rc_ = L.rec[cell];
+      v = 1; pr = kps[i].r + rec_fx(rc_) * mul; pc = kps[i].c + rec_fy(rc_) * mul; d = rec_dist(rc_);
     }
     valid[i] = (unsigned char)v; pos[i].r = pr; pos[i].c = pc; dist[i] = d;
   }
@@ -314,7 +340,7 @@ static long long sched_bytes(int nrows, int ncols, int patch) {
 }
 static long long level_bytes(int cr, int cc) {
   const long long cells = (long long)(cr + 2) * (cc + 2);
-  return ((cells * (8 + 4 + 4 + 4 + 1) + 255) / 256) * 256 + 1024;
+  return ((cells * (8 + 4 + 1) + 255) / 256) * 256 + 1024;
 }
 
 }  // namespace vppb
@@ -350,11 +376,9 @@ int vppb_sdof_u8(const vppb_img* pyr1, const vppb_img* pyr2, const vppb_sdof_par
     const long long cells = (long long)(cr + 2) * (cc + 2);
     L[s].i1 = view(&pyr1[s]); L[s].i2 = view(&pyr2[s]);
     L[s].cr = cr; L[s].cc = cc; L[s].cstride = cc + 2;
-    L[s].flow = reinterpret_cast<int2*>(w);
-    L[s].dist = reinterpret_cast<int*>(w + cells * 8);
-    L[s].owner = reinterpret_cast<int*>(w + cells * 12);
-    L[s].done = reinterpret_cast<int*>(w + cells * 16);
-    L[s].mark = w + cells * 20;
+    L[s].rec = reinterpret_cast<unsigned long long*>(w);
+    L[s].owner = reinterpret_cast<int*>(w + cells * 8);
+    L[s].mark = w + cells * 12;
     w += level_bytes(cr, cc);
   }
   // opt-in: VPPB_SDOF_SCHEDULE=levels runs every sweep as dependency levels of the marked cells when that is shorter than the
