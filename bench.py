@@ -479,12 +479,22 @@ def main():
     h2d = (th * rowb) if world == 1 else (th + 4) * (W + 4) * 3
     e_frames = min(frames_per_step, 256)  # frames per e2e step (a bounded sample of the step: PCIe time dominates)
 
+    # Two ways to bring a whole host frame into the bordered device image (N = 1), both through the public C-ABI, same launch count:
+    #   direct: vppb_upload straight into the pitched image (a 2-D copy: host rows are tight, device rows are padded), then vppb_fill_border_mirror;
+    #   staged: vppb_upload into a border-less image whose rows are as tight as the host's (ONE linear copy), then vppb_copy2d_mirror
+    #           (copy + mirror border in one launch).  Both are timed; the faster carries the e2e number, both times are reported.
+    e_stage = [vpp.Image2d(th, W, "vuchar3") for _ in range(NE2E)] if world == 1 else []
+    e2e_mode = ["direct"]
+
     def e2e_step():
         for i in range(e_frames):
             k = i % NE2E
             st = C.c_void_p(streams[k].cuda_stream)
             hin = host_in[i % len(host_in)]
-            if world == 1:
+            if world == 1 and e2e_mode[0] == "staged":
+                capi.check(capi.lib.vppb_upload(e_stage[k].ptr(), C.c_void_p(hin.data_ptr()), rowb, 0, st))
+                capi.check(capi.lib.vppb_copy2d_mirror(e_stage[k].ptr(), e_src[k].ptr(), st))
+            elif world == 1:
                 capi.check(capi.lib.vppb_upload(e_src[k].ptr(), C.c_void_p(hin.data_ptr()), rowb, 0, st))
                 capi.check(capi.lib.vppb_fill_border_mirror(e_src[k].ptr(), st))
             else:
@@ -495,6 +505,19 @@ def main():
         for s_ in streams:
             s_.synchronize()
 
+    e2e_ms = {}
+    for m_ in (["direct", "staged"] if world == 1 else ["direct"]):
+        e2e_mode[0] = m_
+        e2e_step()
+        torch.cuda.synchronize()
+        if not np.array_equal(host_out[0].numpy(), hd[0]):
+            sys.stderr.write("e2e form %s gives a different result: not used\n" % m_)
+            continue
+        t0 = time.perf_counter()
+        e2e_step()
+        torch.cuda.synchronize()
+        e2e_ms[m_] = (time.perf_counter() - t0) * 1e3
+    e2e_mode[0] = min(e2e_ms, key=e2e_ms.get) if e2e_ms else "direct"
     for _ in range(2):
         e2e_step()
     barrier()
@@ -509,7 +532,8 @@ def main():
     dt = float(te.item())
     e2e = {"value": esteps * e_frames * H * W / 1e6 / dt, "unit": "Mpix/s", "h2d_bytes_per_step": e_frames * h2d * world,
            "d2h_bytes_per_step": e_frames * th * rowb * world, "ms_per_step": dt / esteps * 1e3, "frames_per_e2e_step": e_frames,
-           "note": "pinned host frames -> vppb_upload + vppb_fill_border_mirror -> vppb_box5x5_u8c3 -> vppb_download, 4 frames in flight per rank, max over ranks"}
+           "upload": {"used": e2e_mode[0], "ms_per_step_by_form": e2e_ms},
+           "note": "pinned host frames -> vppb_upload (+ mirror border: direct 2-D copy + vppb_fill_border_mirror, or linear copy + vppb_copy2d_mirror, the faster of the two) -> vppb_box5x5_u8c3 -> vppb_download, 4 frames in flight per rank, max over ranks"}
     parity_ok = parity_ok and bool(np.array_equal(host_out[0].numpy(), hd[0]))
     if dist is not None:  # every rank checked its own tile
         pk = torch.tensor([1.0 if parity_ok else 0.0], dtype=torch.float64, device=dev)
