@@ -210,6 +210,10 @@ inline unsigned __funnelshift_l(unsigned lo, unsigned hi, unsigned shift) {  // 
   shift &= 31;
   return shift ? (hi << shift) | (lo >> (32 - shift)) : hi;
 }
+inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned shift) {  // SHF.R.W: lower word of (hi:lo) >> (shift & 31)
+  shift &= 31;
+  return shift ? (lo >> shift) | (hi << (32 - shift)) : lo;
+}
 inline unsigned __byte_perm(unsigned x, unsigned y, unsigned s) {  // PRMT, default mode, selectors 0..7
   const uint64_t v = ((uint64_t)y << 32) | x;
   unsigned r = 0;

@@ -46,38 +46,99 @@ __device__ __forceinline__ int rec_fy(unsigned long long r) { return (int)(short
 __device__ __forceinline__ int rec_dist(unsigned long long r) { const unsigned d = (unsigned)((r >> 32) & 0xFFFFFFu); return d == 0xFFFFFFu ? INT_MAX : (int)d; }
 __device__ __forceinline__ int rec_sweep(unsigned long long r) { return (int)(r >> 56); }
 
-__device__ __forceinline__ int sad_warp(const Img& a, const Img& b, int ar, int ac, int br, int bc, int ws) {
-  if (ar < 0 || ar >= a.nrows || ac < 0 || ac >= a.ncols || br < 0 || br >= b.nrows || bc < 0 || bc >= b.ncols) return INT_MAX;  // :102-108
-  const int lane = threadIdx.x & 31, h = ws / 2, n = ws * ws;
-  const unsigned char* pa = a.base + (long long)(ar - h) * a.pitch + (ac - h);
-  const unsigned char* pb = b.base + (long long)(br - h) * b.pitch + (bc - h);
-  int s = 0;
-  for (int i = lane; i < n; i += 32) {
-    const int r = i / ws, c = i - r * ws;
-    s += abs((int)pa[(long long)r * a.pitch + c] - (int)pb[(long long)r * b.pitch + c]);
+__constant__ int c_c8_it[9][2] = {{6, 3}, {0, 3}, {0, 5}, {2, 5}, {2, 7}, {4, 7}, {4, 1}, {6, 1}, {0, 0}};
+__constant__ int c_c8[8][2] = {{-1, 1}, {0, 1}, {1, 1}, {-1, 0}, {1, 0}, {-1, -1}, {0, -1}, {1, -1}};
+// c_c8 for a lane-dependent index without a constant-bank replay: (offset + 1) in 2-bit fields
+__device__ __forceinline__ int c8_dr(int i) { return (int)((0x9224u >> (2 * i)) & 3u) - 1; }
+__device__ __forceinline__ int c8_dc(int i) { return (int)((0x016Au >> (2 * i)) & 3u) - 1; }
+
+// ---- batched SADs -----------------------------------------------------------------------------------------------------------
+// A propagation iteration needs the SADs of up to 8 candidate flows, a descent step those of the 8 neighbours of the current
+// position: independent sums that the reference evaluates one after the other.  Here a group of 4 lanes owns one candidate
+// (8 candidates per warp at once); a lane sums whole window rows (rows sub, sub + 4, ...) with aligned 32-bit loads, a funnel
+// shift to the window's byte offset and VABSDIFF4-with-sum, all loads of a lane in flight together: one memory round trip per
+// batch instead of one per candidate.  Integer sums: the grouping changes nothing in the result.
+__device__ __forceinline__ unsigned sad_rows(const unsigned char* pa, long long apitch, const unsigned char* pb, long long bpitch, int ws, int sub, int nl) {
+  unsigned s = 0;
+  const bool words = ((apitch | bpitch) & 3) == 0;  // aligned words never leave a row allocation whose pitch is a multiple of 4
+  if (!words) {  // rows whose pitch is not a multiple of 4 (wrapped user memory): byte loads
+    for (int row = sub; row < ws; row += nl)
+      for (int x = 0; x < ws; x++) s += (unsigned)abs((int)pa[row * apitch + x] - (int)pb[row * bpitch + x]);
+    return s;
   }
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULLM, s, o);
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const int row = sub + j * nl;
+    if (row < ws) {
+      const unsigned char* ra = pa + row * apitch;
+      const unsigned char* rb = pb + row * bpitch;
+      const unsigned oa = (unsigned)(unsigned long long)ra & 3u, ob = (unsigned)(unsigned long long)rb & 3u;
+      const unsigned* wa = reinterpret_cast<const unsigned*>(ra - oa);
+      const unsigned* wb = reinterpret_cast<const unsigned*>(rb - ob);
+      const int la = (int)(oa + ws - 1) >> 2, lb = (int)(ob + ws - 1) >> 2;  // last aligned word the row touches
+      unsigned a[5], b[5];
+#pragma unroll
+      for (int q = 0; q < 5; q++) {
+        a[q] = q <= la ? wa[q] : 0u;
+        b[q] = q <= lb ? wb[q] : 0u;
+      }
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        if (q * 4 < ws) {
+          unsigned va = __funnelshift_r(a[q], a[q + 1], oa * 8), vb = __funnelshift_r(b[q], b[q + 1], ob * 8);
+          const int rem = ws - q * 4;
+          if (rem < 4) { const unsigned m = (1u << (8 * rem)) - 1u; va &= m; vb &= m; }
+          s += __vsadu4(va, vb);
+        }
+      }
+    }
+  }
   return s;
 }
 
-__constant__ int c_c8_it[9][2] = {{6, 3}, {0, 3}, {0, 5}, {2, 5}, {2, 7}, {4, 7}, {4, 1}, {6, 1}, {0, 0}};
-__constant__ int c_c8[8][2] = {{-1, 1}, {0, 1}, {1, 1}, {-1, 0}, {1, 0}, {-1, -1}, {0, -1}, {1, -1}};
+__device__ __forceinline__ bool sad_inside(const Img& a, const Img& b, int ar, int ac, int br, int bc) {
+  return !(ar < 0 || ar >= a.nrows || ac < 0 || ac >= a.ncols || br < 0 || br >= b.nrows || bc < 0 || bc >= b.ncols);  // :102-108
+}
 
-// gradient_descent.hh:10-89 (whole warp, uniform control flow)
-__device__ __forceinline__ void descent_warp(const Img& a, const Img& b, int pr, int pc, int predr, int predc, int ws, int max_it, int& flr,
+// one SAD by the whole warp (a lane per window row)
+__device__ __forceinline__ int sad_warp(const Img& a, const Img& b, int ar, int ac, int br, int bc, int ws) {
+  if (!sad_inside(a, b, ar, ac, br, bc)) return INT_MAX;
+  const int lane = threadIdx.x & 31, h = ws / 2;
+  unsigned s = sad_rows(a.base + (long long)(ar - h) * a.pitch + (ac - h), a.pitch, b.base + (long long)(br - h) * b.pitch + (bc - h), b.pitch, ws, lane, 32);
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULLM, s, o);
+  return (int)s;
+}
+
+// the SAD of the candidate of this lane's group of 4 (all four lanes pass the same arguments); every lane of the warp calls it
+__device__ __forceinline__ int sad_group4(const Img& a, const Img& b, int ar, int ac, int br, int bc, int ws, bool active) {
+  const bool inside = sad_inside(a, b, ar, ac, br, bc);
+  const int h = ws / 2;
+  unsigned s = 0;
+  if (active && inside)
+    s = sad_rows(a.base + (long long)(ar - h) * a.pitch + (ac - h), a.pitch, b.base + (long long)(br - h) * b.pitch + (bc - h), b.pitch, ws, threadIdx.x & 3, 4);
+  s += __shfl_xor_sync(FULLM, s, 1);
+  s += __shfl_xor_sync(FULLM, s, 2);
+  return inside ? (int)s : INT_MAX;
+}
+
+// gradient_descent.hh:10-89 (whole warp, uniform control flow).  `md` = the SAD at the prediction (the caller has it).  A step
+// evaluates the 8 neighbours of the current position at once (group i <-> c_c8[i]) and then replays the reference's visiting
+// order and strict comparisons on the eight values, so the walk is the reference's.
+__device__ __forceinline__ void descent_warp(const Img& a, const Img& b, int pr, int pc, int predr, int predc, int ws, int max_it, int md, int& flr,
                                              int& flc, int& dist) {
+  const int g = (threadIdx.x & 31) >> 2;
+  const int gdr = c8_dr(g), gdc = c8_dc(g);
   int mr = predr, mc = predc;
-  int md = sad_warp(a, b, pr, pc, predr, predc, ws);
   int mi = 8;
   for (int search = 0; search < max_it; search++) {
+    const int dg = sad_group4(a, b, pr, pc, predr + gdr, predc + gdc, ws, true);
     int i = c_c8_it[mi][0];
     const int end = c_c8_it[mi][1];
     bool first = true;
     while (first || i != end) {
       first = false;
-      const int nr = predr + c_c8[i][0], nc = predc + c_c8[i][1];
-      const int d = sad_warp(a, b, pr, pc, nr, nc, ws);
-      if (d < md) { mr = nr; mc = nc; mi = i; md = d; }
+      const int d = __shfl_sync(FULLM, dg, i * 4);
+      if (d < md) { mr = predr + c_c8[i][0]; mc = predc + c_c8[i][1]; mi = i; md = d; }
       i = (i + 1) & 7;
     }
     if (predr == mr && predc == mc) break;
@@ -117,7 +178,7 @@ __global__ void __launch_bounds__(128) k_sdof_match(SdofLevel L, SdofLevel coars
       if (coarser.mark[m]) { const unsigned long long cr_ = coarser.rec[m]; predr = pr + rec_fx(cr_) * 2; predc = pc + rec_fy(cr_) * 2; }
     }
     int flr, flc, d;
-    descent_warp(L.i1, L.i2, pr, pc, predr, predc, ws, 5, flr, flc, d);
+    descent_warp(L.i1, L.i2, pr, pc, predr, predc, ws, 5, sad_warp(L.i1, L.i2, pr, pc, predr, predc, ws), flr, flc, d);
     if (lane == 0) { L.rec[cell] = rec_pack(flr, flc, d, 0); L.mark[cell] = 2; }
   }
 }
@@ -126,43 +187,19 @@ __global__ void __launch_bounds__(128) k_sdof_match(SdofLevel L, SdofLevel coars
 // +patch, backward sweeps start at the last pixel and step -patch (so p is not the cell corner there)
 // `epoch` > 0 (dataflow sweeps): the lanes that hold a PREDECESSOR of the sweep order wait until its record carries this sweep's number;
 // the cell's own record is published with it.  epoch == 0 (launch-ordered schedules): plain loads, the stamp stays 0.
-__device__ __forceinline__ void sdof_prop_cell(const SdofLevel& L, int kr, int kc, int forward, int patch, int ws, int lane, int epoch = 0, int nkc = 0) {
-  const int inr = L.i1.nrows, inc = L.i1.ncols;
-  const int r = forward ? kr * patch : inr - 1 - kr * patch, c = forward ? kc * patch : inc - 1 - kc * patch;
-  const int fr = r / patch, fc = c / patch;
-  const int cell = fr * L.cstride + fc;
-  if (!L.mark[cell]) return;  // warp-uniform
-  // the cell's own record and its 8 neighbours' are fetched at once, one per lane (lane k = (dr + 1) * 3 + (dc + 1); lane 4 = the
-  // cell itself): the neighbours do not change while this iteration runs - predecessors of the sweep are done, successors wait
-  // for it - so one memory round trip replaces eight.
-  int nmark = 0;
-  unsigned long long nrec = 0;
-  if (lane < 9) {
-    const int dr = lane / 3 - 1, dc = lane % 3 - 1;
-    const int nr = fr + dr, nc = fc + dc;
-    if (nr >= 0 && nr < L.cr && nc >= 0 && nc < L.cc) {
-      const int ncell = nr * L.cstride + nc;
-      nmark = L.mark[ncell];
-      if (nmark) {
-        if (epoch > 0) {
-          // predecessors in sweep coordinates: (kr, kc-1), (kr-1, kc-1), (kr-1, kc), (kr-1, kc+1); a step of +1 in sweep coordinates is a
-          // step of sgn in cell coordinates
-          const int sgn = forward ? 1 : -1;
-          const int skr = dr * sgn, skc = dc * sgn;  // the neighbour's offset in sweep coordinates
-          const bool pred = (skr == -1 || (skr == 0 && skc == -1)) && kr + skr >= 0 && kc + skc >= 0 && kc + skc < nkc;
-          nrec = ld_acquire64(&L.rec[ncell]);
-          if (pred)
-            while (rec_sweep(nrec) < epoch) { spin_pause(); nrec = ld_acquire64(&L.rec[ncell]); }
-        } else {
-          nrec = __ldcg(&L.rec[ncell]);
-        }
-      }
-    }
-  }
+// the arithmetic of one iteration: lanes 0..8 hold the mark and the record of the 3 x 3 cells around the iteration's cell (lane 4 = the
+// cell itself); returns the cell's new flow and distance on every lane
+__device__ __forceinline__ void sdof_prop_eval(const SdofLevel& L, int r, int c, int ws, int nmark, unsigned long long nrec, int2& cur, int& d1) {
+  const int lane = threadIdx.x & 31;
   const unsigned long long own = __shfl_sync(FULLM, nrec, 4);
-  int2 cur = make_int2(rec_fx(own), rec_fy(own));
+  cur = make_int2(rec_fx(own), rec_fy(own));
   const int2 prev = cur;
-  int d1 = rec_dist(own);
+  d1 = rec_dist(own);
+  // the SADs of all marked neighbours' flows at once: group g of 4 lanes <-> neighbour k = g (+1 past the centre)
+  const int g = lane >> 2, kg = g + (g >= 4);
+  const int mg = __shfl_sync(FULLM, nmark, kg);
+  const unsigned long long rg = __shfl_sync(FULLM, nrec, kg);
+  const int dg = sad_group4(L.i1, L.i2, r, c, r + rec_fx(rg), c + rec_fy(rg), ws, mg != 0);
 #pragma unroll 1
   for (int k = 0; k < 9; k++) {
     if (k == 4) continue;
@@ -171,14 +208,66 @@ __device__ __forceinline__ void sdof_prop_cell(const SdofLevel& L, int kr, int k
     const int2 nf = make_int2(rec_fx(nr_), rec_fy(nr_));
     const int a0 = cur.x - nf.x, a1 = cur.y - nf.y, b0 = prev.x - nf.x, b1 = prev.y - nf.y;
     if (a0 * a0 + a1 * a1 < 9 || b0 * b0 + b1 * b1 < 9) continue;  // integer norm() > 2
-    const int d2 = sad_warp(L.i1, L.i2, r, c, r + nf.x, c + nf.y, ws);
+    const int d2 = __shfl_sync(FULLM, dg, (k - (k > 4)) * 4);
     if (d2 < d1) {
       int flr, flc, d;
-      descent_warp(L.i1, L.i2, r, c, r + nf.x, c + nf.y, ws, 5, flr, flc, d);
+      descent_warp(L.i1, L.i2, r, c, r + nf.x, c + nf.y, ws, 5, d2, flr, flc, d);
       if (d < d1) { cur = make_int2(flr, flc); d1 = d; }
     }
   }
-  const bool changed = cur.x != prev.x || cur.y != prev.y || d1 != rec_dist(own);
+}
+
+__device__ __forceinline__ void sdof_prop_cell(const SdofLevel& L, int kr, int kc, int forward, int patch, int ws, int lane, int epoch = 0, int nkc = 0) {
+  const int inr = L.i1.nrows, inc = L.i1.ncols;
+  const int r = forward ? kr * patch : inr - 1 - kr * patch, c = forward ? kc * patch : inc - 1 - kc * patch;
+  const int fr = r / patch, fc = c / patch;
+  const int cell = fr * L.cstride + fc;
+  if (!L.mark[cell]) return;  // warp-uniform
+  // the cell's own record and its 8 neighbours' are fetched at once, one per lane (lane k = (dr + 1) * 3 + (dc + 1); lane 4 = the
+  // cell itself)
+  int nmark = 0;
+  bool pred = false;
+  unsigned long long nrec = 0;
+  const unsigned long long* nptr = L.rec;
+  if (lane < 9) {
+    const int dr = lane / 3 - 1, dc = lane % 3 - 1;
+    const int nr = fr + dr, nc = fc + dc;
+    if (nr >= 0 && nr < L.cr && nc >= 0 && nc < L.cc) {
+      const int ncell = nr * L.cstride + nc;
+      nmark = L.mark[ncell];
+      if (nmark) {
+        nptr = &L.rec[ncell];
+        if (epoch > 0) {
+          // predecessors in sweep coordinates: (kr, kc-1), (kr-1, kc-1), (kr-1, kc), (kr-1, kc+1); a step of +1 in sweep coordinates is a
+          // step of sgn in cell coordinates
+          const int sgn = forward ? 1 : -1;
+          const int skr = dr * sgn, skc = dc * sgn;  // the neighbour's offset in sweep coordinates
+          pred = (skr == -1 || (skr == 0 && skc == -1)) && kr + skr >= 0 && kc + skc >= 0 && kc + skc < nkc;
+          nrec = ld_acquire64(nptr);
+        } else {
+          nrec = __ldcg(nptr);
+        }
+      }
+    }
+  }
+  const int d0 = rec_dist(__shfl_sync(FULLM, nrec, 4));
+  const int2 prev = make_int2(rec_fx(__shfl_sync(FULLM, nrec, 4)), rec_fy(__shfl_sync(FULLM, nrec, 4)));
+  int2 cur;
+  int d1;
+  // Dataflow sweeps SPECULATE: the iteration is evaluated on the records as they are now, without waiting for the predecessors; only
+  // then do the lanes that hold a predecessor wait for its stamp of this sweep.  A record whose flow did not change (the usual case: a
+  // sweep moves few cells) validates the speculation - the result is a function of the nine flows and the cell's own distance - and the
+  // warp publishes at once: the chain of dependent iterations then costs one flag hop per cell instead of hop + SADs.  Otherwise
+  // the iteration is redone on the final records (successors cannot have changed: they wait for this cell's stamp).
+  sdof_prop_eval(L, r, c, ws, nmark, nrec, cur, d1);
+  if (epoch > 0) {
+    unsigned long long fin = nrec;
+    if (pred)
+      while (rec_sweep(fin) < epoch) { spin_pause(); fin = ld_acquire64(nptr); }
+    const bool moved = nmark && (unsigned)fin != (unsigned)nrec;  // flow.x | flow.y are the low 32 bits
+    if (__any_sync(FULLM, moved)) sdof_prop_eval(L, r, c, ws, nmark, fin, cur, d1);
+  }
+  const bool changed = cur.x != prev.x || cur.y != prev.y || d1 != d0;
   if (lane == 0) {
     if (changed) L.mark[cell] = 1;
     if (epoch > 0) st_release64(&L.rec[cell], rec_pack(cur.x, cur.y, d1, epoch));  // flow, distance and the "done" stamp in one store
