@@ -834,7 +834,7 @@ def gpu_extras(vpp, capi, torch, stream, sp, dev):
         ms = timed(run, 5)
         ms_pyr = timed(pyr, 5)
         return {"ms": ms + ms_pyr, "ms_flow": ms, "ms_pyramids": ms_pyr, "keypoints": n, "parity": ok,
-                "note": "video_extruder's settings (winsize 9, 3 scales, patch 5, 2 sweeps); one persistent dataflow launch per sweep"}
+                "note": "video_extruder's settings (winsize 9, 3 scales, patch 5, 2 sweeps); the whole flow (3 scales: claim, match, sweeps by relaxation, emit) in ONE cooperative launch"}
 
     def sdof_1080p():
         return sdof(1080, 1920)

@@ -34,6 +34,14 @@ inline cudaError_t launch_dependent(void (*kernel)(KArgs...), int grid, int bloc
   ::emu::launch((long long)grid, (long long)block, [&]() { kernel(static_cast<KArgs>(args)...); }, smem);  // kernels run to completion one after another here
   return cudaSuccess;
 }
+// blocks run one after another here, so a kernel with grid-wide barriers gets a grid of ONE block
+template <typename K> inline int cooperative_grid_limit(K, int) { return 1; }
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_cooperative(void (*kernel)(KArgs...), int grid, int block, cudaStream_t, Args... args) {
+  if (grid != 1) return 1;
+  ::emu::launch((long long)grid, (long long)block, [&]() { kernel(static_cast<KArgs>(args)...); }, 0);
+  return cudaSuccess;
+}
 int sm_count();  // core.cu: cudaDeviceGetAttribute -> 2 here, so every thread runs several trips of its grid-stride loop
 
 struct Img {

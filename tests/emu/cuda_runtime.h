@@ -181,6 +181,7 @@ template <typename T> inline T __ldcg(const T* p) { return *p; }
 inline void __threadfence() {}
 inline void __nanosleep(unsigned) {}
 template <typename T> inline void __stcs(T* p, T v) { *p = v; }
+template <typename T> inline void __stcg(T* p, T v) { *p = v; }
 inline float __fdiv_rn(float a, float b) { return a / b; }
 inline float __fadd_rn(float a, float b) { return a + b; }
 inline float __fsub_rn(float a, float b) { return a - b; }

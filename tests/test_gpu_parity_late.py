@@ -188,15 +188,18 @@ def test_cpp_programs(gpu, name):
     assert r.returncode == 0 and "ALL OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 
+@pytest.mark.parametrize("schedule", ["levels", "dataflow", "antidiagonals"])
 @pytest.mark.parametrize("density", ["sparse", "dense"])
-def test_semi_dense_flow_level_schedule(vpp, monkeypatch, density):
-    """VPPB_SDOF_SCHEDULE=levels (opt-in): the propagation sweeps run as dependency levels of the marked cells instead of
-    anti-diagonals - same serial semantics, so the results must equal the oracle bit for bit.  sparse: blockwise-FAST
-    keypoints (video_extruder's case: few levels); dense: a keypoint in every cell (the schedule falls back to anti-diagonals
-    wherever levels would not halve the launches)."""
+def test_semi_dense_flow_level_schedule(vpp, monkeypatch, density, schedule):
+    """The opt-in schedules of the propagation sweeps (the default, one cooperative launch that solves every sweep by
+    relaxation, is what every other flow test runs): VPPB_SDOF_SCHEDULE=levels runs dependency levels of the marked cells,
+    =dataflow one persistent launch per sweep with flags between cells, =antidiagonals one launch per anti-diagonal - same
+    serial semantics, so the results must equal the oracle bit for bit.  sparse: blockwise-FAST keypoints (video_extruder's
+    case: few levels); dense: a keypoint in every cell (the level schedule falls back to anti-diagonals wherever levels would
+    not halve the launches)."""
     from tests import scenes
 
-    monkeypatch.setenv("VPPB_SDOF_SCHEDULE", "levels")
+    monkeypatch.setenv("VPPB_SDOF_SCHEDULE", schedule)
     nr, nc = 121, 161
     f1, f2, _ = scenes.lk_pair(nr, nc, 4, seed=23, shift=(3.0, -2.0), margin=10)
     o = orc.load()
@@ -218,6 +221,34 @@ def test_semi_dense_flow_level_schedule(vpp, monkeypatch, density):
         assert np.array_equal(valid, rvalid.astype(bool)) and valid.sum() > 10
         ok = rvalid > 0
         assert np.array_equal(pos[ok], rpos[ok]) and np.array_equal(dist[ok], rdist[ok]), (density, ws, nscales, prop, patch)
+
+
+@pytest.mark.parametrize("shape,shift,nscales,prop", [((96, 131), (6.0, -5.0), 1, 4), ((121, 161), (9.0, 8.0), 2, 3), ((64, 203), (-5.0, 6.0), 1, 2)])
+def test_semi_dense_flow_long_propagation_chains(vpp, shape, shift, nscales, prop):
+    """A shift the greedy descent cannot reach from a zero prediction: most cells start on a wrong local minimum and the few
+    lucky ones spread their flow along the sweeps, cell after cell - the worst case of the relaxation schedule (one round
+    per link of the chain, many rounds, work lists refilled round after round).  A keypoint in every cell; exact against
+    the oracle."""
+    from tests import scenes
+
+    nr, nc = shape
+    f1, f2, _ = scenes.lk_pair(nr, nc, 4, seed=31, shift=shift, margin=10)
+    o = orc.load()
+    rr, cc = np.meshgrid(np.arange(2, nr, 5), np.arange(2, nc, 5), indexing="ij")
+    kps = np.stack([rr.ravel(), cc.ravel()], axis=1).astype(np.int32)
+    m = len(kps)
+    res = {}
+    for p in (0, prop):
+        pos, dist, valid = vpp.semi_dense_optical_flow(kps, vpp.Image2d.from_host(f1, "u8"), vpp.Image2d.from_host(f2, "u8"), winsize=9, nscales=nscales,
+                                                       propagation=p, patchsize=5)
+        h1, h2 = orc.HostImage(nr, nc, "u8", data=f1), orc.HostImage(nr, nc, "u8", data=f2)
+        rpos, rdist, rvalid = np.zeros((m, 2), np.int32), np.zeros(m, np.int32), np.zeros(m, np.uint8)
+        o.vo_semi_dense_flow(h1.ptr(), h2.ptr(), kps.ctypes.data, m, 9, nscales, 0, p, 5, rpos.ctypes.data, rdist.ctypes.data, rvalid.ctypes.data)
+        assert np.array_equal(valid, rvalid.astype(bool)) and valid.sum() > m // 2
+        assert np.array_equal(pos, rpos) and np.array_equal(dist, rdist), (shape, shift, p)
+        res[p] = pos
+    moved = (res[0] != res[prop]).any(axis=1).sum()
+    assert moved > m // 4, "the sweeps were meant to move many cells (moved %d of %d)" % (moved, m)
 
 
 # ------------------------------------------------------------------ FAST9 band kernel: several TMA boxes per band, ragged tails

@@ -34,7 +34,7 @@ for (H, W) in [(1080, 1920), (4320, 7680)]:
         capi.check(capi.lib.vppb_sdof_u8(p1.desc_array(), p2.desc_array(), C.byref(P), d_kp.ptr, n, ws.ptr, ws.nbytes, d_pos.ptr, d_dist.ptr, d_valid.ptr, None))
         capi.check(capi.lib.vppb_sync(None))
 
-    for sched in ("levels", None):  # the opt-in dependency-level schedule first, the default (anti-diagonals) last: its numbers print below
+    for sched in ("levels", "dataflow", None):  # the opt-in schedules first, the default (one cooperative launch, relaxation) last: its numbers print below
         if sched:
             os.environ["VPPB_SDOF_SCHEDULE"] = sched
         else:

@@ -54,6 +54,29 @@ inline cudaError_t launch_dependent(void (*kernel)(KArgs...), int grid, int bloc
 // Number of SMs of the current device (148 on B200); cached per process.
 int sm_count();
 
+// cooperative launch: every CTA of the grid is resident at the same time, so the kernel may use grid-wide barriers.
+// cooperative_grid_limit = the largest such grid of `kernel` with `block` threads and no dynamic shared memory.
+template <typename K>
+inline int cooperative_grid_limit(K kernel, int block) {
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+  return per_sm * sm_count();
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_cooperative(void (*kernel)(KArgs...), int grid, int block, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)grid, 1, 1);
+  cfg.blockDim = dim3((unsigned)block, 1, 1);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // Device-side image view (a trimmed vppb_img passed by value to kernels).
 struct Img {
   unsigned char* base;  // pixel (0,0)

@@ -34,6 +34,12 @@ struct SdofLevel {
   unsigned char* mark;
   int* owner;
   int cr, cc, cstride;   // cell-map domain (pf_domain pyramid level) and row stride
+  // relaxation schedule (k_sdof_fused): second record buffer (a sweep reads `old`, writes `cur`), a stamp per cell that dedups the
+  // work lists, the list of marked cells and two alternating work lists
+  unsigned long long* rec2;
+  int* stamp;
+  int* mlist;
+  int* wl[2];
 };
 
 __device__ __forceinline__ unsigned long long rec_pack(int fx, int fy, int dist, int sweep) {
@@ -399,6 +405,178 @@ __global__ void __launch_bounds__(128) k_sdof_prop_list(SdofLevel L, const unsig
   }
 }
 
+// ---- relaxation schedule (default): the WHOLE flow (all scales: clear, claim, match, sweeps, emit) in ONE cooperative launch ----
+// A Gauss-Seidel sweep is the unique solution X of  X(c) = f(old(c), X(predecessors of c), old(successors of c))  over the marked
+// cells, where the predecessors of an iteration are the 4 neighbours the sweep visits before it.  That system is triangular, so it
+// can also be solved by relaxation:  round 0 evaluates every marked cell on the pre-sweep records (all cells at once); round k >= 1
+// re-evaluates exactly the cells one of whose predecessors changed its FLOW in round k-1 (a work list, deduplicated by a stamp per
+// cell), reading predecessors from `cur` and successors / the cell itself from `old`.  A cell read while its predecessor is being
+// rewritten is re-queued by that predecessor, so when a round queues nothing every cell has been evaluated on the final records of
+// its predecessors: the fixed point is the serial sweep, bit for bit, whatever the order inside a round.  A sweep moves few cells,
+// so the number of rounds is the length of the longest chain of *moving* cells (a handful), not the number of anti-diagonals; each
+// round is one grid-wide barrier.  Worst case (a flow that propagates along a whole row): as many rounds as the dataflow schedule
+// has hops.
+struct SdofFused {
+  SdofLevel L[8];
+  int nscales, min_scale, patch, ws, propagation, n;
+  const vppb_int2* kps;
+  vppb_int2* out_pos;
+  int* out_dist;
+  unsigned char* out_valid;
+  int* ctr;  // zeroed before the launch: [0] grid barrier, [1], [2] statistics, [8 + 128 * scale] marked cells of the scale, [.. + 4 + 4 * sweep + 0..2] work-list lengths
+};
+
+// all CTAs of a cooperative launch are resident: a counter barrier.  `gen` counts the barriers passed (uniform over the grid).
+__device__ __forceinline__ void grid_barrier(int* bar, int& gen) {
+  __syncthreads();
+  gen++;
+  if (threadIdx.x == 0) {
+    const int target = gen * (int)gridDim.x;
+    __threadfence();
+    atomicAdd(bar, 1);
+    while (ld_acquire(bar) < target) spin_pause();
+  }
+  __syncthreads();
+}
+
+// one evaluation of cell `cell` in a relaxation round (one warp).  first: round 0 of the sweep (everything read from `old`, `cur`
+// written unconditionally); later rounds compare with the cell's previous `cur`.  A cell whose flow moved queues its successors.
+__device__ __forceinline__ void sdof_relax_cell(const SdofLevel& L, const unsigned long long* old, unsigned long long* cur, int cell, int forward, int nkr,
+                                                int nkc, int patch, int ws, bool first, int stampval, int* wl_next, int* cnt_next) {
+  const int lane = threadIdx.x & 31;
+  const int inr = L.i1.nrows, inc = L.i1.ncols;
+  const int fr = cell / L.cstride, fc = cell - fr * L.cstride;
+  const int kr = forward ? fr : (inr - 1) / patch - fr, kc = forward ? fc : (inc - 1) / patch - fc;
+  if (kr < 0 || kr >= nkr || kc < 0 || kc >= nkc) {  // a marked cell no iteration of the sweep visits keeps its record (warp-uniform)
+    if (first && lane == 0) __stcg(cur + cell, __ldcg(old + cell));
+    return;
+  }
+  const int r = forward ? kr * patch : inr - 1 - kr * patch, c = forward ? kc * patch : inc - 1 - kc * patch;
+  const int sgn = forward ? 1 : -1;  // a step of +1 in sweep coordinates is a step of sgn in cell coordinates
+  int nmark = 0;
+  unsigned long long nrec = 0;
+  if (lane < 9) {
+    const int dr = lane / 3 - 1, dc = lane % 3 - 1;
+    const int nr = fr + dr, nc = fc + dc;
+    if (nr >= 0 && nr < L.cr && nc >= 0 && nc < L.cc) {
+      const int ncell = nr * L.cstride + nc;
+      nmark = __ldcg(L.mark + ncell);
+      if (nmark) {
+        const int skr = dr * sgn, skc = dc * sgn;
+        const bool pred = !first && (skr == -1 || (skr == 0 && skc == -1)) && kr + skr >= 0 && kc + skc >= 0 && kc + skc < nkc;
+        nrec = __ldcg(pred ? cur + ncell : old + ncell);
+      }
+    }
+  }
+  unsigned long long mine = 0;
+  if (lane == 9 && !first) mine = __ldcg(cur + cell);
+  const unsigned long long ref = first ? __shfl_sync(FULLM, nrec, 4) : __shfl_sync(FULLM, mine, 9);
+  int2 res;
+  int d1;
+  sdof_prop_eval(L, r, c, ws, nmark, nrec, res, d1);
+  const unsigned long long out = rec_pack(res.x, res.y, d1, 0);
+  if ((first || out != ref) && lane == 0) __stcg(cur + cell, out);
+  if ((unsigned)out != (unsigned)ref && lane < 4) {  // flow.x | flow.y are the low 32 bits
+    // successors in sweep coordinates: (0, +1), (+1, -1), (+1, 0), (+1, +1)
+    const int skr = lane == 0 ? 0 : 1, skc = lane == 0 ? 1 : lane - 2;
+    const int kr2 = kr + skr, kc2 = kc + skc;
+    const int nr = fr + skr * sgn, nc = fc + skc * sgn;
+    if (kr2 < nkr && kc2 >= 0 && kc2 < nkc && nr >= 0 && nr < L.cr && nc >= 0 && nc < L.cc) {
+      const int ncell = nr * L.cstride + nc;
+      if (__ldcg(L.mark + ncell) && atomicMax(L.stamp + ncell, stampval) < stampval) wl_next[atomicAdd(cnt_next, 1)] = ncell;
+    }
+  }
+}
+
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB) k_sdof_fused(const SdofFused P) {
+  const int lane = threadIdx.x & 31;
+  const int gthreads = gridDim.x * blockDim.x, gtid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nwarps = gthreads >> 5, gwarp = gtid >> 5;
+  int gen = 0;
+  int* const bar = P.ctr;
+  // clear + claim of every scale (a claim depends on nothing but the keypoints)
+  for (int scale = P.nscales - 1; scale >= P.min_scale; scale--) {
+    const SdofLevel& L = P.L[scale];
+    const int total = (L.cr + 2) * L.cstride;
+    for (int i = gtid; i < total; i += gthreads) { L.mark[i] = 0; L.owner[i] = INT_MAX; L.stamp[i] = 0; }
+  }
+  grid_barrier(bar, gen);
+  for (int scale = P.nscales - 1; scale >= P.min_scale; scale--) {
+    const SdofLevel& L = P.L[scale];
+    const int scale_div = 1 << scale;
+    for (int i = gtid; i < P.n; i += gthreads) {
+      const int kr_ = P.kps[i].r, kc_ = P.kps[i].c;
+      if (kr_ < 0 || kc_ < 0) continue;
+      const int fr = (kr_ / scale_div) / P.patch, fc = (kc_ / scale_div) / P.patch;
+      if (fr >= L.cr || fc >= L.cc || kr_ / scale_div >= L.i1.nrows || kc_ / scale_div >= L.i1.ncols) continue;
+      atomicMin(&L.owner[fr * L.cstride + fc], i);
+    }
+  }
+  grid_barrier(bar, gen);
+  const unsigned long long* coarser_rec = nullptr;  // final records of the scale above
+  for (int scale = P.nscales - 1; scale >= P.min_scale; scale--) {
+    const SdofLevel& L = P.L[scale];
+    const int scale_div = 1 << scale;
+    int* const sctr = P.ctr + 8 + 128 * scale;
+    // match (:114-143): the owner of a cell (lowest keypoint index == first in serial order), one warp per keypoint
+    for (int i = gwarp; i < P.n; i += nwarps) {
+      const int kr_ = P.kps[i].r, kc_ = P.kps[i].c;
+      if (kr_ < 0 || kc_ < 0) continue;  // warp-uniform
+      const int pr = kr_ / scale_div, pc = kc_ / scale_div;
+      if (pr >= L.i1.nrows || pc >= L.i1.ncols || pr / P.patch >= L.cr || pc / P.patch >= L.cc) continue;
+      const int cell = (pr / P.patch) * L.cstride + (pc / P.patch);
+      if (__ldcg(L.owner + cell) != i) continue;  // warp-uniform
+      int predr = pr, predc = pc;
+      if (coarser_rec) {
+        const SdofLevel& C = P.L[scale + 1];
+        const int m = (pr / (2 * P.patch)) * C.cstride + (pc / (2 * P.patch));
+        if (__ldcg(C.mark + m)) { const unsigned long long cr_ = __ldcg(coarser_rec + m); predr = pr + rec_fx(cr_) * 2; predc = pc + rec_fy(cr_) * 2; }
+      }
+      int flr, flc, d;
+      descent_warp(L.i1, L.i2, pr, pc, predr, predc, P.ws, 5, sad_warp(L.i1, L.i2, pr, pc, predr, predc, P.ws), flr, flc, d);
+      if (lane == 0) { __stcg(L.rec + cell, rec_pack(flr, flc, d, 0)); L.mark[cell] = 2; L.mlist[atomicAdd(sctr, 1)] = cell; }
+    }
+    grid_barrier(bar, gen);
+    const int nm = __ldcg(sctr);
+    const int nkr = (L.i1.nrows + P.patch - 1) / P.patch, nkc = (L.i1.ncols + P.patch - 1) / P.patch;
+    unsigned long long* old = L.rec;
+    unsigned long long* cur = L.rec2;
+    for (int Ki = 0; Ki < P.propagation; Ki++) {
+      const int forward = Ki % 2;  // :191-200: odd iterations forward, even (incl. the first) backward
+      int* const cnt = sctr + 4 + 4 * Ki;
+      const int stamp0 = Ki << 20;
+      for (int i = gwarp; i < nm; i += nwarps)
+        sdof_relax_cell(L, old, cur, __ldcg(L.mlist + i), forward, nkr, nkc, P.patch, P.ws, true, stamp0 + 1, L.wl[0], cnt);
+      grid_barrier(bar, gen);
+      for (int k = 1;; k++) {
+        const int nq = __ldcg(cnt + (k - 1) % 3);
+        if (nq == 0) break;  // grid-uniform: the counter is stable until every CTA has passed the next barrier
+        if (gtid == 0) { cnt[(k + 1) % 3] = 0; P.ctr[1] += 1; P.ctr[2] += nq; }  // statistics: rounds and re-evaluations of the call
+        for (int i = gwarp; i < nq; i += nwarps)
+          sdof_relax_cell(L, old, cur, __ldcg(L.wl[(k - 1) & 1] + i), forward, nkr, nkc, P.patch, P.ws, false, stamp0 + k + 1, L.wl[k & 1], cnt + k % 3);
+        grid_barrier(bar, gen);
+      }
+      unsigned long long* t = old; old = cur; cur = t;
+    }
+    coarser_rec = old;  // the last sweep's result (or the matches if there is no sweep)
+  }
+  // results (:205-212)
+  const SdofLevel& L = P.L[P.min_scale];
+  const int div = P.patch * (1 << P.min_scale), mul = 1 << P.min_scale;
+  for (int i = gtid; i < P.n; i += gthreads) {
+    const int kr_ = P.kps[i].r, kc_ = P.kps[i].c;
+    const int fr = kr_ / div, fc = kc_ / div;
+    int v = 0, pr = 0, pc = 0, d = 0;
+    if (kr_ >= 0 && kc_ >= 0 && fr < L.cr && fc < L.cc && __ldcg(L.mark + fr * L.cstride + fc)) {
+      const unsigned long long rc_ = __ldcg(coarser_rec + fr * L.cstride + fc);
+      v = 1; pr = kr_ + rec_fx(rc_) * mul; pc = kc_ + rec_fy(rc_) * mul; d = rec_dist(rc_);
+    }
+    P.out_valid[i] = (unsigned char)v; P.out_pos[i].r = pr; P.out_pos[i].c = pc; P.out_dist[i] = d;
+  }
+}
+
+
 __global__ void k_sdof_emit(SdofLevel L, const vppb_int2* kps, int n, int div, int mul, vppb_int2* pos, int* dist, unsigned char* valid) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const int fr = kps[i].r / div, fc = kps[i].c / div;
@@ -422,14 +600,15 @@ static void sched_dims(int nrows, int ncols, int patch, long long& cells, int& c
   cells = (long long)(nkr + 3) * (nkc + 3);
   cap = nkc + 2 * nkr + 2;  // more than the number of anti-diagonals = upper bound of the number of levels
 }
+constexpr long long kCtrBytes = 8192;  // 2048 ints: dataflow tickets (256) or the relaxation schedule's barrier + 128 per scale
 static long long sched_bytes(int nrows, int ncols, int patch) {
   long long cells; int cap;
   sched_dims(nrows, ncols, patch, cells, cap);
-  return ((cells * 8 + (2LL + 2LL * (cap + 1)) * 4 + 255) / 256) * 256 + 256 + 1024;  // + the ticket counters of the dataflow sweeps
+  return ((cells * 8 + (2LL + 2LL * (cap + 1)) * 4 + 255) / 256) * 256 + 256 + kCtrBytes;  // + the counters of the dataflow / relaxation sweeps
 }
 static long long level_bytes(int cr, int cc) {
   const long long cells = (long long)(cr + 2) * (cc + 2);
-  return ((cells * (8 + 4 + 1) + 255) / 256) * 256 + 1024;
+  return ((cells * (8 + 8 + 4 + 4 + 3 * 4 + 1) + 255) / 256) * 256 + 1024;  // rec, rec2, owner, stamp, mlist + 2 work lists, mark
 }
 
 }  // namespace vppb
@@ -466,8 +645,13 @@ int vppb_sdof_u8(const vppb_img* pyr1, const vppb_img* pyr2, const vppb_sdof_par
     L[s].i1 = view(&pyr1[s]); L[s].i2 = view(&pyr2[s]);
     L[s].cr = cr; L[s].cc = cc; L[s].cstride = cc + 2;
     L[s].rec = reinterpret_cast<unsigned long long*>(w);
-    L[s].owner = reinterpret_cast<int*>(w + cells * 8);
-    L[s].mark = w + cells * 12;
+    L[s].rec2 = reinterpret_cast<unsigned long long*>(w + cells * 8);
+    L[s].owner = reinterpret_cast<int*>(w + cells * 16);
+    L[s].stamp = reinterpret_cast<int*>(w + cells * 20);
+    L[s].mlist = reinterpret_cast<int*>(w + cells * 24);
+    L[s].wl[0] = reinterpret_cast<int*>(w + cells * 28);
+    L[s].wl[1] = reinterpret_cast<int*>(w + cells * 32);
+    L[s].mark = w + cells * 36;
     w += level_bytes(cr, cc);
   }
   // opt-in: VPPB_SDOF_SCHEDULE=levels runs every sweep as dependency levels of the marked cells when that is shorter than the
@@ -475,15 +659,47 @@ int vppb_sdof_u8(const vppb_img* pyr1, const vppb_img* pyr2, const vppb_sdof_par
   const char* sched_env = getenv("VPPB_SDOF_SCHEDULE");
   const bool use_levels = sched_env && strcmp(sched_env, "levels") == 0;
   const bool use_waves = sched_env && strcmp(sched_env, "antidiagonals") == 0;
-  const bool use_dataflow = !use_levels && !use_waves;  // default: one persistent launch per sweep
+  const bool use_flags = sched_env && strcmp(sched_env, "dataflow") == 0;  // one persistent launch per sweep, flags between cells
+  // default: the relaxation schedule, the whole call in ONE cooperative launch (needs the keypoints' outputs, at most 30 sweeps per scale)
+  const bool use_relax = !use_levels && !use_waves && !use_flags && p->propagation <= 30;
+  const bool use_dataflow = !use_levels && !use_waves && !use_relax;
   long long sched_cells; int sched_cap;
   sched_dims(pyr1[0].nrows, pyr1[0].ncols, p->patchsize, sched_cells, sched_cap);
   int* lvl = reinterpret_cast<int*>(w);
   unsigned* cell_list = reinterpret_cast<unsigned*>(w + sched_cells * 4);
   int* sched = reinterpret_cast<int*>(w + sched_cells * 8);
-  int* tickets = reinterpret_cast<int*>(w + sched_bytes(pyr1[0].nrows, pyr1[0].ncols, p->patchsize) - 1024);  // 256 counters, one per (scale, sweep)
+  int* tickets = reinterpret_cast<int*>(w + sched_bytes(pyr1[0].nrows, pyr1[0].ncols, p->patchsize) - kCtrBytes);  // 256 counters, one per (scale, sweep)
   VPPB_REQUIRE(!use_dataflow || p->nscales * p->propagation <= 256, VPPB_E_ARG, "vppb_sdof_u8: more than 256 sweeps");
   if (use_dataflow) VPPB_CUDA(cudaMemsetAsync(tickets, 0, 1024, st));
+  if (use_relax) {
+    SdofFused F;
+    memset(&F, 0, sizeof(F));
+    for (int s = 0; s < p->nscales; s++) F.L[s] = L[s];
+    F.nscales = p->nscales; F.min_scale = p->min_scale; F.patch = p->patchsize; F.ws = p->winsize; F.propagation = p->propagation; F.n = n;
+    F.kps = kps; F.out_pos = out_pos; F.out_dist = out_dist; F.out_valid = out_valid; F.ctr = tickets;
+    VPPB_CUDA(cudaMemsetAsync(tickets, 0, kCtrBytes, st));
+    // work: a warp per keypoint / marked cell; the grid never exceeds what is resident at once (cooperative launch)
+    int cr0, cc0;
+    cell_dims(pyr1[0].nrows, pyr1[0].ncols, p->patchsize, p->min_scale, cr0, cc0);
+    const long long want_warps = n > (long long)cr0 * cc0 ? n : (long long)cr0 * cc0;
+    long long blocks = (want_warps + 7) / 8;
+    const char* occ_env = getenv("VPPB_SDOF_OCC");  // experiment knob: CTAs of 256 threads per SM the kernel is compiled for (2, 3 or 4)
+    const int occ = occ_env ? atoi(occ_env) : 2;
+    void (*kern)(const SdofFused) = occ == 4 ? k_sdof_fused<4> : occ == 3 ? k_sdof_fused<3> : k_sdof_fused<2>;
+    const int cap = cooperative_grid_limit(kern, 256);
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    VPPB_CUDA(launch_cooperative(kern, (int)blocks, 256, st, F));
+    VPPB_LAUNCH_CHECK("vppb_sdof_u8 (fused)");
+    if (getenv("VPPB_SDOF_STATS")) {  // debugging aid: blocks
+      int h[3] = {0, 0, 0};
+      VPPB_CUDA(cudaMemcpyAsync(h, tickets, sizeof(h), cudaMemcpyDeviceToHost, st));
+      VPPB_CUDA(cudaStreamSynchronize(st));
+      fprintf(stderr, "vppb_sdof_u8: grid %lld x 256, %d grid barriers, %d relaxation rounds after the first of each sweep, %d re-evaluations\n", blocks,
+              h[0] / (int)blocks, h[1], h[2]);
+    }
+    return VPPB_OK;
+  }
   std::vector<int> h_sched;
   const int sms = sm_count();
   for (int scale = p->nscales - 1; scale >= p->min_scale; scale--) {
