@@ -836,13 +836,57 @@ def gpu_extras(vpp, capi, torch, stream, sp, dev):
         return {"ms": ms + ms_pyr, "ms_flow": ms, "ms_pyramids": ms_pyr, "keypoints": n, "parity": ok,
                 "note": "video_extruder's settings (winsize 9, 3 scales, patch 5, 2 sweeps); the whole flow (3 scales: claim, match, sweeps by relaxation, emit) in ONE cooperative launch"}
 
+    def lbp_u8_4k():  # lbp_transform, 2 B/px algorithmic
+        f = np.random.default_rng(4).integers(0, 256, (2160, 3840), dtype=np.uint8)
+        pairs = []
+        for _ in range(16):  # 16 x (8.3 + 8.3 MB) > L2
+            a_ = vpp.Image2d.from_host(f, "u8", border=1)
+            vpp.fill_border_mirror(a_)
+            pairs.append((a_, vpp.Image2d(2160, 3840, "u8")))
+
+        def lbp_all():
+            for s_, d_ in pairs:
+                capi.check(capi.lib.vppb_lbp_u8(s_.ptr(), d_.ptr(), sp))
+
+        ms = timed(lbp_all, 10) / len(pairs)
+        hs = orc.HostImage(2160, 3840, "u8", border=1, data=f, fill_border="mirror")
+        hd_ = orc.HostImage(2160, 3840, "u8")
+        orc.load(omp=True).vo_lbp_u8(hs.ptr(), hd_.ptr())
+        ok = bool(np.array_equal(pairs[0][1].download(), hd_.get()) and np.array_equal(pairs[-1][1].download(), hd_.get()))
+        return {"mpix_per_s": 2160 * 3840 / 1e6 / (ms / 1e3), "us_per_launch": ms * 1e3, "hbm_frac": 2.0 * 2160 * 3840 / (ms / 1e3) / 1e9 / peak, "parity": ok}
+
+    def local_maxima_filter_1080p():  # in-place filter with the reference's serial semantics, on a FAST-like sparse score image
+        r_ = np.random.default_rng(6)
+        sc_ = np.where(r_.random((1080, 1920)) < 0.03, r_.integers(1, 250, (1080, 1920)), 0).astype(np.uint8)
+        sc_[100:140, 200:900] = (250 - (np.arange(700) % 200))[None, :].astype(np.uint8)  # ramps: chains of dependent decisions
+        A_ = vpp.Image2d.from_host(sc_, "u8", border=1)
+        vpp.fill_border_with_value(A_, 0)
+        src_ = vpp.clone(A_)
+        wsb = _DeviceBuffer(capi.lib.vppb_local_maxima_filter_workspace_bytes(1080, 1920, 1))
+
+        def run():
+            vpp.copy(src_, A_, sp)
+            capi.check(capi.lib.vppb_local_maxima_filter(A_.ptr(), wsb.ptr, wsb.nbytes, sp))
+
+        def copy_only():
+            vpp.copy(src_, A_, sp)
+
+        ms = timed(run, 10) - timed(copy_only, 10)
+        run()
+        hs = orc.HostImage(1080, 1920, "u8", border=1, data=sc_)
+        orc.load().vo_local_maxima_filter(hs.ptr())
+        ok = bool(np.array_equal(A_.download(), hs.get()))
+        return {"mpix_per_s": 1080 * 1920 / 1e6 / (ms / 1e3), "us_per_launch": ms * 1e3, "parity": ok,
+                "note": "one cooperative launch: relaxation passes to the fixed point of the serial raster-order filter"}
+
     def sdof_1080p():
         return sdof(1080, 1920)
 
     def sdof_8k():  # config 5's kernel on a single GPU: a 7680 x 4320 frame pair
         return sdof(4320, 7680)
 
-    for row in (add_i32_4k, box5x5_vuchar3_4k, box5x5_vuchar3_4k_x16, box5x5_vuchar3_8k_x32, ingest_rgb_4k, fast9_4k, pyrlk_1080p_10k, sdof_1080p, sdof_8k):
+    for row in (add_i32_4k, box5x5_vuchar3_4k, box5x5_vuchar3_4k_x16, box5x5_vuchar3_8k_x32, ingest_rgb_4k, fast9_4k, pyrlk_1080p_10k, sdof_1080p, sdof_8k, lbp_u8_4k,
+                local_maxima_filter_1080p):
         try:
             out[row.__name__] = row()
         except Exception as ex:  # pragma: no cover - a broken extra must not cost the headline line

@@ -171,6 +171,25 @@ int vppb_fast9_u8_async(const vppb_img* img, int32_t th, const vppb_img* mask, i
 int vppb_fast9_scores(const vppb_img* img, int32_t th, const vppb_int2* kps, int32_t n, int32_t* scores_out,
                       void* stream);
 
+/* fast_detector9_blockwise_rank (fast.hpp:801-886, on fast_detector9_maxima2 fast.hpp:710-740): up to max_points (<= 16) ranked
+ * keypoints per block_size x block_size block - the strict 3x3 maxima of the RAW score image (0 where nothing was detected), kept by
+ * the reference's table rule and sorted by decreasing score.  kps3_out (device int32 triples): (row, col, rank), blocks in raster
+ * order, ranks ascending; scores_out (device, may be NULL): raw scores; count_out (host).  Synchronises the stream. */
+int64_t vppb_fast9_rank_workspace_bytes(int32_t nrows, int32_t ncols, int32_t block_size, int32_t max_points);
+int vppb_fast9_blockwise_rank_u8(const vppb_img* img, int32_t th, const vppb_img* mask, int32_t block_size, int32_t max_points,
+                                 int32_t ring, void* workspace, int64_t workspace_bytes, int32_t* kps3_out, int32_t* scores_out,
+                                 int32_t capacity, int32_t* count_out, void* stream);
+
+/* ---- the remaining 3x3 stencils of the path ------------------------------- */
+/* lbp_transform(A, B) (lbp_transform.hh:7-38), unsigned char -> unsigned char: bit k of B(r, c) = neighbour k of A(r, c) > A(r, c),
+ * neighbours in raster order without the centre.  A needs a border >= 1, read as it is (the caller fills it). */
+int vppb_lbp_u8(const vppb_img* in, const vppb_img* out, void* stream);
+/* local_maxima_filter(A, nbh_size) (fast.hpp:555-575; nbh_size is ignored there too): IN PLACE, a pixel that is not strictly greater
+ * than its 8 neighbours becomes 0 - with the reference's serial raster-order semantics (the neighbours above and to the left have
+ * already been filtered).  unsigned char or int pixels, border >= 1 (read, never written).  One cooperative launch. */
+int64_t vppb_local_maxima_filter_workspace_bytes(int32_t nrows, int32_t ncols, int32_t elem_bytes);
+int vppb_local_maxima_filter(const vppb_img* img, void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ---- Lucas-Kanade (lucas_kanade.hpp:12-184, lk.hh:42-175, pyrlk_match.hh:15-55) ----------- */
 enum { VPPB_LK_ERR_SAD = 0 /* lucas_kanade.hpp:116-128 */, VPPB_LK_ERR_SAD_OVER_MAD = 1 /* lk.hh:151-173 */ };
 typedef struct vppb_lk_params {
@@ -192,6 +211,14 @@ typedef struct vppb_lk_params {
 int vppb_lk_match_u8(const vppb_img* prev, const vppb_img* next, const vppb_img* grad,
                      const vppb_lk_params* params, const vppb_float2* kps, const vppb_float2* prediction,
                      int32_t n, vppb_float2* flow_out, float* err_out, void* stream);
+
+/* oriented_lk_match_point_square_win<WS>::operator() (lk.hh:180-317) for n points of ONE level: template window rotated to dir1[i],
+ * search window rotated to dir2[i] (unit vectors, (row, col)), steps clamped to max_step_norm, at most max_iter steps.
+ * flow_out[i] = v - p or the reference's failure codes ((-1,-1) / (0,0) with err FLT_MAX); err = SAD / (cpt * MAD). */
+int vppb_lk_match_oriented_u8(const vppb_img* a, const vppb_img* b, const vppb_img* grad, int32_t grad_is_float, int32_t winsize,
+                              float min_ev, int32_t max_iter, float delta, float max_step_norm, const vppb_float2* kps,
+                              const vppb_float2* prediction, const vppb_float2* dir1, const vppb_float2* dir2, int32_t n,
+                              vppb_float2* flow_out, float* err_out, void* stream);
 
 /* ---- semi-dense optical flow of video_extruder (semi_dense_optical_flow.hpp:46-214, gradient_descent.hh:10-89) --- */
 typedef struct vppb_sdof_params {

@@ -9,6 +9,7 @@
 #include <vpp/algorithms/fast_detector/fast.hh>
 #include <vpp/algorithms/lucas_kanade.hh>
 #include <vpp/algorithms/pyrlk/lk.hh>
+#include <vpp/algorithms/lbp/lbp_transform.hh>
 #include <vpp/algorithms/optical_flow/semi_dense_optical_flow.hpp>
 #include <climits>
 #include <vpp/algorithms/video_extruder.hh>
@@ -266,4 +267,44 @@ int vppref_video_extruder(const vo_img* frames, int nframes, int detector_th, in
   return n;
 }
 
+}  // extern "C"
+
+
+// ---- SURVEY 8(f) N4 ----------------------------------------------------------------------------------------------
+// oriented_lk_match_point_square_win<WS> (lk.hh:180-317), one level, called keypoint by keypoint
+template <unsigned WS>
+static void oriented_points(const vo_img* a, const vo_img* b, const vo_img* ag, float min_ev, int max_iter, float delta, float max_step,
+                            const vo_float2* kps, const vo_float2* pred, const vo_float2* d1, const vo_float2* d2, int n, vo_float2* flow_out,
+                            float* err_out) {
+  auto A = wrap<unsigned char>(a), B = wrap<unsigned char>(b);
+  auto G = wrap<vfloat2>(ag);
+  oriented_lk_match_point_square_win<WS> matcher;
+  for (int i = 0; i < n; i++) {
+    auto m = matcher(vfloat2(kps[i].r, kps[i].c), vfloat2(pred[i].r, pred[i].c), A, B, G, min_ev, max_iter, delta, max_step, vfloat2(d1[i].r, d1[i].c),
+                     vfloat2(d2[i].r, d2[i].c));
+    flow_out[i].r = m.first[0]; flow_out[i].c = m.first[1]; err_out[i] = m.second;
+  }
+}
+
+extern "C" {
+// lbp_transform (lbp_transform.hh:7-38), unsigned char -> unsigned char
+void vppref_lbp_u8(const vo_img* in, const vo_img* out) {
+  auto A = wrap<unsigned char>(in), B = wrap<unsigned char>(out);
+  lbp_transform(A, B);
+}
+// local_maxima_filter (fast.hpp:555-575), in place; serial in libvppref.so (no OpenMP)
+void vppref_local_maxima_filter(const vo_img* img) {
+  if (img->elem == 1) { auto A = wrap<unsigned char>(img); local_maxima_filter(A, 3); }
+  else { auto A = wrap<int>(img); local_maxima_filter(A, 3); }
+}
+void vppref_lk_match_oriented(const vo_img* a, const vo_img* b, const vo_img* ag, int winsize, float min_ev, int max_iter, float delta, float max_step,
+                              const vo_float2* kps, const vo_float2* pred, const vo_float2* d1, const vo_float2* d2, int n, vo_float2* flow_out,
+                              float* err_out) {
+  switch (winsize) {
+    case 5: oriented_points<5>(a, b, ag, min_ev, max_iter, delta, max_step, kps, pred, d1, d2, n, flow_out, err_out); break;
+    case 7: oriented_points<7>(a, b, ag, min_ev, max_iter, delta, max_step, kps, pred, d1, d2, n, flow_out, err_out); break;
+    case 9: oriented_points<9>(a, b, ag, min_ev, max_iter, delta, max_step, kps, pred, d1, d2, n, flow_out, err_out); break;
+    default: oriented_points<11>(a, b, ag, min_ev, max_iter, delta, max_step, kps, pred, d1, d2, n, flow_out, err_out); break;
+  }
+}
 }  // extern "C"

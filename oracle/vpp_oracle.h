@@ -87,6 +87,15 @@ int vo_flow_error_stats(const vo_img* flow, const vo_img* ref, float* out, const
 void vo_semi_dense_flow(const vo_img* i1, const vo_img* i2, const vo_int2* kps, int n, int winsize, int nscales, int min_scale,
                         int propagation, int patchsize, vo_int2* out_pos, int32_t* out_dist, unsigned char* out_valid);
 
+/* lbp_transform.hh:7-38; fast.hpp:555-575 (serial order, in place); fast.hpp:710-740 + 801-886; lk.hh:180-317 */
+void vo_lbp_u8(const vo_img* in, const vo_img* out);
+void vo_local_maxima_filter(const vo_img* img);
+int vo_fast9_blockwise_rank(const vo_img* img, int th, const vo_img* mask, int block_size, int max_points, int ring, int32_t* kps3, int32_t* scores,
+                            int capacity);
+void vo_lk_match_oriented_u8(const vo_img* A, const vo_img* B, const vo_img* Ag, int grad_is_float, int winsize, float min_ev_th, int max_iter,
+                             float delta, float max_step_norm, const vo_float2* kps, const vo_float2* prediction, const vo_float2* dir1,
+                             const vo_float2* dir2, int n, vo_float2* flow_out, float* err_out);
+
 int vo_num_threads(void);
 void vo_set_num_threads(int n);
 

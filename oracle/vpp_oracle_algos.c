@@ -332,3 +332,198 @@ int vo_flow_error_stats(const vo_img* flow, const vo_img* ref, float* out, const
   out[5] = 100.f * (float)cpt / (flow->nrows * flow->ncols);
   return n;
 }
+
+/* ==========================================================================================
+ * the remaining stencils on the same path.
+ * ========================================================================================== */
+
+/* lbp_transform (vpp/algorithms/lbp/lbp_transform.hh:7-38), V = U = unsigned char: bit k of out(r, c) = neighbour k > centre, neighbours
+ * in the order (-1,-1) (-1,0) (-1,1) (0,-1) (0,1) (1,-1) (1,0) (1,1).  `in` needs a border >= 1 (read as it is: the caller fills it). */
+void vo_lbp_u8(const vo_img* in, const vo_img* out) {
+#pragma omp parallel for
+  for (int r = 0; r < in->nrows; r++) {
+    const unsigned char *r0 = ROW(in, r - 1), *r1 = ROW(in, r), *r2 = ROW(in, r + 1);
+    unsigned char* o = ROW(out, r);
+    for (int i = 0; i < in->ncols; i++)
+      o[i] = (unsigned char)(((r0[i - 1] > r1[i]) << 0) + ((r0[i] > r1[i]) << 1) + ((r0[i + 1] > r1[i]) << 2) + ((r1[i - 1] > r1[i]) << 3) +
+                             ((r1[i + 1] > r1[i]) << 4) + ((r2[i - 1] > r1[i]) << 5) + ((r2[i] > r1[i]) << 6) + ((r2[i + 1] > r1[i]) << 7));
+  }
+}
+
+/* local_maxima_filter (fast.hpp:555-575): IN PLACE, a pixel that is not strictly greater than its 8 neighbours becomes 0 - and the
+ * neighbours above / to the left have already been filtered when it is looked at.  The reference runs it through pixel_wise (rows in
+ * parallel under OpenMP: racy); this is the serial order (row by row, left to right), which is what a build without OpenMP computes.
+ * elem 1 = unsigned char, elem 4 = int32 / unsigned int values below 2^31.  Needs a border >= 1 (read as it is, never written). */
+void vo_local_maxima_filter(const vo_img* img) {
+  for (int r = 0; r < img->nrows; r++)
+    for (int c = 0; c < img->ncols; c++) {
+      int is_max = 1;
+      if (img->elem == 1) {
+        const unsigned char *r0 = ROW(img, r - 1) + c, *r1 = ROW(img, r) + c, *r2 = ROW(img, r + 1) + c;
+        const unsigned char a = *r1;
+        is_max &= a > r0[-1]; is_max &= a > r0[0]; is_max &= a > r0[1]; is_max &= a > r1[-1]; is_max &= a > r1[1];
+        is_max &= a > r2[-1]; is_max &= a > r2[0]; is_max &= a > r2[1];
+        if (!is_max) ROW(img, r)[c] = 0;
+      } else {
+        const int32_t *r0 = (const int32_t*)ROW(img, r - 1) + c, *r1 = (const int32_t*)ROW(img, r) + c, *r2 = (const int32_t*)ROW(img, r + 1) + c;
+        const int32_t a = *r1;
+        is_max &= a > r0[-1]; is_max &= a > r0[0]; is_max &= a > r0[1]; is_max &= a > r1[-1]; is_max &= a > r1[1];
+        is_max &= a > r2[-1]; is_max &= a > r2[0]; is_max &= a > r2[1];
+        if (!is_max) ((int32_t*)ROW(img, r))[c] = 0;
+      }
+    }
+}
+
+/* fast_detector9_blockwise_rank (fast.hpp:801-886) on fast_detector9_maxima2 (fast.hpp:710-740): raw fast9_score at every detected corner
+ * (0 elsewhere, border 1 of zeros); per block_size x block_size block the strict 3x3 maxima of that image enter a table of
+ * max_points slots by the reference's rule - a candidate REPLACES the first slot whose score is smaller (it is not an insertion: the
+ * slot's previous point is lost) -, the table is sorted by decreasing score and every non-empty slot k is reported as (row, col, k).
+ * The reference never instantiates this template (fast.hpp:949-952 is commented out, and its mask parameter types do not match), so this
+ * restatement is NOT pinned to a build of the reference; std::sort on <= 16 elements is libstdc++'s insertion sort, i.e. stable.
+ * Blocks in raster order (the serial order of the reference's loops).  kps3: (row, col, k) triples; scores (may be NULL): raw scores.
+ * Returns the number of records, or -(needed) if capacity is too small. */
+int vo_fast9_blockwise_rank(const vo_img* img, int th, const vo_img* mask, int block_size, int max_points, int ring, int32_t* kps3, int32_t* scores,
+                            int capacity) {
+  const int nr = img->nrows, nc = img->ncols;
+  if (max_points < 1 || max_points > 16 || block_size < 1) return 0;
+  int32_t* S = (int32_t*)calloc((size_t)(nr + 2) * (nc + 2), sizeof(int32_t));
+#define S_(r, c) S[(size_t)((r) + 1) * (nc + 2) + (c) + 1]
+#pragma omp parallel for
+  for (int r = 0; r < nr; r++)
+    for (int c = 0; c < nc; c++) {
+      const int m = (mask && mask->base) ? ROW(mask, r)[c] : 255;
+      if (is_corner(img, th, ring, m, r, c)) S_(r, c) = vo_fast9_score(img, th, r, c);
+    }
+  int n = 0;
+  for (int r = 0; r < nr; r += block_size)
+    for (int c = 0; c < nc; c += block_size) {
+      int pv[16], pr[16], pc[16];
+      for (int k = 0; k < max_points; k++) { pv[k] = 0; pr[k] = 0; pc[k] = 0; }
+      for (int br = 0; br < block_size; br++)
+        for (int bc = c; bc < c + block_size; bc++)
+          if (r + br < nr && bc < nc) {
+            const int v = S_(r + br, bc);
+            if (v > 0) {
+              int is_max = 1;
+              for (int dr = -1; dr <= 1; dr++)
+                for (int dc = -1; dc <= 1; dc++)
+                  if (dr || dc) is_max &= v > S_(r + br + dr, bc + dc);
+              if (is_max)
+                for (int k = 0; k < max_points; k++)
+                  if (pv[k] < v) { pv[k] = v; pr[k] = br; pc[k] = bc; break; }
+            }
+          }
+      /* stable insertion sort, decreasing score */
+      for (int i = 1; i < max_points; i++) {
+        const int v = pv[i], a = pr[i], b = pc[i];
+        int j = i - 1;
+        while (j >= 0 && pv[j] < v) { pv[j + 1] = pv[j]; pr[j + 1] = pr[j]; pc[j + 1] = pc[j]; j--; }
+        pv[j + 1] = v; pr[j + 1] = a; pc[j + 1] = b;
+      }
+      for (int k = 0; k < max_points; k++)
+        if (pv[k] > 0) {
+          if (n < capacity) {
+            kps3[3 * n] = r + pr[k]; kps3[3 * n + 1] = pc[k]; kps3[3 * n + 2] = k;
+            if (scores) scores[n] = pv[k];
+          }
+          n++;
+        }
+    }
+#undef S_
+  free(S);
+  return n <= capacity ? n : -n;
+}
+
+/* oriented_lk_match_point_square_win<WS>::operator() (lk.hh:180-317), one level, per keypoint: the gradient matrix over the axis-aligned
+ * window, the template sampled on a window rotated to `dir1` (columns along dir1, rows along its normal), the search window rotated
+ * to `dir2`; min |eigenvalue| of G itself (not G / cpt, lk.hh:219), steps clamped to max_step_norm (lk.hh:276-280), k < max_iter
+ * (lk.hh:258), the search confined to B's domain shrunk by 3 (lk.hh:251,283), error = SAD / (cpt * MAD) (lk.hh:288-314).
+ * Same deviations as vo_lk_match_u8: as[] / gs[] of samples outside the domain are zero, bilinear footprints are clamped into the frame. */
+void vo_lk_match_oriented_u8(const vo_img* A, const vo_img* B, const vo_img* Ag, int grad_is_float, int winsize, float min_ev_th, int max_iter,
+                             float delta, float max_step_norm, const vo_float2* kps, const vo_float2* prediction, const vo_float2* dir1,
+                             const vo_float2* dir2, int n, vo_float2* flow_out, float* err_out) {
+#pragma omp parallel for schedule(dynamic, 16)
+  for (int q = 0; q < n; q++) {
+    const int ws = winsize, hws = ws / 2, npix = ws * ws;
+    const float p0 = kps[q].r, p1 = kps[q].c;
+    float gs0[225], gs1[225];
+    int as[225];
+    float G00 = 0, G01 = 0, G11 = 0;
+    int cpt = 0;
+    for (int r = -hws; r <= hws; r++)
+      for (int c = -hws; c <= hws; c++) {
+        const float n0 = p0 + (float)r * 1.f, n1 = p1 + (float)c * 1.f;
+        const int i0 = (int)n0, i1 = (int)n1;
+        if (i0 >= 0 && i0 < A->nrows && i1 >= 0 && i1 < A->ncols) {
+          float gx, gy;
+          interp_grad(Ag, grad_is_float, n0, n1, &gx, &gy);
+          G00 += gx * gx; G01 += gx * gy; G11 += gy * gy;
+          cpt++;
+        }
+      }
+    {
+      const float half = (G00 + G11) * 0.5f, diff = (G00 - G11) * 0.5f;
+      const float root = sqrtf(diff * diff + G01 * G01);
+      const float e1 = fabsf(half + root), e2 = fabsf(half - root);
+      float min_ev = 99999.f;
+      if (e1 < min_ev) min_ev = e1;
+      if (e2 < min_ev) min_ev = e2;
+      if (min_ev < min_ev_th) { flow_out[q].r = -1.f; flow_out[q].c = -1.f; err_out[q] = FLT_MAX; continue; }
+    }
+    const float det = G00 * G11 - G01 * G01, invdet = 1.f / det;
+    const float I00 = G11 * invdet, I01 = -G01 * invdet, I11 = G00 * invdet;
+    float v0 = p0 + prediction[q].r, v1 = p1 + prediction[q].c;
+    float nk0 = 1.f, nk1 = 1.f;
+    float mx0 = dir1[q].r, mx1 = dir1[q].c, my0 = -mx1, my1 = mx0;
+    int i = 0;
+    for (int r = -hws; r <= hws; r++)
+      for (int c = -hws; c <= hws; c++, i++) {
+        /* p + (r * my + c * mx) * factor, factor = 1: the products are rounded before they are added */
+        const float n0 = p0 + ((float)r * my0 + (float)c * mx0) * 1.f, n1 = p1 + ((float)r * my1 + (float)c * mx1) * 1.f;
+        const int i0 = (int)n0, i1 = (int)n1;
+        gs0[i] = 0; gs1[i] = 0; as[i] = 0;
+        if (i0 >= 0 && i0 < Ag->nrows && i1 >= 0 && i1 < Ag->ncols) {
+          interp_grad(Ag, grad_is_float, n0, n1, &gs0[i], &gs1[i]);
+          as[i] = vo_interp_u8(A, n0, n1);
+        }
+      }
+    mx0 = dir2[q].r; mx1 = dir2[q].c; my0 = -mx1; my1 = mx0;
+    int failed = 0;
+    for (int k = 0; k < max_iter && sqrtf(nk0 * nk0 + nk1 * nk1) >= delta; k++) {
+      float bk0 = 0, bk1 = 0;
+      i = 0;
+      for (int r = -hws; r <= hws; r++)
+        for (int c = -hws; c <= hws; c++, i++) {
+          const float n0 = v0 + ((float)r * my0 + (float)c * mx0) * 1.f, n1 = v1 + ((float)r * my1 + (float)c * mx1) * 1.f;
+          const float dt = (float)as[i] - (float)vo_interp_u8(B, n0, n1);
+          bk0 += gs0[i] * dt;
+          bk1 += gs1[i] * dt;
+        }
+      nk0 = I00 * bk0 + I01 * bk1;
+      nk1 = I01 * bk0 + I11 * bk1;
+      const float nn = sqrtf(nk0 * nk0 + nk1 * nk1);
+      if (nn > max_step_norm) { nk0 /= nn; nk1 /= nn; nk0 *= max_step_norm; nk1 *= max_step_norm; }
+      v0 += nk0;
+      v1 += nk1;
+      const int iv0 = (int)v0, iv1 = (int)v1;
+      if (!isfinite(v0) || !isfinite(v1) || iv0 < 3 || iv0 > B->nrows - 1 - 3 || iv1 < 3 || iv1 > B->ncols - 1 - 3) { failed = 1; break; }
+    }
+    if (failed) { flow_out[q].r = 0.f; flow_out[q].c = 0.f; err_out[q] = FLT_MAX; continue; }
+    float avg = 0, stddev = 0;
+    for (i = 0; i < npix; i++) avg += (float)as[i];
+    avg /= (float)npix;
+    for (i = 0; i < npix; i++) stddev += fabsf(avg - (float)as[i]);
+    stddev /= (float)npix;
+    float err = 0;
+    i = 0;
+    for (int r = -hws; r <= hws; r++)
+      for (int c = -hws; c <= hws; c++, i++) {
+        const float n0 = v0 + ((float)r * my0 + (float)c * mx0) * 1.f, n1 = v1 + ((float)r * my1 + (float)c * mx1) * 1.f;
+        err += fabsf((float)(as[i] - vo_interp_u8(B, n0, n1)));
+        cpt++;
+      }
+    flow_out[q].r = v0 - p0;
+    flow_out[q].c = v1 - p1;
+    err_out[q] = err / ((float)cpt * stddev);
+  }
+}

@@ -10,6 +10,8 @@
 #include <vpp/algorithms/lucas_kanade.hh>
 #include <vpp/algorithms/optical_flow.hh>
 #include <vpp/algorithms/pyrlk/pyrlk_match.hh>
+#include <vpp/algorithms/pyrlk/lk.hh>
+#include <vpp/algorithms/lbp/lbp_transform.hh>
 
 using namespace vpp;
 
@@ -107,6 +109,61 @@ int main(int argc, char** argv) {
                             f1, f2, _winsize = 9, _nscales = 3, _patchsize = 5, _propagation = 2);
     std::printf("semi_dense_optical_flow: %d callbacks, %d with flow (3,-2)\n", calls, good);
     assert(calls > 50 && good * 10 >= calls * 7);
+  }
+  {  // tests/lbp.cc:9-41 (the reference's own test, verbatim values)
+    image2d<unsigned char> V(3, 3, _border = 1);
+    image2d<unsigned char> lbp(3, 3);
+    V(1, 1) = 1;
+    V(0, 0) = 0; V(0, 1) = 2; V(0, 2) = 2;
+    V(1, 0) = 2; V(1, 2) = 0;
+    V(2, 0) = 2; V(2, 1) = 0; V(2, 2) = 2;
+    unsigned char x = 0b10101110;
+    lbp_transform(V, lbp);
+    assert(lbp(1, 1) == x);
+    assert(lbp_hamming_distance(0b01010101, 0b01010101) == 0);
+    assert(lbp_hamming_distance(0b11010101, 0b01010101) == 1);
+    assert(lbp_hamming_distance(0b11111111, 0b00000000) == 8);
+  }
+  {  // local_maxima_filter (fast.hpp:555-575), serial in-place semantics: on a row that decreases to the right every pixel's left
+     // neighbour is larger - but it has been zeroed before the pixel is looked at, so every second pixel survives
+    image2d<int> S(3, 8, _border = 1);
+    fill_with_border(S, 0);
+    for (int c = 0; c < 8; c++) S(1, c) = 100 - c;
+    local_maxima_filter(S, 3);
+    for (int c = 0; c < 8; c++) assert(S(1, c) == ((c % 2 == 0) ? 100 - c : 0));
+    for (int c = 0; c < 8; c++) assert(S(0, c) == 0 && S(2, c) == 0);
+  }
+  {  // fast_detector9_blockwise_rank (fast.hpp:801-886): ranks per block ascend, scores descend, every point is a detected corner
+    image2d<uint8_t> img(96, 128, _border = 3);
+    fill(img, 40);
+    for (int i = 0; i < 6; i++)
+      for (int j = 0; j < 8; j++) fill(img, (uint8_t)(120 + 10 * ((i + j) % 5)), box2d(vint2(16 * i + 3, 16 * j + 3), vint2(16 * i + 11, 16 * j + 10)));  // 48 bright rectangles
+    fill_border_mirror(img);
+    std::vector<int> sc;
+    auto r3 = fast_detector9_blockwise_rank(img, 20, 16, 3, image2d<unsigned char>(), &sc, 1);
+    auto all = fast9(img, 20, _ring = 1);
+    assert(r3.size() > 10 && sc.size() == r3.size());
+    for (size_t i = 0; i < r3.size(); i++) {
+      assert(r3[i][2] >= 0 && r3[i][2] < 3 && sc[i] > 0);
+      bool found = false;
+      for (auto& k : all) found = found || (k[0] == r3[i][0] && k[1] == r3[i][1]);
+      assert(found);
+      if (r3[i][2] > 0) assert(i > 0 && r3[i - 1][2] == r3[i][2] - 1 && sc[i - 1] >= sc[i]);
+    }
+  }
+  {  // oriented_lk_match_point_square_win (lk.hh:180-317): the tests/pyrlk.cc scene moved by (2, 2); axis-aligned directions
+    image2d<uint8_t> i1 = load_u8(gold + "/pyrlk_i1_100x100.u8", 100, 100), i2 = load_u8(gold + "/pyrlk_i2_100x100.u8", 100, 100);
+    image2d<uint8_t> a = clone(i1, _border = 3), b = clone(i2, _border = 3);
+    fill_border_mirror(a); fill_border_mirror(b);
+    image2d<vfloat2> g(100, 100, _border = 3);
+    scharr(a, g);
+    fill_border_mirror(g);
+    oriented_lk_match_point_square_win<9> matcher;
+    auto m = matcher(vfloat2(50, 50), vfloat2(1.5f, 1.5f), a, b, g, 0.0001f, 30, 0.01f, 1.f, vfloat2(0, 1), vfloat2(0, 1));
+    std::printf("oriented LK: flow (%f, %f) err %f\n", m.first[0], m.first[1], m.second);
+    assert(std::fabs(m.first[0] - 2.f) < 0.3f && std::fabs(m.first[1] - 2.f) < 0.3f && m.second < 1.f);
+    auto out = matcher(vfloat2(50, 50), vfloat2(60.f, 0.f), a, b, g, 0.0001f, 30, 0.01f, 100.f, vfloat2(0, 1), vfloat2(0, 1));
+    assert(out.second > 1e30f);  // driven out of the domain shrunk by 3: ((0,0), FLT_MAX)
   }
   std::puts("ALL OK");
   return 0;

@@ -5,6 +5,8 @@
 #include <vpp/algorithms/lucas_kanade.hh>
 #include <vpp/algorithms/optical_flow.hh>
 #include <vpp/algorithms/pyrlk/pyrlk_match.hh>
+#include <vpp/algorithms/pyrlk/lk.hh>
+#include <vpp/algorithms/lbp/lbp_transform.hh>
 #include <vpp/algorithms/video_extruder.hh>
 
 int host_only_demo() {
@@ -19,5 +21,9 @@ int host_only_demo() {
   image2d<unsigned char> f1(270, 480, _border = 3), f2(270, 480, _border = 3);
   auto ctx = video_extruder_init(f1.domain());
   video_extruder_update(ctx, f1, f2, _detector_th = 10, _keypoint_spacing = 10);
-  return b(0, 0)[0] + sum(x) + ctx.keypoints.size();
+  image2d<unsigned char> l(270, 480);
+  lbp_transform(f1, l);
+  local_maxima_filter(x, 3);
+  auto ranked = fast_detector9_blockwise_rank(f1, 10, 10, 3);
+  return b(0, 0)[0] + sum(x) + ctx.keypoints.size() + l(0, 0) + ranked.size();
 }

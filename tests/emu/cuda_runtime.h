@@ -199,6 +199,12 @@ inline unsigned __vabsdiffu4(unsigned a, unsigned b) {  // VABSDIFF4.U8: per-byt
   }
   return r;
 }
+inline unsigned __vcmpgtu4(unsigned a, unsigned b) {  // per byte: 0xFF where a > b (unsigned), else 0
+  unsigned r = 0;
+  for (int i = 0; i < 4; i++)
+    if (((a >> (8 * i)) & 0xFF) > ((b >> (8 * i)) & 0xFF)) r |= 0xFFu << (8 * i);
+  return r;
+}
 inline unsigned __vsadu4(unsigned a, unsigned b) {  // sum of the four per-byte absolute differences
   unsigned r = 0;
   for (int i = 0; i < 4; i++) {

@@ -51,6 +51,10 @@ def load(omp=False):
         lib.vo_lk_match_u8.argtypes = [I, I, I, P(VoLkParams), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         lib.vo_semi_dense_flow.argtypes = [I, I, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.vo_flow_error_stats.argtypes = [I, I, C.c_void_p, I]
+        lib.vo_lbp_u8.argtypes = [I, I]
+        lib.vo_local_maxima_filter.argtypes = [I]
+        lib.vo_fast9_blockwise_rank.argtypes = [I, C.c_int, I, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+        lib.vo_lk_match_oriented_u8.argtypes = [I, I, I, C.c_int, C.c_int, C.c_float, C.c_int, C.c_float, C.c_float] + [C.c_void_p] * 4 + [C.c_int, C.c_void_p, C.c_void_p]
         lib.vo_num_threads.restype = C.c_int
         _LIBS[key] = lib
     return _LIBS[key]
@@ -63,7 +67,7 @@ PIXEL_TYPES = {"u8": (np.uint8, 1), "i8": (np.int8, 1), "vuchar3": (np.uint8, 3)
 class HostImage:
     """image2d<V> in host memory with the reference layout (imageNd.hpp:151-196)."""
 
-    def __init__(self, nrows, ncols, pixel="u8", border=0, aligned=128, data=None, fill_border=None):
+    def __init__(self, nrows, ncols, pixel="u8", border=0, aligned=128, data=None, fill_border=None, border_value=0):
         self.pixel = pixel
         self.dtype, self.channels = PIXEL_TYPES[pixel]
         self.elem = np.dtype(self.dtype).itemsize * self.channels
@@ -80,6 +84,9 @@ class HostImage:
             self.set(data)
         if fill_border == "mirror":
             load().vo_fill_border_mirror(self.ptr())
+        elif fill_border == "value":
+            v = np.full(self.channels, border_value, dtype=self.dtype)
+            load().vo_fill_border_value(self.ptr(), v.ctypes.data)
 
     def ptr(self):
         return C.byref(self.desc)

@@ -107,3 +107,11 @@ test_box5x5_row_tiles_read_neighbours = L.test_box5x5_row_tiles_read_neighbours
 test_video_extruder_device_container_equals_reference_tables = L.test_video_extruder_device_container_equals_reference_tables
 test_video_extruder_device_container_merge_cases = L.test_video_extruder_device_container_merge_cases
 test_out_of_frame_keypoints_are_skipped = L.test_out_of_frame_keypoints_are_skipped
+
+# lbp_transform, local_maxima_filter (cooperative relaxation kernel on a grid of one block), blockwise_rank, oriented LK
+from tests import test_gpu_n4 as N4  # noqa: E402
+
+test_lbp_transform = N4.test_lbp_transform
+test_local_maxima_filter_serial_semantics = N4.test_local_maxima_filter_serial_semantics
+test_fast9_blockwise_rank = N4.test_fast9_blockwise_rank
+test_oriented_lk_matcher = N4.test_oriented_lk_matcher

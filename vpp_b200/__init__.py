@@ -9,6 +9,7 @@ from .image import Box2d, Image2d, make_box2d, layout, DEFAULT_ALIGNMENT  # noqa
 from .ops import (  # noqa: F401
     Pyramid2d, box5x5, box5x5_batch, clone, copy, copy_with_border, fast9, fast9_scores, fill, fill_border_closest,
     fill_border_mirror, fill_border_with_value, fill_with_border, ingest_rgb_frame, lucas_kanade, pixel_wise_add,
-    pyrlk_match, pyrlk_prepare, rgb_to_graylevel, scharr, semi_dense_optical_flow, sum,
+    pyrlk_match, pyrlk_prepare, rgb_to_graylevel, scharr, semi_dense_optical_flow, sum, fast9_blockwise_rank, lbp_transform,
+    local_maxima_filter, oriented_lk_match,
 )
 from . import video_extruder  # noqa: F401,E402

@@ -109,6 +109,12 @@ PROTOTYPES = {
     "vppb_fast9_u8": (C.c_int, [_IMG, _I32, _IMG, _I32, _I32, _I32, _VP, _I64, _VP, _VP, _I32, _P(_I32), _VP]),
     "vppb_fast9_u8_async": (C.c_int, [_IMG, _I32, _IMG, _I32, _I32, _I32, _VP, _I64, _VP, _VP, _I32, _VP, _VP]),
     "vppb_fast9_scores": (C.c_int, [_IMG, _I32, _VP, _I32, _VP, _VP]),
+    "vppb_fast9_rank_workspace_bytes": (_I64, [_I32, _I32, _I32, _I32]),
+    "vppb_fast9_blockwise_rank_u8": (C.c_int, [_IMG, _I32, _IMG, _I32, _I32, _I32, _VP, _I64, _VP, _VP, _I32, _P(_I32), _VP]),
+    "vppb_lbp_u8": (C.c_int, [_IMG, _IMG, _VP]),
+    "vppb_local_maxima_filter_workspace_bytes": (_I64, [_I32, _I32, _I32]),
+    "vppb_local_maxima_filter": (C.c_int, [_IMG, _VP, _I64, _VP]),
+    "vppb_lk_match_oriented_u8": (C.c_int, [_IMG, _IMG, _IMG, _I32, _I32, C.c_float, _I32, C.c_float, C.c_float, _VP, _VP, _VP, _VP, _I32, _VP, _VP, _VP]),
     "vppb_lk_match_u8": (C.c_int, [_IMG, _IMG, _IMG, _P(VppbLkParams), _VP, _VP, _I32, _VP, _VP, _VP]),
     "vppb_sdof_workspace_bytes": (_I64, [_I32, _I32, _P(VppbSdofParams)]),
     "vppb_sdof_u8": (C.c_int, [_IMG, _IMG, _P(VppbSdofParams), _VP, _I32, _VP, _I64, _VP, _VP, _VP, _VP]),

@@ -509,6 +509,92 @@ __global__ void __launch_bounds__(256) k_fast9_emit_cells(Img im, int th, const 
   }
 }
 
+// fast_detector9_blockwise_rank (fast.hpp:801-886) on the raw score image of fast_detector9_maxima2 (fast.hpp:710-740): per block the strict
+// 3x3 maxima of the raw scores (0 where nothing was detected) enter a table of maxp slots by the reference's rule - a candidate REPLACES
+// the first slot whose score is smaller -, the table is sorted by decreasing score (stable), slot k of a block is rank k.  One thread
+// per block; the tables go to cellpts / cellsc (maxp entries per block, (row << 16 | col) and raw score), cellcnt = used slots.
+constexpr int FR_MAXP = 16;
+__global__ void __launch_bounds__(128) k_fast9_block_rank(Img im, int th, int bs, int maxp, const uint32_t* bits, int wpr, int* cellpts, int* cellsc,
+                                                         int* cellcnt, int* rowcount, int cells_r, int cells_c) {
+  const long long total = (long long)cells_r * cells_c;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int r0 = (int)(i / cells_c) * bs, c0 = (int)(i % cells_c) * bs;
+    int pv[FR_MAXP], pp[FR_MAXP];
+    for (int k = 0; k < maxp; k++) { pv[k] = 0; pp[k] = 0; }
+    for (int r = r0; r < min(r0 + bs, im.nrows); r++) {
+      int c = c0;
+      const int cend = min(c0 + bs, im.ncols);
+      while (c < cend) {
+        uint32_t word = bits[(long long)r * wpr + (c >> 5)] >> (c & 31);
+        const int span = min(32 - (c & 31), cend - c);
+        if (span < 32) word &= (1u << span) - 1u;
+        while (word) {
+          const int b = __ffs(word) - 1;
+          word &= word - 1;
+          const int cc = c + b;
+          const int v = fast9_score_at(im, r, cc, th);
+          if (v <= 0) continue;  // detected on the reference's ring, scored on the true one: the score can be 0 (fast.hpp:839)
+          bool is_max = true;
+          for (int dr = -1; dr <= 1 && is_max; dr++)
+            for (int dc = -1; dc <= 1; dc++) {
+              if (dr == 0 && dc == 0) continue;
+              const int nv = bit_at(bits, wpr, im.nrows, im.ncols, r + dr, cc + dc) ? fast9_score_at(im, r + dr, cc + dc, th) : 0;
+              if (!(v > nv)) { is_max = false; break; }
+            }
+          if (is_max)
+            for (int k = 0; k < maxp; k++)
+              if (pv[k] < v) { pv[k] = v; pp[k] = (r << 16) | cc; break; }
+        }
+        c += span;
+      }
+    }
+    for (int a = 1; a < maxp; a++) {  // std::sort on <= 16 elements == insertion sort: stable
+      const int v = pv[a], q = pp[a];
+      int j = a - 1;
+      while (j >= 0 && pv[j] < v) { pv[j + 1] = pv[j]; pp[j + 1] = pp[j]; j--; }
+      pv[j + 1] = v; pp[j + 1] = q;
+    }
+    int cnt = 0;
+    for (int k = 0; k < maxp; k++) {
+      cellpts[i * maxp + k] = pp[k];
+      cellsc[i * maxp + k] = pv[k];
+      cnt += pv[k] > 0 ? 1 : 0;
+    }
+    cellcnt[i] = cnt;
+    if (cnt) atomicAdd(&rowcount[(int)(i / cells_c)], cnt);
+  }
+}
+
+// one warp per row of blocks: records (row, col, rank) leave in block raster order, ranks ascending
+__global__ void __launch_bounds__(256) k_fast9_emit_rank(const int* cellpts, const int* cellsc, const int* cellcnt, int cells_r, int cells_c, int maxp,
+                                                        const int* rowoff, int* kps3, int* scores, int capacity) {
+  const int lane = threadIdx.x & 31;
+  const int warp0 = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int nwarps = (int)(((long long)gridDim.x * blockDim.x) >> 5);
+  for (int cr = warp0; cr < cells_r; cr += nwarps) {
+    int off = rowoff[cr];
+    if (rowoff[cr + 1] == off) continue;
+    for (int c0 = 0; c0 < cells_c; c0 += 32) {
+      const int cc = c0 + lane;
+      const long long cell = (long long)cr * cells_c + cc;
+      const int cnt = cc < cells_c ? cellcnt[cell] : 0;
+      int incl = cnt;
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += y;
+      }
+      int pos = off + incl - cnt;
+      for (int k = 0; k < cnt; k++, pos++)
+        if (pos < capacity) {
+          const int v = cellpts[cell * maxp + k];
+          kps3[3 * pos] = v >> 16; kps3[3 * pos + 1] = v & 0xFFFF; kps3[3 * pos + 2] = k;
+          if (scores) scores[pos] = cellsc[cell * maxp + k];
+        }
+      off += __shfl_sync(0xffffffffu, incl, 31);
+    }
+  }
+}
+
 __global__ void k_fast9_scores(Img im, int th, const vppb_int2* kps, int n, int* scores) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const bool inside = kps[i].r >= 0 && kps[i].r < im.nrows && kps[i].c >= 0 && kps[i].c < im.ncols;  // the ring of an in-frame point stays inside the 3-px border
@@ -564,23 +650,30 @@ static bool fast_band_eligible(const vppb_img* img) {
   return img->ncols <= FB_MAXW;
 }
 
+struct FastRank { int maxp; int* kps3; };  // fast_detector9_blockwise_rank: a blockwise run that reports up to maxp ranked points per block
+static long long fast_rank_bytes(int nrows, int ncols, int block_size, int maxp) {
+  const long long cells = (long long)((nrows + block_size - 1) / block_size) * ((ncols + block_size - 1) / block_size);
+  return ((cells * (2LL * maxp + 1) * 4 + 255) / 256) * 256;
+}
+
 static int fast9_core(const vppb_img* img, int32_t th, const vppb_img* mask, int32_t mode, int32_t block_size, int32_t ring, void* workspace,
                       int64_t workspace_bytes, vppb_int2* kps_out, int32_t* scores_out, int32_t capacity, int32_t* count_dev, int** count_src, void* stream,
-                      const char* name) {
+                      const char* name, const FastRank* rank = nullptr) {
   VPPB_REQUIRE(img && img->base && workspace, VPPB_E_ARG, "%s: NULL argument", name);
   VPPB_REQUIRE(img->elem_bytes == 1, VPPB_E_ARG, "%s: image must be u8", name);
   // fast.hpp:937-938
   VPPB_REQUIRE(img->border >= 3, VPPB_E_BORDER, "Image need a border of 3px at least for the FAST detector");
   VPPB_REQUIRE(mode >= 0 && mode <= 2 && (ring == 0 || ring == 1), VPPB_E_ARG, "%s: bad mode/ring", name);
   VPPB_REQUIRE(mode != VPPB_FAST_BLOCKWISE || block_size > 0, VPPB_E_ARG, "%s: block_size must be > 0", name);
-  VPPB_REQUIRE(capacity == 0 || kps_out, VPPB_E_ARG, "%s: NULL keypoint buffer", name);
+  VPPB_REQUIRE(capacity == 0 || kps_out || (rank && rank->kps3), VPPB_E_ARG, "%s: NULL keypoint buffer", name);
   const bool has_mask = mask && mask->base;
   if (has_mask)
     VPPB_REQUIRE(mask->elem_bytes == 1 && mask->nrows >= img->nrows && mask->ncols >= img->ncols, VPPB_E_ARG, "%s: mask must be u8 and cover the image", name);
   VPPB_REQUIRE(img->nrows < 65536 && img->ncols < 65536, VPPB_E_ARG, "%s: image larger than 65535 in one dimension", name);
   // the reference ignores block_size outside the blockwise mode: so does the workspace rule
-  FastWs ws = fast_ws_layout(workspace, img->nrows, img->ncols, mode == VPPB_FAST_BLOCKWISE ? block_size : (1 << 30));
-  VPPB_REQUIRE(workspace_bytes >= ws.bytes, VPPB_E_ARG, "%s: workspace %lld < %lld bytes", name, (long long)workspace_bytes, ws.bytes);
+  FastWs ws = fast_ws_layout(workspace, img->nrows, img->ncols, mode == VPPB_FAST_BLOCKWISE && !rank ? block_size : (1 << 30));
+  const long long need = ws.bytes + (rank ? fast_rank_bytes(img->nrows, img->ncols, block_size, rank->maxp) : 0);
+  VPPB_REQUIRE(workspace_bytes >= need, VPPB_E_ARG, "%s: workspace %lld < %lld bytes", name, (long long)workspace_bytes, need);
   cudaStream_t st = as_stream(stream);
   const int wpr = (img->ncols + 31) / 32;
   const long long words = (long long)img->nrows * wpr;
@@ -641,6 +734,20 @@ static int fast9_core(const vppb_img* img, int32_t th, const vppb_img* mask, int
       long long cells = (long long)cells_r * cells_c;
       long long blocks = (cells + 127) / 128;
       int grid = (int)(blocks < (long long)sms * 16 ? blocks : (long long)sms * 16);
+      if (rank) {
+        int* cellpts = reinterpret_cast<int*>(static_cast<unsigned char*>(workspace) + ws.bytes);
+        int* cellsc = cellpts + cells * rank->maxp;
+        int* cellcnt = cellsc + cells * rank->maxp;
+        k_fast9_block_rank<<<grid, 128, 0, st>>>(im, th, block_size, rank->maxp, ws.bits_a, wpr, cellpts, cellsc, cellcnt, ws.rowcount, cells_r, cells_c);
+        k_fast9_scan<<<1, 1024, 0, st>>>(ws.rowcount, ws.rowoff, cells_r);
+        long long eb = ((long long)cells_r + 7) / 8;
+        k_fast9_emit_rank<<<(int)(eb < (long long)sms * 8 ? eb : (long long)sms * 8), 256, 0, st>>>(cellpts, cellsc, cellcnt, cells_r, cells_c, rank->maxp, ws.rowoff,
+                                                                                                  rank->kps3, scores_out, capacity);
+        VPPB_LAUNCH_CHECK(name);
+        *count_src = ws.rowoff + cells_r;
+        if (count_dev) VPPB_CUDA(cudaMemcpyAsync(count_dev, ws.rowoff + cells_r, sizeof(int), cudaMemcpyDeviceToDevice, st));
+        return VPPB_OK;
+      }
       k_fast9_block_max<<<grid, 128, 0, st>>>(im, th, block_size, ws.bits_a, ws.cellkp, wpr, ws.rowcount, cells_r, cells_c);
       k_fast9_scan<<<1, 1024, 0, st>>>(ws.rowcount, ws.rowoff, cells_r);
       long long eb = ((long long)cells_r + 7) / 8;
@@ -693,6 +800,29 @@ int vppb_fast9_u8_async(const vppb_img* img, int32_t th, const vppb_img* mask, i
   VPPB_REQUIRE(count_dev, VPPB_E_ARG, "vppb_fast9_u8_async: NULL argument");
   int* src = nullptr;
   return fast9_core(img, th, mask, mode, block_size, ring, workspace, workspace_bytes, kps_out, scores_out, capacity, count_dev, &src, stream, "vppb_fast9_u8_async");
+}
+
+int64_t vppb_fast9_rank_workspace_bytes(int32_t nrows, int32_t ncols, int32_t block_size, int32_t max_points) {
+  if (nrows <= 0 || ncols <= 0 || block_size <= 0 || max_points < 1 || max_points > FR_MAXP) return 0;
+  return fast_ws_layout(nullptr, nrows, ncols, 1 << 30).bytes + fast_rank_bytes(nrows, ncols, block_size, max_points);
+}
+
+int vppb_fast9_blockwise_rank_u8(const vppb_img* img, int32_t th, const vppb_img* mask, int32_t block_size, int32_t max_points, int32_t ring,
+                                 void* workspace, int64_t workspace_bytes, int32_t* kps3_out, int32_t* scores_out, int32_t capacity, int32_t* count_out,
+                                 void* stream) {
+  VPPB_REQUIRE(count_out, VPPB_E_ARG, "vppb_fast9_blockwise_rank_u8: NULL argument");
+  VPPB_REQUIRE(max_points >= 1 && max_points <= FR_MAXP && block_size > 0, VPPB_E_ARG, "vppb_fast9_blockwise_rank_u8: 1 <= max_points <= %d, block_size > 0", FR_MAXP);
+  FastRank rk{max_points, kps3_out};
+  int* src = nullptr;
+  int rc = fast9_core(img, th, mask, VPPB_FAST_BLOCKWISE, block_size, ring, workspace, workspace_bytes, nullptr, scores_out, capacity, nullptr, &src, stream,
+                      "vppb_fast9_blockwise_rank_u8", &rk);
+  if (rc) return rc;
+  int total = 0;
+  VPPB_CUDA(cudaMemcpyAsync(&total, src, sizeof(int), cudaMemcpyDeviceToHost, as_stream(stream)));
+  VPPB_CUDA(cudaStreamSynchronize(as_stream(stream)));
+  *count_out = total;
+  VPPB_REQUIRE(total <= capacity, VPPB_E_CAPACITY, "vppb_fast9_blockwise_rank_u8: %d records exceed the capacity %d", total, capacity);
+  return VPPB_OK;
 }
 
 int vppb_fast9_scores(const vppb_img* img, int32_t th, const vppb_int2* kps, int32_t n, int32_t* scores_out, void* stream) {

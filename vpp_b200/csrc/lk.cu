@@ -466,6 +466,161 @@ static void lk_launch(int ppl, int grid, cudaStream_t st, const LkLevels& L, con
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// oriented_lk_match_point_square_win<WS> (lk.hh:180-317), one level.  One warp per keypoint, the same ordered float sums as
+// k_lk_match.  Differences from the square-window matcher: the gradient matrix is summed over the axis-aligned window but the
+// template is sampled on a window rotated to dir1 and the search window is rotated to dir2; the eigenvalue test uses G itself
+// (lk.hh:219); steps longer than max_step are shortened to it (lk.hh:276-280); at most max_iter steps (k < max_iter, lk.hh:258);
+// the search is confined to B's domain shrunk by 3 pixels (lk.hh:251,283); error = SAD / (cpt * MAD) (lk.hh:288-314).
+struct LkOriented {
+  Img A, B, Ag;
+  int winsize, max_iter;
+  float min_ev, delta, max_step;
+};
+
+template <int PPL, bool GRAD_FLOAT>
+__global__ void __launch_bounds__(128) k_lk_match_oriented(LkOriented P, const vppb_float2* __restrict__ kps, const vppb_float2* __restrict__ prediction,
+                                                           const vppb_float2* __restrict__ dir1, const vppb_float2* __restrict__ dir2, int n,
+                                                           vppb_float2* __restrict__ flow_out, float* __restrict__ err_out) {
+  const int lane = threadIdx.x & 31;
+  const int q = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  if (q >= n) return;  // warp-uniform
+  const int ws = P.winsize, hws = ws / 2, npix = ws * ws;
+  const Img& A = P.A;
+  const Img& B = P.B;
+  const Img& Ag = P.Ag;
+  const float p0 = kps[q].r, p1 = kps[q].c;
+  float off_r[PPL], off_c[PPL];
+  bool have[PPL];
+#pragma unroll
+  for (int j = 0; j < PPL; j++) {
+    const int i = lane + 32 * j;
+    have[j] = i < npix;
+    off_r[j] = (float)(i / ws - hws);
+    off_c[j] = (float)(i % ws - hws);
+  }
+  // gradient matrix over the axis-aligned window (lk.hh:198-216)
+  float t00[PPL], t01[PPL], t11[PPL];
+  int cpt = 0;
+#pragma unroll
+  for (int j = 0; j < PPL; j++) {
+    const float n0 = __fadd_rn(p0, off_r[j]), n1 = __fadd_rn(p1, off_c[j]);
+    const int i0 = (int)n0, i1 = (int)n1;
+    const bool ok = have[j] && i0 >= 0 && i0 < A.nrows && i1 >= 0 && i1 < A.ncols;
+    float2 g = make_float2(0.f, 0.f);
+    if (ok) g = interp_grad<GRAD_FLOAT>(Ag, n0, n1);
+    t00[j] = __fmul_rn(g.x, g.x); t01[j] = __fmul_rn(g.x, g.y); t11[j] = __fmul_rn(g.y, g.y);
+    cpt += __popc(__ballot_sync(FULL, ok));
+  }
+  float G00, G01, G11;
+  seq_sum2<PPL>(t00, t01, npix, G00, G01);
+  G11 = seq_sum<PPL>(t11, npix);
+  float m0 = -1.f, m1 = -1.f, merr = FLT_MAX;
+  bool done = false;
+  {
+    const float half = __fmul_rn(__fadd_rn(G00, G11), 0.5f), diff = __fmul_rn(__fsub_rn(G00, G11), 0.5f);
+    const float root = __fsqrt_rn(__fadd_rn(__fmul_rn(diff, diff), __fmul_rn(G01, G01)));
+    const float e1 = fabsf(__fadd_rn(half, root)), e2 = fabsf(__fsub_rn(half, root));
+    float min_ev = 99999.f;
+    if (e1 < min_ev) min_ev = e1;
+    if (e2 < min_ev) min_ev = e2;
+    if (min_ev < P.min_ev) done = true;
+  }
+  if (!done) {
+    const float det = __fsub_rn(__fmul_rn(G00, G11), __fmul_rn(G01, G01));
+    const float invdet = __fdiv_rn(1.f, det);
+    const float I00 = __fmul_rn(G11, invdet), I01 = __fmul_rn(-G01, invdet), I11 = __fmul_rn(G00, invdet);
+    float v0 = __fadd_rn(p0, prediction[q].r), v1 = __fadd_rn(p1, prediction[q].c);
+    float nk0 = 1.f, nk1 = 1.f;
+    // template on the window rotated to dir1: columns along mx = dir1, rows along my = (-mx[1], mx[0]) (lk.hh:231-249)
+    float mx0 = dir1[q].r, mx1 = dir1[q].c, my0 = -mx1, my1 = mx0;
+    float gs0[PPL], gs1[PPL], asv[PPL];
+#pragma unroll
+    for (int j = 0; j < PPL; j++) {
+      const float n0 = __fadd_rn(p0, __fadd_rn(__fmul_rn(off_r[j], my0), __fmul_rn(off_c[j], mx0)));
+      const float n1 = __fadd_rn(p1, __fadd_rn(__fmul_rn(off_r[j], my1), __fmul_rn(off_c[j], mx1)));
+      const int i0 = (int)n0, i1 = (int)n1;
+      gs0[j] = 0.f; gs1[j] = 0.f; asv[j] = 0.f;
+      if (have[j] && i0 >= 0 && i0 < Ag.nrows && i1 >= 0 && i1 < Ag.ncols) {
+        const float2 g = interp_grad<GRAD_FLOAT>(Ag, n0, n1);
+        gs0[j] = g.x; gs1[j] = g.y;
+        asv[j] = (float)interp_u8(A, n0, n1);
+      }
+    }
+    mx0 = dir2[q].r; mx1 = dir2[q].c; my0 = -mx1; my1 = mx0;
+    bool failed = false;
+    for (int k = 0; k < P.max_iter; k++) {
+      const float nrm = __fsqrt_rn(__fadd_rn(__fmul_rn(nk0, nk0), __fmul_rn(nk1, nk1)));
+      if (!(nrm >= P.delta)) break;
+      float c0[PPL], c1[PPL];
+#pragma unroll
+      for (int j = 0; j < PPL; j++) {
+        c0[j] = 0.f; c1[j] = 0.f;
+        if (have[j]) {
+          const float n0 = __fadd_rn(v0, __fadd_rn(__fmul_rn(off_r[j], my0), __fmul_rn(off_c[j], mx0)));
+          const float n1 = __fadd_rn(v1, __fadd_rn(__fmul_rn(off_r[j], my1), __fmul_rn(off_c[j], mx1)));
+          const float dt = __fsub_rn(asv[j], (float)interp_u8(B, n0, n1));
+          c0[j] = __fmul_rn(gs0[j], dt);
+          c1[j] = __fmul_rn(gs1[j], dt);
+        }
+      }
+      float bk0, bk1;
+      seq_sum2<PPL>(c0, c1, npix, bk0, bk1);
+      nk0 = __fadd_rn(__fmul_rn(I00, bk0), __fmul_rn(I01, bk1));
+      nk1 = __fadd_rn(__fmul_rn(I01, bk0), __fmul_rn(I11, bk1));
+      const float nn = __fsqrt_rn(__fadd_rn(__fmul_rn(nk0, nk0), __fmul_rn(nk1, nk1)));
+      if (nn > P.max_step) {
+        nk0 = __fmul_rn(__fdiv_rn(nk0, nn), P.max_step);
+        nk1 = __fmul_rn(__fdiv_rn(nk1, nn), P.max_step);
+      }
+      v0 = __fadd_rn(v0, nk0);
+      v1 = __fadd_rn(v1, nk1);
+      const int iv0 = (int)v0, iv1 = (int)v1;
+      if (!finite2(v0, v1) || iv0 < 3 || iv0 > B.nrows - 4 || iv1 < 3 || iv1 > B.ncols - 4) { failed = true; break; }
+    }
+    if (failed) {
+      m0 = 0.f; m1 = 0.f; merr = FLT_MAX;
+    } else {
+      const float wsq = (float)npix;
+      const float avg = __fdiv_rn(seq_sum<PPL>(asv, npix), wsq);
+      float dv[PPL], e[PPL];
+#pragma unroll
+      for (int j = 0; j < PPL; j++) {
+        dv[j] = have[j] ? fabsf(__fsub_rn(avg, asv[j])) : 0.f;
+        e[j] = 0.f;
+        if (have[j]) {
+          const float n0 = __fadd_rn(v0, __fadd_rn(__fmul_rn(off_r[j], my0), __fmul_rn(off_c[j], mx0)));
+          const float n1 = __fadd_rn(v1, __fadd_rn(__fmul_rn(off_r[j], my1), __fmul_rn(off_c[j], mx1)));
+          e[j] = fabsf((float)((int)asv[j] - interp_u8(B, n0, n1)));
+        }
+      }
+      const float stddev = __fdiv_rn(seq_sum<PPL>(dv, npix), wsq);
+      const float err = seq_sum<PPL>(e, npix);
+      merr = __fdiv_rn(err, __fmul_rn((float)(cpt + npix), stddev));
+      m0 = __fsub_rn(v0, p0);
+      m1 = __fsub_rn(v1, p1);
+    }
+  }
+  if (lane == 0) {
+    flow_out[q].r = m0;
+    flow_out[q].c = m1;
+    err_out[q] = merr;
+  }
+}
+
+template <bool GF>
+static void lk_oriented_launch(int ppl, int grid, cudaStream_t st, const LkOriented& P, const vppb_float2* kps, const vppb_float2* pred,
+                               const vppb_float2* d1, const vppb_float2* d2, int n, vppb_float2* flow, float* err) {
+  switch (ppl) {
+    case 1: k_lk_match_oriented<1, GF><<<grid, 128, 0, st>>>(P, kps, pred, d1, d2, n, flow, err); break;
+    case 2: k_lk_match_oriented<2, GF><<<grid, 128, 0, st>>>(P, kps, pred, d1, d2, n, flow, err); break;
+    case 3: k_lk_match_oriented<3, GF><<<grid, 128, 0, st>>>(P, kps, pred, d1, d2, n, flow, err); break;
+    case 4: k_lk_match_oriented<4, GF><<<grid, 128, 0, st>>>(P, kps, pred, d1, d2, n, flow, err); break;
+    case 6: k_lk_match_oriented<6, GF><<<grid, 128, 0, st>>>(P, kps, pred, d1, d2, n, flow, err); break;
+    default: k_lk_match_oriented<8, GF><<<grid, 128, 0, st>>>(P, kps, pred, d1, d2, n, flow, err); break;
+  }
+}
+
 }  // namespace vppb
 
 using namespace vppb;
@@ -508,6 +663,30 @@ int vppb_lk_match_u8(const vppb_img* prev, const vppb_img* next, const vppb_img*
     else lk_launch<false>(ppl, grid, as_stream(stream), L, P, kps, prediction, n, flow_out, err_out);
   }
   VPPB_LAUNCH_CHECK("vppb_lk_match_u8");
+  return VPPB_OK;
+}
+
+int vppb_lk_match_oriented_u8(const vppb_img* a, const vppb_img* b, const vppb_img* grad, int32_t grad_is_float, int32_t winsize, float min_ev,
+                              int32_t max_iter, float delta, float max_step_norm, const vppb_float2* kps, const vppb_float2* prediction,
+                              const vppb_float2* dir1, const vppb_float2* dir2, int32_t n, vppb_float2* flow_out, float* err_out, void* stream) {
+  VPPB_REQUIRE(a && b && grad && a->base && b->base && grad->base, VPPB_E_ARG, "vppb_lk_match_oriented_u8: NULL argument");
+  VPPB_REQUIRE(n == 0 || (kps && prediction && dir1 && dir2 && flow_out && err_out), VPPB_E_ARG, "vppb_lk_match_oriented_u8: NULL keypoint/output array");
+  VPPB_REQUIRE(winsize >= 1 && winsize <= 15 && (winsize & 1), VPPB_E_ARG, "vppb_lk_match_oriented_u8: winsize %d must be odd and <= 15", winsize);
+  VPPB_REQUIRE(a->elem_bytes == 1 && b->elem_bytes == 1 && grad->elem_bytes == 8, VPPB_E_ARG, "vppb_lk_match_oriented_u8: element sizes must be 1/1/8");
+  VPPB_REQUIRE(same_domain(a, b) && same_domain(a, grad), VPPB_E_ARG, "vppb_lk_match_oriented_u8: domains differ");
+  VPPB_REQUIRE(a->border >= 1 && b->border >= 1 && grad->border >= 1, VPPB_E_BORDER, "vppb_lk_match_oriented_u8: border >= 1 needed");
+  VPPB_REQUIRE(((uintptr_t)grad->base % 8) == 0 && (grad->pitch % 8) == 0, VPPB_E_ARG, "vppb_lk_match_oriented_u8: gradient not 8-byte aligned");
+  if (n == 0) return VPPB_OK;
+  LkOriented P;
+  P.A = view(a); P.B = view(b); P.Ag = view(grad);
+  P.winsize = winsize; P.max_iter = max_iter; P.min_ev = min_ev; P.delta = delta; P.max_step = max_step_norm;
+  int ppl = (winsize * winsize + 31) / 32;
+  if (ppl == 5) ppl = 6;
+  if (ppl == 7) ppl = 8;
+  const int grid = (n + 3) / 4;
+  if (grad_is_float) lk_oriented_launch<true>(ppl, grid, as_stream(stream), P, kps, prediction, dir1, dir2, n, flow_out, err_out);
+  else lk_oriented_launch<false>(ppl, grid, as_stream(stream), P, kps, prediction, dir1, dir2, n, flow_out, err_out);
+  VPPB_LAUNCH_CHECK("vppb_lk_match_oriented_u8");
   return VPPB_OK;
 }
 

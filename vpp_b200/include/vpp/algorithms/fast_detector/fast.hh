@@ -76,6 +76,37 @@ void fast9_scores(const image2d<unsigned char>& A, int th, const KPS& keypoints,
   vppb_check(vppb_fast9_scores(A.device_read(), th, (const vppb_int2*)dk.ptr(), (int)n, (int32_t*)ds.ptr(), nullptr));
   ds.to_host(scores.data(), n * 4);
 }
+// local_maxima_filter(A, nbh_size) (fast.hpp:555-575; nbh_size is ignored by the reference as well): in place, every pixel that is not
+// strictly greater than its 8 neighbours becomes zero - in the reference's serial raster order (the neighbours above / to the left
+// have already been filtered).  unsigned char or int images with a border >= 1.
+template <typename V>
+void local_maxima_filter(const image2d<V>& A, int /*nbh_size*/ = 3) {
+  static_assert(sizeof(V) == 1 || sizeof(V) == 4, "local_maxima_filter: unsigned char or int images");
+  const int64_t bytes = vppb_local_maxima_filter_workspace_bytes(A.nrows(), A.ncols(), (int)sizeof(V));
+  internals::device_array ws((size_t)bytes);
+  vppb_check(vppb_local_maxima_filter(A.device_write(), ws.ptr(), bytes, nullptr));
+  vppb_check(vppb_sync(nullptr));  // the workspace is released on return
+}
+
+// fast_detector9_blockwise_rank(A, th, block_size, max_point_per_block, mask, scores) (fast.hpp:801-886): (row, col, rank) of up to
+// max_point_per_block (<= 16) keypoints per block, blocks in raster order, ranks by decreasing raw score.
+inline std::vector<vint3> fast_detector9_blockwise_rank(const image2d<unsigned char>& A, int th, int block_size, int max_point_per_block,
+                                                        const image2d<unsigned char>& mask = image2d<unsigned char>(), std::vector<int>* scores = nullptr,
+                                                        int ring = 0) {
+  if (A.border() < 3) throw std::runtime_error("Image need a border of 3px at least for the FAST detector");
+  const int cells = ((A.nrows() + block_size - 1) / block_size) * ((A.ncols() + block_size - 1) / block_size);
+  const int capacity = std::max(1, cells * max_point_per_block);
+  const int64_t bytes = vppb_fast9_rank_workspace_bytes(A.nrows(), A.ncols(), block_size, max_point_per_block);
+  internals::device_array ws((size_t)bytes), kps((size_t)capacity * 12), sc((size_t)capacity * 4);
+  int count = 0;
+  vppb_check(vppb_fast9_blockwise_rank_u8(A.device_read(), th, mask.has_data() ? mask.device_read() : nullptr, block_size, max_point_per_block, ring, ws.ptr(), bytes,
+                                          (int32_t*)kps.ptr(), (int32_t*)sc.ptr(), capacity, &count, nullptr));
+  std::vector<vint3> out(count);
+  kps.to_host(out.data(), (size_t)count * sizeof(vint3));
+  if (scores) { scores->resize(count); sc.to_host(scores->data(), (size_t)count * 4); }
+  return out;
+}
+
 inline int fast9_score(const image2d<unsigned char>& A, int th, vint2 p) {  // fast.hpp:655-660
   std::vector<vint2> k(1, p); std::vector<int> s;
   fast9_scores(A, th, k, s);

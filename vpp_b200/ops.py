@@ -254,7 +254,54 @@ def fast9_scores(img, th, keypoints, stream=None):  # fast.hpp:643-652
     return d_sc.to_host(np.int32, len(kp), stream)
 
 
+def fast9_blockwise_rank(img, th, block_size=10, max_points_per_block=3, mask=None, scores=None, ring="reference", stream=None):
+    """std::vector<vint3> fast_detector9_blockwise_rank(A, th, block_size, max_point_per_block, mask, scores) (fast.hpp:801-886):
+    (n, 3) int32 array of (row, col, rank), blocks in raster order; `scores` (a list) receives the raw scores."""
+    ring_id = capi.FAST_REFERENCE_RING if ring == "reference" else capi.FAST_TRUE_RING
+    cells = ((img.nrows + block_size - 1) // block_size) * ((img.ncols + block_size - 1) // block_size)
+    cap = max(1, cells * max_points_per_block)
+    ws = _DeviceBuffer(lib.vppb_fast9_rank_workspace_bytes(img.nrows, img.ncols, block_size, max_points_per_block))
+    kps, sc = _DeviceBuffer(cap * 12), _DeviceBuffer(cap * 4)
+    count = C.c_int32(0)
+    check(lib.vppb_fast9_blockwise_rank_u8(img.ptr(), th, mask.ptr() if mask is not None else None, block_size, max_points_per_block, ring_id, ws.ptr,
+                                           ws.nbytes, kps.ptr, sc.ptr, cap, C.byref(count), stream))
+    out = kps.to_host(np.int32, count.value * 3, stream).reshape(-1, 3)
+    if scores is not None:
+        scores[:] = list(sc.to_host(np.int32, count.value, stream))
+    return out
+
+
+# ---- the remaining 3x3 stencils (SURVEY 8(f) N4) ------------------------------------------------------
+def lbp_transform(a, b=None, stream=None):  # lbp_transform.hh:7-38
+    """lbp_transform(A, B): A u8 with a filled border >= 1, B u8 of the same domain (allocated if None)."""
+    if b is None:
+        b = Image2d(a.nrows, a.ncols, "u8")
+    check(lib.vppb_lbp_u8(a.ptr(), b.ptr(), stream))
+    return b
+
+
+def local_maxima_filter(a, nbh_size=3, stream=None):  # fast.hpp:555-575 (nbh_size is ignored by the reference too)
+    """In place: pixels that are not strict 3x3 maxima become 0, in the reference's serial raster order.  u8 or i32, border >= 1."""
+    ws = _DeviceBuffer(lib.vppb_local_maxima_filter_workspace_bytes(a.nrows, a.ncols, a.desc.elem_bytes))
+    check(lib.vppb_local_maxima_filter(a.ptr(), ws.ptr, ws.nbytes, stream))
+    check(lib.vppb_sync(stream))  # the workspace is released on return
+    return a
+
+
 # ---- Lucas-Kanade -----------------------------------------------------------------------------
+def oriented_lk_match(a, b, grad, keypoints, prediction, dir1, dir2, winsize, min_ev, max_iterations, convergence_delta, max_step_norm, stream=None):
+    """oriented_lk_match_point_square_win<winsize>()(p, tr_prediction, A, B, Ag, min_ev, max_iterations, convergence_delta, max_step_norm,
+    match_direction1, match_direction2) (lk.hh:180-317) for every keypoint: returns (flow (n, 2) float32, err (n,) float32)."""
+    f32 = lambda x: np.ascontiguousarray(x, dtype=np.float32).reshape(-1, 2)
+    kp, pr, d1, d2 = f32(keypoints), f32(prediction), f32(dir1), f32(dir2)
+    n = len(kp)
+    bufs = [_DeviceBuffer(x.nbytes).from_host(x, stream) for x in (kp, pr, d1, d2)]
+    d_flow, d_err = _DeviceBuffer(n * 8), _DeviceBuffer(n * 4)
+    check(lib.vppb_lk_match_oriented_u8(a.ptr(), b.ptr(), grad.ptr(), 1 if grad.pixel == "vfloat2" else 0, winsize, min_ev, max_iterations, convergence_delta,
+                                        max_step_norm, bufs[0].ptr, bufs[1].ptr, bufs[2].ptr, bufs[3].ptr, n, d_flow.ptr, d_err.ptr, stream))
+    return d_flow.to_host(np.float32, n * 2, stream).reshape(-1, 2), d_err.to_host(np.float32, n, stream)
+
+
 def _lk_run(pyr_prev, pyr_next, pyr_grad, params, keypoints, prediction, stream):
     kp = np.ascontiguousarray(keypoints, dtype=np.float32).reshape(-1, 2)
     n = len(kp)
