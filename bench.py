@@ -467,7 +467,7 @@ def main():
                 "how": "6 B/px x %d frames of a launch / (CUDA-event time of the timed region / launches); traffic = dram read + write bytes per launch of the same "
                        "command under ncu (--cache-control none, steady state), profiles/box_traffic.json" % BATCH}
 
-    # ---- e2e: HOST buffers through the C-ABI (pinned), copies inside the timed region, 4 frames in flight per rank.
+    # ---- e2e: HOST buffers through the C-ABI (pinned), copies inside the timed region, NE2E frames in flight per rank.
     # N > 1: the host holds whole frames, so the 2 halo rows above / below a tile ride along with the tile's upload.
     esets = 8
     if world == 1:
@@ -475,7 +475,7 @@ def main():
     else:
         host_in = [torch.from_numpy(np.ascontiguousarray(upad[i % 4][r0:r1 + 4])).pin_memory() for i in range(4)]
     host_out = [torch.empty((th, W, 3), dtype=torch.uint8).pin_memory() for _ in range(esets)]
-    NE2E = 4
+    NE2E = int(os.environ.get("VPPB_BENCH_INFLIGHT", "12"))  # frames in flight per rank (one stream each)
     e_src = [vpp.Image2d(th, W, "vuchar3", border=2) for _ in range(NE2E)]
     e_dst = [vpp.Image2d(th, W, "vuchar3") for _ in range(NE2E)]
     streams = [torch.cuda.Stream(device=dev) for _ in range(NE2E)]
@@ -537,7 +537,7 @@ def main():
     e2e = {"value": esteps * e_frames * H * W / 1e6 / dt, "unit": "Mpix/s", "h2d_bytes_per_step": e_frames * h2d * world,
            "d2h_bytes_per_step": e_frames * th * rowb * world, "ms_per_step": dt / esteps * 1e3, "frames_per_e2e_step": e_frames,
            "upload": {"used": e2e_mode[0], "ms_per_step_by_form": e2e_ms},
-           "note": "pinned host frames -> vppb_upload (+ mirror border: direct 2-D copy + vppb_fill_border_mirror, or linear copy + vppb_copy2d_mirror, the faster of the two) -> vppb_box5x5_u8c3 -> vppb_download, 4 frames in flight per rank, max over ranks"}
+           "note": "pinned host frames -> vppb_upload (+ mirror border: direct 2-D copy + vppb_fill_border_mirror, or linear copy + vppb_copy2d_mirror, the faster of the two) -> vppb_box5x5_u8c3 -> vppb_download, %d frames in flight per rank, max over ranks" % NE2E}
     parity_ok = parity_ok and bool(np.array_equal(host_out[0].numpy(), hd[0]))
     if dist is not None:  # every rank checked its own tile
         pk = torch.tensor([1.0 if parity_ok else 0.0], dtype=torch.float64, device=dev)
@@ -769,7 +769,7 @@ def gpu_extras(vpp, capi, torch, stream, sp, dev):
                 "ms_python_call": ms_py, "keypoints": nk, "parity": ok,
                 "note": "us_device: detect + raster emit queued by vppb_fast9_u8_async (2 launches, no host sync); ms_python_call adds the count read-back and the keypoint download"}
 
-    def pyrlk_1080p_10k():  # pyramids (copy+mirror, one fused launch per level, Scharr+mirror) + pyrlk_match of 10k keypoints, vfloat2 gradient
+    def pyrlk_1080p_10k():  # pyramids + Scharr gradient pyramid (one cooperative launch) + pyrlk_match of 10k keypoints, vfloat2 gradient
         f1, f2, pts = scenes.lk_pair(1080, 1920, 10000, seed=5)
         I1, I2 = vpp.Image2d.from_host(f1, "u8"), vpp.Image2d.from_host(f2, "u8")
         prev, nxt = vpp.Pyramid2d((1080, 1920), 3, 2, pixel="u8", border=4), vpp.Pyramid2d((1080, 1920), 3, 2, pixel="u8", border=4)
@@ -799,7 +799,7 @@ def gpu_extras(vpp, capi, torch, stream, sp, dev):
         ms_lk = timed(lk, 10)
         return {"kpts_per_s": len(pts) / ((ms_lk + ms_build) / 1e3), "kpts_per_s_match_only": len(pts) / (ms_lk / 1e3),
                 "ms_match": ms_lk, "ms_pyramids_scharr": ms_build, "parity": ok, "max_rel_err": float(rel.max()),
-                "note": "kpts_per_s includes both u8 pyramids and the Scharr gradient pyramid (vppb_pyrlk_prepare: 9 launches on 3 streams); parity = failure flags identical and displacement rel. err <= 1e-4 against the oracle "
+                "note": "kpts_per_s includes both u8 pyramids and the Scharr gradient pyramid (vppb_pyrlk_prepare: ONE cooperative launch - 4 phases of concatenated work items, 3 grid barriers); parity = failure flags identical and displacement rel. err <= 1e-4 against the oracle "
                         "(whose 3-level definition clamps the reads the reference makes outside its border, tests/test_oracle_vs_ref.py)"}
 
     def sdof(H_, W_):

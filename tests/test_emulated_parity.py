@@ -101,6 +101,7 @@ test_video_extruder_eventful_sequence_equals_reference_tables = L.test_video_ext
 test_linear_copy_path_of_upload_download = L.test_linear_copy_path_of_upload_download
 test_semi_dense_flow_level_schedule = L.test_semi_dense_flow_level_schedule
 test_semi_dense_flow_long_propagation_chains = L.test_semi_dense_flow_long_propagation_chains
+test_pyrlk_prepare_one_launch_equals_streams = L.test_pyrlk_prepare_one_launch_equals_streams
 test_fast9_wide_images_multibox = L.test_fast9_wide_images_multibox
 test_fast9_threshold_extremes = L.test_fast9_threshold_extremes
 test_box5x5_row_tiles_read_neighbours = L.test_box5x5_row_tiles_read_neighbours

@@ -223,6 +223,35 @@ def test_semi_dense_flow_level_schedule(vpp, monkeypatch, density, schedule):
         assert np.array_equal(pos[ok], rpos[ok]) and np.array_equal(dist[ok], rdist[ok]), (density, ws, nscales, prop, patch)
 
 
+@pytest.mark.parametrize("shape,nlevels,grad", [((121, 163), 3, "vfloat2"), ((64, 96), 4, "vint2"), ((270, 481), 3, "vint2"), ((37, 50), 1, "vfloat2")])
+def test_pyrlk_prepare_one_launch_equals_streams(vpp, monkeypatch, shape, nlevels, grad):
+    """vppb_pyrlk_prepare as ONE cooperative launch (phases of concatenated work items, grid barriers between them) against its
+    multi-stream form (one launch per step): both u8 pyramids and the gradient pyramid, every level, whole buffers incl. borders;
+    and against the oracle's pyramids."""
+    from tests import scenes
+    from tests.oracle_ops import oracle_grad_pyramid, oracle_pyramid
+
+    nr, nc = shape
+    f1, f2, _ = scenes.lk_pair(nr, nc, 4, seed=nc, margin=10)
+    I1, I2 = vpp.Image2d.from_host(f1, "u8"), vpp.Image2d.from_host(f2, "u8")
+    got = {}
+    for form in ("fused", "streams"):
+        monkeypatch.setenv("VPPB_PREPARE", form)
+        prev, nxt = vpp.Pyramid2d((nr, nc), nlevels, 2, pixel="u8", border=4), vpp.Pyramid2d((nr, nc), nlevels, 2, pixel="u8", border=4)
+        g = vpp.Pyramid2d((nr, nc), nlevels, 2, pixel=grad, border=4)
+        vpp.pyrlk_prepare(I1, I2, prev, nxt, g)
+        got[form] = [[l.download(with_border=True) for l in p.levels] for p in (prev, nxt, g)]
+    for a, b in zip(got["fused"], got["streams"]):
+        for x, y in zip(a, b):
+            assert np.array_equal(x.view(np.uint8), y.view(np.uint8))
+    o = orc.load()
+    rprev = oracle_pyramid(f1, nlevels, "u8", 4, o)
+    rgrad = oracle_grad_pyramid(rprev, grad, 4, o)
+    for l in range(nlevels):
+        assert np.array_equal(got["fused"][0][l], rprev[l].get(True))
+        assert np.array_equal(got["fused"][2][l].view(np.int32), rgrad[l].get(True).view(np.int32))
+
+
 @pytest.mark.parametrize("shape,shift,nscales,prop", [((96, 131), (6.0, -5.0), 1, 4), ((121, 161), (9.0, 8.0), 2, 3), ((64, 203), (-5.0, 6.0), 1, 2)])
 def test_semi_dense_flow_long_propagation_chains(vpp, shape, shift, nscales, prop):
     """A shift the greedy descent cannot reach from a zero prediction: most cells start on a wrong local minimum and the few

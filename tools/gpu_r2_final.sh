@@ -23,6 +23,12 @@ print(len(k))
 PY
 timeout -k 10 300 ncu --set full --clock-control none --import-source on -k regex:k_fast9 -s 2 -c 2 -f -o gpurun_out/z_prof_fast4k python /tmp/fast4k.py > gpurun_out/z_ncu_fast.log 2>&1
 timeout -k 10 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 40 --csv --log-file gpurun_out/z_fast_launches.csv python /tmp/fast4k.py > /dev/null 2>&1
+# semi-dense flow: ncu of the single cooperative launch (1080p, a keypoint in every 10 x 10 block), its relaxation statistics, all schedules timed
+sed -n '/^cat > \/tmp\/sdof1.py/,/^PY$/p' tools/gpu_r2_m.sh | sed '1d;$d' > /tmp/sdof1.py
+timeout -k 10 400 ncu --set full --clock-control none --import-source on -k regex:k_sdof_fused -s 1 -c 1 -f -o gpurun_out/z_prof_sdof python /tmp/sdof1.py > gpurun_out/z_ncu_sdof.log 2>&1
+VPPB_SDOF_STATS=1 timeout 120 python /tmp/sdof1.py > /dev/null 2> gpurun_out/z_sdof_stats.txt
+timeout 300 python tools/sdof_bench.py > gpurun_out/z_sdof_bench.txt 2>&1
+timeout 300 python tools/pcie_probe.py > gpurun_out/z_pcie.json 2> gpurun_out/z_pcie.err
 timeout 120 tests/cpp/_build/pw_bench > gpurun_out/z_pw_bench.json 2> gpurun_out/z_pw_bench.err
 timeout -k 10 200 python tools/kitti_eval.py none 3 > gpurun_out/z_kitti_eval.json 2> gpurun_out/z_kitti_eval.err
 tail -2 gpurun_out/z_pytest.log; tail -2 gpurun_out/z_smoke.log

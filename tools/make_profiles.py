@@ -93,29 +93,35 @@ def main():
             o.write("\nCUDA-event time of the queued work (tile kernel + emit kernel, no host sync) from bench.py: extras.fast9_4k.us_device; round 1: 97 us (5 launches + 2 memsets + a blocking count read-back).\n"
                     "The tile kernel is bound by its exact test (one candidate per thread, ~8.8 % of the pixels of this scene are candidates: 116 instructions each); the emit kernel by fixed latencies "
                     "(launch + three dependent memory round trips for 270 CTAs).\n")
-    # ---- sdof launch list
-    sl = os.path.join(G, "m_sdof_launches.csv")
-    if os.path.exists(sl):
-        rows = list(csv.reader(open(sl)))
-        hdr = next(i for i, r in enumerate(rows) if r and r[0] == "ID")
-        ix = {h: i for i, h in enumerate(rows[hdr])}
-        seq = []
-        for r in rows[hdr + 1:]:
-            if len(r) > ix["Metric Value"] and "k_sdof" in r[ix["Kernel Name"]]:
-                seq.append((r[ix["ID"]], r[ix["Kernel Name"]].split("(")[0].replace("vppb::", ""), r[ix["Metric Name"]], float(r[ix["Metric Value"]].replace(",", ""))))
-        with open(os.path.join(P, "r2_sdof_launches.md"), "w") as o:
-            o.write("# Semi-dense flow, 1080p, video_extruder's settings, a keypoint in every 10x10 block (20 736): launches of one vppb_sdof_u8 call (coarsest scale first)\n\n| kernel | us | warp instructions |\n|---|---|---|\n")
-            byid = {}
-            for i, k, m, v in seq:
-                byid.setdefault(i, [k, None, None])[1 if m.startswith("gpu__time") else 2] = v
-            ids = sorted(byid, key=int)
-            one = ids[len(ids) // 3:len(ids) // 3 + 16]  # the middle call of three
-            for i in one:
-                k, t, n = byid[i]
-                o.write("| `%s` | %.1f | %.2f M |\n" % (k, (t or 0) / 1e3, (n or 0) / 1e6))
-            o.write("\nThe finest scale's sweeps are short (marked cells are rarely adjacent there: 0.11 ms each); at the two coarser scales every cell is marked and every iteration does real work "
-                    "(~15 k warp-instructions per cell: SADs of up to 8 neighbour flows and their descents), serialised by the Gauss-Seidel order - 1.2 ms and 2.6 ms per sweep, ~6 us per "
-                    "anti-diagonal step.  That per-cell work, not launch or flag latency, bounds the dense case.\n")
+    # ---- semi-dense flow: the single cooperative launch
+    rep = os.path.join(G, "z_prof_sdof.ncu-rep")
+    if os.path.exists(rep):
+        with open(os.path.join(P, "r2_sdof.md"), "w") as o:
+            o.write("# Semi-dense flow (vppb_sdof_u8), 1080p, video_extruder's settings, a keypoint in every 10x10 block (20 736): ncu --set full of the ONE cooperative launch "
+                    "(all scales: clear, claim, match, relaxation sweeps, results)\n\n")
+            o.write(summary_table(rep) + "\n")
+            st = os.path.join(G, "z_sdof_stats.txt")
+            if os.path.exists(st):
+                lines = [l.strip() for l in open(st) if l.startswith("vppb_sdof_u8:")]
+                if lines:
+                    o.write("Relaxation statistics of one call (VPPB_SDOF_STATS=1): `%s`\n\n" % lines[-1])
+            sb = os.path.join(G, "z_sdof_bench.txt")
+            if os.path.exists(sb):
+                o.write("`tools/sdof_bench.py` (rectangles scene, blockwise FAST keypoints, wall clock around call + sync; schedules: levels / dataflow are the opt-in round-1 / early round-2 forms, "
+                        "the last line of a size is the default):\n\n```\n%s```\n\n" % open(sb).read())
+            o.write("History of the dense 1080p case (bench.py extras.sdof_1080p, flow only): round 1 one launch per anti-diagonal 14 ms; dataflow sweeps (one persistent launch per sweep, flags between "
+                    "cells) 7.7 ms; + batched SADs and speculation 1.68 ms; relaxation schedule in one cooperative launch 0.29 ms.  The reference's own OpenMP path on the box's 16 threads: 3.8 ms.\n")
+    pc = os.path.join(G, "z_pcie.json")
+    if os.path.exists(pc):
+        try:
+            d = last_json(pc)
+            with open(os.path.join(P, "r2_host_link.md"), "w") as o:
+                o.write("# Host link of the box (tools/pcie_probe.py: pinned host <-> device, GB/s per direction)\n\n| chunk | H2D alone | D2H alone | both at once (each) |\n|---|---|---|---|\n")
+                for k, v in d.items():
+                    o.write("| %s | %.1f | %.1f | %.1f |\n" % (k, v["h2d_GBps_per_direction"], v["d2h_GBps_per_direction"], v["both_GBps_per_direction"]))
+                o.write("\nThe e2e leg of bench.py moves one 1080p vuchar3 frame (6.2 MB) per call in each direction, both directions busy: its GB/s per direction = e2e.value x 3 B/px.\n")
+        except Exception:
+            pass
     # ---- bench lines + scaling
     with open(os.path.join(P, "r2_bench_lines.md"), "w") as o:
         o.write("# bench.py lines of round 2 (B200, measured peak %.1f GB/s)\n\n" % PEAK)

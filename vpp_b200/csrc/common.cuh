@@ -133,4 +133,52 @@ __device__ __forceinline__ void spin_pause() { __nanosleep(20); }
 __device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void grid_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// Work item i of copy + fill_border_mirror in one pass (k_copy_mirror of pixelwise.cu, phase 0 of vppb_pyrlk_prepare): rows * nvec
+// 16-byte vectors, then rows * tail single bytes, then one item per border pixel of dst - read from the mirrored position in SRC (the
+// same value dst's domain receives), so nothing depends on the copy having landed.
+__host__ __device__ __forceinline__ long long copy_mirror_items(const Img& dst, int nvec, int tail) {
+  const long long b = dst.border;
+  return (long long)dst.nrows * (nvec + tail) + 2 * b * (dst.ncols + 2 * b) + 2 * b * dst.nrows;
+}
+__device__ __forceinline__ void copy_mirror_item(const Img& src, const Img& dst, int nvec, int tail, int elem, long long i) {
+  const int b = dst.border, nr = dst.nrows, nc = dst.ncols;
+  const long long n_vec = (long long)nr * nvec, n_tail = (long long)nr * tail;
+  const long long wfull = nc + 2LL * b, n_top = (long long)b * wfull, n_side = (long long)nr * b;
+  if (i < n_vec) {
+    const long long r = i / nvec;
+    const int k = (int)(i - r * nvec);
+    st_stream(reinterpret_cast<int4*>(dst.base + r * dst.pitch + (long long)k * 16), ld_stream(reinterpret_cast<const int4*>(src.base + r * src.pitch + (long long)k * 16)));
+  } else if (i < n_vec + n_tail) {
+    const long long j = i - n_vec, r = j / tail;
+    const long long off = (long long)nvec * 16 + (j - r * tail);
+    dst.base[r * dst.pitch + off] = src.base[r * src.pitch + off];
+  } else {
+    long long j = i - n_vec - n_tail;
+    int r, c;
+    if (j < n_top) { r = (int)(j / wfull) - b; c = (int)(j % wfull) - b; }
+    else if (j < 2 * n_top) { j -= n_top; r = nr + (int)(j / wfull); c = (int)(j % wfull) - b; }
+    else if (j < 2 * n_top + n_side) { j -= 2 * n_top; r = (int)(j / b); c = (int)(j % b) - b; }
+    else { j -= 2 * n_top + n_side; r = (int)(j / b); c = nc + (int)(j % b); }
+    const int sr = r < 0 ? -r - 1 : (r >= nr ? 2 * nr - r - 1 : r);  // fill.hh:59-82
+    const int sc = c < 0 ? -c - 1 : (c >= nc ? 2 * nc - c - 1 : c);
+    const unsigned char* s = src.base + (long long)sr * src.pitch + (long long)sc * elem;
+    unsigned char* d = dst.base + (long long)r * dst.pitch + (long long)c * elem;
+    for (int k = 0; k < elem; k++) d[k] = s[k];
+  }
+}
+
+// all CTAs of a cooperative launch are resident: a counter barrier in global memory.  `gen` counts the barriers passed (uniform
+// over the grid); the counter starts at 0 (the host zeroes it before the launch).
+__device__ __forceinline__ void grid_barrier(int* bar, int& gen) {
+  __syncthreads();
+  gen++;
+  if (threadIdx.x == 0) {
+    const int target = gen * (int)gridDim.x;
+    __threadfence();
+    atomicAdd(bar, 1);
+    while (ld_acquire(bar) < target) spin_pause();
+  }
+  __syncthreads();
+}
+
 }  // namespace vppb

@@ -349,34 +349,8 @@ int vppb_copy2d(const vppb_img* src, const vppb_img* dst, int with_border, void*
 // mirrored position in src (the same value dst's domain receives), so nothing depends on the copy having landed.
 // Work items: rows*nvec 16-byte vectors, then rows*tail single bytes, then one item per border pixel of dst.
 __global__ void __launch_bounds__(kThreads) k_copy_mirror(Img src, Img dst, int nvec, int tail, int elem) {
-  const int b = dst.border, nr = dst.nrows, nc = dst.ncols;
-  const long long n_vec = (long long)nr * nvec, n_tail = (long long)nr * tail;
-  const long long wfull = nc + 2LL * b, n_top = (long long)b * wfull, n_side = (long long)nr * b;
-  const long long total = n_vec + n_tail + 2 * n_top + 2 * n_side;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    if (i < n_vec) {
-      const long long r = i / nvec;
-      const int k = (int)(i - r * nvec);
-      st_stream(reinterpret_cast<int4*>(dst.base + r * dst.pitch + (long long)k * 16),
-                ld_stream(reinterpret_cast<const int4*>(src.base + r * src.pitch + (long long)k * 16)));
-    } else if (i < n_vec + n_tail) {
-      const long long j = i - n_vec, r = j / tail;
-      const long long off = (long long)nvec * 16 + (j - r * tail);
-      dst.base[r * dst.pitch + off] = src.base[r * src.pitch + off];
-    } else {
-      long long j = i - n_vec - n_tail;
-      int r, c;
-      if (j < n_top) { r = (int)(j / wfull) - b; c = (int)(j % wfull) - b; }
-      else if (j < 2 * n_top) { j -= n_top; r = nr + (int)(j / wfull); c = (int)(j % wfull) - b; }
-      else if (j < 2 * n_top + n_side) { j -= 2 * n_top; r = (int)(j / b); c = (int)(j % b) - b; }
-      else { j -= 2 * n_top + n_side; r = (int)(j / b); c = nc + (int)(j % b); }
-      const int sr = r < 0 ? -r - 1 : (r >= nr ? 2 * nr - r - 1 : r);  // fill.hh:59-82
-      const int sc = c < 0 ? -c - 1 : (c >= nc ? 2 * nc - c - 1 : c);
-      const unsigned char* s = src.base + (long long)sr * src.pitch + (long long)sc * elem;
-      unsigned char* d = dst.base + (long long)r * dst.pitch + (long long)c * elem;
-      for (int k = 0; k < elem; k++) d[k] = s[k];
-    }
-  }
+  const long long total = copy_mirror_items(dst, nvec, tail);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) copy_mirror_item(src, dst, nvec, tail, elem, i);
 }
 
 int vppb_copy2d_mirror(const vppb_img* src, const vppb_img* dst, void* stream) {

@@ -8,6 +8,8 @@
 // un-contracted evaluation order bit for bit.
 #include "common.cuh"
 
+#include <atomic>
+
 #include <algorithm>
 
 namespace vppb {
@@ -48,21 +50,25 @@ __device__ __forceinline__ void scharr_border_item(const Img& in, const Img& out
 }
 __host__ __device__ __forceinline__ long long border_items(int nr, int nc, int mb) { return 2LL * mb * (nc + 2LL * mb) + 2LL * nr * mb; }
 
-template <bool AS_FLOAT>
-__global__ void __launch_bounds__(256) k_scharr_u8_v8(Img in, Img out, int groups_per_row, int mb) {
+// loads of image data: read-only path (NC) in the one-kernel-per-step launches; plain loads inside the cooperative kernel of
+// vppb_pyrlk_prepare, where an earlier phase of the same kernel wrote the image
+template <bool NC, typename T> __device__ __forceinline__ T ld_img(const T* p) { return NC ? __ldg(p) : *p; }
+
+// work item i of scharr (8 pixels of a row per item, then one item per mirror-border pixel)
+template <bool AS_FLOAT, bool NC>
+__device__ __forceinline__ void scharr_v8_item(const Img& in, const Img& out, int groups_per_row, int mb, long long i) {
   const long long total = (long long)out.nrows * groups_per_row;
-  const long long n_border = border_items(out.nrows, out.ncols, mb);
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total + n_border; i += (long long)gridDim.x * blockDim.x) {
-    if (i >= total) { scharr_border_item<AS_FLOAT>(in, out, i - total, mb); continue; }
+  {
+    if (i >= total) { scharr_border_item<AS_FLOAT>(in, out, i - total, mb); return; }
     const int r = (int)(i / groups_per_row);
     const int c0 = (int)(i - (long long)r * groups_per_row) * 8;
     int px[3][10];  // columns c0-1 .. c0+8
 #pragma unroll
     for (int k = 0; k < 3; k++) {
       const unsigned char* row = row_ptr<unsigned char>(in, r - 1 + k) + c0;
-      const uint32_t left = __ldg(reinterpret_cast<const uint32_t*>(row - 4));
-      const uint2 mid = __ldg(reinterpret_cast<const uint2*>(row));
-      const uint32_t right = __ldg(reinterpret_cast<const uint32_t*>(row + 8));
+      const uint32_t left = ld_img<NC>(reinterpret_cast<const uint32_t*>(row - 4));
+      const uint2 mid = ld_img<NC>(reinterpret_cast<const uint2*>(row));
+      const uint32_t right = ld_img<NC>(reinterpret_cast<const uint32_t*>(row + 8));
       px[k][0] = byte_of(left, 3);
 #pragma unroll
       for (int j = 0; j < 4; j++) { px[k][1 + j] = byte_of(mid.x, j); px[k][5 + j] = byte_of(mid.y, j); }
@@ -92,17 +98,25 @@ __global__ void __launch_bounds__(256) k_scharr_u8_v8(Img in, Img out, int group
     }
   }
 }
+template <bool AS_FLOAT>
+__global__ void __launch_bounds__(256) k_scharr_u8_v8(Img in, Img out, int groups_per_row, int mb) {
+  const long long total = (long long)out.nrows * groups_per_row + border_items(out.nrows, out.ncols, mb);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
+    scharr_v8_item<AS_FLOAT, true>(in, out, groups_per_row, mb, i);
+}
 
 // any layout: 1 pixel per thread, byte loads
 template <bool AS_FLOAT>
-__global__ void __launch_bounds__(256) k_scharr_u8(Img in, Img out, int mb) {
+__device__ __forceinline__ void scharr_px_item(const Img& in, const Img& out, int mb, long long i) {
   const long long total = (long long)out.nrows * out.ncols;
-  const long long n_border = border_items(out.nrows, out.ncols, mb);
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total + n_border; i += (long long)gridDim.x * blockDim.x) {
-    if (i >= total) { scharr_border_item<AS_FLOAT>(in, out, i - total, mb); continue; }
-    const int r = (int)(i / out.ncols), c = (int)(i - (long long)r * out.ncols);
-    scharr_px<AS_FLOAT>(in, out, r, c, r, c);
-  }
+  if (i >= total) { scharr_border_item<AS_FLOAT>(in, out, i - total, mb); return; }
+  const int r = (int)(i / out.ncols), c = (int)(i - (long long)r * out.ncols);
+  scharr_px<AS_FLOAT>(in, out, r, c, r, c);
+}
+template <bool AS_FLOAT>
+__global__ void __launch_bounds__(256) k_scharr_u8(Img in, Img out, int mb) {
+  const long long total = (long long)out.nrows * out.ncols + border_items(out.nrows, out.ncols, mb);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) scharr_px_item<AS_FLOAT>(in, out, mb, i);
 }
 
 // ------------------------------------------------------------------ low-pass + subsample2
@@ -148,12 +162,11 @@ __device__ __forceinline__ void store_mirrored(const Img& out, int r, int c, T v
 // H rows with mirrored indices (the mirror-filled temp of pyramid.hh:36), H reads in(row, x-2..x+2)
 // from the image's own (caller-filled) column border.
 template <int KIND>
-__global__ void __launch_bounds__(256) k_lowpass_sub2(Img in, Img out, int step, int mb) {
+__device__ __forceinline__ void lowpass_sub2_item(const Img& in, const Img& out, int step, int mb, long long i) {
   typedef typename LpT<KIND>::elem E;
   typedef typename LpT<KIND>::acc A;
   constexpr int COMPS = LpT<KIND>::comps;
-  long long total = (long long)out.nrows * out.ncols * COMPS;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+  {
     const int k = (int)(i % COMPS);
     const long long pix = i / COMPS;
     const int r = (int)(pix / out.ncols);
@@ -170,6 +183,11 @@ __global__ void __launch_bounds__(256) k_lowpass_sub2(Img in, Img out, int step,
     }
     store_mirrored<E>(out, r, c, (E)lp5(h[0], h[1], h[2], h[3], h[4]), mb, COMPS, k);
   }
+}
+template <int KIND>
+__global__ void __launch_bounds__(256) k_lowpass_sub2(Img in, Img out, int step, int mb) {
+  const long long total = (long long)out.nrows * out.ncols * LpT<KIND>::comps;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) lowpass_sub2_item<KIND>(in, out, step, mb, i);
 }
 
 // u8 fast path: one thread = 8 x 2 outputs.  The 7 input rows it needs (mirrored indices at the top /
@@ -196,12 +214,17 @@ __device__ __forceinline__ void put_u8x8(const Img& out, int tr, int c0, uint32_
 // Work items [0, total) are 8 x 2 output groups; items [total, total + n_row + n_col) are the outputs of the
 // mirrored last row / last column of an even-sized parent (centre on an odd pixel), one per thread, with the
 // arithmetic of k_lowpass_sub2<0>.  mb > 0: the mirror border of `out` is written too (store_mirrored).
-__global__ void __launch_bounds__(128) k_lowpass_sub2_u8_fast(Img in, Img out, int fast_rows, int fast_cols, int groups_per_row, int mb) {
+__host__ __device__ __forceinline__ long long lowpass_u8_fast_items(int out_nrows, int out_ncols, int fast_rows, int fast_cols, int groups_per_row) {
+  const int n_row = out_nrows > fast_rows ? out_ncols : 0;
+  const int n_col = out_ncols > fast_cols ? out_nrows - (n_row ? 1 : 0) : 0;
+  return (long long)((fast_rows + 1) / 2) * groups_per_row + n_row + n_col;
+}
+template <bool NC>
+__device__ __forceinline__ void lowpass_sub2_u8_fast_item(const Img& in, const Img& out, int fast_rows, int fast_cols, int groups_per_row, int mb, long long i) {
   const int row_pairs = (fast_rows + 1) / 2;
   const long long total = (long long)row_pairs * groups_per_row;
   const int n_row = out.nrows > fast_rows ? out.ncols : 0;
-  const int n_col = out.ncols > fast_cols ? out.nrows - (n_row ? 1 : 0) : 0;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total + n_row + n_col; i += (long long)gridDim.x * blockDim.x) {
+  {
     if (i >= total) {
       const int e = (int)(i - total);
       const int r = e < n_row ? out.nrows - 1 : e - n_row;
@@ -214,7 +237,7 @@ __global__ void __launch_bounds__(128) k_lowpass_sub2_u8_fast(Img in, Img out, i
         h[d] = lp5((int)row[x - 2], (int)row[x - 1], (int)row[x], (int)row[x + 1], (int)row[x + 2]);
       }
       store_mirrored<unsigned char>(out, r, c, (unsigned char)lp5(h[0], h[1], h[2], h[3], h[4]), mb);
-      continue;
+      return;
     }
     const int rp = (int)(i / groups_per_row), g = (int)(i - (long long)rp * groups_per_row);
     const int r0 = 2 * rp, c0 = 8 * g;
@@ -223,9 +246,9 @@ __global__ void __launch_bounds__(128) k_lowpass_sub2_u8_fast(Img in, Img out, i
     for (int d = 0; d < 7; d++) {
       const int yy = mirror_idx(2 * r0 - 2 + d, in.nrows);
       const unsigned char* row = row_ptr<unsigned char>(in, yy) + 16 * g;
-      const uint32_t left = __ldg(reinterpret_cast<const uint32_t*>(row - 4));
-      const uint4 mid = __ldg(reinterpret_cast<const uint4*>(row));
-      const uint32_t right = __ldg(reinterpret_cast<const uint32_t*>(row + 16));
+      const uint32_t left = ld_img<NC>(reinterpret_cast<const uint32_t*>(row - 4));
+      const uint4 mid = ld_img<NC>(reinterpret_cast<const uint4*>(row));
+      const uint32_t right = ld_img<NC>(reinterpret_cast<const uint32_t*>(row + 16));
       int p[19];  // bytes 16g-2 .. 16g+16
       p[0] = byte_of(left, 2); p[1] = byte_of(left, 3);
 #pragma unroll
@@ -252,6 +275,11 @@ __global__ void __launch_bounds__(128) k_lowpass_sub2_u8_fast(Img in, Img out, i
     }
   }
 }
+__global__ void __launch_bounds__(128) k_lowpass_sub2_u8_fast(Img in, Img out, int fast_rows, int fast_cols, int groups_per_row, int mb) {
+  const long long total = lowpass_u8_fast_items(out.nrows, out.ncols, fast_rows, fast_cols, groups_per_row);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
+    lowpass_sub2_u8_fast_item<true>(in, out, fast_rows, fast_cols, groups_per_row, mb, i);
+}
 
 // 8-byte pixels (vint2 / vfloat2 gradient pyramids): one thread per output pixel, both components;
 // each of the 5 rows is read as 16 + 16 + 8 bytes when the centre column is even (always, except for
@@ -261,12 +289,11 @@ template <> struct vec2_of<int> { typedef int2 type; typedef int4 type4; };
 template <> struct vec2_of<float> { typedef float2 type; typedef float4 type4; };
 
 template <int KIND>
-__global__ void __launch_bounds__(256) k_lowpass_sub2_px8(Img in, Img out, int aligned16, int mb) {
+__device__ __forceinline__ void lowpass_sub2_px8_item(const Img& in, const Img& out, int aligned16, int mb, long long i) {
   typedef typename LpT<KIND>::acc A;
   typedef typename vec2_of<A>::type V2;
   typedef typename vec2_of<A>::type4 V4;
-  const long long total = (long long)out.nrows * out.ncols;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+  {
     const int r = (int)(i / out.ncols), c = (int)(i - (long long)r * out.ncols);
     const int y = mirror_idx(r * 2, in.nrows), x = mirror_idx(c * 2, in.ncols);
     A hx[5], hy[5];
@@ -289,6 +316,71 @@ __global__ void __launch_bounds__(256) k_lowpass_sub2_px8(Img in, Img out, int a
     o.x = lp5(hx[0], hx[1], hx[2], hx[3], hx[4]);
     o.y = lp5(hy[0], hy[1], hy[2], hy[3], hy[4]);
     store_mirrored<V2>(out, r, c, o, mb);
+  }
+}
+template <int KIND>
+__global__ void __launch_bounds__(256) k_lowpass_sub2_px8(Img in, Img out, int aligned16, int mb) {
+  const long long total = (long long)out.nrows * out.ncols;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) lowpass_sub2_px8_item<KIND>(in, out, aligned16, mb, i);
+}
+
+// ---- vppb_pyrlk_prepare as ONE cooperative launch -----------------------------------------------------------------------------------
+// Everything lucas_kanade() / a pyrlk_match caller builds before matching is a short DAG of the work-item loops above:
+//   phase 0: prev[0] <- copy + mirror(i1), next[0] <- copy + mirror(i2)
+//   phase 1: grad[0] <- scharr + mirror(prev[0]), prev[1] <- lowpass(prev[0]), next[1] <- lowpass(next[0])
+//   phase l: grad[l-1] <- lowpass(grad[l-2]), prev[l] <- ..., next[l] <- ...;   last phase: grad[L-1] <- lowpass(grad[L-2])
+// The ops of a phase are independent: their work items are concatenated and shared out over the whole (resident) grid; phases are
+// separated by a grid-wide barrier.  L barriers instead of 3 L launches on three streams with four event hops.
+enum { PREP_COPY_MIRROR = 0, PREP_SCHARR_V8, PREP_SCHARR_PX, PREP_LP_U8_FAST, PREP_LP_GENERIC, PREP_LP_PX8 };
+struct PrepOp {
+  int kind, variant;  // variant: as_float (scharr) / KIND (lowpass)
+  Img in, out;
+  int p0, p1, p2, mb;
+  long long items;
+};
+constexpr int PREP_MAX_LEVELS = 8;
+struct PrepProg {
+  PrepOp op[3 * PREP_MAX_LEVELS + 3];
+  int phase_end[PREP_MAX_LEVELS + 2];
+  int nphases;
+  int* bar;
+};
+
+__device__ __forceinline__ void prep_item(const PrepOp& o, long long i) {
+  switch (o.kind) {
+    case PREP_COPY_MIRROR: copy_mirror_item(o.in, o.out, o.p0, o.p1, o.p2, i); break;
+    case PREP_SCHARR_V8:
+      if (o.variant) scharr_v8_item<true, false>(o.in, o.out, o.p0, o.mb, i); else scharr_v8_item<false, false>(o.in, o.out, o.p0, o.mb, i);
+      break;
+    case PREP_SCHARR_PX:
+      if (o.variant) scharr_px_item<true>(o.in, o.out, o.mb, i); else scharr_px_item<false>(o.in, o.out, o.mb, i);
+      break;
+    case PREP_LP_U8_FAST: lowpass_sub2_u8_fast_item<false>(o.in, o.out, o.p0, o.p1, o.p2, o.mb, i); break;
+    case PREP_LP_GENERIC:
+      if (o.variant == 0) lowpass_sub2_item<0>(o.in, o.out, 2, o.mb, i);
+      else if (o.variant == 1) lowpass_sub2_item<1>(o.in, o.out, 2, o.mb, i);
+      else lowpass_sub2_item<2>(o.in, o.out, 2, o.mb, i);
+      break;
+    default:
+      if (o.variant == 1) lowpass_sub2_px8_item<1>(o.in, o.out, o.p0, o.mb, i); else lowpass_sub2_px8_item<2>(o.in, o.out, o.p0, o.mb, i);
+      break;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_pyrlk_prepare(const __grid_constant__ PrepProg P) {
+  const long long gthreads = (long long)gridDim.x * blockDim.x, gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  int gen = 0;
+  for (int ph = 0; ph < P.nphases; ph++) {
+    const int first = ph ? P.phase_end[ph - 1] : 0, last = P.phase_end[ph];
+    long long total = 0;
+    for (int o = first; o < last; o++) total += P.op[o].items;
+    for (long long i = gtid; i < total; i += gthreads) {
+      long long j = i;
+      int o = first;
+      while (j >= P.op[o].items) { j -= P.op[o].items; o++; }
+      prep_item(P.op[o], j);
+    }
+    if (ph + 1 < P.nphases) grid_barrier(P.bar, gen);
   }
 }
 
@@ -376,6 +468,107 @@ int vppb_lowpass_sub2(const vppb_img* in, const vppb_img* out, int kind, void* s
 int vppb_lowpass_sub2_mirror(const vppb_img* in, const vppb_img* out, int kind, void* stream) { return lowpass_sub2(in, out, kind, 1, stream); }
 
 
+// ---- the ops of the fused vppb_pyrlk_prepare: the same checks and the same choice of variant as the stand-alone entry points ----
+static bool prep_copy_mirror(const vppb_img* src, const vppb_img* dst, PrepOp& o) {
+  if (!src || !dst || !src->base || !dst->base || src->elem_bytes != dst->elem_bytes || src->elem_bytes > 64 || !same_domain(src, dst)) return false;
+  if (dst->border > dst->nrows || dst->border > dst->ncols || src->base == dst->base) return false;
+  if (((uintptr_t)src->base % 16) || ((uintptr_t)dst->base % 16) || (src->pitch % 16) || (dst->pitch % 16)) return false;
+  const long long wbytes = (long long)src->ncols * src->elem_bytes;
+  o.kind = PREP_COPY_MIRROR; o.variant = 0; o.in = view(src); o.out = view(dst);
+  o.p0 = (int)(wbytes / 16); o.p1 = (int)(wbytes - (long long)o.p0 * 16); o.p2 = src->elem_bytes; o.mb = dst->border;
+  o.items = copy_mirror_items(o.out, o.p0, o.p1);
+  return true;
+}
+static bool prep_scharr(const vppb_img* in, const vppb_img* out, int as_float, PrepOp& o) {
+  if (!in || !out || !in->base || !out->base || in->elem_bytes != 1 || out->elem_bytes != 8 || in->nrows < out->nrows || in->ncols < out->ncols) return false;
+  if (in->border < 1 || ((uintptr_t)out->base % 8) || (out->pitch % 8) || out->border > out->nrows || out->border > out->ncols) return false;
+  const int mb = out->border, groups = (out->ncols + 7) / 8;
+  const bool fast = ((uintptr_t)in->base % 8) == 0 && (in->pitch % 8) == 0 && ((uintptr_t)out->base % 16) == 0 && (out->pitch % 16) == 0 &&
+                    in->align >= 16 && (long long)groups * 8 + 4 <= in->pitch - (long long)in->align;
+  o.kind = fast ? PREP_SCHARR_V8 : PREP_SCHARR_PX; o.variant = as_float ? 1 : 0; o.in = view(in); o.out = view(out);
+  o.p0 = groups; o.p1 = o.p2 = 0; o.mb = mb;
+  o.items = (fast ? (long long)out->nrows * groups : (long long)out->nrows * out->ncols) + border_items(out->nrows, out->ncols, mb);
+  return true;
+}
+static bool prep_lowpass(const vppb_img* in, const vppb_img* out, int kind, PrepOp& o) {
+  const int e = kind == 0 ? 1 : 8;
+  if (!in || !out || !in->base || !out->base || in->elem_bytes != e || out->elem_bytes != e || in->border < 2) return false;
+  if (out->nrows > 1 + in->nrows / 2 || out->ncols > 1 + in->ncols / 2 || out->border > out->nrows || out->border > out->ncols) return false;
+  o.variant = kind; o.in = view(in); o.out = view(out); o.mb = out->border; o.p0 = o.p1 = o.p2 = 0;
+  if (kind == 0) {
+    const bool fast = in->align >= 32 && ((uintptr_t)in->base % 16) == 0 && (in->pitch % 16) == 0 && ((uintptr_t)out->base % 8) == 0 &&
+                      (out->pitch % 8) == 0 && in->nrows >= 4 && in->ncols >= 4;
+    if (fast) {
+      o.kind = PREP_LP_U8_FAST;
+      o.p0 = std::min(out->nrows, (in->nrows + 1) / 2); o.p1 = std::min(out->ncols, (in->ncols + 1) / 2); o.p2 = (o.p1 + 7) / 8;
+      o.items = lowpass_u8_fast_items(out->nrows, out->ncols, o.p0, o.p1, o.p2);
+    } else {
+      o.kind = PREP_LP_GENERIC;
+      o.items = (long long)out->nrows * out->ncols;
+    }
+  } else {
+    o.kind = PREP_LP_PX8;
+    o.p0 = (((uintptr_t)in->base % 16) == 0 && (in->pitch % 16) == 0) ? 1 : 0;
+    o.items = (long long)out->nrows * out->ncols;
+  }
+  return true;
+}
+
+// barrier counters of the cooperative launches (64 slots handed out round-robin: a slot is zeroed on the stream right before its launch)
+static int* prep_barrier_slot() {
+  static std::atomic<int*> pool{nullptr};
+  static std::atomic<unsigned> next{0};
+  int* p = pool.load(std::memory_order_acquire);
+  if (!p) {
+    int* q = nullptr;
+    if (cudaMalloc(&q, 64 * 256) != cudaSuccess) return nullptr;
+    int* expected = nullptr;
+    if (!pool.compare_exchange_strong(expected, q, std::memory_order_acq_rel)) { cudaFree(q); q = expected; }
+    p = q;
+  }
+  return p + (size_t)(next.fetch_add(1) % 64) * 64;
+}
+
+static int pyrlk_prepare_fused(const vppb_img* i1, const vppb_img* i2, const vppb_img* prev, const vppb_img* next, const vppb_img* grad, int nlevels,
+                               int grad_is_float, cudaStream_t st, bool* done) {
+  *done = false;
+  if (nlevels > PREP_MAX_LEVELS) return VPPB_OK;
+  PrepProg P;
+  memset(&P, 0, sizeof(P));
+  int n = 0, ph = 0;
+  const int gk = grad_is_float ? 2 : 1;
+  if (!prep_copy_mirror(i1, &prev[0], P.op[n]) || !prep_copy_mirror(i2, &next[0], P.op[n + 1])) return VPPB_OK;
+  n += 2; P.phase_end[ph++] = n;
+  for (int l = 1; l <= nlevels; l++) {  // phase l
+    if (l == 1) { if (!prep_scharr(&prev[0], &grad[0], grad_is_float, P.op[n])) return VPPB_OK; n++; }
+    else { if (!prep_lowpass(&grad[l - 2], &grad[l - 1], gk, P.op[n])) return VPPB_OK; n++; }
+    if (l < nlevels) {
+      if (!prep_lowpass(&prev[l - 1], &prev[l], 0, P.op[n]) || !prep_lowpass(&next[l - 1], &next[l], 0, P.op[n + 1])) return VPPB_OK;
+      n += 2;
+    }
+    P.phase_end[ph++] = n;
+  }
+  P.nphases = ph;
+  // the images of one call must be distinct buffers (a phase reads what an earlier phase wrote, never what it writes itself)
+  P.bar = prep_barrier_slot();
+  if (!P.bar) return VPPB_OK;
+  long long most = 0;
+  for (int p = 0, first = 0; p < P.nphases; first = P.phase_end[p], p++) {
+    long long t = 0;
+    for (int o = first; o < P.phase_end[p]; o++) t += P.op[o].items;
+    most = std::max(most, t);
+  }
+  long long blocks = (most + 255) / 256;
+  const int cap = cooperative_grid_limit(k_pyrlk_prepare, 256);
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  VPPB_CUDA(cudaMemsetAsync(P.bar, 0, sizeof(int), st));
+  VPPB_CUDA(launch_cooperative(k_pyrlk_prepare, (int)blocks, 256, st, P));
+  VPPB_LAUNCH_CHECK("vppb_pyrlk_prepare");
+  *done = true;
+  return VPPB_OK;
+}
+
 // pyramid2d<uchar> of two frames + the Scharr gradient pyramid of the first (what lucas_kanade.hpp:150-157 and every
 // pyrlk_match caller build before matching: pyramid2d::update(i1), ::update(i2), scharr(prev[0], grad[0]),
 // grad.propagate_level0()).  Nine small launches; the three chains (prev levels, next levels, gradient levels) are
@@ -384,6 +577,15 @@ int vppb_lowpass_sub2_mirror(const vppb_img* in, const vppb_img* out, int kind, 
 int vppb_pyrlk_prepare(const vppb_img* i1, const vppb_img* i2, const vppb_img* prev, const vppb_img* next, const vppb_img* grad, int32_t nlevels,
                        int32_t grad_is_float, void* stream) {
   VPPB_REQUIRE(i1 && i2 && prev && next && grad && nlevels >= 1 && nlevels <= 16, VPPB_E_ARG, "vppb_pyrlk_prepare: bad argument");
+  {  // one cooperative launch when every step has a work-item form (library layout); VPPB_PREPARE=streams forces the multi-stream form
+    const char* e = getenv("VPPB_PREPARE");  // "streams": the multi-stream form; "fused": fail instead of falling back to it (tests)
+    bool done = false;
+    if (!(e && !strcmp(e, "streams"))) {
+      const int rc_ = pyrlk_prepare_fused(i1, i2, prev, next, grad, nlevels, grad_is_float, as_stream(stream), &done);
+      if (rc_ != VPPB_OK || done) return rc_;
+      VPPB_REQUIRE(!(e && !strcmp(e, "fused")), VPPB_E_ARG, "vppb_pyrlk_prepare: VPPB_PREPARE=fused but the images do not have the library layout");
+    }
+  }
   static thread_local cudaStream_t side[2] = {nullptr, nullptr};
   static thread_local cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   static thread_local int side_dev = -1;

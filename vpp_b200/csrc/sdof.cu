@@ -426,19 +426,6 @@ struct SdofFused {
   int* ctr;  // zeroed before the launch: [0] grid barrier, [1], [2] statistics, [8 + 128 * scale] marked cells of the scale, [.. + 4 + 4 * sweep + 0..2] work-list lengths
 };
 
-// all CTAs of a cooperative launch are resident: a counter barrier.  `gen` counts the barriers passed (uniform over the grid).
-__device__ __forceinline__ void grid_barrier(int* bar, int& gen) {
-  __syncthreads();
-  gen++;
-  if (threadIdx.x == 0) {
-    const int target = gen * (int)gridDim.x;
-    __threadfence();
-    atomicAdd(bar, 1);
-    while (ld_acquire(bar) < target) spin_pause();
-  }
-  __syncthreads();
-}
-
 // one evaluation of cell `cell` in a relaxation round (one warp).  first: round 0 of the sweep (everything read from `old`, `cur`
 // written unconditionally); later rounds compare with the cell's previous `cur`.  A cell whose flow moved queues its successors.
 __device__ __forceinline__ void sdof_relax_cell(const SdofLevel& L, const unsigned long long* old, unsigned long long* cur, int cell, int forward, int nkr,

@@ -40,10 +40,18 @@ __global__ void __launch_bounds__(256) k_lbp_u8(Img in, Img out, int xthreads) {
   const int x0 = xt * 16;
   const int r_end = min(r_first + LBP_ROWS, in.nrows);
   if (VEC && x0 + 16 <= in.ncols) {
-    LbpRow a = lbp_load(in.base + (long long)(r_first - 1) * in.pitch, x0);
-    LbpRow b = lbp_load(in.base + (long long)r_first * in.pitch, x0);
-    for (int r = r_first; r < r_end; r++) {
-      const LbpRow c = lbp_load(in.base + (long long)(r + 1) * in.pitch, x0);
+    // all LBP_ROWS + 2 input rows of the thread are requested before the first is used: one memory latency per thread, not one per row
+    LbpRow v[LBP_ROWS + 2];
+#pragma unroll
+    for (int j = 0; j < LBP_ROWS + 2; j++) {
+      const int r = min(r_first - 1 + j, in.nrows);  // rows below the bottom border row are not read (nor used)
+      v[j] = lbp_load(in.base + (long long)r * in.pitch, x0);
+    }
+#pragma unroll
+    for (int j = 0; j < LBP_ROWS; j++) {
+      const int r = r_first + j;
+      if (r >= r_end) break;
+      const LbpRow &a = v[j], &b = v[j + 1], &c = v[j + 2];
       uint32_t o[4];
 #pragma unroll
       for (int k = 0; k < 4; k++) {
@@ -59,8 +67,6 @@ __global__ void __launch_bounds__(256) k_lbp_u8(Img in, Img out, int xthreads) {
         o[k] = acc;
       }
       *reinterpret_cast<uint4*>(out.base + (long long)r * out.pitch + x0) = make_uint4(o[0], o[1], o[2], o[3]);
-      a = b;
-      b = c;
     }
     return;
   }
@@ -77,23 +83,13 @@ __global__ void __launch_bounds__(256) k_lbp_u8(Img in, Img out, int xthreads) {
 // The result of the serial order is the unique solution X of
 //     X(p) = orig(p)  if  orig(p) > max(X(NW), X(N), X(NE), X(W), orig(E), orig(SW), orig(S), orig(SE)),  else 0
 // - a triangular system (X(p) only depends on X of earlier pixels), solved here by relaxation exactly like the sweeps of the
-// semi-dense flow: every pass re-evaluates all pixels on the current X of their predecessors, passes are separated by a
+// semi-dense flow: every pass re-evaluates all pixels on the current X of their predecessors (runs of 16 pixels of a row are
+// walked serially, so chains along a row shorten 16-fold), passes are separated by a
 // grid-wide barrier, and a pass that changes nothing has reached the fixed point.  X only ever takes the values orig(p) and 0, the
 // number of passes is the longest chain of decisions that flip (2 - 4 on score images, the length of a ramp at worst).
 template <typename T> __device__ __forceinline__ T ld_cg(const T* p) { return __ldcg(p); }
 
-__device__ __forceinline__ void lmf_barrier(int* bar, int& gen) {
-  __syncthreads();
-  gen++;
-  if (threadIdx.x == 0) {
-    const int target = gen * (int)gridDim.x;
-    __threadfence();
-    atomicAdd(bar, 1);
-    while (ld_acquire(bar) < target) spin_pause();
-  }
-  __syncthreads();
-}
-
+constexpr int LMF_RUN = 16;
 template <typename T>
 __global__ void __launch_bounds__(256) k_local_maxima_filter(Img im, T* orig, int wcols, int* ctr) {
   const long long gthreads = (long long)gridDim.x * blockDim.x, gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -104,25 +100,36 @@ __global__ void __launch_bounds__(256) k_local_maxima_filter(Img im, T* orig, in
     const int r = (int)(i / wcols) - 1, c = (int)(i % wcols) - 1;
     orig[i] = reinterpret_cast<const T*>(im.base + (long long)r * im.pitch)[c];
   }
-  lmf_barrier(ctr, gen);
-  const long long total = (long long)im.nrows * im.ncols;
+  grid_barrier(ctr, gen);
+  // a thread owns a run of LMF_RUN consecutive pixels of a row and walks it left to right with its own fresh result as the left
+  // neighbour (Gauss-Seidel inside the run): a horizontal chain of dependent decisions costs one pass per run it crosses, not one per pixel
+  const int runs_per_row = (im.ncols + LMF_RUN - 1) / LMF_RUN;
+  const long long total = (long long)im.nrows * runs_per_row;
   for (int pass = 0;; pass++) {
     int changed = 0;
     for (long long i = gtid; i < total; i += gthreads) {
-      const int r = (int)(i / im.ncols), c = (int)(i % im.ncols);
-      const T* o1 = orig + (long long)(r + 1) * wcols + (c + 1);
-      const T a = o1[0];
-      T* x1 = reinterpret_cast<T*>(im.base + (long long)r * im.pitch) + c;
-      const T* x0 = reinterpret_cast<const T*>(im.base + (long long)(r - 1) * im.pitch) + c;
+      const int r = (int)(i / runs_per_row), c0 = (int)(i % runs_per_row) * LMF_RUN;
+      const int c1 = min(c0 + LMF_RUN, im.ncols);
+      const T* o1 = orig + (long long)(r + 1) * wcols + (c0 + 1);   // orig(r, c0)
+      const T* o2 = o1 + wcols;                                       // orig(r + 1, c0)
+      T* x1 = reinterpret_cast<T*>(im.base + (long long)r * im.pitch) + c0;
+      const T* x0 = reinterpret_cast<const T*>(im.base + (long long)(r - 1) * im.pitch) + c0;
       // successors: original values; predecessors: their current X (read from L2: other CTAs rewrite it between passes)
-      bool is_max = a > o1[1] && a > o1[wcols - 1] && a > o1[wcols] && a > o1[wcols + 1];
-      if (is_max) is_max = a > ld_cg(x0 - 1) && a > ld_cg(x0) && a > ld_cg(x0 + 1) && a > ld_cg(x1 - 1);
-      const T res = is_max ? a : (T)0;
-      if (ld_cg(x1) != res) { *x1 = res; changed = 1; }
+      T w = ld_cg(x1 - 1);
+      T nl = ld_cg(x0 - 1), nm = ld_cg(x0);
+      T sl = o2[-1], sm = o2[0];
+      T a = o1[0];
+      for (int c = c0; c < c1; c++, o1++, o2++, x0++, x1++) {
+        const T nr = ld_cg(x0 + 1), sr = o2[1], e = o1[1];
+        const bool is_max = a > e && a > sl && a > sm && a > sr && a > nl && a > nm && a > nr && a > w;
+        const T res = is_max ? a : (T)0;
+        if (ld_cg(x1) != res) { *x1 = res; changed = 1; }
+        w = res; nl = nm; nm = nr; sl = sm; sm = sr; a = e;
+      }
     }
     if (__any_sync(0xffffffffu, changed) && (threadIdx.x & 31) == 0) atomicAdd(ctr + 1 + pass % 3, 1);
     if (gtid == 0) ctr[1 + (pass + 1) % 3] = 0;  // next pass's counter: nobody reads or writes it during this pass
-    lmf_barrier(ctr, gen);
+    grid_barrier(ctr, gen);
     if (ld_cg(ctr + 1 + pass % 3) == 0) break;  // grid-uniform: the counter is stable until every CTA has passed the next barrier
   }
 }
@@ -163,7 +170,7 @@ int vppb_local_maxima_filter(const vppb_img* img, void* workspace, int64_t works
   cudaStream_t st = as_stream(stream);
   int* ctr = reinterpret_cast<int*>(static_cast<unsigned char*>(workspace) + need - 256);
   VPPB_CUDA(cudaMemsetAsync(ctr, 0, 256, st));
-  const long long total = (long long)img->nrows * img->ncols;
+  const long long total = (long long)img->nrows * ((img->ncols + LMF_RUN - 1) / LMF_RUN);
   long long blocks = (total + 255) / 256;
   if (img->elem_bytes == 1) {
     const int cap = cooperative_grid_limit(k_local_maxima_filter<unsigned char>, 256);

@@ -337,7 +337,7 @@ def lucas_kanade(i1, i2, keypoints, niterations=21, winsize=11, nscales=3, min_e
 
 def pyrlk_prepare(i1, i2, prev, nxt, grad, stream=None):
     """The two u8 pyramids and the Scharr gradient pyramid of frame 1 (lucas_kanade.hpp:150-157) in one call: three
-    independent chains of launches on three streams (vppb_pyrlk_prepare)."""
+    independent chains (vppb_pyrlk_prepare: one cooperative launch for images in the library layout)."""
     check(lib.vppb_pyrlk_prepare(i1.ptr(), i2.ptr(), prev.desc_array(), nxt.desc_array(), grad.desc_array(), len(prev),
                                  1 if grad.pixel == "vfloat2" else 0, stream))
 
