@@ -821,8 +821,8 @@ def gpu_extras(vpp, capi, torch, stream, sp, dev):
         def run():
             capi.check(capi.lib.vppb_sdof_u8(a1, a2, C.byref(P), d_kp.ptr, n, wsb.ptr, wsb.nbytes, d_pos.ptr, d_dist.ptr, d_valid.ptr, sp))
 
-        def pyr():
-            p1.update(I1, sp); p2.update(I2, sp)
+        def pyr():  # both pyramids in one launch, as vpp_b200.semi_dense_optical_flow / semi_dense_optical_flow() build them
+            capi.check(capi.lib.vppb_pyrlk_prepare(I1.ptr(), I2.ptr(), a1, a2, None, 3, 0, sp))
 
         run()
         got = (d_pos.to_host(np.int32, n * 2, sp).reshape(-1, 2), d_dist.to_host(np.int32, n, sp), d_valid.to_host(np.uint8, n, sp))

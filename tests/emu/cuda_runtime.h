@@ -182,6 +182,8 @@ inline void __threadfence() {}
 inline void __nanosleep(unsigned) {}
 template <typename T> inline void __stcs(T* p, T v) { *p = v; }
 template <typename T> inline void __stcg(T* p, T v) { *p = v; }
+inline float __uint_as_float(unsigned v) { float f; memcpy(&f, &v, 4); return f; }
+inline unsigned __float_as_uint(float f) { unsigned v; memcpy(&v, &f, 4); return v; }
 inline float __fdiv_rn(float a, float b) { return a / b; }
 inline float __fadd_rn(float a, float b) { return a + b; }
 inline float __fsub_rn(float a, float b) { return a - b; }

@@ -133,6 +133,13 @@ __device__ __forceinline__ void spin_pause() { __nanosleep(20); }
 __device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void grid_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// q = i / d, r = i % d for a work-item index: 32-bit arithmetic whenever the index fits (always, short of 2^31 items per launch) -
+// a 64-bit division costs ~4x the instructions of a 32-bit one, and the item loops do one or two per item
+__device__ __forceinline__ void item_divmod(long long i, int d, int& q, int& r) {
+  if (i < 0x7fffffffLL) { const unsigned u = (unsigned)i, qq = u / (unsigned)d; q = (int)qq; r = (int)(u - qq * (unsigned)d); }
+  else { const long long qq = i / d; q = (int)qq; r = (int)(i - qq * d); }
+}
+
 // Work item i of copy + fill_border_mirror in one pass (k_copy_mirror of pixelwise.cu, phase 0 of vppb_pyrlk_prepare): rows * nvec
 // 16-byte vectors, then rows * tail single bytes, then one item per border pixel of dst - read from the mirrored position in SRC (the
 // same value dst's domain receives), so nothing depends on the copy having landed.
@@ -145,9 +152,9 @@ __device__ __forceinline__ void copy_mirror_item(const Img& src, const Img& dst,
   const long long n_vec = (long long)nr * nvec, n_tail = (long long)nr * tail;
   const long long wfull = nc + 2LL * b, n_top = (long long)b * wfull, n_side = (long long)nr * b;
   if (i < n_vec) {
-    const long long r = i / nvec;
-    const int k = (int)(i - r * nvec);
-    st_stream(reinterpret_cast<int4*>(dst.base + r * dst.pitch + (long long)k * 16), ld_stream(reinterpret_cast<const int4*>(src.base + r * src.pitch + (long long)k * 16)));
+    int r, k;
+    item_divmod(i, nvec, r, k);
+    st_stream(reinterpret_cast<int4*>(dst.base + (long long)r * dst.pitch + k * 16), ld_stream(reinterpret_cast<const int4*>(src.base + (long long)r * src.pitch + k * 16)));
   } else if (i < n_vec + n_tail) {
     const long long j = i - n_vec, r = j / tail;
     const long long off = (long long)nvec * 16 + (j - r * tail);

@@ -48,6 +48,38 @@ __device__ __forceinline__ int interp_u8(const Img& im, float p0, float p1) {
   return ((int)res) & 255;
 }
 
+// The same sample for the inner loop of the v2 kernel: the image's fields live in registers for the whole level (the Img structs sit
+// in the parameter bank behind a run-time level index: three constant loads per sample otherwise), the clamp bounds are precomputed,
+// and the byte -> float conversions are the full-rate I2FP of the integer pipe rather than the quarter-rate I2F.U16 / I2F.U8.
+struct ImgU8 {
+  const unsigned char* base;
+  int pitch, lo, hi_r, hi_c, nrows, ncols;
+};
+__device__ __forceinline__ ImgU8 sampler_of(const Img& im) {
+  ImgU8 s;
+  s.base = im.base; s.pitch = im.pitch; s.lo = -im.border; s.hi_r = im.nrows + im.border - 2; s.hi_c = im.ncols + im.border - 2;
+  s.nrows = im.nrows; s.ncols = im.ncols;
+  return s;
+}
+// (float)v for v < 2^23 without the conversion unit: 2^23 + v is exactly representable, subtract 2^23 (LOP3 + FADD, both full rate;
+// the compiler turns a plain cast of a loaded byte into the quarter-rate I2F.U16)
+__device__ __forceinline__ float byte_to_float(unsigned v) { return __fsub_rn(__uint_as_float(0x4B000000u | v), 8388608.f); }
+__device__ __forceinline__ int interp_u8(const ImgU8& im, float p0, float p1) {
+  const int x0 = (int)p0, x1 = (int)p1;
+  const float a0 = __fsub_rn(p0, (float)x0), a1 = __fsub_rn(p1, (float)x1);
+  // 32-bit offset from pixel (0,0): the host only takes this kernel for images whose frame stays below 2 GB
+  const unsigned char* l1 = im.base + (min(max(x0, im.lo), im.hi_r) * im.pitch + min(max(x1, im.lo), im.hi_c));
+  const unsigned char* l2 = l1 + im.pitch;
+  const float b0 = __fsub_rn(1.f, a0), b1 = __fsub_rn(1.f, a1);
+  float res = __fmul_rn(__fmul_rn(b0, b1), byte_to_float(l1[0]));
+  res = __fadd_rn(res, __fmul_rn(__fmul_rn(a0, b1), byte_to_float(l2[0])));
+  res = __fadd_rn(res, __fmul_rn(__fmul_rn(b0, a1), byte_to_float(l1[1])));
+  res = __fadd_rn(res, __fmul_rn(__fmul_rn(a0, a1), byte_to_float(l2[1])));
+  return ((int)res) & 255;
+}
+// the sample as a float (the truncated uchar converted back, as `cast<float>(B.linear_interpolate(n))` does)
+__device__ __forceinline__ float interp_u8f(const ImgU8& im, float p0, float p1) { return byte_to_float((unsigned)interp_u8(im, p0, p1)); }
+
 // same on image2d<vint2> (result truncated per component) or image2d<vfloat2>
 template <bool GRAD_FLOAT>
 __device__ __forceinline__ float2 interp_grad(const Img& im, float p0, float p1) {
@@ -264,17 +296,18 @@ constexpr int LK2_LPK = 8;    // lanes per keypoint
 constexpr int LK2_KPW = 4;    // keypoints per warp
 constexpr int LK2_WARPS = 4;  // warps per CTA
 constexpr int LK2_MAXPIX = 121;
+constexpr int LK2_ROW = 124;
 
 template <int PPL, bool GRAD_FLOAT>
 __global__ void __launch_bounds__(LK2_WARPS * 32) k_lk_match_v2(LkLevels L, vppb_lk_params P, const vppb_float2* __restrict__ kps,
                                                              const vppb_float2* __restrict__ prediction, int n,
                                                              vppb_float2* __restrict__ flow_out, float* __restrict__ err_out) {
-  __shared__ float sbuf[LK2_WARPS][3][LK2_KPW][LK2_MAXPIX + 2];
+  __align__(16) __shared__ float sbuf[LK2_WARPS][3][LK2_KPW][LK2_ROW];  // rows of 124 floats: 16-byte aligned, 28 banks apart (no conflicts between the 8 summing lanes)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int k = lane >> 3, sl = lane & 7, lead = lane & ~7;
   const int kp_idx = (blockIdx.x * LK2_WARPS + warp) * LK2_KPW + k;
   const bool kp_ok = kp_idx < n;
-  float (*buf)[LK2_KPW][LK2_MAXPIX + 2] = sbuf[warp];
+  float (*buf)[LK2_KPW][LK2_ROW] = sbuf[warp];
   const int ws = P.winsize, hws = ws / 2, npix = ws * ws;
   const int kload = kp_ok ? kp_idx : 0;
   const float kp0 = kps[kload].r, kp1 = kps[kload].c;
@@ -294,8 +327,13 @@ __global__ void __launch_bounds__(LK2_WARPS * 32) k_lk_match_v2(LkLevels L, vppb
     float acc = 0.f;
     if (sl < ncomp) {
       const float* src = buf[sl][k];
-#pragma unroll 7
-      for (int i = 0; i < npix; i++) acc = __fadd_rn(acc, src[i]);
+      int i = 0;
+#pragma unroll 3
+      for (; i + 4 <= npix; i += 4) {  // four terms per shared-memory load, added in window order
+        const float4 q = *reinterpret_cast<const float4*>(src + i);
+        acc = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(acc, q.x), q.y), q.z), q.w);
+      }
+      for (; i < npix; i++) acc = __fadd_rn(acc, src[i]);
     }
     __syncwarp();
     return acc;
@@ -316,6 +354,7 @@ __global__ void __launch_bounds__(LK2_WARPS * 32) k_lk_match_v2(LkLevels L, vppb
     const float scale = (float)(1 << S);
     const float p0 = __fdiv_rn(kp0, scale), p1 = __fdiv_rn(kp1, scale);
 
+    const ImgU8 sA = sampler_of(A), sB = sampler_of(B);
     float gs0[PPL], gs1[PPL], asv[PPL];
     bool valid[PPL];
     int cpt_l = 0;
@@ -328,7 +367,7 @@ __global__ void __launch_bounds__(LK2_WARPS * 32) k_lk_match_v2(LkLevels L, vppb
       if (valid[j]) {
         const float2 g = interp_grad<GRAD_FLOAT>(Ag, n0, n1);
         gs0[j] = g.x; gs1[j] = g.y;
-        asv[j] = (float)interp_u8(A, n0, n1);
+        asv[j] = interp_u8f(sA, n0, n1);
         cpt_l++;
       }
       if (have[j]) {
@@ -375,7 +414,7 @@ __global__ void __launch_bounds__(LK2_WARPS * 32) k_lk_match_v2(LkLevels L, vppb
         if (have[j]) {
           float c0 = 0.f, c1 = 0.f;
           if (valid[j] && active) {
-            const float dt = __fsub_rn(asv[j], (float)interp_u8(B, __fadd_rn(v0, off_r[j]), __fadd_rn(v1, off_c[j])));
+            const float dt = __fsub_rn(asv[j], interp_u8f(sB, __fadd_rn(v0, off_r[j]), __fadd_rn(v1, off_c[j])));
             c0 = __fmul_rn(gs0[j], dt);
             c1 = __fmul_rn(gs1[j], dt);
           }
@@ -392,7 +431,7 @@ __global__ void __launch_bounds__(LK2_WARPS * 32) k_lk_match_v2(LkLevels L, vppb
         v0 = __fadd_rn(v0, nk0);
         v1 = __fadd_rn(v1, nk1);
         const int iv0 = (int)v0, iv1 = (int)v1;
-        if (!finite2(v0, v1) || iv0 < 0 || iv0 >= B.nrows || iv1 < 0 || iv1 >= B.ncols) { failed = true; active = false; }
+        if (!finite2(v0, v1) || iv0 < 0 || iv0 >= sB.nrows || iv1 < 0 || iv1 >= sB.ncols) { failed = true; active = false; }
       }
     }
     // ---- matching error for the keypoints that neither were rejected nor left the domain
@@ -402,7 +441,7 @@ __global__ void __launch_bounds__(LK2_WARPS * 32) k_lk_match_v2(LkLevels L, vppb
       if (have[j]) {
         float e = 0.f;
         if (want_err) {
-          const int bi = interp_u8(B, __fadd_rn(v0, off_r[j]), __fadd_rn(v1, off_c[j]));
+          const int bi = interp_u8(sB, __fadd_rn(v0, off_r[j]), __fadd_rn(v1, off_c[j]));
           e = fabsf((float)((int)asv[j] - bi));
         }
         const int i = sl + LK2_LPK * j;
@@ -655,7 +694,10 @@ int vppb_lk_match_u8(const vppb_img* prev, const vppb_img* next, const vppb_img*
   static int use_v1 = -1;  // VPPB_LK_V1=1 forces the one-keypoint-per-warp kernel (A/B comparisons)
   if (use_v1 < 0) { const char* e = getenv("VPPB_LK_V1"); use_v1 = (e && atoi(e)) ? 1 : 0; }
   bool done = false;
-  if (!use_v1)
+  bool small = true;  // the v2 kernel addresses samples with 32-bit offsets from pixel (0,0)
+  for (int s = 0; s < P.nlevels; s++)
+    small = small && ((long long)(prev[s].nrows + 2LL * prev[s].border) * prev[s].pitch < (1LL << 31)) && ((long long)(next[s].nrows + 2LL * next[s].border) * next[s].pitch < (1LL << 31));
+  if (!use_v1 && small)
     done = P.grad_is_float ? lk_launch_v2<true>(P.winsize, as_stream(stream), L, P, kps, prediction, n, flow_out, err_out)
                            : lk_launch_v2<false>(P.winsize, as_stream(stream), L, P, kps, prediction, n, flow_out, err_out);
   if (!done) {

@@ -30,7 +30,7 @@ __device__ __forceinline__ void scharr_px(const Img& in, const Img& out, int r, 
   const unsigned char* r3 = row_ptr<unsigned char>(in, r + 1) + c - 1;
   const int a = 3 * (int)r3[0] + 10 * (int)r3[1] + 3 * (int)r3[2] - 3 * (int)r1[0] - 10 * (int)r1[1] - 3 * (int)r1[2];
   const int b = 3 * (int)r1[2] + 10 * (int)r2[2] + 3 * (int)r3[2] - 3 * (int)r1[0] - 10 * (int)r2[0] - 3 * (int)r3[0];
-  const float fa = __fdiv_rn((float)a, 32.f), fb = __fdiv_rn((float)b, 32.f);
+  const float fa = __fmul_rn((float)a, 0.03125f), fb = __fmul_rn((float)b, 0.03125f);  // x / 32.f exactly
   if (AS_FLOAT) reinterpret_cast<float2*>(row_ptr<unsigned char>(out, orow))[ocol] = make_float2(fa, fb);
   else reinterpret_cast<int2*>(row_ptr<unsigned char>(out, orow))[ocol] = make_int2((int)fa, (int)fb);  // trunc toward 0
 }
@@ -60,8 +60,9 @@ __device__ __forceinline__ void scharr_v8_item(const Img& in, const Img& out, in
   const long long total = (long long)out.nrows * groups_per_row;
   {
     if (i >= total) { scharr_border_item<AS_FLOAT>(in, out, i - total, mb); return; }
-    const int r = (int)(i / groups_per_row);
-    const int c0 = (int)(i - (long long)r * groups_per_row) * 8;
+    int r, c0;
+    item_divmod(i, groups_per_row, r, c0);
+    c0 *= 8;
     int px[3][10];  // columns c0-1 .. c0+8
 #pragma unroll
     for (int k = 0; k < 3; k++) {
@@ -86,8 +87,8 @@ __device__ __forceinline__ void scharr_v8_item(const Img& in, const Img& out, in
         a[t] = 3 * r3[0] + 10 * r3[1] + 3 * r3[2] - 3 * r1[0] - 10 * r1[1] - 3 * r1[2];  // scharr.hh:64-83
         b[t] = 3 * r1[2] + 10 * r2[2] + 3 * r3[2] - 3 * r1[0] - 10 * r2[0] - 3 * r3[0];
       }
-      const float fa0 = __fdiv_rn((float)a[0], 32.f), fb0 = __fdiv_rn((float)b[0], 32.f);
-      const float fa1 = __fdiv_rn((float)a[1], 32.f), fb1 = __fdiv_rn((float)b[1], 32.f);
+      const float fa0 = __fmul_rn((float)a[0], 0.03125f), fb0 = __fmul_rn((float)b[0], 0.03125f);  // x / 32.f exactly
+      const float fa1 = __fmul_rn((float)a[1], 0.03125f), fb1 = __fmul_rn((float)b[1], 0.03125f);
       if (c0 + j + 1 < out.ncols) {
         if (AS_FLOAT) *reinterpret_cast<float4*>(orow + j * 8) = make_float4(fa0, fb0, fa1, fb1);
         else *reinterpret_cast<int4*>(orow + j * 8) = make_int4((int)fa0, (int)fb0, (int)fa1, (int)fb1);
@@ -110,7 +111,8 @@ template <bool AS_FLOAT>
 __device__ __forceinline__ void scharr_px_item(const Img& in, const Img& out, int mb, long long i) {
   const long long total = (long long)out.nrows * out.ncols;
   if (i >= total) { scharr_border_item<AS_FLOAT>(in, out, i - total, mb); return; }
-  const int r = (int)(i / out.ncols), c = (int)(i - (long long)r * out.ncols);
+  int r, c;
+  item_divmod(i, out.ncols, r, c);
   scharr_px<AS_FLOAT>(in, out, r, c, r, c);
 }
 template <bool AS_FLOAT>
@@ -128,11 +130,12 @@ template <> struct LpT<2> { typedef float elem; typedef float acc; static conste
 __device__ __forceinline__ int lp5(int a, int b, int c, int d, int e) { return (1 * a + 4 * b + 6 * c + 4 * d + 1 * e) / 16; }
 __device__ __forceinline__ float lp5(float a, float b, float c, float d, float e) {
   // ((((1*a + 4*b) + 6*c) + 4*d) + 1*e) / 16, no contraction (pyramid.hh:27-32)
-  float s = __fadd_rn(__fmul_rn(1.f, a), __fmul_rn(4.f, b));
+  // 1 * x is x and s / 16 is s * 0.0625 for every float (power-of-two scale: one rounding either way): no division routine
+  float s = __fadd_rn(a, __fmul_rn(4.f, b));
   s = __fadd_rn(s, __fmul_rn(6.f, c));
   s = __fadd_rn(s, __fmul_rn(4.f, d));
-  s = __fadd_rn(s, __fmul_rn(1.f, e));
-  return __fdiv_rn(s, 16.f);
+  s = __fadd_rn(s, e);
+  return __fmul_rn(s, 0.0625f);
 }
 
 
@@ -168,9 +171,8 @@ __device__ __forceinline__ void lowpass_sub2_item(const Img& in, const Img& out,
   constexpr int COMPS = LpT<KIND>::comps;
   {
     const int k = (int)(i % COMPS);
-    const long long pix = i / COMPS;
-    const int r = (int)(pix / out.ncols);
-    const int c = (int)(pix - (long long)r * out.ncols);
+    int r, c;
+    item_divmod(i / COMPS, out.ncols, r, c);
     const int y = mirror_idx(r * step, in.nrows);
     const int x = mirror_idx(c * step, in.ncols);
     A h[5];
@@ -239,7 +241,8 @@ __device__ __forceinline__ void lowpass_sub2_u8_fast_item(const Img& in, const I
       store_mirrored<unsigned char>(out, r, c, (unsigned char)lp5(h[0], h[1], h[2], h[3], h[4]), mb);
       return;
     }
-    const int rp = (int)(i / groups_per_row), g = (int)(i - (long long)rp * groups_per_row);
+    int rp, g;
+    item_divmod(i, groups_per_row, rp, g);
     const int r0 = 2 * rp, c0 = 8 * g;
     int H[7][8];
 #pragma unroll
@@ -294,7 +297,8 @@ __device__ __forceinline__ void lowpass_sub2_px8_item(const Img& in, const Img& 
   typedef typename vec2_of<A>::type V2;
   typedef typename vec2_of<A>::type4 V4;
   {
-    const int r = (int)(i / out.ncols), c = (int)(i - (long long)r * out.ncols);
+    int r, c;
+    item_divmod(i, out.ncols, r, c);
     const int y = mirror_idx(r * 2, in.nrows), x = mirror_idx(c * 2, in.ncols);
     A hx[5], hy[5];
 #pragma unroll
@@ -540,8 +544,12 @@ static int pyrlk_prepare_fused(const vppb_img* i1, const vppb_img* i2, const vpp
   if (!prep_copy_mirror(i1, &prev[0], P.op[n]) || !prep_copy_mirror(i2, &next[0], P.op[n + 1])) return VPPB_OK;
   n += 2; P.phase_end[ph++] = n;
   for (int l = 1; l <= nlevels; l++) {  // phase l
-    if (l == 1) { if (!prep_scharr(&prev[0], &grad[0], grad_is_float, P.op[n])) return VPPB_OK; n++; }
-    else { if (!prep_lowpass(&grad[l - 2], &grad[l - 1], gk, P.op[n])) return VPPB_OK; n++; }
+    if (grad) {
+      if (l == 1) { if (!prep_scharr(&prev[0], &grad[0], grad_is_float, P.op[n])) return VPPB_OK; n++; }
+      else { if (!prep_lowpass(&grad[l - 2], &grad[l - 1], gk, P.op[n])) return VPPB_OK; n++; }
+    } else if (l == nlevels) {
+      break;  // without a gradient pyramid the last phase is the one that writes level nlevels - 1 of the two u8 pyramids
+    }
     if (l < nlevels) {
       if (!prep_lowpass(&prev[l - 1], &prev[l], 0, P.op[n]) || !prep_lowpass(&next[l - 1], &next[l], 0, P.op[n + 1])) return VPPB_OK;
       n += 2;
@@ -576,7 +584,7 @@ static int pyrlk_prepare_fused(const vppb_img* i1, const vppb_img* i2, const vpp
 // valid inside a stream capture): the critical path is 4 launches instead of 9.
 int vppb_pyrlk_prepare(const vppb_img* i1, const vppb_img* i2, const vppb_img* prev, const vppb_img* next, const vppb_img* grad, int32_t nlevels,
                        int32_t grad_is_float, void* stream) {
-  VPPB_REQUIRE(i1 && i2 && prev && next && grad && nlevels >= 1 && nlevels <= 16, VPPB_E_ARG, "vppb_pyrlk_prepare: bad argument");
+  VPPB_REQUIRE(i1 && i2 && prev && next && nlevels >= 1 && nlevels <= 16, VPPB_E_ARG, "vppb_pyrlk_prepare: bad argument");
   {  // one cooperative launch when every step has a work-item form (library layout); VPPB_PREPARE=streams forces the multi-stream form
     const char* e = getenv("VPPB_PREPARE");  // "streams": the multi-stream form; "fused": fail instead of falling back to it (tests)
     bool done = false;
@@ -610,9 +618,11 @@ int vppb_pyrlk_prepare(const vppb_img* i1, const vppb_img* i2, const vppb_img* p
   if ((rc = vppb_copy2d_mirror(i1, &prev[0], st))) return rc;
   VPPB_CUDA(cudaEventRecord(ev[2], st));
   VPPB_CUDA(cudaStreamWaitEvent(side[0], ev[2], 0));
-  if ((rc = vppb_scharr_u8_mirror(&prev[0], &grad[0], grad_is_float, side[0]))) return rc;
-  for (int l = 1; l < nlevels; l++)
-    if ((rc = vppb_lowpass_sub2_mirror(&grad[l - 1], &grad[l], gk, side[0]))) return rc;
+  if (grad) {
+    if ((rc = vppb_scharr_u8_mirror(&prev[0], &grad[0], grad_is_float, side[0]))) return rc;
+    for (int l = 1; l < nlevels; l++)
+      if ((rc = vppb_lowpass_sub2_mirror(&grad[l - 1], &grad[l], gk, side[0]))) return rc;
+  }
   VPPB_CUDA(cudaEventRecord(ev[3], side[0]));
   for (int l = 1; l < nlevels; l++)
     if ((rc = vppb_lowpass_sub2_mirror(&prev[l - 1], &prev[l], 0, st))) return rc;

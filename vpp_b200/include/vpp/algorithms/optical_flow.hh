@@ -28,9 +28,11 @@ void semi_dense_optical_flow(const K& keypoints, MC match_callback, const image2
   const int n = (int)keypoints.size();
   std::vector<vint2> kps(n);
   for (int i = 0; i < n; i++) kps[i] = keypoints[i];
-  pyramid2d<unsigned char> p1(i1, P.nscales, 2, s::_border = 2 * P.winsize), p2(i2, P.nscales, 2, s::_border = 2 * P.winsize);
+  // both pyramids (semi_dense_optical_flow.hpp:70-100) in one launch
+  pyramid2d<unsigned char> p1(i1.domain(), P.nscales, 2, s::_border = 2 * P.winsize), p2(i2.domain(), P.nscales, 2, s::_border = 2 * P.winsize);
   std::vector<vppb_img> a(P.nscales), b(P.nscales);
-  for (int l = 0; l < P.nscales; l++) { a[l] = *p1[l].device_read(); b[l] = *p2[l].device_read(); }
+  for (int l = 0; l < P.nscales; l++) { a[l] = *p1[l].device_write(); b[l] = *p2[l].device_write(); }
+  vppb_check(vppb_pyrlk_prepare(i1.device_read(), i2.device_read(), a.data(), b.data(), nullptr, P.nscales, 0, nullptr));
   const int64_t wsb = vppb_sdof_workspace_bytes(i1.nrows(), i1.ncols(), &P);
   internals::device_array ws((size_t)wsb), dk((size_t)n * 8), dpos((size_t)n * 8), ddist((size_t)n * 4), dvalid((size_t)n);
   dk.from_host(kps.data(), (size_t)n * 8);

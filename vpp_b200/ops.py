@@ -366,8 +366,9 @@ def semi_dense_optical_flow(keypoints, i1, i2, winsize=7, nscales=4, min_scale=0
     Returns (pos[n,2], dist[n], valid[n]): for every i with valid[i] the reference calls match_callback(i, pos[i], dist[i])."""
     kp = np.ascontiguousarray(keypoints, dtype=np.int32).reshape(-1, 2)
     n = len(kp)
-    p1 = Pyramid2d(i1, nscales, 2, border=2 * winsize)  # :72-73
-    p2 = Pyramid2d(i2, nscales, 2, border=2 * winsize)
+    p1 = Pyramid2d((i1.nrows, i1.ncols), nscales, 2, pixel="u8", border=2 * winsize)  # :72-73
+    p2 = Pyramid2d((i2.nrows, i2.ncols), nscales, 2, pixel="u8", border=2 * winsize)
+    check(lib.vppb_pyrlk_prepare(i1.ptr(), i2.ptr(), p1.desc_array(), p2.desc_array(), None, nscales, 0, stream))  # both pyramids in one launch
     P = capi.VppbSdofParams(winsize, nscales, min_scale, propagation, patchsize)
     ws = _DeviceBuffer(lib.vppb_sdof_workspace_bytes(i1.nrows, i1.ncols, C.byref(P)))
     d_kp = _DeviceBuffer(kp.nbytes).from_host(kp, stream)
