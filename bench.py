@@ -291,6 +291,26 @@ def graph_of(torch, fn):
         return fn, False
 
 
+def bind_to_gpu_numa_node(dev_index):
+    """One process per GPU: run (and therefore first-touch / pin the host frames of the e2e leg) on the CPUs NVML lists as local to the GPU.
+    Returns the number of CPUs bound to, or None when NVML / the affinity call is not available (nothing changes then)."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(dev_index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, m in enumerate(words) for b in range(64) if (m >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def box_traffic(key):
     """DRAM bytes per launch of the streaming kernel from the committed ncu capture of this bench regime (profiles/box_traffic.json)"""
     tp = os.path.join(ROOT, "profiles", "box_traffic.json")
@@ -365,6 +385,7 @@ def main():
     else:
         torch.cuda.set_device(0)
     dev_index = local_rank if world > 1 else 0
+    numa = bind_to_gpu_numa_node(dev_index) if world > 1 else None  # pinned host frames then live on the socket the GPU hangs off
     capi.check(capi.lib.vppb_init(dev_index))
     dev = torch.device("cuda", dev_index)
     stream = torch.cuda.current_stream()
@@ -536,7 +557,7 @@ def main():
     dt = float(te.item())
     e2e = {"value": esteps * e_frames * H * W / 1e6 / dt, "unit": "Mpix/s", "h2d_bytes_per_step": e_frames * h2d * world,
            "d2h_bytes_per_step": e_frames * th * rowb * world, "ms_per_step": dt / esteps * 1e3, "frames_per_e2e_step": e_frames,
-           "upload": {"used": e2e_mode[0], "ms_per_step_by_form": e2e_ms},
+           "upload": {"used": e2e_mode[0], "ms_per_step_by_form": e2e_ms}, "cpus_bound_to_gpu_numa_node": numa,
            "note": "pinned host frames -> vppb_upload (+ mirror border: direct 2-D copy + vppb_fill_border_mirror, or linear copy + vppb_copy2d_mirror, the faster of the two) -> vppb_box5x5_u8c3 -> vppb_download, %d frames in flight per rank, max over ranks" % NE2E}
     parity_ok = parity_ok and bool(np.array_equal(host_out[0].numpy(), hd[0]))
     if dist is not None:  # every rank checked its own tile
@@ -769,7 +790,7 @@ def gpu_extras(vpp, capi, torch, stream, sp, dev):
                 "ms_python_call": ms_py, "keypoints": nk, "parity": ok,
                 "note": "us_device: detect + raster emit queued by vppb_fast9_u8_async (2 launches, no host sync); ms_python_call adds the count read-back and the keypoint download"}
 
-    def pyrlk_1080p_10k():  # pyramids + Scharr gradient pyramid (one cooperative launch) + pyrlk_match of 10k keypoints, vfloat2 gradient
+    def pyrlk_1080p_10k():  # pyramids + Scharr gradient pyramid (vppb_pyrlk_prepare) + pyrlk_match of 10k keypoints, vfloat2 gradient
         f1, f2, pts = scenes.lk_pair(1080, 1920, 10000, seed=5)
         I1, I2 = vpp.Image2d.from_host(f1, "u8"), vpp.Image2d.from_host(f2, "u8")
         prev, nxt = vpp.Pyramid2d((1080, 1920), 3, 2, pixel="u8", border=4), vpp.Pyramid2d((1080, 1920), 3, 2, pixel="u8", border=4)
@@ -799,7 +820,7 @@ def gpu_extras(vpp, capi, torch, stream, sp, dev):
         ms_lk = timed(lk, 10)
         return {"kpts_per_s": len(pts) / ((ms_lk + ms_build) / 1e3), "kpts_per_s_match_only": len(pts) / (ms_lk / 1e3),
                 "ms_match": ms_lk, "ms_pyramids_scharr": ms_build, "parity": ok, "max_rel_err": float(rel.max()),
-                "note": "kpts_per_s includes both u8 pyramids and the Scharr gradient pyramid (vppb_pyrlk_prepare: ONE cooperative launch - 4 phases of concatenated work items, 3 grid barriers); parity = failure flags identical and displacement rel. err <= 1e-4 against the oracle "
+                "note": "kpts_per_s includes both u8 pyramids and the Scharr gradient pyramid (vppb_pyrlk_prepare: 9 launches, the three independent chains on three streams); parity = failure flags identical and displacement rel. err <= 1e-4 against the oracle "
                         "(whose 3-level definition clamps the reads the reference makes outside its border, tests/test_oracle_vs_ref.py)"}
 
     def sdof(H_, W_):

@@ -140,10 +140,10 @@ int vppb_lowpass_sub2_mirror(const vppb_img* in, const vppb_img* out, int kind, 
 /* Everything lucas_kanade() / a pyrlk_match caller builds before matching, in one call: pyramid2d<uchar>::update(i1) -> prev[],
  * ::update(i2) -> next[], scharr(prev[0], grad[0]) + propagate_level0 -> grad[] (lucas_kanade.hpp:150-157).  prev / next /
  * grad: nlevels descriptors each (allocated by the caller, borders >= 2 / >= 1; all distinct buffers); grad may be NULL: only the two
- * u8 pyramids are built (what semi_dense_optical_flow.hpp:70-100 needs).  With the library layout
- * (16-byte aligned rows, <= 8 levels) the whole preparation is ONE cooperative launch: the steps of a level are independent, their work
- * items are concatenated and shared out over the resident grid, a grid-wide barrier separates the levels.  Otherwise (views, odd
- * alignments, VPPB_PREPARE=streams) the three chains run as one launch per step on three streams forked from / joined into `stream`. */
+ * u8 pyramids are built (what semi_dense_optical_flow.hpp:70-100 needs).  Two forms: one launch per step with the three independent
+ * chains on three streams forked from / joined into `stream` (default with a gradient pyramid), or ONE cooperative launch - the steps of
+ * a level concatenated into a phase of work items, grid-wide barriers between the levels - for images in the library layout (16-byte
+ * aligned rows, <= 8 levels; default without a gradient pyramid).  VPPB_PREPARE=fused|streams overrides the choice. */
 int vppb_pyrlk_prepare(const vppb_img* i1, const vppb_img* i2, const vppb_img* prev, const vppb_img* next, const vppb_img* grad,
                        int32_t nlevels, int32_t grad_is_float, void* stream);
 

@@ -585,13 +585,19 @@ static int pyrlk_prepare_fused(const vppb_img* i1, const vppb_img* i2, const vpp
 int vppb_pyrlk_prepare(const vppb_img* i1, const vppb_img* i2, const vppb_img* prev, const vppb_img* next, const vppb_img* grad, int32_t nlevels,
                        int32_t grad_is_float, void* stream) {
   VPPB_REQUIRE(i1 && i2 && prev && next && nlevels >= 1 && nlevels <= 16, VPPB_E_ARG, "vppb_pyrlk_prepare: bad argument");
-  {  // one cooperative launch when every step has a work-item form (library layout); VPPB_PREPARE=streams forces the multi-stream form
-    const char* e = getenv("VPPB_PREPARE");  // "streams": the multi-stream form; "fused": fail instead of falling back to it (tests)
-    bool done = false;
-    if (!(e && !strcmp(e, "streams"))) {
+  {  // Two forms.  "streams": one launch per step, the three independent chains on three streams (forked from / joined into `stream`);
+     // "fused": ONE cooperative launch, the steps of a level concatenated into a phase, grid barriers between phases (needs the library
+     // layout).  Measured on a B200 at 1080p, 3 levels: with the gradient pyramid the three concurrent chains win (0.036 ms against 0.040 ms:
+     // a phase lasts as long as its slowest step, and the chains overlap steps of different levels), without it (the two u8 pyramids
+     // of the semi-dense flow) the single launch does (0.028 ms against 0.042 ms for the per-level launches).  VPPB_PREPARE=fused|streams
+     // overrides the choice ("fused" fails instead of falling back: tests).
+    const char* e = getenv("VPPB_PREPARE");
+    const bool want_fused = e ? !strcmp(e, "fused") : (grad == nullptr);
+    if (want_fused) {
+      bool done = false;
       const int rc_ = pyrlk_prepare_fused(i1, i2, prev, next, grad, nlevels, grad_is_float, as_stream(stream), &done);
       if (rc_ != VPPB_OK || done) return rc_;
-      VPPB_REQUIRE(!(e && !strcmp(e, "fused")), VPPB_E_ARG, "vppb_pyrlk_prepare: VPPB_PREPARE=fused but the images do not have the library layout");
+      VPPB_REQUIRE(!e, VPPB_E_ARG, "vppb_pyrlk_prepare: VPPB_PREPARE=fused but the images do not have the library layout");
     }
   }
   static thread_local cudaStream_t side[2] = {nullptr, nullptr};

@@ -73,7 +73,7 @@ __device__ __forceinline__ unsigned sad_rows(const unsigned char* pa, long long 
     return s;
   }
 #pragma unroll
-  for (int j = 0; j < 4; j++) {
+  for (int j = 0; j < 5; j++) {  // nl = 4: rows sub, sub + 4, ... (j = 4 never below ws <= 15 ... 16); nl = 3: up to 5 rows per lane
     const int row = sub + j * nl;
     if (row < ws) {
       const unsigned char* ra = pa + row * apitch;
@@ -125,6 +125,48 @@ __device__ __forceinline__ int sad_group4(const Img& a, const Img& b, int ar, in
   s += __shfl_xor_sync(FULLM, s, 1);
   s += __shfl_xor_sync(FULLM, s, 2);
   return inside ? (int)s : INT_MAX;
+}
+
+// the same with groups of 3 lanes: ten candidates per warp (lanes 30, 31 idle) - the eight neighbours of a position AND the position
+// itself in one batch; for winsize 9 a lane sums exactly 3 rows, as the busiest lane of a group of 4 does
+__device__ __forceinline__ int sad_group3(const Img& a, const Img& b, int ar, int ac, int br, int bc, int ws, bool active) {
+  const int lane = threadIdx.x & 31;
+  const bool inside = sad_inside(a, b, ar, ac, br, bc);
+  const int h = ws / 2, g3 = lane / 3;
+  unsigned s = 0;
+  if (active && inside && lane < 30)
+    s = sad_rows(a.base + (long long)(ar - h) * a.pitch + (ac - h), a.pitch, b.base + (long long)(br - h) * b.pitch + (bc - h), b.pitch, ws, lane - 3 * g3, 3);
+  const int base = min(3 * g3, 29);
+  const unsigned t = __shfl_sync(FULLM, s, base) + __shfl_sync(FULLM, s, base + 1) + __shfl_sync(FULLM, s, base + 2);
+  return inside ? (int)t : INT_MAX;
+}
+
+// gradient_descent.hh:10-89 for a match that starts at its prediction: the SAD at the prediction (the reference evaluates it first,
+// :52) rides in the batch of the first step's eight neighbours (group 8), so a match that stays where it was predicted - the usual
+// case below the coarsest scale - costs ONE memory round trip.  Later steps as descent_warp.
+__device__ __forceinline__ void descent_from_prediction(const Img& a, const Img& b, int pr, int pc, int predr, int predc, int ws, int max_it, int& flr,
+                                                        int& flc, int& dist) {
+  const int lane = threadIdx.x & 31;
+  const int g3 = min(lane / 3, 8);  // groups 0..7: the neighbours c_c8[g], group 8 (lanes 24..26): the position itself; lanes 27..31 idle
+  const int gdr = g3 < 8 ? c8_dr(g3) : 0, gdc = g3 < 8 ? c8_dc(g3) : 0;
+  int mr = predr, mc = predc, md = INT_MAX;
+  int mi = 8;
+  for (int search = 0; search < max_it; search++) {
+    const int dg = sad_group3(a, b, pr, pc, predr + gdr, predc + gdc, ws, lane < (search == 0 ? 27 : 24));
+    if (search == 0) md = __shfl_sync(FULLM, dg, 24);
+    int i = c_c8_it[mi][0];
+    const int end = c_c8_it[mi][1];
+    bool first = true;
+    while (first || i != end) {
+      first = false;
+      const int d = __shfl_sync(FULLM, dg, i * 3);
+      if (d < md) { mr = predr + c_c8[i][0]; mc = predc + c_c8[i][1]; mi = i; md = d; }
+      i = (i + 1) & 7;
+    }
+    if (predr == mr && predc == mc) break;
+    predr = mr; predc = mc;
+  }
+  flr = mr - pr; flc = mc - pc; dist = md;
 }
 
 // gradient_descent.hh:10-89 (whole warp, uniform control flow).  `md` = the SAD at the prediction (the caller has it).  A step
@@ -184,7 +226,7 @@ __global__ void __launch_bounds__(128) k_sdof_match(SdofLevel L, SdofLevel coars
       if (coarser.mark[m]) { const unsigned long long cr_ = coarser.rec[m]; predr = pr + rec_fx(cr_) * 2; predc = pc + rec_fy(cr_) * 2; }
     }
     int flr, flc, d;
-    descent_warp(L.i1, L.i2, pr, pc, predr, predc, ws, 5, sad_warp(L.i1, L.i2, pr, pc, predr, predc, ws), flr, flc, d);
+    descent_from_prediction(L.i1, L.i2, pr, pc, predr, predc, ws, 5, flr, flc, d);
     if (lane == 0) { L.rec[cell] = rec_pack(flr, flc, d, 0); L.mark[cell] = 2; }
   }
 }
@@ -205,7 +247,12 @@ __device__ __forceinline__ void sdof_prop_eval(const SdofLevel& L, int r, int c,
   const int g = lane >> 2, kg = g + (g >= 4);
   const int mg = __shfl_sync(FULLM, nmark, kg);
   const unsigned long long rg = __shfl_sync(FULLM, nrec, kg);
-  const int dg = sad_group4(L.i1, L.i2, r, c, r + rec_fx(rg), c + rec_fy(rg), ws, mg != 0);
+  // a neighbour whose flow is within 2 pixels of the cell's pre-sweep flow is skipped whatever happens (the `prev` half of the test
+  // below): its SAD is never looked at.  In a smooth flow field that is every neighbour - no window is read at all.
+  const int q0 = prev.x - rec_fx(rg), q1 = prev.y - rec_fy(rg);
+  const bool need = mg != 0 && q0 * q0 + q1 * q1 >= 9;
+  if (!__any_sync(FULLM, need)) return;
+  const int dg = sad_group4(L.i1, L.i2, r, c, r + rec_fx(rg), c + rec_fy(rg), ws, need);
 #pragma unroll 1
   for (int k = 0; k < 9; k++) {
     if (k == 4) continue;
@@ -521,7 +568,7 @@ __global__ void __launch_bounds__(256, MINB) k_sdof_fused(const SdofFused P) {
         if (__ldcg(C.mark + m)) { const unsigned long long cr_ = __ldcg(coarser_rec + m); predr = pr + rec_fx(cr_) * 2; predc = pc + rec_fy(cr_) * 2; }
       }
       int flr, flc, d;
-      descent_warp(L.i1, L.i2, pr, pc, predr, predc, P.ws, 5, sad_warp(L.i1, L.i2, pr, pc, predr, predc, P.ws), flr, flc, d);
+      descent_from_prediction(L.i1, L.i2, pr, pc, predr, predc, P.ws, 5, flr, flc, d);
       if (lane == 0) { __stcg(L.rec + cell, rec_pack(flr, flc, d, 0)); L.mark[cell] = 2; L.mlist[atomicAdd(sctr, 1)] = cell; }
     }
     grid_barrier(bar, gen);
