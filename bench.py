@@ -665,7 +665,7 @@ def sdof_tiled(vpp, capi, torch, dist, tiles, orc, rank, world, dev, sp, H=4320,
 
     def frame_pair():
         capi.check(capi.lib.vppb_halo_exchange(comm, rank, world, descs, 2, halo, sp))
-        p1.update(E[0], sp); p2.update(E[1], sp)
+        capi.check(capi.lib.vppb_pyrlk_prepare(E[0].ptr(), E[1].ptr(), a1, a2, None, 3, 0, sp))  # both pyramids of the extended tile in one launch
         capi.check(capi.lib.vppb_sdof_u8(a1, a2, C.byref(P), d_kp.ptr, n, wsb.ptr, wsb.nbytes, d_pos.ptr, d_dist.ptr, d_valid.ptr, sp))
 
     frame_pair()
@@ -676,13 +676,33 @@ def sdof_tiled(vpp, capi, torch, dist, tiles, orc, rank, world, dev, sp, H=4320,
     orc.load().vo_semi_dense_flow(h1.ptr(), h2.ptr(), kps.ctypes.data, n, 9, 3, 0, 2, 5, rp.ctypes.data, rd.ctypes.data, rv.ctypes.data)
     ok = bool(np.array_equal(got[0], rp) and np.array_equal(got[1], rd) and np.array_equal(got[2], rv))
     ms = device_ms(torch, dist, dev, frame_pair, 5)
-    tot = torch.tensor([float(n), 1.0 if ok else 0.0], dtype=torch.float64, device=dev)
+    # how far tile-local semantics are from the full-frame flow: every rank runs the oracle on the WHOLE frame pair with the keypoints of all
+    # ranks (tiles are bands of whole cells, so their keypoint lists concatenate to the full frame's list) and compares its own rows
+    agree = None
+    try:
+        lists = [None] * world
+        dist.all_gather_object(lists, (r0 - top, kps))
+        allk = np.ascontiguousarray(np.concatenate([k_ + np.array([off, 0], np.int32) for off, k_ in lists]).astype(np.int32))
+        first = int(np.sum([len(k_) for _, k_ in lists[:rank]]))
+        m = len(allk)
+        fp, fd, fv = np.zeros((m, 2), np.int32), np.zeros(m, np.int32), np.zeros(m, np.uint8)
+        F1, F2 = orc.HostImage(H, W, "u8", data=g1), orc.HostImage(H, W, "u8", data=g2)
+        orc.load().vo_semi_dense_flow(F1.ptr(), F2.ptr(), allk.ctypes.data, m, 9, 3, 0, 2, 5, fp.ctypes.data, fd.ctypes.data, fv.ctypes.data)
+        mine = slice(first, first + n)
+        same = (fv[mine] == got[2]) & ((fp[mine] - np.array([r0 - top, 0], np.int32)) == got[0]).all(axis=1) & (fd[mine] == got[1])
+        agree = float(same.sum())
+    except Exception as ex_:  # pragma: no cover
+        agree = None
+    tot = torch.tensor([float(n), 1.0 if ok else 0.0, agree if agree is not None else -1e18], dtype=torch.float64, device=dev)
     dist.all_reduce(tot[:1], op=dist.ReduceOp.SUM)
-    dist.all_reduce(tot[1:], op=dist.ReduceOp.MIN)
+    dist.all_reduce(tot[1:2], op=dist.ReduceOp.MIN)
+    dist.all_reduce(tot[2:], op=dist.ReduceOp.SUM)
     capi.lib.vppb_comm_destroy(comm)
     return {"ms_per_frame_pair": ms, "keypoints": int(tot[0].item()), "parity": bool(tot[1].item() > 0.5), "halo_rows": halo,
+            "full_frame_agreement": (float(tot[2].item()) / float(tot[0].item())) if tot[2].item() >= 0 and tot[0].item() > 0 else None,
             "note": "NCCL halo exchange (80 rows each way, both frames) + pyramids + matching + sweeps per tile, max over ranks; tile-local semantics, each tile bit-exact "
-                    "against the oracle on the same extended tile; single-GPU anchor: extras.sdof_8k of the N = 1 run"}
+                    "against the oracle on the same extended tile; full_frame_agreement = fraction of all keypoints whose reported position and distance equal the "
+                    "oracle's on the whole frame pair (sweeps do not cross the tile seams); single-GPU anchor: extras.sdof_8k of the N = 1 run"}
 
 
 def gpu_extras(vpp, capi, torch, stream, sp, dev):
