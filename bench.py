@@ -385,7 +385,7 @@ def main():
     else:
         torch.cuda.set_device(0)
     dev_index = local_rank if world > 1 else 0
-    numa = bind_to_gpu_numa_node(dev_index) if world > 1 else None  # pinned host frames then live on the socket the GPU hangs off
+    numa = bind_to_gpu_numa_node(dev_index) if world > 1 and os.environ.get("VPPB_BENCH_BIND", "0") == "1" else None  # opt-in: no effect measured at N = 2  # pinned host frames then live on the socket the GPU hangs off
     capi.check(capi.lib.vppb_init(dev_index))
     dev = torch.device("cuda", dev_index)
     stream = torch.cuda.current_stream()
