@@ -110,7 +110,7 @@ def main():
                 o.write("`tools/sdof_bench.py` (rectangles scene, blockwise FAST keypoints, wall clock around call + sync; schedules: levels / dataflow are the opt-in round-1 / early round-2 forms, "
                         "the last line of a size is the default):\n\n```\n%s```\n\n" % open(sb).read())
             o.write("History of the dense 1080p case (bench.py extras.sdof_1080p, flow only): round 1 one launch per anti-diagonal 14 ms; dataflow sweeps (one persistent launch per sweep, flags between "
-                    "cells) 7.7 ms; + batched SADs and speculation 1.68 ms; relaxation schedule in one cooperative launch 0.29 ms.  The reference's own OpenMP path on the box's 16 threads: 3.8 ms.\n")
+                    "cells) 7.7 ms; + batched SADs and speculation 1.68 ms; relaxation schedule in one cooperative launch 0.29 ms; sweeps that skip the SAD batch when no neighbour can become a candidate 0.22 ms; the prediction's SAD in the first descent batch 0.21 ms (8K, 331 776 keypoints: 9.4 -> 3.7 -> 2.4 -> 2.3 ms).  The reference's own OpenMP path on the box's 16 threads: 3.8 ms at 1080p.\n")
     pc = os.path.join(G, "z_pcie.json")
     if os.path.exists(pc):
         try:
@@ -151,6 +151,8 @@ def main():
                 l = last_json(fp)
                 o.write("| %d | %.0f | %.3f | %.3f | %s | %.0f |\n" % (n, l["value"], l["roofline"]["us_per_launch"] / 1e3, l["roofline"]["frac"],
                                                                  ("%.2fx" % (l["value"] / anchor)) if anchor else "-", l["e2e"]["value"]))
+        o.write("\nThe rows come from different `gpurun` boxes: N = 1 and N = 2 are this round's last calls (clocks under the power cap differ from box to box: the same N = 1 extra "
+                "read 852 535 Mpix/s on the box of the N = 4 / 8 calls, which puts those at 3.43x / 6.64x of their own run's anchor); the driver's SCALE run measures all N on one box.\n")
         o.write("\n`tools/tiles_check.py` (same kernels, 20 launches, CUDA events, max over ranks):\n\n| N | fused ms / 32 frames | same kernel without any halo | grouped NCCL exchange alone | NCCL exchange + batch kernel |\n|---|---|---|---|---|\n")
         for n in (2, 8):
             fp = os.path.join(P, "r2_tiles_check_n%d.json" % n)

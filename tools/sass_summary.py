@@ -38,7 +38,8 @@ for kname, c in counts.items():
     d = demangle(kname)
     d = re.sub(r"\(.*", "", d).replace("void vppb::", "").replace("vppb::", "")
     if not any(x in d for x in ("k_box5_stream", "k_box5_bytes_tma<", "k_fast9_band", "k_fast9_emit_bands", "k_sdof_sweep", "k_sdof_match", "k_lk_match_v2<7", "k_add_i32_vec",
-                                "k_kpc_merge", "k_rgb_to_gray<3", "k_lowpass_sub2_u8_fast", "k_scharr_u8_v8<")):
+                                "k_kpc_merge", "k_rgb_to_gray<3", "k_lowpass_sub2_u8_fast", "k_scharr_u8_v8<", "k_sdof_fused<2", "k_pyrlk_prepare", "k_lbp_u8<true", "k_local_maxima_filter<unsigned char",
+                                "k_lk_match_oriented<2, true", "k_fast9_block_rank")):
         continue
     if "k_box5_stream" in d and not re.search(r"<3, 4, 0, (1|128), 0>", d):
         continue
