@@ -496,7 +496,9 @@ def main():
     else:
         host_in = [torch.from_numpy(np.ascontiguousarray(upad[i % 4][r0:r1 + 4])).pin_memory() for i in range(4)]
     host_out = [torch.empty((th, W, 3), dtype=torch.uint8).pin_memory() for _ in range(esets)]
-    NE2E = int(os.environ.get("VPPB_BENCH_INFLIGHT", "12"))  # frames in flight per rank (one stream each)
+    # frames in flight per rank (one stream each): 12 on one GPU (13.5 k Mpix/s against 12.8 k with 4); with several ranks on one host deeper queues
+    # hurt (N = 8: 35.8 k Mpix/s with 12 in flight against 64.2 k with 4; N = 2: 25.5 k against 28.0 k), so 4 there
+    NE2E = int(os.environ.get("VPPB_BENCH_INFLIGHT", "12" if world == 1 else "4"))
     e_src = [vpp.Image2d(th, W, "vuchar3", border=2) for _ in range(NE2E)]
     e_dst = [vpp.Image2d(th, W, "vuchar3") for _ in range(NE2E)]
     streams = [torch.cuda.Stream(device=dev) for _ in range(NE2E)]
