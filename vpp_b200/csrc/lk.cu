@@ -294,18 +294,18 @@ __global__ void __launch_bounds__(128) k_lk_match(LkLevels L, vppb_lk_params P, 
 // the warp-instruction count per keypoint ~3.5x.  Used for WS <= 11.
 constexpr int LK2_LPK = 8;    // lanes per keypoint
 constexpr int LK2_KPW = 4;    // keypoints per warp
-constexpr int LK2_WARPS = 4;  // warps per CTA
+constexpr int LK2_WARPS = 4;  // warps per CTA (default; the kernel is also instantiated for 1 and 2: see lk_launch_v2)
 constexpr int LK2_MAXPIX = 121;
 constexpr int LK2_ROW = 124;
 
-template <int PPL, bool GRAD_FLOAT>
-__global__ void __launch_bounds__(LK2_WARPS * 32) k_lk_match_v2(LkLevels L, vppb_lk_params P, const vppb_float2* __restrict__ kps,
+template <int PPL, bool GRAD_FLOAT, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) k_lk_match_v2(LkLevels L, vppb_lk_params P, const vppb_float2* __restrict__ kps,
                                                              const vppb_float2* __restrict__ prediction, int n,
                                                              vppb_float2* __restrict__ flow_out, float* __restrict__ err_out) {
-  __align__(16) __shared__ float sbuf[LK2_WARPS][3][LK2_KPW][LK2_ROW];  // rows of 124 floats: 16-byte aligned, 28 banks apart (no conflicts between the 8 summing lanes)
+  __align__(16) __shared__ float sbuf[WARPS][3][LK2_KPW][LK2_ROW];  // rows of 124 floats: 16-byte aligned, 28 banks apart (no conflicts between the 8 summing lanes)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int k = lane >> 3, sl = lane & 7, lead = lane & ~7;
-  const int kp_idx = (blockIdx.x * LK2_WARPS + warp) * LK2_KPW + k;
+  const int kp_idx = (blockIdx.x * WARPS + warp) * LK2_KPW + k;
   const bool kp_ok = kp_idx < n;
   float (*buf)[LK2_KPW][LK2_ROW] = sbuf[warp];
   const int ws = P.winsize, hws = ws / 2, npix = ws * ws;
@@ -478,18 +478,30 @@ __global__ void __launch_bounds__(LK2_WARPS * 32) k_lk_match_v2(LkLevels L, vppb
   }
 }
 
+// Warps per CTA: the whole problem is one wave of resident CTAs and the kernel is issue-bound, so the launch lasts as long as the SM that
+// holds the most warps.  10 000 keypoints are 2 500 warps: in CTAs of 4 warps (625 CTAs over 148 SMs) the fullest SM holds 5 x 4 = 20 warps
+// against an average of 16.9; single-warp CTAs level that out.  VPPB_LK_WARPS=1|2|4 selects the instantiation (A/B timing).
+template <bool GF, int WARPS>
+static bool lk_launch_v2w(int winsize, cudaStream_t st, const LkLevels& L, const vppb_lk_params& P, const vppb_float2* kps, const vppb_float2* pred, int n,
+                          vppb_float2* flow, float* err) {
+  const int per_cta = WARPS * LK2_KPW;
+  const int grid = (n + per_cta - 1) / per_cta;
+  switch (winsize) {
+    case 1: case 3: case 5: k_lk_match_v2<4, GF, WARPS><<<grid, WARPS * 32, 0, st>>>(L, P, kps, pred, n, flow, err); return true;
+    case 7: k_lk_match_v2<7, GF, WARPS><<<grid, WARPS * 32, 0, st>>>(L, P, kps, pred, n, flow, err); return true;
+    case 9: k_lk_match_v2<11, GF, WARPS><<<grid, WARPS * 32, 0, st>>>(L, P, kps, pred, n, flow, err); return true;
+    case 11: k_lk_match_v2<16, GF, WARPS><<<grid, WARPS * 32, 0, st>>>(L, P, kps, pred, n, flow, err); return true;
+    default: return false;
+  }
+}
 template <bool GF>
 static bool lk_launch_v2(int winsize, cudaStream_t st, const LkLevels& L, const vppb_lk_params& P, const vppb_float2* kps,
                          const vppb_float2* pred, int n, vppb_float2* flow, float* err) {
-  const int per_cta = LK2_WARPS * LK2_KPW;
-  const int grid = (n + per_cta - 1) / per_cta;
-  switch (winsize) {
-    case 1: case 3: case 5: k_lk_match_v2<4, GF><<<grid, LK2_WARPS * 32, 0, st>>>(L, P, kps, pred, n, flow, err); return true;
-    case 7: k_lk_match_v2<7, GF><<<grid, LK2_WARPS * 32, 0, st>>>(L, P, kps, pred, n, flow, err); return true;
-    case 9: k_lk_match_v2<11, GF><<<grid, LK2_WARPS * 32, 0, st>>>(L, P, kps, pred, n, flow, err); return true;
-    case 11: k_lk_match_v2<16, GF><<<grid, LK2_WARPS * 32, 0, st>>>(L, P, kps, pred, n, flow, err); return true;
-    default: return false;
-  }
+  const char* e = getenv("VPPB_LK_WARPS");
+  const int w = e ? atoi(e) : LK2_WARPS;
+  if (w == 1) return lk_launch_v2w<GF, 1>(winsize, st, L, P, kps, pred, n, flow, err);
+  if (w == 2) return lk_launch_v2w<GF, 2>(winsize, st, L, P, kps, pred, n, flow, err);
+  return lk_launch_v2w<GF, 4>(winsize, st, L, P, kps, pred, n, flow, err);
 }
 
 template <bool GF>
