@@ -142,3 +142,59 @@ def test_semi_dense_flow(vpp, seed, ws, nscales, min_scale, prop, patch, nk):
     assert np.array_equal(valid, rvalid.astype(bool))
     ok = rvalid > 0
     assert np.array_equal(pos[ok], rpos[ok]) and np.array_equal(dist[ok], rdist[ok])
+
+
+# ---- SURVEY 8(f) N4 stencils -----------------------------------------------------------------------------------------------------
+@settings(max_examples=int(80 * SCALE), **SET)
+@given(nr=st.integers(1, 23), nc=st.one_of(st.integers(1, 50), st.sampled_from([15, 16, 17, 31, 32, 33, 47, 48, 49, 64, 65])), levels=st.integers(1, 255),
+       aligned=st.sampled_from([4, 16, 128]), seed=st.integers(0, 1000))
+def test_lbp_transform(vpp, nr, nc, levels, aligned, seed):
+    """widths around the 16-pixel vectors of the kernel (full vectors, the ragged right edge, images narrower than one vector), row counts
+    around its 4-row strips, 16-byte aligned and unaligned rows"""
+    img = np.random.default_rng(seed).integers(0, levels + 1, (nr, nc)).astype(np.uint8)
+    A = vpp.Image2d.from_host(img, "u8", border=1, aligned=aligned)
+    vpp.fill_border_with_value(A, seed % 256)
+    B = vpp.lbp_transform(A, vpp.Image2d(nr, nc, "u8", aligned=aligned))
+    h = orc.HostImage(nr, nc, "u8", border=1, aligned=aligned, data=img, fill_border="value", border_value=seed % 256)
+    r = orc.HostImage(nr, nc, "u8", aligned=aligned)
+    orc.load().vo_lbp_u8(h.ptr(), r.ptr())
+    assert np.array_equal(B.download(), r.get())
+
+
+@settings(max_examples=int(60 * SCALE), **SET)
+@given(nr=st.integers(1, 20), nc=st.one_of(st.integers(1, 40), st.sampled_from([15, 16, 17, 32, 33])), levels=st.integers(1, 30), pix=st.sampled_from(["u8", "i32"]),
+       signed=st.booleans(), seed=st.integers(0, 1000))
+def test_local_maxima_filter(vpp, nr, nc, levels, pix, signed, seed):
+    """few grey levels (ties, plateaus, chains of dependent decisions across the 16-pixel runs of the kernel), signed values, any border value:
+    the relaxation passes must land on the serial raster-order result"""
+    lo = -levels if (signed and pix == "i32") else 0
+    img = np.random.default_rng(seed).integers(lo, levels + 1, (nr, nc)).astype(np.uint8 if pix == "u8" else np.int32)
+    bv = seed % 5
+    A = vpp.Image2d.from_host(img, pix, border=1)
+    vpp.fill_border_with_value(A, bv)
+    vpp.local_maxima_filter(A)
+    h = orc.HostImage(nr, nc, pix, border=1, data=img, fill_border="value", border_value=bv)
+    orc.load().vo_local_maxima_filter(h.ptr())
+    assert np.array_equal(A.download(with_border=True), h.get(True))
+
+
+@settings(max_examples=int(25 * SCALE), **SET)
+@given(nr=st.integers(8, 60), nc=st.integers(8, 90), th=st.integers(2, 60), bs=st.integers(1, 24), mp=st.integers(1, 16), ring=st.sampled_from(["reference", "true"]),
+       masked=st.booleans(), seed=st.integers(0, 1000))
+def test_fast9_blockwise_rank(vpp, nr, nc, th, bs, mp, ring, masked, seed):
+    """fast_detector9_blockwise_rank: any block size (1 pixel to larger than the image), table sizes 1 .. 16, both rings, masks"""
+    img = scenes.rectangles_scene(nr, nc, seed=seed, nrect=max(4, nr * nc // 150))
+    G = vpp.Image2d.from_host(img, "u8", border=3)
+    vpp.fill_border_mirror(G)
+    h = orc.HostImage(nr, nc, "u8", border=3, data=img, fill_border="mirror")
+    M = hm = None
+    if masked:
+        m = np.random.default_rng(seed).choice(np.array([0, 0x01, 0x10, 0xFF], np.uint8), (nr, nc))
+        M, hm = vpp.Image2d.from_host(m, "u8"), orc.HostImage(nr, nc, "u8", data=m)
+    sc = []
+    got = vpp.fast9_blockwise_rank(G, th, block_size=bs, max_points_per_block=mp, mask=M, scores=sc, ring=ring)
+    cap = nr * nc * 2
+    k3, s = np.zeros((cap, 3), np.int32), np.zeros(cap, np.int32)
+    n = orc.load().vo_fast9_blockwise_rank(h.ptr(), th, hm.ptr() if hm else None, bs, mp, 0 if ring == "reference" else 1, k3.ctypes.data, s.ctypes.data, cap)
+    assert n >= 0 and len(got) == n
+    assert np.array_equal(got, k3[:n]) and np.array_equal(np.array(sc, np.int32).reshape(-1), s[:n])

@@ -142,3 +142,37 @@ def test_blockwise_rank_properties(o):
             m = blocks == b
             assert list(k3[m, 2]) == list(range(m.sum())) or mp > 1 and (np.diff(k3[m, 2]) > 0).all()
             assert (np.diff(sc[m]) <= 0).all()
+
+
+# ---- property-based pins (hypothesis, derandomized like tests/test_oracle_vs_ref_property.py): random geometries and value ranges
+from hypothesis import HealthCheck, given, settings  # noqa: E402
+from hypothesis import strategies as st  # noqa: E402
+
+PSET = dict(max_examples=300, deadline=None, derandomize=True, suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow])
+
+
+@needs_ref
+@settings(**PSET)
+@given(nr=st.integers(1, 30), nc=st.integers(1, 70), levels=st.integers(1, 255), aligned=st.sampled_from([1, 4, 16, 128]), seed=st.integers(0, 2 ** 16))
+def test_lbp_any_geometry(ref, o, nr, nc, levels, aligned, seed):
+    img = np.random.default_rng(seed).integers(0, levels + 1, (nr, nc)).astype(np.uint8)
+    h = orc.HostImage(nr, nc, "u8", border=1, aligned=aligned, data=img, fill_border="value", border_value=seed % 256)
+    a, b = orc.HostImage(nr, nc, "u8", aligned=aligned), orc.HostImage(nr, nc, "u8", aligned=aligned)
+    ref.vppref_lbp_u8(h.ptr(), a.ptr())
+    o.vo_lbp_u8(h.ptr(), b.ptr())
+    assert np.array_equal(a.get(), b.get())
+
+
+@needs_ref
+@settings(**PSET)
+@given(nr=st.integers(1, 24), nc=st.integers(1, 40), levels=st.integers(1, 40), pix=st.sampled_from(["u8", "i32"]), signed=st.booleans(), seed=st.integers(0, 2 ** 16))
+def test_local_maxima_filter_any_image(ref, o, nr, nc, levels, pix, signed, seed):
+    """few grey levels = many ties and plateaus: the strict comparisons and the in-place order decide everything"""
+    lo = -levels if (signed and pix == "i32") else 0
+    img = np.random.default_rng(seed).integers(lo, levels + 1, (nr, nc)).astype(np.uint8 if pix == "u8" else np.int32)
+    bv = seed % 5
+    a = orc.HostImage(nr, nc, pix, border=1, data=img, fill_border="value", border_value=bv)
+    b = orc.HostImage(nr, nc, pix, border=1, data=img, fill_border="value", border_value=bv)
+    ref.vppref_local_maxima_filter(a.ptr())
+    o.vo_local_maxima_filter(b.ptr())
+    assert np.array_equal(a.get(True), b.get(True))
