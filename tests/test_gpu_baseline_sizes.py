@@ -162,3 +162,28 @@ def test_semi_dense_flow_full_frame(vpp, shape):
     assert np.array_equal(valid, rvalid.astype(bool)) and valid.sum() > 1000
     assert np.array_equal(pos, rpos)
     assert np.array_equal(dist, rdist)
+
+
+# ------------------------------------------------------------------ SURVEY 8(f) N4 at frame sizes (the inputs bench.py's extras time and check)
+def test_lbp_transform_4k(vpp, omp):
+    f = np.random.default_rng(4).integers(0, 256, (2160, 3840), dtype=np.uint8)
+    A = vpp.Image2d.from_host(f, "u8", border=1)
+    vpp.fill_border_mirror(A)
+    B = vpp.lbp_transform(A)
+    hs = orc.HostImage(2160, 3840, "u8", border=1, data=f, fill_border="mirror")
+    hd = orc.HostImage(2160, 3840, "u8")
+    omp.vo_lbp_u8(hs.ptr(), hd.ptr())
+    assert np.array_equal(B.download(), hd.get())
+
+
+def test_local_maxima_filter_1080p(vpp):
+    """a FAST-like sparse score image with 200-pixel ramps (chains of dependent decisions): the serial raster-order result, many CTAs"""
+    r_ = np.random.default_rng(6)
+    sc_ = np.where(r_.random((1080, 1920)) < 0.03, r_.integers(1, 250, (1080, 1920)), 0).astype(np.uint8)
+    sc_[100:140, 200:900] = (250 - (np.arange(700) % 200))[None, :].astype(np.uint8)
+    A = vpp.Image2d.from_host(sc_, "u8", border=1)
+    vpp.fill_border_with_value(A, 0)
+    vpp.local_maxima_filter(A)
+    hs = orc.HostImage(1080, 1920, "u8", border=1, data=sc_)
+    orc.load().vo_local_maxima_filter(hs.ptr())
+    assert np.array_equal(A.download(), hs.get())
